@@ -1,0 +1,175 @@
+/*
+ * yara_b200.h -- C ABI of the B200 (sm_100a) scan engine: libyrb200.so.
+ *
+ * Plain pointers and sizes only; no libyara types, no torch types.  This is the
+ * layer the reference's `libyara/cuda` glue binds (yara_b200/host/yr_b200_glue.c
+ * is that glue; INTEGRATION.md shows the three lines it adds to the reference).
+ *
+ * Reference interface each entry point stands in for (libyara 4.2.1):
+ *
+ *   yrb_rules_create / _release   "rules upload": the tables yr_rules_from_arena
+ *                                 wires up (rules.c:326-370) and that
+ *                                 _yr_scanner_scan_mem_block reads
+ *                                 (scanner.c:61-63); lifetime of yr_rules_destroy
+ *                                 (rules.c:515).
+ *   yrb_scanner_create / _destroy per-scanner scan state: yr_scanner_create /
+ *                                 yr_scanner_destroy (scanner.c:205,287) -- the
+ *                                 re_fiber_pool / re_fast_exec_position_pool /
+ *                                 matches[] of YR_SCAN_CONTEXT (types.h:740-821)
+ *                                 become device work areas.
+ *   yrb_scan_host                 _yr_scanner_scan_mem_block(scanner, block_data,
+ *                                 block) (scanner.c:45-176) + everything it
+ *                                 calls: yr_scan_verify_match (scan.c:992),
+ *                                 _yr_scan_verify_literal_match (scan.c:887),
+ *                                 _yr_scan_verify_re_match (scan.c:778),
+ *                                 yr_re_exec / yr_re_fast_exec (re.c:1693,2150),
+ *                                 _yr_scan_match_callback (scan.c:634),
+ *                                 _yr_scan_add_match_to_list (scan.c:290),
+ *                                 _yr_scan_verify_chained_string_match (scan.c:406).
+ *   yrb_scan_device               same, for a block already resident in HBM
+ *                                 (no reference equivalent; used for the
+ *                                 HBM-resident throughput figure and by callers
+ *                                 that produce data on the device).
+ *   yrb_shard_*                   byte-range sharding of ONE block over several
+ *                                 GPUs/processes; no reference
+ *                                 equivalent (a buffer is always scanned by one
+ *                                 thread there, cli/yara.c:1246).
+ *
+ * Errors are the reference's ERROR_* values (error.h:40-109): 0 success,
+ * 1 insufficient memory, 30 too many matches, 46 too many RE fibers, 31 internal.
+ * There is NO CPU fallback: without a usable CUDA device every call fails with
+ * YRB_ERROR_NO_DEVICE.
+ */
+#ifndef YARA_B200_H
+#define YARA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "yrb_image.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YRB_ERROR_NO_DEVICE     1001
+#define YRB_ERROR_BAD_IMAGE     1002
+#define YRB_ERROR_CUDA          1003
+#define YRB_ERROR_BAD_ARGUMENT  1004
+#define YRB_ERROR_MARGIN        1005 /* a shard's read margin was too small for a verification */
+
+typedef struct yrb_rules yrb_rules;
+typedef struct yrb_scanner yrb_scanner;
+
+/* Which AC scan kernel to use (yrb_scanner_set_option YRB_OPT_SCAN_KERNEL). */
+#define YRB_KERNEL_AUTO   0
+#define YRB_KERNEL_WALK   1 /* per-thread chunked walk of the transition table */
+#define YRB_KERNEL_FILTER 2 /* shared-memory atom prefilter + exact walk of survivors */
+
+#define YRB_OPT_SCAN_KERNEL   1
+#define YRB_OPT_H2D_CHUNK     2 /* bytes per H2D slice in yrb_scan_host (default 64 MiB) */
+
+typedef struct yrb_scan_params
+{
+  uint64_t base;           /* block->base (only added to fixed_offset checks, scan.c:1025) */
+  int32_t scan_flags;      /* SCAN_FLAGS_* (scan.h:38-42) */
+  int32_t too_many_action; /* what the user's callback would answer to
+                              CALLBACK_MSG_TOO_MANY_MATCHES: 0 = CALLBACK_CONTINUE
+                              (string gets disabled, scan.c:1064-1067), else abort */
+  /* Byte-range shard of a larger block.  For a whole block leave all zero.
+     data[0] is byte `data_offset` of the block, whose full length is
+     `block_size`; this call owns the AC events i in (own_begin, own_end]
+     (plus i == 0 when own_begin == 0).  Bytes outside the owned range are
+     read-only margin (3 bytes before for the AC state, up to
+     max(YR_RE_SCAN_LIMIT, 2*longest literal) either side for verification). */
+  uint64_t data_offset;
+  uint64_t block_size;
+  uint64_t own_begin;
+  uint64_t own_end;
+  int32_t defer_resolve;   /* 1: stop after verification; fetch raw records with
+                              yrb_shard_raw and resolve all shards together with
+                              yrb_resolve_raw */
+  int32_t reserved;
+} yrb_scan_params;
+
+typedef struct yrb_scan_stats
+{
+  uint64_t bytes;          /* bytes whose AC events were owned by this call */
+  uint64_t n_candidates;   /* yr_scan_verify_match calls that passed the cheap guards */
+  uint64_t n_raw;          /* _yr_scan_match_callback calls that recorded a match */
+  uint32_t kernel_launches;
+  uint32_t scan_kernel;    /* YRB_KERNEL_* actually used */
+  float ms_h2d;            /* CUDA-event times of the last call */
+  float ms_scan;
+  float ms_verify;
+  float ms_resolve;
+  float ms_total;
+} yrb_scan_stats;
+
+typedef struct yrb_scan_result
+{
+  int32_t error;           /* ERROR_* of the block scan */
+  uint32_t error_string;   /* idx for scanner->last_error_string, YRB_NONE if none */
+  size_t n_matches;        /* confirmed matches: by string_idx asc, YR_MATCHES list order inside */
+  const yrb_match* matches;
+  size_t n_unconfirmed;    /* unconfirmed chain-part matches left at end of block */
+  const yrb_match* unconfirmed;
+  uint32_t n_too_many;     /* strings that hit YR_MAX_STRING_MATCHES, in firing order */
+  const uint32_t* too_many;
+  yrb_scan_stats stats;
+} yrb_scan_result;
+/* Pointers inside a result are owned by the scanner and stay valid until its
+   next scan/resolve call or its destruction. */
+
+int yrb_device_count(void);
+const char* yrb_version(void);
+
+int yrb_rules_create(const void* image, size_t image_size, int device, yrb_rules** out);
+void yrb_rules_retain(yrb_rules* rules);
+void yrb_rules_release(yrb_rules* rules);
+
+int yrb_scanner_create(yrb_rules* rules, yrb_scanner** out);
+void yrb_scanner_destroy(yrb_scanner* scanner);
+int yrb_scanner_set_option(yrb_scanner* scanner, int option, uint64_t value);
+
+/* Scan one block held in host memory: H2D (sliced, overlapped with the scan
+   kernel), AC scan, verification, resolve, D2H of the match records. */
+int yrb_scan_host(
+    yrb_scanner* scanner, const uint8_t* data, size_t size, const yrb_scan_params* params,
+    yrb_scan_result* result);
+
+/* Same for a block already in this scanner's device memory. */
+int yrb_scan_device(
+    yrb_scanner* scanner, const uint8_t* d_data, size_t size, const yrb_scan_params* params,
+    yrb_scan_result* result);
+
+/* Sharded scans: raw (pre-resolve) records of the last defer_resolve scan, as
+   opaque 32-byte records in host memory ... */
+int yrb_shard_raw(yrb_scanner* scanner, const void** records, size_t* n_records);
+/* ... and the global resolve over the concatenated records of all shards. */
+int yrb_resolve_raw(
+    yrb_scanner* scanner, const void* records, size_t n_records, const yrb_scan_params* params,
+    yrb_scan_result* result);
+
+/* Copies min(match_length, max_match_data) bytes of every match of the last
+   yrb_scan_device result into out (packed back to back, offsets[] = start of
+   each, offsets[n] = total): the data copy of scan.c:723-737 for callers whose
+   block lives in HBM. */
+int yrb_gather_match_data(
+    yrb_scanner* scanner, const uint8_t* d_data, uint32_t max_match_data, uint8_t* out, size_t out_cap,
+    uint64_t* offsets);
+
+/* Utilities for benchmarks/tests: device memory owned by the scanner's device,
+   counter-based corpus bytes (identical to yara_b200.synth.rand_bytes) and
+   planting.  They exist so that a 16 GiB corpus never has to cross PCIe. */
+int yrb_dev_alloc(int device, size_t bytes, void** d_ptr);
+int yrb_dev_free(int device, void* d_ptr);
+int yrb_dev_fill_random(int device, void* d_ptr, size_t bytes, uint64_t seed, uint64_t stream_offset);
+int yrb_dev_write(int device, void* d_ptr, size_t d_offset, const void* src, size_t bytes);
+int yrb_dev_read(int device, const void* d_ptr, size_t d_offset, void* dst, size_t bytes);
+int yrb_dev_flush_l2(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,849 @@
+// api.cu -- the extern "C" layer of libyrb200.so (include/yara_b200.h):
+// rules upload, per-scanner device state, and the block-scan pipeline
+//
+//   H2D slices --> AC scan (per slice) --> verify --> resolve --> D2H records
+//
+// One CUDA stream per scanner (plus a copy stream for the H2D slices), so the
+// up-to-YR_MAX_THREADS scanners that may share one YR_RULES (limits.h:45-51)
+// run concurrently against one read-only device image.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "engine.cuh"
+#include "resolve.cuh"
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      if (getenv("YRB_DEBUG")) fprintf(stderr, "yrb200: %s -> %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return (e_ == cudaErrorMemoryAllocation) ? YRB_ERROR_INSUFFICIENT_MEMORY : YRB_ERROR_CUDA;  \
+    }                                                                                             \
+  } while (0)
+
+// ------------------------------------------------------------------- structs
+
+struct yrb_rules
+{
+  int device;
+  std::atomic<int> refs;
+  void* d_image;
+  size_t image_size;
+  yrb_image_header h;
+  DevRules R;
+  FilterTables F;
+  void* d_filter;
+  int num_sms;
+};
+
+template <typename T>
+struct DevBuf
+{
+  T* p = nullptr;
+  size_t cap = 0; // elements
+
+  int ensure(size_t n, bool keep = false)
+  {
+    if (n <= cap) return YRB_SUCCESS;
+    size_t ncap = cap ? cap : 1;
+    while (ncap < n) ncap *= 2;
+    T* np = nullptr;
+    cudaError_t e = cudaMalloc((void**) &np, ncap * sizeof(T));
+    if (e != cudaSuccess) { cudaGetLastError(); return YRB_ERROR_INSUFFICIENT_MEMORY; }
+    if (keep && p && cap) cudaMemcpy(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);
+    if (p) cudaFree(p);
+    p = np;
+    cap = ncap;
+    return YRB_SUCCESS;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf
+{
+  T* p = nullptr;
+  size_t cap = 0;
+
+  int ensure(size_t n)
+  {
+    if (n <= cap) return YRB_SUCCESS;
+    size_t ncap = cap ? cap : 1;
+    while (ncap < n) ncap *= 2;
+    T* np = nullptr;
+    if (cudaHostAlloc((void**) &np, ncap * sizeof(T), cudaHostAllocDefault) != cudaSuccess)
+    { cudaGetLastError(); return YRB_ERROR_INSUFFICIENT_MEMORY; }
+    if (p) cudaFreeHost(p);
+    p = np;
+    cap = ncap;
+    return YRB_SUCCESS;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct yrb_scanner
+{
+  yrb_rules* rules;
+  int device;
+  cudaStream_t stream, copy_stream;
+  cudaEvent_t ev[6];
+  std::vector<cudaEvent_t> slice_ev;
+
+  int opt_kernel = YRB_KERNEL_AUTO;
+  size_t opt_h2d_chunk = 64u << 20;
+
+  DevBuf<uint8_t> d_data;
+  DevBuf<Cand> d_cand[NUM_CLS];
+  DevBuf<Raw> d_raw;
+  DevBuf<uint8_t> ws_fast, ws_re;
+  size_t ws_fast_threads = 0, ws_re_threads = 0;
+  ScanStatus* d_status = nullptr;
+  ScanStatus* h_status = nullptr;
+
+  // resolve scratch
+  DevBuf<uint64_t> k0, k1, kF;
+  DevBuf<uint32_t> ix0, ix1, scr32;
+  DevBuf<uint8_t> cub_tmp;
+  DevBuf<int32_t> c_nxt, c_prv, c_clen, c_mlen, s_lists;
+  DevBuf<uint8_t> c_where;
+  DevBuf<yrb_match> outU, finals, unconf;
+  DevBuf<unsigned long long> str_min_key, str_cut_key;
+  DevBuf<uint32_t> str_count, too_many;
+  bool cut_dirty = true;
+
+  PinBuf<yrb_match> h_finals, h_unconf;
+  PinBuf<uint32_t> h_too_many, h_str_count;
+  PinBuf<Raw> h_raw;
+  size_t h_raw_n = 0;
+
+  // last device-resident result (for yrb_gather_match_data)
+  size_t last_n_final = 0;
+  ScanView last_view;
+  DevBuf<uint64_t> g_offsets;
+  DevBuf<uint8_t> g_data;
+};
+
+// ------------------------------------------------------------------- helpers
+
+extern "C" int yrb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" const char* yrb_version(void) { return "yara_b200 0.1 (sm_100a; libyara 4.2.1 hot path)"; }
+
+// ---------------------------------------------------------------------- rules
+
+extern "C" int yrb_rules_create(const void* image, size_t image_size, int device, yrb_rules** out)
+{
+  if (image == nullptr || out == nullptr || image_size < sizeof(yrb_image_header))
+    return YRB_ERROR_BAD_ARGUMENT;
+
+  const yrb_image_header* h = (const yrb_image_header*) image;
+  if (h->magic != YRB_IMAGE_MAGIC || h->version != YRB_IMAGE_VERSION || h->total_size != image_size)
+    return YRB_ERROR_BAD_IMAGE;
+
+  if (device < 0 || device >= yrb_device_count())
+    return YRB_ERROR_NO_DEVICE;
+
+  CK(cudaSetDevice(device));
+
+  yrb_rules* r = new (std::nothrow) yrb_rules();
+  if (!r) return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  r->device = device;
+  r->refs = 1;
+  r->image_size = image_size;
+  r->h = *h;
+  r->d_image = nullptr;
+  r->d_filter = nullptr;
+
+  if (cudaMalloc(&r->d_image, image_size) != cudaSuccess) { cudaGetLastError(); delete r; return YRB_ERROR_INSUFFICIENT_MEMORY; }
+  if (cudaMemcpy(r->d_image, image, image_size, cudaMemcpyHostToDevice) != cudaSuccess)
+  { cudaFree(r->d_image); delete r; return YRB_ERROR_CUDA; }
+
+  const uint8_t* b = (const uint8_t*) r->d_image;
+  r->R.T = (const uint32_t*) (b + h->off_trans);
+  r->R.M = (const uint32_t*) (b + h->off_match);
+  r->R.acm = (const yrb_acm*) (b + h->off_acm);
+  r->R.S = (const yrb_string*) (b + h->off_strings);
+  r->R.lit = b + h->off_lit;
+  r->R.code = b + h->off_code;
+  r->R.lower = b + h->off_lower;
+  r->R.alter = b + h->off_alter;
+  r->R.tables_size = h->tables_size;
+  r->R.num_acm = h->num_acm;
+  r->R.num_strings = h->num_strings;
+  r->R.stack_words = h->max_re_stack + 1;
+
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  r->num_sms = prop.multiProcessorCount;
+
+  memset(&r->F, 0, sizeof(r->F));
+  int rc = build_filter_tables(image, device, &r->F, &r->d_filter);
+  if (rc != YRB_SUCCESS) { cudaFree(r->d_image); delete r; return rc; }
+
+  *out = r;
+  return YRB_SUCCESS;
+}
+
+extern "C" void yrb_rules_retain(yrb_rules* r) { if (r) r->refs++; }
+
+extern "C" void yrb_rules_release(yrb_rules* r)
+{
+  if (!r) return;
+  if (--r->refs == 0)
+  {
+    cudaSetDevice(r->device);
+    if (r->d_image) cudaFree(r->d_image);
+    if (r->d_filter) cudaFree(r->d_filter);
+    delete r;
+  }
+}
+
+// -------------------------------------------------------------------- scanner
+
+extern "C" int yrb_scanner_create(yrb_rules* rules, yrb_scanner** out)
+{
+  if (!rules || !out) return YRB_ERROR_BAD_ARGUMENT;
+  CK(cudaSetDevice(rules->device));
+
+  yrb_scanner* s = new (std::nothrow) yrb_scanner();
+  if (!s) return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  s->rules = rules;
+  s->device = rules->device;
+  yrb_rules_retain(rules);
+
+  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 6; i++) CK(cudaEventCreate(&s->ev[i]));
+  CK(cudaMalloc((void**) &s->d_status, sizeof(ScanStatus)));
+  CK(cudaHostAlloc((void**) &s->h_status, sizeof(ScanStatus), cudaHostAllocDefault));
+
+  *out = s;
+  return YRB_SUCCESS;
+}
+
+extern "C" void yrb_scanner_destroy(yrb_scanner* s)
+{
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  cudaStreamSynchronize(s->copy_stream);
+  s->d_data.release();
+  for (int c = 0; c < NUM_CLS; c++) s->d_cand[c].release();
+  s->d_raw.release(); s->ws_fast.release(); s->ws_re.release();
+  s->k0.release(); s->k1.release(); s->kF.release(); s->ix0.release(); s->ix1.release(); s->scr32.release();
+  s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release();
+  s->s_lists.release(); s->c_where.release(); s->outU.release(); s->finals.release(); s->unconf.release();
+  s->str_min_key.release(); s->str_cut_key.release(); s->str_count.release(); s->too_many.release();
+  s->g_offsets.release(); s->g_data.release();
+  s->h_finals.release(); s->h_unconf.release(); s->h_too_many.release(); s->h_str_count.release(); s->h_raw.release();
+  if (s->d_status) cudaFree(s->d_status);
+  if (s->h_status) cudaFreeHost(s->h_status);
+  for (auto e : s->slice_ev) cudaEventDestroy(e);
+  for (int i = 0; i < 6; i++) cudaEventDestroy(s->ev[i]);
+  cudaStreamDestroy(s->stream);
+  cudaStreamDestroy(s->copy_stream);
+  yrb_rules_release(s->rules);
+  delete s;
+}
+
+extern "C" int yrb_scanner_set_option(yrb_scanner* s, int option, uint64_t value)
+{
+  if (!s) return YRB_ERROR_BAD_ARGUMENT;
+  switch (option)
+  {
+  case YRB_OPT_SCAN_KERNEL:
+    if (value > YRB_KERNEL_FILTER) return YRB_ERROR_BAD_ARGUMENT;
+    s->opt_kernel = (int) value;
+    return YRB_SUCCESS;
+  case YRB_OPT_H2D_CHUNK:
+    if (value < 4096) return YRB_ERROR_BAD_ARGUMENT;
+    s->opt_h2d_chunk = (size_t) value & ~(size_t) 255;
+    return YRB_SUCCESS;
+  }
+  return YRB_ERROR_BAD_ARGUMENT;
+}
+
+// ------------------------------------------------------------- scan pipeline
+
+static int pick_kernel(const yrb_scanner* s)
+{
+  if (s->opt_kernel == YRB_KERNEL_WALK) return YRB_KERNEL_WALK;
+  if (s->rules->F.usable) return YRB_KERNEL_FILTER;
+  return YRB_KERNEL_WALK;
+}
+
+static void launch_scan_slice(yrb_scanner* s, int kernel, const ScanView& V, const CandOut& co, int64_t lo, int64_t hi)
+{
+  if (kernel == YRB_KERNEL_FILTER)
+    launch_ac_scan_filter(s->rules->R, s->rules->F, V, co, lo, hi, s->rules->num_sms, s->stream);
+  else
+    launch_ac_scan_walk(s->rules->R, V, co, lo, hi, s->stream);
+}
+
+static int read_status(yrb_scanner* s)
+{
+  CK(cudaMemcpyAsync(s->h_status, s->d_status, sizeof(ScanStatus), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return YRB_SUCCESS;
+}
+
+static int ensure_resolve_scratch(yrb_scanner* s, uint32_t n)
+{
+  const uint32_t ns = s->rules->R.num_strings ? s->rules->R.num_strings : 1;
+  int rc = 0;
+  rc |= s->k0.ensure(n); rc |= s->k1.ensure(n); rc |= s->kF.ensure(n);
+  rc |= s->ix0.ensure(n); rc |= s->ix1.ensure(n); rc |= s->scr32.ensure(n);
+  rc |= s->outU.ensure(n); rc |= s->finals.ensure(n); rc |= s->unconf.ensure(n);
+  rc |= s->cub_tmp.ensure(resolve_cub_temp_bytes(n));
+  if (s->rules->h.num_chains > 0)
+  {
+    rc |= s->c_nxt.ensure(n); rc |= s->c_prv.ensure(n); rc |= s->c_clen.ensure(n); rc |= s->c_mlen.ensure(n);
+    rc |= s->c_where.ensure(n); rc |= s->s_lists.ensure((size_t) 6 * ns);
+  }
+  rc |= s->str_min_key.ensure(ns); rc |= s->str_cut_key.ensure(ns); rc |= s->str_count.ensure(ns);
+  rc |= s->too_many.ensure(1024);
+  return rc ? YRB_ERROR_INSUFFICIENT_MEMORY : YRB_SUCCESS;
+}
+
+static void fill_work(yrb_scanner* s, ResolveWork& w, const Raw* raw, uint32_t n, int scan_flags)
+{
+  w.raw = raw;
+  w.n_raw = n;
+  w.R = s->rules->R;
+  w.scan_flags = scan_flags;
+  w.has_chains = s->rules->h.num_chains > 0;
+  w.use_cut = 0;
+  w.k0 = s->k0.p; w.k1 = s->k1.p; w.kF = s->kF.p; w.ix0 = s->ix0.p; w.ix1 = s->ix1.p; w.c_scratch_u32 = s->scr32.p;
+  w.cub_tmp = s->cub_tmp.p; w.cub_tmp_bytes = s->cub_tmp.cap;
+  w.c_nxt = s->c_nxt.p; w.c_prv = s->c_prv.p; w.c_clen = s->c_clen.p; w.c_mlen = s->c_mlen.p; w.c_where = s->c_where.p;
+  w.outU = s->outU.p;
+  w.str_min_key = s->str_min_key.p; w.str_cut_key = s->str_cut_key.p; w.str_count = s->str_count.p;
+  w.s_lists = s->s_lists.p;
+  w.finals = s->finals.p; w.unconf = s->unconf.p;
+  w.too_many = s->too_many.p; w.too_many_cap = 1024;
+  w.st = s->d_status;
+}
+
+// Resolve `n` raw records resident at d_raw; fills result (matches, unconfirmed, too_many, error).
+static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_scan_params* params, yrb_scan_result* res,
+                       unsigned* launches)
+{
+  ScanStatus* hs = s->h_status;
+  res->n_matches = res->n_unconfirmed = 0;
+  res->n_too_many = 0;
+  std::vector<std::pair<unsigned long long, uint32_t>> cuts; // (cut key, string)
+
+  if (n > 0)
+  {
+    int rc = ensure_resolve_scratch(s, n);
+    if (rc != YRB_SUCCESS) return rc;
+
+    ResolveWork w;
+    fill_work(s, w, d_raw, n, params->scan_flags);
+
+    launch_resolve_sorts(w, s->stream, launches);
+    launch_resolve_select(w, s->stream, launches);
+    rc = read_status(s);
+    if (rc != YRB_SUCCESS) return rc;
+
+    if (hs->over_cap)
+    {
+      // rare, exact path: find each over-cap string's cut key, then redo sort+select without the cut records
+      const uint32_t ns = s->rules->R.num_strings;
+      if (s->h_str_count.ensure(ns) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+      CK(cudaMemsetAsync(s->str_cut_key.p, 0xFF, sizeof(unsigned long long) * ns, s->stream));
+      CK(cudaMemcpyAsync(s->h_str_count.p, s->str_count.p, sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaStreamSynchronize(s->stream));
+      for (uint32_t t = 0; t < ns; t++)
+      {
+        if (s->h_str_count.p[t] > YRB_MAX_STRING_MATCHES)
+        {
+          unsigned long long cut = ~0ULL;
+          rc = resolve_cap_cut(w, t, s->stream, &cut);
+          if (rc != YRB_SUCCESS) return rc;
+          if (cut != ~0ULL) cuts.push_back(std::make_pair(cut, t));
+        }
+      }
+      w.use_cut = 1;
+      CK(cudaMemsetAsync(&s->d_status->n_final, 0, sizeof(unsigned long long), s->stream));
+      CK(cudaMemsetAsync(&s->d_status->over_cap, 0, sizeof(unsigned int), s->stream));
+      launch_resolve_sorts(w, s->stream, launches);
+      launch_resolve_select(w, s->stream, launches);
+    }
+
+    launch_resolve_chains_and_order(w, s->stream, launches);
+    rc = read_status(s);
+    if (rc != YRB_SUCCESS) return rc;
+
+    const size_t nf = (size_t) hs->n_final, nu = (size_t) hs->n_unconf;
+    uint32_t ntm = hs->n_too_many > 1024 ? 1024 : hs->n_too_many;
+
+    if (s->h_finals.ensure(nf ? nf : 1) || s->h_unconf.ensure(nu ? nu : 1) || s->h_too_many.ensure(1024 + cuts.size() + 1))
+      return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+    if (nf) CK(cudaMemcpyAsync(s->h_finals.p, s->finals.p, nf * sizeof(yrb_match), cudaMemcpyDeviceToHost, s->stream));
+    if (nu) CK(cudaMemcpyAsync(s->h_unconf.p, s->unconf.p, nu * sizeof(yrb_match), cudaMemcpyDeviceToHost, s->stream));
+    if (ntm) CK(cudaMemcpyAsync(s->h_too_many.p, s->too_many.p, ntm * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+
+    // cut strings fire their TOO_MANY callback in discovery order of the cut
+    std::sort(cuts.begin(), cuts.end());
+    for (auto& c : cuts) s->h_too_many.p[ntm++] = c.second;
+
+    res->n_matches = nf;
+    res->n_unconfirmed = nu;
+    res->n_too_many = ntm;
+    s->last_n_final = nf;
+  }
+  else
+  {
+    s->last_n_final = 0;
+  }
+
+  res->matches = s->h_finals.p;
+  res->unconfirmed = s->h_unconf.p;
+  res->too_many = s->h_too_many.p;
+
+  // error precedence: the earliest failing candidate in discovery order
+  // (scanner.c:111 GOTO_EXIT_ON_ERROR) vs. the earliest TOO_MANY abort
+  unsigned long long first_abort = ~0ULL;
+  if (params->too_many_action != 0 && res->n_too_many > 0)
+  {
+    first_abort = cuts.empty() ? 0 : cuts[0].first;
+    res->error = YRB_ERROR_TOO_MANY_MATCHES;
+    res->error_string = res->too_many[0];
+  }
+  if (hs->err_key != ~0ULL && (hs->err_key | KEY_SEQ_MAX) < (first_abort | KEY_SEQ_MAX))
+  {
+    res->error = (int32_t) (hs->err_key & KEY_SEQ_MAX);
+    res->error_string = YRB_NONE;
+  }
+  return YRB_SUCCESS;
+}
+
+static int scan_impl(
+    yrb_scanner* s, const uint8_t* h_data, const uint8_t* d_data_in, size_t size, const yrb_scan_params* params,
+    yrb_scan_result* res)
+{
+  if (!s || !params || !res || (size > 0 && !h_data && !d_data_in)) return YRB_ERROR_BAD_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+
+  memset(res, 0, sizeof(*res));
+  res->error_string = YRB_NONE;
+  unsigned launches = 0;
+
+  ScanView V;
+  memset(&V, 0, sizeof(V));
+  V.g0 = (int64_t) params->data_offset;
+  V.g1 = V.g0 + (int64_t) size;
+  V.gsize = params->block_size ? (int64_t) params->block_size : (int64_t) size;
+  V.own_lo = params->block_size ? (int64_t) params->own_begin : 0;
+  V.own_hi = params->block_size ? (int64_t) params->own_end : (int64_t) size;
+  V.base = params->base;
+  V.scan_flags = params->scan_flags;
+
+  if (V.gsize >= (1LL << 40) || V.g1 > V.gsize || V.own_hi > V.gsize || V.own_lo > V.own_hi)
+    return YRB_ERROR_BAD_ARGUMENT;
+
+  const uint8_t* d_data = d_data_in;
+  if (h_data)
+  {
+    int rc = s->d_data.ensure(size ? size + 16 : 16);
+    if (rc != YRB_SUCCESS) return rc;
+    d_data = s->d_data.p;
+  }
+  V.d = d_data;
+
+  // bytes whose events this call owns, clipped to what is locally present
+  int64_t lo = V.own_lo > V.g0 ? V.own_lo : V.g0;
+  int64_t hi = V.own_hi < V.g1 ? V.own_hi : V.g1;
+  // events i in (own_lo, own_hi] are produced by consuming bytes [own_lo, own_hi)
+  if (hi < lo) hi = lo;
+  res->stats.bytes = (uint64_t) (hi - lo);
+
+  const int kernel = pick_kernel(s);
+  res->stats.scan_kernel = (uint32_t) kernel;
+
+  // candidate capacities: generous first guess, exact retry on overflow
+  size_t cap_guess = (size_t) ((hi - lo) / 2048) + 65536;
+  for (int c = 0; c < NUM_CLS; c++)
+    if (s->d_cand[c].ensure(cap_guess) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  CK(cudaEventRecord(s->ev[0], s->stream));
+
+  // ---- H2D slices, each followed by its AC scan slice
+  const size_t chunk = s->opt_h2d_chunk;
+  size_t n_slices = h_data ? (size + chunk - 1) / chunk : 0;
+  while (s->slice_ev.size() < n_slices)
+  {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    s->slice_ev.push_back(e);
+  }
+
+  ScanStatus* hs = s->h_status;
+
+  for (int attempt = 0;; attempt++)
+  {
+    CK(cudaMemsetAsync(s->d_status, 0, sizeof(ScanStatus), s->stream));
+    CK(cudaMemsetAsync(&s->d_status->err_key, 0xFF, sizeof(unsigned long long), s->stream));
+
+    CandOut co;
+    for (int c = 0; c < NUM_CLS; c++) { co.cand[c] = s->d_cand[c].p; co.cap[c] = s->d_cand[c].cap; }
+    co.st = s->d_status;
+
+    if (V.own_lo == 0)
+    {
+      launch_ac_event0(s->rules->R, V, co, s->stream);
+      launches++;
+    }
+
+    if (h_data && attempt == 0)
+    {
+      CK(cudaEventRecord(s->ev[5], s->stream));
+      CK(cudaStreamWaitEvent(s->copy_stream, s->ev[5], 0)); // d_data may still be read by the previous scan
+      for (size_t k = 0; k < n_slices; k++)
+      {
+        const size_t o = k * chunk;
+        const size_t nb = (o + chunk <= size) ? chunk : size - o;
+        CK(cudaMemcpyAsync(s->d_data.p + o, h_data + o, nb, cudaMemcpyHostToDevice, s->copy_stream));
+        CK(cudaEventRecord(s->slice_ev[k], s->copy_stream));
+        CK(cudaStreamWaitEvent(s->stream, s->slice_ev[k], 0));
+        // local bytes [o, o+nb) are block bytes [g0+o, g0+o+nb)
+        int64_t slo = V.g0 + (int64_t) o, shi = V.g0 + (int64_t) (o + nb);
+        if (slo < lo) slo = lo;
+        if (shi > hi) shi = hi;
+        if (shi > slo) { launch_scan_slice(s, kernel, V, co, slo, shi); launches++; }
+      }
+    }
+    else if (hi > lo)
+    {
+      launch_scan_slice(s, kernel, V, co, lo, hi);
+      launches++;
+    }
+
+    CK(cudaEventRecord(s->ev[1], s->stream));
+    int rc = read_status(s);
+    if (rc != YRB_SUCCESS) return rc;
+
+    bool overflow = false;
+    for (int c = 0; c < NUM_CLS; c++)
+    {
+      if (hs->n_cand[c] > s->d_cand[c].cap)
+      {
+        overflow = true;
+        if (s->d_cand[c].ensure((size_t) hs->n_cand[c] + 1024) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+      }
+    }
+    if (!overflow) break;
+    if (attempt > 3) return YRB_ERROR_INTERNAL_FATAL;
+  }
+
+  if (hs->margin_fault)
+    return YRB_ERROR_MARGIN;
+
+  unsigned long long n_cand[NUM_CLS];
+  unsigned long long total_cand = 0;
+  for (int c = 0; c < NUM_CLS; c++) { n_cand[c] = hs->n_cand[c]; total_cand += n_cand[c]; }
+  res->stats.n_candidates = total_cand;
+
+  // ---- verification
+  if (n_cand[CLS_FAST] > 0)
+  {
+    size_t want = (size_t) ((n_cand[CLS_FAST] + 127) / 128) * 128;
+    const size_t maxt = (size_t) s->rules->num_sms * 256; // bounds the work area (55 KB per thread)
+    if (want > maxt) want = maxt;
+    if (want > s->ws_fast_threads)
+    {
+      if (s->ws_fast.ensure(want * fast_ws_bytes_per_thread()) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+      s->ws_fast_threads = want;
+    }
+  }
+  if (n_cand[CLS_RE] > 0)
+  {
+    size_t want = (size_t) ((n_cand[CLS_RE] + 127) / 128) * 128;
+    const size_t maxt = (size_t) s->rules->num_sms * 512;
+    if (want > maxt) want = maxt;
+    if (want > s->ws_re_threads)
+    {
+      if (s->ws_re.ensure(want * re_ws_bytes_per_thread(s->rules->R.stack_words)) != YRB_SUCCESS)
+        return YRB_ERROR_INSUFFICIENT_MEMORY;
+      s->ws_re_threads = want;
+    }
+  }
+
+  if (s->d_raw.ensure((size_t) total_cand * 2 + 4096) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  for (int attempt = 0;; attempt++)
+  {
+    CandOut co;
+    for (int c = 0; c < NUM_CLS; c++) { co.cand[c] = s->d_cand[c].p; co.cap[c] = s->d_cand[c].cap; }
+    co.st = s->d_status;
+    RawOut ro;
+    ro.raw = s->d_raw.p;
+    ro.cap = s->d_raw.cap;
+    ro.st = s->d_status;
+
+    launch_verify(s->rules->R, V, co, n_cand, ro, s->ws_fast.p, s->ws_fast_threads, s->ws_re.p, s->ws_re_threads,
+                  s->stream, &launches);
+    CK(cudaEventRecord(s->ev[2], s->stream));
+    int rc = read_status(s);
+    if (rc != YRB_SUCCESS) return rc;
+
+    if (hs->n_raw <= s->d_raw.cap) break;
+    if (attempt > 2) return YRB_ERROR_INTERNAL_FATAL;
+    if (s->d_raw.ensure((size_t) hs->n_raw + 1024) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+    CK(cudaMemsetAsync(&s->d_status->n_raw, 0, sizeof(unsigned long long), s->stream));
+    CK(cudaMemsetAsync(&s->d_status->err_key, 0xFF, sizeof(unsigned long long), s->stream));
+  }
+
+  if (hs->margin_fault)
+    return YRB_ERROR_MARGIN;
+
+  const unsigned long long n_raw = hs->n_raw;
+  if (n_raw >= (1ULL << 31)) return YRB_ERROR_INSUFFICIENT_MEMORY;
+  res->stats.n_raw = n_raw;
+  s->last_view = V;
+
+  int rc = YRB_SUCCESS;
+  if (params->defer_resolve)
+  {
+    if (s->h_raw.ensure(n_raw ? (size_t) n_raw : 1) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+    if (n_raw) CK(cudaMemcpyAsync(s->h_raw.p, s->d_raw.p, (size_t) n_raw * sizeof(Raw), cudaMemcpyDeviceToHost, s->stream));
+    s->h_raw_n = (size_t) n_raw;
+    if (hs->err_key != ~0ULL) res->error = (int32_t) (hs->err_key & KEY_SEQ_MAX);
+    CK(cudaEventRecord(s->ev[3], s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  else
+  {
+    rc = run_resolve(s, s->d_raw.p, (uint32_t) n_raw, params, res, &launches);
+    CK(cudaEventRecord(s->ev[3], s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
+
+  res->stats.kernel_launches = launches;
+  cudaEventElapsedTime(&res->stats.ms_scan, s->ev[0], s->ev[1]);
+  cudaEventElapsedTime(&res->stats.ms_verify, s->ev[1], s->ev[2]);
+  cudaEventElapsedTime(&res->stats.ms_resolve, s->ev[2], s->ev[3]);
+  cudaEventElapsedTime(&res->stats.ms_total, s->ev[0], s->ev[3]);
+  res->stats.ms_h2d = h_data ? res->stats.ms_scan : 0.f;
+  return rc;
+}
+
+extern "C" int yrb_scan_host(
+    yrb_scanner* s, const uint8_t* data, size_t size, const yrb_scan_params* params, yrb_scan_result* result)
+{
+  static const uint8_t dummy = 0;
+  return scan_impl(s, data ? data : &dummy, nullptr, size, params, result);
+}
+
+extern "C" int yrb_scan_device(
+    yrb_scanner* s, const uint8_t* d_data, size_t size, const yrb_scan_params* params, yrb_scan_result* result)
+{
+  static const uint8_t dummy = 0;
+  return scan_impl(s, nullptr, d_data ? d_data : &dummy, size, params, result);
+}
+
+extern "C" int yrb_shard_raw(yrb_scanner* s, const void** records, size_t* n_records)
+{
+  if (!s || !records || !n_records) return YRB_ERROR_BAD_ARGUMENT;
+  *records = s->h_raw.p;
+  *n_records = s->h_raw_n;
+  return YRB_SUCCESS;
+}
+
+extern "C" int yrb_resolve_raw(
+    yrb_scanner* s, const void* records, size_t n_records, const yrb_scan_params* params, yrb_scan_result* res)
+{
+  if (!s || !params || !res || (n_records && !records) || n_records >= (1ULL << 31)) return YRB_ERROR_BAD_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  memset(res, 0, sizeof(*res));
+  res->error_string = YRB_NONE;
+  unsigned launches = 0;
+
+  if (s->d_raw.ensure(n_records ? n_records : 1) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+  CK(cudaEventRecord(s->ev[2], s->stream));
+  CK(cudaMemsetAsync(s->d_status, 0, sizeof(ScanStatus), s->stream));
+  CK(cudaMemsetAsync(&s->d_status->err_key, 0xFF, sizeof(unsigned long long), s->stream));
+  if (n_records)
+    CK(cudaMemcpyAsync(s->d_raw.p, records, n_records * sizeof(Raw), cudaMemcpyHostToDevice, s->stream));
+  int rc = read_status(s);
+  if (rc != YRB_SUCCESS) return rc;
+  rc = run_resolve(s, s->d_raw.p, (uint32_t) n_records, params, res, &launches);
+  CK(cudaEventRecord(s->ev[3], s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  res->stats.n_raw = n_records;
+  res->stats.kernel_launches = launches;
+  cudaEventElapsedTime(&res->stats.ms_resolve, s->ev[2], s->ev[3]);
+  return rc;
+}
+
+// ------------------------------------------------------------ match data copy
+
+__global__ void match_len_kernel(const yrb_match* m, uint32_t n, uint32_t max_match_data, uint64_t* lens)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int32_t l = m[j].match_length;
+  lens[j] = (uint64_t) (l < 0 ? 0 : (l > (int32_t) max_match_data ? (int32_t) max_match_data : l));
+}
+
+__global__ void match_copy_kernel(const yrb_match* m, uint32_t n, const uint64_t* offs, ScanView V, uint8_t* out)
+{
+  // one warp per match
+  const uint32_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (j >= n) return;
+  const uint64_t o0 = offs[j], o1 = offs[j + 1];
+  const int64_t src = m[j].offset;
+  for (uint64_t k = lane; k < o1 - o0; k += 32)
+  {
+    const int64_t p = src + (int64_t) k;
+    out[o0 + k] = (p >= V.g0 && p < V.g1) ? V.d[p - V.g0] : 0;
+  }
+}
+
+extern "C" int yrb_gather_match_data(
+    yrb_scanner* s, const uint8_t* d_data, uint32_t max_match_data, uint8_t* out, size_t out_cap, uint64_t* offsets)
+{
+  if (!s || !offsets) return YRB_ERROR_BAD_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  const uint32_t n = (uint32_t) s->last_n_final;
+  offsets[0] = 0;
+  if (n == 0) return YRB_SUCCESS;
+
+  if (s->g_offsets.ensure((size_t) n + 1) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint64_t*) nullptr, (uint64_t*) nullptr, (int) n + 1);
+  if (s->cub_tmp.ensure(tb + 256) != YRB_SUCCESS || s->kF.ensure((size_t) n + 1) != YRB_SUCCESS)
+    return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  CK(cudaMemsetAsync(s->kF.p, 0, ((size_t) n + 1) * sizeof(uint64_t), s->stream));
+  match_len_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->finals.p, n, max_match_data, s->kF.p);
+  size_t tb2 = s->cub_tmp.cap;
+  cub::DeviceScan::ExclusiveSum(s->cub_tmp.p, tb2, s->kF.p, s->g_offsets.p, (int) n + 1, s->stream);
+  CK(cudaMemcpyAsync(offsets, s->g_offsets.p, ((size_t) n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+
+  const uint64_t total = offsets[n];
+  if (total > out_cap) return YRB_ERROR_INSUFFICIENT_MEMORY;
+  if (total == 0) return YRB_SUCCESS;
+  if (s->g_data.ensure((size_t) total) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  ScanView V = s->last_view;
+  V.d = d_data;
+  match_copy_kernel<<<(unsigned) (((uint64_t) n * 32 + 255) / 256), 256, 0, s->stream>>>(s->finals.p, n, s->g_offsets.p, V, s->g_data.p);
+  CK(cudaMemcpyAsync(out, s->g_data.p, (size_t) total, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  return YRB_SUCCESS;
+}
+
+// ------------------------------------------------------------------ utilities
+
+extern "C" int yrb_dev_alloc(int device, size_t bytes, void** d_ptr)
+{
+  if (device < 0 || device >= yrb_device_count()) return YRB_ERROR_NO_DEVICE;
+  CK(cudaSetDevice(device));
+  CK(cudaMalloc(d_ptr, bytes ? bytes : 1));
+  return YRB_SUCCESS;
+}
+
+extern "C" int yrb_dev_free(int device, void* d_ptr)
+{
+  if (device < 0 || device >= yrb_device_count()) return YRB_ERROR_NO_DEVICE;
+  CK(cudaSetDevice(device));
+  CK(cudaFree(d_ptr));
+  return YRB_SUCCESS;
+}
+
+// byte k of the stream = (splitmix64(seed + (k >> 3)) >> (8 * (k & 7))) & 0xFF  -- yara_b200/synth.py rand_bytes
+__global__ void fill_random_kernel(uint8_t* p, size_t bytes, uint64_t seed, uint64_t stream_offset)
+{
+  const size_t nwords = (bytes + 7) / 8 + 1;
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  const uint64_t w0 = stream_offset >> 3;
+  const unsigned shift_bytes = (unsigned) (stream_offset & 7);
+
+  for (size_t w = (size_t) blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += stride)
+  {
+    uint64_t z = (w0 + w + seed + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    // word w covers stream bytes [8*(w0+w), +8) = local bytes [8*w - shift_bytes, +8)
+    const int64_t l0 = (int64_t) (8 * w) - (int64_t) shift_bytes;
+    if (shift_bytes == 0 && l0 + 8 <= (int64_t) bytes && ((uintptr_t) (p + l0) & 7) == 0)
+    {
+      *reinterpret_cast<uint64_t*>(p + l0) = z;
+    }
+    else
+    {
+      for (int j = 0; j < 8; j++)
+      {
+        const int64_t l = l0 + j;
+        if (l >= 0 && l < (int64_t) bytes) p[l] = (uint8_t) (z >> (8 * j));
+      }
+    }
+  }
+}
+
+extern "C" int yrb_dev_fill_random(int device, void* d_ptr, size_t bytes, uint64_t seed, uint64_t stream_offset)
+{
+  if (device < 0 || device >= yrb_device_count()) return YRB_ERROR_NO_DEVICE;
+  CK(cudaSetDevice(device));
+  if (bytes == 0) return YRB_SUCCESS;
+  fill_random_kernel<<<148 * 8, 256>>>((uint8_t*) d_ptr, bytes, seed, stream_offset);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  return YRB_SUCCESS;
+}
+
+extern "C" int yrb_dev_write(int device, void* d_ptr, size_t d_offset, const void* src, size_t bytes)
+{
+  if (device < 0 || device >= yrb_device_count()) return YRB_ERROR_NO_DEVICE;
+  CK(cudaSetDevice(device));
+  CK(cudaMemcpy((uint8_t*) d_ptr + d_offset, src, bytes, cudaMemcpyHostToDevice));
+  return YRB_SUCCESS;
+}
+
+extern "C" int yrb_dev_read(int device, const void* d_ptr, size_t d_offset, void* dst, size_t bytes)
+{
+  if (device < 0 || device >= yrb_device_count()) return YRB_ERROR_NO_DEVICE;
+  CK(cudaSetDevice(device));
+  CK(cudaMemcpy(dst, (const uint8_t*) d_ptr + d_offset, bytes, cudaMemcpyDeviceToHost));
+  return YRB_SUCCESS;
+}
+
+__global__ void flush_kernel(uint32_t* p, size_t n)
+{
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = (uint32_t) i;
+}
+
+extern "C" int yrb_dev_flush_l2(int device)
+{
+  static void* buf[16] = {nullptr};
+  const size_t bytes = 256u << 20; // > 126 MB L2
+  if (device < 0 || device >= yrb_device_count() || device >= 16) return YRB_ERROR_NO_DEVICE;
+  CK(cudaSetDevice(device));
+  if (!buf[device]) CK(cudaMalloc(&buf[device], bytes));
+  flush_kernel<<<148 * 4, 256>>>((uint32_t*) buf[device], bytes / 4);
+  CK(cudaDeviceSynchronize());
+  return YRB_SUCCESS;
+}

@@ -1,0 +1,81 @@
+// emit.cuh -- turning an Aho-Corasick hit (position i, state) into verifier
+// candidates: the `match_table[state] != 0` branch of scanner.c:98-122 plus the
+// data-independent guards of yr_scan_verify_match (scan.c:1015,1025-1027).
+#pragma once
+
+#include "engine.cuh"
+
+// One candidate per YR_AC_MATCH of the state's chain with backtrack <= i.
+// chain_pos numbers the chain entries so that (i, chain_pos) reproduces the
+// order in which the reference would have called yr_scan_verify_match.
+static __device__ __forceinline__ void emit_events(
+    const DevRules& R, const ScanView& V, const CandOut& out, int64_t i, uint32_t first /* M[state], 1-based */)
+{
+  uint32_t k = first;
+  uint32_t chain_pos = 0;
+
+  while (k != 0)
+  {
+    const yrb_acm m = R.acm[k - 1];
+
+    if ((int64_t) m.backtrack <= i)
+    {
+      int64_t offset = i - (int64_t) m.backtrack;
+
+      // scan.c:1015  `data_size - offset <= 0` (size_t arithmetic: only == 0)
+      if (offset != V.gsize)
+      {
+        const uint32_t sflags = R.S[m.string_idx].flags;
+        bool ok = true;
+
+        // scan.c:1025-1027 FIXED_OFFSET guard
+        if (sflags & YRB_SF_FIXED_OFFSET)
+          ok = (R.S[m.string_idx].fixed_offset == (int64_t) (V.base + (uint64_t) offset));
+
+        if (ok)
+        {
+          int cls = (sflags & YRB_SF_LITERAL) ? CLS_LITERAL : ((sflags & YRB_SF_FAST_REGEXP) ? CLS_FAST : CLS_RE);
+          unsigned long long slot = atomicAdd(&out.st->n_cand[cls], 1ULL);
+
+          if (slot < out.cap[cls])
+          {
+            Cand c;
+            c.key = ((uint64_t) i << KEY_I_SHIFT) |
+                    ((uint64_t) (chain_pos < KEY_CHAIN_MAX ? chain_pos : KEY_CHAIN_MAX) << KEY_SEQ_BITS);
+            c.acm_idx = k - 1;
+            c.pad = 0;
+            out.cand[cls][slot] = c;
+          }
+        }
+      }
+    }
+
+    chain_pos++;
+    k = m.next;
+  }
+}
+
+// One transition of the interleaved table (scanner.c:124-141,
+// ahocorasick.h:39-51): slot = target << 9 | (byte + 1); slot 0 of a state is
+// its failure link.
+static __device__ __forceinline__ uint32_t ac_step(const uint32_t* __restrict__ T, uint32_t state, uint32_t byte)
+{
+  const uint32_t index = byte + 1;
+  uint32_t t = __ldg(&T[state + index]);
+
+  while ((t & 0x1FF) != index)
+  {
+    if (state != 0)
+    {
+      state = __ldg(&T[state]) >> 9;
+      t = __ldg(&T[state + index]);
+    }
+    else
+    {
+      t = 0;
+      break;
+    }
+  }
+
+  return t >> 9;
+}

@@ -1,0 +1,158 @@
+// engine.cuh -- internal types shared by the kernels of libyrb200.so.
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   rules image   one blob, byte-identical to the host image (yrb_image.h)
+//   block bytes   the scanned block (or byte-range shard + read margins), u8
+//   candidates    Cand[]  16 B: (discovery key, YR_AC_MATCH index); one array
+//                 per verifier class (literal / fast hex VM / fiber VM)
+//   raw matches   Raw[]   32 B: what _yr_scan_match_callback (scan.c:634) was
+//                 called with, plus the discovery key that orders them
+//   final matches yrb_match[] 24 B: YR_MATCHES lists, string-major
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "yara_b200.h"
+
+// Discovery key (SURVEY.md 8(a) "Order dependence"): lexicographic in
+// (i ascending, position in the state's match chain, callback order inside one
+// exhaustive backward exec).
+#define KEY_SEQ_BITS   13
+#define KEY_CHAIN_BITS 10
+#define KEY_I_SHIFT    (KEY_SEQ_BITS + KEY_CHAIN_BITS)
+#define KEY_SEQ_MAX    ((1u << KEY_SEQ_BITS) - 1)
+#define KEY_CHAIN_MAX  ((1u << KEY_CHAIN_BITS) - 1)
+
+#define CLS_LITERAL 0
+#define CLS_FAST    1
+#define CLS_RE      2
+#define NUM_CLS     3
+
+// RE_FLAGS_* (re.h:94-102)
+#define RE_FLAGS_BACKWARDS  0x04
+#define RE_FLAGS_EXHAUSTIVE 0x08
+#define RE_FLAGS_WIDE       0x10
+#define RE_FLAGS_NO_CASE    0x20
+#define RE_FLAGS_DOT_ALL    0x80
+#define RE_FLAGS_GREEDY     0x400
+
+struct DevRules
+{
+  const uint32_t* T;      // transition table
+  const uint32_t* M;      // match table
+  const yrb_acm* acm;
+  const yrb_string* S;
+  const uint8_t* lit;
+  const uint8_t* code;
+  const uint8_t* lower;
+  const uint8_t* alter;
+  uint32_t tables_size;
+  uint32_t num_acm;
+  uint32_t num_strings;
+  uint32_t stack_words;   // max_re_stack + 1
+};
+
+// The bytes a scan can see, in BLOCK coordinates: d[0] is block byte g0, the
+// local buffer covers [g0, g1), the whole block is [0, gsize).
+struct ScanView
+{
+  const uint8_t* d;
+  int64_t g0;
+  int64_t g1;
+  int64_t gsize;
+  int64_t own_lo;   // events owned: own_lo < i <= own_hi, plus i == 0 if own_lo == 0 ... see ac_scan.cu
+  int64_t own_hi;
+  uint64_t base;
+  int32_t scan_flags;
+  int32_t pad;
+};
+
+struct Cand
+{
+  uint64_t key;      // i << KEY_I_SHIFT | chain_pos << KEY_SEQ_BITS
+  uint32_t acm_idx;
+  uint32_t pad;
+};
+
+struct Raw
+{
+  uint64_t key;       // candidate key | seq
+  int64_t offset;     // block-relative match offset
+  uint32_t string_idx;
+  int32_t length;
+  uint32_t misc;      // bits 0-7 xor_key
+  uint32_t group;     // chain head idx for CHAIN_PART strings, else YRB_NONE
+};
+
+// Device-side counters / status of one scan, one 256-byte struct.
+struct ScanStatus
+{
+  unsigned long long n_cand[NUM_CLS];
+  unsigned long long n_raw;
+  unsigned long long err_key;   // min over failing candidates of (key & ~seq) | error code
+  unsigned long long n_final;
+  unsigned long long n_unconf;
+  unsigned long long n_chain_out;
+  unsigned int margin_fault;    // a verifier needed bytes outside [g0, g1)
+  unsigned int n_too_many;
+  unsigned int over_cap;        // some plain string has more than YR_MAX_STRING_MATCHES distinct offsets
+  unsigned int ws_overflow;     // a per-candidate work area was too small
+  unsigned int survivors;       // filter kernel statistics
+  unsigned int pad[3];
+};
+
+struct CandOut
+{
+  Cand* cand[NUM_CLS];
+  unsigned long long cap[NUM_CLS];
+  ScanStatus* st;
+};
+
+struct RawOut
+{
+  Raw* raw;
+  unsigned long long cap;
+  ScanStatus* st;
+};
+
+// Atom prefilter tables of one ruleset (ac_scan.cu, filter kernel).
+struct FilterTables
+{
+  const uint32_t* b3;     // 2^20-bit bitmap over hashed 3-byte keys (pair probe)
+  const uint32_t* b4;     // 2^19-bit bitmap over hashed 4-byte windows
+  const uint32_t* b2;     // 2^16-bit direct bitmap over 2-byte suffixes (depth-2 states)
+  uint32_t b1[8];         // 256-bit direct bitmap over 1-byte suffixes (depth-1 states)
+  int has_d1, has_d2, root_match, usable;
+};
+
+#define B3_BITS 20
+#define B4_BITS 19
+#define B3_WORDS (1u << (B3_BITS - 5))
+#define B4_WORDS (1u << (B4_BITS - 5))
+#define B2_WORDS (1u << (16 - 5))
+#define HASH3_MUL 0x9E3779B1u
+#define HASH4_MUL 0x85EBCA6Bu
+
+__host__ __device__ static inline uint32_t hash3(uint32_t key3) { return ((key3 << 8) * HASH3_MUL) >> (32 - B3_BITS); }
+__host__ __device__ static inline uint32_t hash4(uint32_t w) { return (w * HASH4_MUL) >> (32 - B4_BITS); }
+
+static __device__ __forceinline__ void report_error(ScanStatus* st, uint64_t cand_key, int code)
+{
+  atomicMin(&st->err_key, (unsigned long long) ((cand_key & ~(uint64_t) KEY_SEQ_MAX) | (uint64_t) code));
+}
+
+// ---- launch helpers implemented across the .cu files -------------------------
+void launch_ac_event0(const DevRules& R, const ScanView& V, const CandOut& out, cudaStream_t s);
+void launch_ac_scan_walk(const DevRules& R, const ScanView& V, const CandOut& out, int64_t lo, int64_t hi, cudaStream_t s);
+void launch_ac_scan_filter(
+    const DevRules& R, const FilterTables& F, const ScanView& V, const CandOut& out, int64_t lo, int64_t hi,
+    int num_sms, cudaStream_t s);
+int build_filter_tables(const void* host_image, int device, FilterTables* out, void** d_storage);
+
+void launch_verify(
+    const DevRules& R, const ScanView& V, const CandOut& cands, const unsigned long long n_cand[NUM_CLS],
+    const RawOut& out, void* ws_fast, size_t ws_fast_threads, void* ws_re, size_t ws_re_threads, cudaStream_t s,
+    unsigned* launches);
+size_t fast_ws_bytes_per_thread();
+size_t re_ws_bytes_per_thread(uint32_t stack_words);

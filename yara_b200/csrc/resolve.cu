@@ -1,0 +1,588 @@
+// resolve.cu -- from Raw records (one per _yr_scan_match_callback call) to the
+// final YR_MATCHES lists, on the device:
+//   _yr_scan_add_match_to_list                 scan.c:290-368   (a10)
+//   _yr_scan_verify_chained_string_match       scan.c:406-632   (a11)
+//   _yr_scan_update_match_chain_length         scan.c:257-288
+//   FAST_MODE / SINGLE_MATCH guard             scan.c:1021-1023 (a4)
+//
+// The reference applies these one candidate at a time in discovery order.  Here
+// every record carries its discovery key, so the same result is computed as:
+//   plain strings   stable radix sort by (string, offset, key); of each
+//                   (string, offset) group the first discovered record survives,
+//                   or the last one for GREEDY_REGEXP strings (replace_if_exists)
+//   chained strings records of one chain sorted by key and replayed by ONE thread
+//                   through a verbatim restatement of the list logic (chains are
+//                   independent of each other; quirk 10 of SURVEY.md 8(a) rules
+//                   out a relational formulation)
+//   1M cap          detected per string; see cap_* below
+#include <cub/cub.cuh>
+
+#include "resolve.cuh"
+
+#define OFFSET_BITS 40
+#define A_CHAIN_BIT (1ULL << 63)
+#define A_DROPPED   (~0ULL)
+
+// ----------------------------------------------------------------- key building
+
+__global__ void fastmode_min_kernel(const Raw* raw, uint32_t n, DevRules R, unsigned long long* str_min_key)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const Raw r = raw[j];
+  if (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH)
+    atomicMin(&str_min_key[r.string_idx], (unsigned long long) (r.key >> KEY_SEQ_BITS));
+}
+
+__global__ void build_key_b_kernel(const Raw* raw, uint32_t n, uint64_t* kB, uint32_t* ix)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  kB[j] = raw[j].key;
+  ix[j] = j;
+}
+
+// After the sort by discovery key: the (string, offset) key for plain strings,
+// the chain key for chain parts.
+__global__ void build_key_a_kernel(
+    const Raw* raw, const uint32_t* ix, uint32_t n, DevRules R, int scan_flags, const unsigned long long* str_min_key,
+    const unsigned long long* str_cut_key, uint64_t* kA)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+
+  const Raw r = raw[ix[j]];
+  const uint32_t sflags = R.S[r.string_idx].flags;
+  uint64_t a;
+
+  if (r.group != YRB_NONE)
+    a = A_CHAIN_BIT | ((uint64_t) r.group << 24);
+  else
+    a = ((uint64_t) r.string_idx << OFFSET_BITS) | (uint64_t) r.offset;
+
+  // scan.c:1021-1023: in fast mode, once a SINGLE_MATCH string has a match, later
+  // candidates are not verified; all callbacks of the first matching candidate stay.
+  if ((scan_flags & YRB_SCAN_FAST_MODE) && (sflags & YRB_SF_SINGLE_MATCH) && r.group == YRB_NONE &&
+      (r.key >> KEY_SEQ_BITS) != str_min_key[r.string_idx])
+    a = A_DROPPED;
+
+  // 1M cap: records discovered at or after the string's cut key never reached a list
+  if (str_cut_key != nullptr && r.key >= str_cut_key[r.string_idx])
+    a = A_DROPPED;
+
+  kA[j] = a;
+}
+
+// --------------------------------------------------------------- plain strings
+
+__global__ void select_plain_kernel(
+    const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, DevRules R, uint32_t* str_count,
+    uint64_t* kF, yrb_match* outU, ScanStatus* st)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+
+  const uint64_t a = kA[j];
+  if (a & A_CHAIN_BIT) return; // chain record or dropped
+
+  const bool is_first = (j == 0) || (kA[j - 1] != a);
+  const bool is_last = (j + 1 == n) || (kA[j + 1] != a);
+
+  const Raw r = raw[ix[j]];
+  const bool greedy = (R.S[r.string_idx].flags & YRB_SF_GREEDY_REGEXP) != 0;
+
+  // replace_if_exists (scan.c:314-319) rewrites length/data of the node that was
+  // inserted first; xor_key of a greedy regexp is always 0, so "last record" is
+  // the same thing.
+  if (greedy ? !is_last : !is_first)
+    return;
+
+  atomicAdd(&str_count[r.string_idx], 1u);
+
+  const unsigned long long slot = atomicAdd(&st->n_final, 1ULL);
+  yrb_match m;
+  m.offset = r.offset;
+  m.string_idx = r.string_idx;
+  m.match_length = r.length;
+  m.xor_key = (uint8_t) (r.misc & 0xFF);
+  m.flags = 0;
+  m.reserved = 0;
+  m.chain_length = 0;
+  outU[slot] = m;
+  kF[slot] = a;
+}
+
+__global__ void check_cap_kernel(const uint32_t* str_count, uint32_t num_strings, ScanStatus* st)
+{
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= num_strings) return;
+  if (str_count[s] > YRB_MAX_STRING_MATCHES)
+    atomicExch(&st->over_cap, 1u);
+}
+
+// -------------------------------------------------------------- chained strings
+
+struct ChainLists
+{
+  int32_t* nxt;   // per sorted record: list links
+  int32_t* prv;
+  int32_t* clen;  // YR_MATCH.chain_length
+  int32_t* mlen;  // YR_MATCH.match_length (rewritten on confirmation)
+  uint8_t* where; // 0 = in no list, 1 = unconfirmed_matches[], 2 = matches[]
+  int32_t* uhead; // per string: unconfirmed_matches[s]
+  int32_t* utail;
+  int32_t* ucnt;
+  int32_t* mhead; // per string: matches[s] (only chain heads are used)
+  int32_t* mtail;
+  int32_t* mcnt;
+};
+
+struct ChainCtx
+{
+  const Raw* raw;
+  const uint32_t* ix;
+  DevRules R;
+  ChainLists L;
+};
+
+static __device__ __forceinline__ int64_t c_off(const ChainCtx& c, int32_t j) { return c.raw[c.ix[j]].offset; }
+
+// scan.c:290-368 over index-linked lists; returns 0 ok / 1 duplicate dropped / 2 too many
+static __device__ int clist_add(ChainCtx& c, int32_t* head, int32_t* tail, int32_t* cnt, uint32_t s, int32_t j)
+{
+  if (cnt[s] == YRB_MAX_STRING_MATCHES)
+    return 2;
+
+  const int64_t off = c_off(c, j);
+  int32_t ip = tail[s];
+
+  while (ip >= 0)
+  {
+    const int64_t o = c_off(c, ip);
+    if (off == o) return 1;
+    if (off > o) break;
+    ip = c.L.prv[ip];
+  }
+
+  c.L.prv[j] = ip;
+  if (ip >= 0)
+  {
+    c.L.nxt[j] = c.L.nxt[ip];
+    c.L.nxt[ip] = j;
+  }
+  else
+  {
+    c.L.nxt[j] = head[s];
+    head[s] = j;
+  }
+  cnt[s]++;
+  if (c.L.nxt[j] >= 0)
+    c.L.prv[c.L.nxt[j]] = j;
+  else
+    tail[s] = j;
+  return 0;
+}
+
+// scan.c:370-389
+static __device__ void clist_remove(ChainCtx& c, int32_t* head, int32_t* tail, int32_t* cnt, uint32_t s, int32_t j)
+{
+  const int32_t p = c.L.prv[j], n = c.L.nxt[j];
+  if (p >= 0) c.L.nxt[p] = n;
+  if (n >= 0) c.L.prv[n] = p;
+  if (head[s] == j) head[s] = n;
+  if (tail[s] == j) tail[s] = p;
+  cnt[s]--;
+  c.L.nxt[j] = c.L.prv[j] = -1;
+}
+
+// scan.c:257-288, recursion turned into an explicit stack of (string, node, length, cursor)
+#define CHAIN_MAX_DEPTH 48
+
+static __device__ void update_chain_length(ChainCtx& c, uint32_t sidx, int32_t node, int chain_length)
+{
+  struct Frame { uint32_t s; int32_t upd; int32_t cur; int len; };
+  Frame fr[CHAIN_MAX_DEPTH];
+  int depth = 0;
+
+  // enter(sidx, node, chain_length)
+  uint32_t s = sidx;
+  int32_t upd = node;
+  int len = chain_length;
+
+  for (;;)
+  {
+    bool descend = false;
+
+    if (c.L.clen[upd] != len)
+    {
+      c.L.clen[upd] = len;
+      const yrb_string st = c.R.S[s];
+      if (st.chained_to != YRB_NONE && depth < CHAIN_MAX_DEPTH)
+      {
+        fr[depth].s = s; fr[depth].upd = upd; fr[depth].len = len;
+        fr[depth].cur = c.L.uhead[st.chained_to];
+        depth++;
+        descend = true;
+      }
+    }
+
+    (void) descend;
+
+    // resume the innermost loop that still has predecessors to visit
+    bool entered = false;
+    while (depth > 0 && !entered)
+    {
+      Frame& f = fr[depth - 1];
+      const yrb_string st = c.R.S[f.s];
+      const int64_t upd_off = c_off(c, f.upd);
+
+      while (f.cur >= 0)
+      {
+        const int32_t k = f.cur;
+        f.cur = c.L.nxt[k];
+        const int64_t ending = c_off(c, k) + c.L.mlen[k];
+        if (ending + st.chain_gap_max >= upd_off && ending + st.chain_gap_min <= upd_off)
+        {
+          s = st.chained_to;
+          upd = k;
+          len = f.len + 1;
+          entered = true;
+          break;
+        }
+      }
+
+      if (!entered)
+        depth--;
+    }
+
+    if (!entered)
+      return;
+  }
+}
+
+// scan.c:406-632.  Returns 0, or 2 when a list hit the 1M cap.
+static __device__ int verify_chained(ChainCtx& c, int32_t j)
+{
+  const Raw r = c.raw[c.ix[j]];
+  const uint32_t sidx = r.string_idx;
+  const yrb_string ms = c.R.S[sidx];
+  const int64_t match_offset = r.offset;
+  const int32_t match_length = r.length;
+  bool add_match = false;
+
+  if (ms.chained_to == YRB_NONE)
+  {
+    add_match = true;
+  }
+  else
+  {
+    const int64_t lowest_offset = c.L.uhead[sidx] >= 0 ? c_off(c, c.L.uhead[sidx]) : match_offset;
+    int32_t k = c.L.uhead[ms.chained_to];
+
+    while (k >= 0)
+    {
+      const int32_t next = c.L.nxt[k];
+      const int64_t ending = c_off(c, k) + c.L.mlen[k];
+
+      if (ending + ms.chain_gap_max < lowest_offset)
+      {
+        clist_remove(c, c.L.uhead, c.L.utail, c.L.ucnt, ms.chained_to, k);
+        c.L.where[k] = 0;
+      }
+      else if (ending + ms.chain_gap_max >= match_offset && ending + ms.chain_gap_min <= match_offset)
+      {
+        add_match = true;
+        break;
+      }
+      k = next;
+    }
+  }
+
+  if (!add_match)
+    return 0;
+
+  if (ms.flags & YRB_SF_CHAIN_TAIL)
+  {
+    for (int32_t k = c.L.uhead[ms.chained_to]; k >= 0; k = c.L.nxt[k])
+    {
+      const int64_t ending = c_off(c, k) + c.L.mlen[k];
+      if (ending + ms.chain_gap_max >= match_offset && ending + ms.chain_gap_min <= match_offset)
+        update_chain_length(c, ms.chained_to, k, 1);
+    }
+
+    int32_t full_chain_length = 0;
+    uint32_t hs = sidx;
+    while (c.R.S[hs].chained_to != YRB_NONE)
+    {
+      full_chain_length++;
+      hs = c.R.S[hs].chained_to;
+    }
+
+    int32_t k = c.L.uhead[hs];
+    while (k >= 0)
+    {
+      const int32_t next = c.L.nxt[k];
+      if (c.L.clen[k] == full_chain_length)
+      {
+        clist_remove(c, c.L.uhead, c.L.utail, c.L.ucnt, hs, k);
+        c.L.mlen[k] = (int32_t) (match_offset - c_off(c, k) + match_length);
+        const int rc = clist_add(c, c.L.mhead, c.L.mtail, c.L.mcnt, hs, k);
+        c.L.where[k] = (rc == 0) ? 2 : 0;
+        if (rc == 2) return 2;
+      }
+      k = next;
+    }
+  }
+  else
+  {
+    c.L.clen[j] = 0;
+    c.L.mlen[j] = match_length;
+    const int rc = clist_add(c, c.L.uhead, c.L.utail, c.L.ucnt, sidx, j);
+    c.L.where[j] = (rc == 0) ? 1 : 0;
+    if (rc == 2) return 2;
+  }
+
+  return 0;
+}
+
+__global__ void chain_init_kernel(ChainLists L, uint32_t num_strings)
+{
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= num_strings) return;
+  L.uhead[s] = L.utail[s] = L.mhead[s] = L.mtail[s] = -1;
+  L.ucnt[s] = L.mcnt[s] = 0;
+}
+
+__global__ void chain_resolve_kernel(
+    const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, DevRules R, ChainLists L, uint64_t* kF,
+    yrb_match* outU, yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap)
+{
+  const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j0 >= n) return;
+
+  const uint64_t a = kA[j0];
+  if (!(a & A_CHAIN_BIT) || a == A_DROPPED) return;
+  if (j0 > 0 && kA[j0 - 1] == a) return; // not the first record of its chain
+
+  ChainCtx c;
+  c.raw = raw;
+  c.ix = ix;
+  c.R = R;
+  c.L = L;
+
+  const uint32_t head_string = raw[ix[j0]].group;
+  uint32_t j = j0;
+  uint64_t prev_key = ~0ULL;
+  uint32_t disabled_string = YRB_NONE; // strings_temp_disabled after a TOO_MANY (at most one tracked per chain)
+
+  for (; j < n && kA[j] == a; j++)
+  {
+    L.nxt[j] = L.prv[j] = -1;
+    L.where[j] = 0;
+
+    const Raw r = raw[ix[j]];
+    if (r.key == prev_key) continue; // idempotent re-emission of the same callback
+    prev_key = r.key;
+
+    if (r.string_idx == disabled_string) continue;
+
+    if (verify_chained(c, (int32_t) j) == 2)
+    {
+      const uint32_t slot = atomicAdd(&st->n_too_many, 1u);
+      if (slot < too_many_cap) too_many[slot] = r.string_idx;
+      disabled_string = r.string_idx;
+    }
+  }
+
+  // confirmed matches of the chain's head string, in list order
+  const int32_t cnt = L.mcnt[head_string];
+  if (cnt > 0)
+  {
+    unsigned long long slot = atomicAdd(&st->n_final, (unsigned long long) cnt);
+    for (int32_t k = L.mhead[head_string]; k >= 0; k = L.nxt[k])
+    {
+      const Raw r = raw[ix[k]];
+      yrb_match m;
+      m.offset = r.offset;
+      m.string_idx = head_string;
+      m.match_length = L.mlen[k];
+      m.xor_key = (uint8_t) (r.misc & 0xFF);
+      m.flags = 0;
+      m.reserved = 0;
+      m.chain_length = L.clen[k];
+      outU[slot] = m;
+      kF[slot] = ((uint64_t) head_string << OFFSET_BITS) | (uint64_t) r.offset;
+      slot++;
+    }
+  }
+
+  // what is left in unconfirmed_matches[] of the chain's strings
+  for (uint32_t k = j0; k < j; k++)
+  {
+    if (L.where[k] == 1)
+    {
+      const Raw r = raw[ix[k]];
+      const unsigned long long slot = atomicAdd(&st->n_unconf, 1ULL);
+      yrb_match m;
+      m.offset = r.offset;
+      m.string_idx = r.string_idx;
+      m.match_length = L.mlen[k];
+      m.xor_key = (uint8_t) (r.misc & 0xFF);
+      m.flags = YRB_MATCH_UNCONFIRMED;
+      m.reserved = 0;
+      m.chain_length = L.clen[k];
+      unconf[slot] = m;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ final order
+
+__global__ void fill_u64_kernel(uint64_t* p, uint32_t n, uint64_t v)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) p[j] = v;
+}
+
+__global__ void iota_kernel(uint32_t* p, uint32_t n)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) p[j] = j;
+}
+
+__global__ void gather_final_kernel(const yrb_match* outU, const uint32_t* ix, const ScanStatus* st, uint32_t n, yrb_match* out)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n || (unsigned long long) j >= st->n_final) return;
+  out[j] = outU[ix[j]];
+}
+
+// ---------------------------------------------------------------- 1M cap (a10)
+//
+// scan.c:303-307 tests `count == YR_MAX_STRING_MATCHES` BEFORE dedup, in
+// discovery order.  For a string whose distinct offsets exceed the cap: the list
+// count grows exactly at first-occurrence records; the error fires at the first
+// record (any, duplicate or not) discovered after the 1,000,000th of them.  That
+// record's key is the string's "cut key": it and everything after it never reach
+// the list (the callback disables the string, scan.c:1064-1067).
+
+__global__ void cap_mark_first_kernel(
+    const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, const uint32_t* str_count, uint64_t* keys_out,
+    uint32_t target, unsigned int* n_out)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint64_t a = kA[j];
+  if (a & A_CHAIN_BIT) return;
+  if ((uint32_t) (a >> OFFSET_BITS) != target) return;
+  if (j > 0 && kA[j - 1] == a) return; // not the first discovered of its offset
+  keys_out[atomicAdd(n_out, 1u)] = raw[ix[j]].key;
+}
+
+__global__ void cap_cut_kernel(
+    const Raw* raw, uint32_t n, uint32_t target, const uint64_t* sorted_first_keys, unsigned long long* cut_key)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const Raw r = raw[j];
+  if (r.string_idx != target || r.group != YRB_NONE) return;
+  const uint64_t k1m = sorted_first_keys[YRB_MAX_STRING_MATCHES - 1];
+  if (r.key > k1m)
+    atomicMin(cut_key, (unsigned long long) r.key);
+}
+
+// ------------------------------------------------------------------- host side
+
+size_t resolve_cub_temp_bytes(uint32_t n)
+{
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (uint64_t*) nullptr, (uint64_t*) nullptr, (uint32_t*) nullptr,
+                                  (uint32_t*) nullptr, (int) n);
+  return b + 256;
+}
+
+#define GRID(n) (unsigned) (((n) + 255) / 256), 256
+
+static void sort_pairs(ResolveWork& w, uint64_t* kin, uint64_t* kout, uint32_t* vin, uint32_t* vout, uint32_t n, cudaStream_t s)
+{
+  size_t b = w.cub_tmp_bytes;
+  cub::DeviceRadixSort::SortPairs(w.cub_tmp, b, kin, kout, vin, vout, (int) n, 0, 64, s);
+}
+
+void launch_resolve_sorts(ResolveWork& w, cudaStream_t s, unsigned* launches)
+{
+  const uint32_t n = w.n_raw;
+
+  if (w.scan_flags & YRB_SCAN_FAST_MODE)
+  {
+    cudaMemsetAsync(w.str_min_key, 0xFF, sizeof(unsigned long long) * w.R.num_strings, s);
+    fastmode_min_kernel<<<GRID(n), 0, s>>>(w.raw, n, w.R, w.str_min_key);
+    (*launches)++;
+  }
+
+  build_key_b_kernel<<<GRID(n), 0, s>>>(w.raw, n, w.k0, w.ix0);
+  sort_pairs(w, w.k0, w.k1, w.ix0, w.ix1, n, s);                       // by discovery key -> ix1
+  build_key_a_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, n, w.R, w.scan_flags, w.str_min_key, w.use_cut ? w.str_cut_key : nullptr, w.k0);
+  sort_pairs(w, w.k0, w.k1, w.ix1, w.ix0, n, s);                       // stable by (string, offset) / chain -> k1, ix0
+  (*launches) += 2 + 2 * 9;
+}
+
+void launch_resolve_select(ResolveWork& w, cudaStream_t s, unsigned* launches)
+{
+  const uint32_t n = w.n_raw;
+
+  cudaMemsetAsync(w.str_count, 0, sizeof(uint32_t) * w.R.num_strings, s);
+  fill_u64_kernel<<<GRID(n), 0, s>>>(w.kF, n, ~0ULL);
+  select_plain_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix0, w.k1, n, w.R, w.str_count, w.kF, w.outU, w.st);
+  check_cap_kernel<<<GRID(w.R.num_strings), 0, s>>>(w.str_count, w.R.num_strings, w.st);
+  (*launches) += 3;
+}
+
+void launch_resolve_chains_and_order(ResolveWork& w, cudaStream_t s, unsigned* launches)
+{
+  const uint32_t n = w.n_raw;
+
+  if (w.has_chains)
+  {
+    ChainLists L;
+    L.nxt = w.c_nxt; L.prv = w.c_prv; L.clen = w.c_clen; L.mlen = w.c_mlen; L.where = w.c_where;
+    L.uhead = w.s_lists; L.utail = w.s_lists + w.R.num_strings; L.ucnt = w.s_lists + 2 * (size_t) w.R.num_strings;
+    L.mhead = w.s_lists + 3 * (size_t) w.R.num_strings; L.mtail = w.s_lists + 4 * (size_t) w.R.num_strings;
+    L.mcnt = w.s_lists + 5 * (size_t) w.R.num_strings;
+    chain_init_kernel<<<GRID(w.R.num_strings), 0, s>>>(L, w.R.num_strings);
+    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix0, w.k1, n, w.R, L, w.kF, w.outU, w.unconf, w.st, w.too_many, w.too_many_cap);
+    (*launches) += 2;
+  }
+
+  // final order: (string, offset); unused slots carry ~0 and sort to the end
+  iota_kernel<<<GRID(n), 0, s>>>(w.ix1, n);
+  sort_pairs(w, w.kF, w.k0, w.ix1, w.ix0, n, s);
+  gather_final_kernel<<<GRID(n), 0, s>>>(w.outU, w.ix0, w.st, n, w.finals);
+  (*launches) += 2 + 9;
+}
+
+// Computes the cut key of one over-cap string (see above).  Synchronises.
+int resolve_cap_cut(ResolveWork& w, uint32_t target, cudaStream_t s, unsigned long long* cut_out)
+{
+  const uint32_t n = w.n_raw;
+  unsigned int* d_n = reinterpret_cast<unsigned int*>(w.str_min_key); // scratch, re-initialised by fast mode anyway
+  cudaMemsetAsync(d_n, 0, sizeof(unsigned int), s);
+  // first-occurrence keys of the target string (k1/ix0 hold the (string, offset, key) order)
+  cap_mark_first_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix0, w.k1, n, w.str_count, w.kF, target, d_n);
+  unsigned int n_first = 0;
+  cudaMemcpyAsync(&n_first, d_n, sizeof(n_first), cudaMemcpyDeviceToHost, s);
+  if (cudaStreamSynchronize(s) != cudaSuccess) return YRB_ERROR_CUDA;
+  if (n_first <= YRB_MAX_STRING_MATCHES)
+  {
+    *cut_out = ~0ULL;
+    return YRB_SUCCESS;
+  }
+  iota_kernel<<<GRID(n_first), 0, s>>>(w.ix1, n_first);
+  size_t b = w.cub_tmp_bytes;
+  cub::DeviceRadixSort::SortPairs(w.cub_tmp, b, w.kF, w.k0, w.ix1, w.c_scratch_u32, (int) n_first, 0, 64, s);
+  unsigned long long* d_cut = w.str_cut_key + target;
+  cap_cut_kernel<<<GRID(n), 0, s>>>(w.raw, n, target, w.k0, d_cut);
+  cudaMemcpyAsync(cut_out, d_cut, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+  if (cudaStreamSynchronize(s) != cudaSuccess) return YRB_ERROR_CUDA;
+  return YRB_SUCCESS;
+}

@@ -1,0 +1,50 @@
+// resolve.cuh -- work descriptor of the resolve stage (resolve.cu).
+#pragma once
+
+#include "engine.cuh"
+
+struct ResolveWork
+{
+  // inputs
+  const Raw* raw;
+  uint32_t n_raw;
+  DevRules R;
+  int scan_flags;
+  int has_chains;
+  int use_cut;
+
+  // scratch, all sized for n_raw records unless noted
+  uint64_t* k0;
+  uint64_t* k1;
+  uint64_t* kF;
+  uint32_t* ix0;
+  uint32_t* ix1;
+  uint32_t* c_scratch_u32;
+  void* cub_tmp;
+  size_t cub_tmp_bytes;
+  int32_t* c_nxt;
+  int32_t* c_prv;
+  int32_t* c_clen;
+  int32_t* c_mlen;
+  uint8_t* c_where;
+  yrb_match* outU;
+
+  // per string
+  unsigned long long* str_min_key; // num_strings
+  unsigned long long* str_cut_key; // num_strings, ~0 = no cut
+  uint32_t* str_count;             // num_strings
+  int32_t* s_lists;                // 6 * num_strings
+
+  // outputs
+  yrb_match* finals;
+  yrb_match* unconf;
+  uint32_t* too_many;
+  uint32_t too_many_cap;
+  ScanStatus* st;
+};
+
+size_t resolve_cub_temp_bytes(uint32_t n);
+void launch_resolve_sorts(ResolveWork& w, cudaStream_t s, unsigned* launches);
+void launch_resolve_select(ResolveWork& w, cudaStream_t s, unsigned* launches);
+void launch_resolve_chains_and_order(ResolveWork& w, cudaStream_t s, unsigned* launches);
+int resolve_cap_cut(ResolveWork& w, uint32_t target, cudaStream_t s, unsigned long long* cut_out);

@@ -1,0 +1,1171 @@
+// verify.cu -- per-candidate verification on the device:
+//   yr_scan_verify_match dispatch             scan.c:992-1089
+//   _yr_scan_verify_literal_match + compares  scan.c:62-255, 887-990
+//   _yr_scan_verify_re_match                  scan.c:778-885
+//   yr_re_fast_exec (fast hex VM)             re.c:2150-2477
+//   yr_re_exec + fiber machinery (Pike VM)    re.c:1214-2068
+//   _yr_scan_match_callback, fullword filter  scan.c:634-694
+//
+// One thread verifies one candidate (candidates are rare: a handful per MiB of
+// input).  Everything order-dependent -- list insertion, dedup, the 1M cap,
+// fast mode, chained strings -- is deferred to resolve.cu; a verifier only
+// appends Raw records that carry the discovery key.
+//
+// The two VMs are restated verbatim (list order IS the matching semantics, see
+// SURVEY.md 8(a) rows a7/a8 and quirk 1); their linked lists live in a
+// per-thread work area in global memory, indexed with 16-bit links.
+#include "engine.cuh"
+
+// ----------------------------------------------------------------- data access
+
+struct Ctx
+{
+  const DevRules* R;
+  const uint8_t* d;   // d[p] = block byte p (pointer pre-biased by -g0)
+  int64_t g0, g1, gsize;
+  RawOut out;
+  uint64_t cand_key;
+  uint32_t seq;
+};
+
+static __device__ __forceinline__ uint8_t byte_at(Ctx& c, int64_t p)
+{
+  if (p < c.g0 || p >= c.g1)
+  {
+    atomicExch(&c.out.st->margin_fault, 1u);
+    return 0;
+  }
+  return __ldg(c.d + p);
+}
+
+struct CbArgs
+{
+  uint32_t sidx;
+  int forward_matches;
+  int full_word;
+  uint32_t xor_key;
+  uint32_t group;
+};
+
+static __device__ __forceinline__ bool is_alnum(uint8_t c)
+{
+  return (c >= 0x30 && c <= 0x39) || (c >= 0x41 && c <= 0x5a) || (c >= 0x61 && c <= 0x7a);
+}
+
+// scan.c:634-765 up to (not including) the list insertion
+static __device__ void match_callback(Ctx& c, int64_t match_pos, int32_t match_length, int re_flags, const CbArgs& a)
+{
+  match_length += a.forward_matches;
+
+  if (a.full_word)
+  {
+    if (re_flags & RE_FLAGS_WIDE)
+    {
+      if (match_pos >= 2 && byte_at(c, match_pos - 1) == 0 && is_alnum(byte_at(c, match_pos - 2)))
+        return;
+      if (match_pos + match_length + 1 < c.gsize && byte_at(c, match_pos + match_length + 1) == 0 &&
+          is_alnum(byte_at(c, match_pos + match_length)))
+        return;
+    }
+    else
+    {
+      if (match_pos >= 1 && is_alnum(byte_at(c, match_pos - 1)))
+        return;
+      if (match_pos + match_length < c.gsize && is_alnum(byte_at(c, match_pos + match_length)))
+        return;
+    }
+  }
+
+  const unsigned long long slot = atomicAdd(&c.out.st->n_raw, 1ULL);
+
+  if (slot < c.out.cap)
+  {
+    Raw r;
+    r.key = c.cand_key | (uint64_t) (c.seq < KEY_SEQ_MAX ? c.seq : KEY_SEQ_MAX);
+    r.offset = match_pos;
+    r.string_idx = a.sidx;
+    r.length = match_length;
+    r.misc = a.xor_key & 0xFF;
+    r.group = a.group;
+    c.out.raw[slot] = r;
+  }
+
+  c.seq++;
+}
+
+// -------------------------------------------------------------------- opcodes
+
+enum
+{
+  OP_ANY = 0xA0, OP_LITERAL = 0xA2, OP_MASKED_LITERAL = 0xA4, OP_CLASS = 0xA5,
+  OP_WORD_CHAR = 0xA7, OP_NON_WORD_CHAR = 0xA8, OP_SPACE = 0xA9, OP_NON_SPACE = 0xAA,
+  OP_DIGIT = 0xAB, OP_NON_DIGIT = 0xAC, OP_MATCH = 0xAD, OP_NOT_LITERAL = 0xAE,
+  OP_MASKED_NOT_LITERAL = 0xAF, OP_MATCH_AT_END = 0xB0, OP_MATCH_AT_START = 0xB1,
+  OP_WORD_BOUNDARY = 0xB2, OP_NON_WORD_BOUNDARY = 0xB3, OP_REPEAT_ANY_GREEDY = 0xB4,
+  OP_REPEAT_ANY_UNGREEDY = 0xB5, OP_SPLIT_A = 0xC0, OP_SPLIT_B = 0xC1, OP_JUMP = 0xC2,
+  OP_REPEAT_START_GREEDY = 0xC3, OP_REPEAT_END_GREEDY = 0xC4,
+  OP_REPEAT_START_UNGREEDY = 0xC5, OP_REPEAT_END_UNGREEDY = 0xC6
+};
+
+static __device__ __forceinline__ uint32_t code_u8(const Ctx& c, uint32_t off) { return __ldg(c.R->code + off); }
+static __device__ __forceinline__ uint32_t code_u16(const Ctx& c, uint32_t off)
+{ return code_u8(c, off) | (code_u8(c, off + 1) << 8); }
+static __device__ __forceinline__ int32_t code_i16(const Ctx& c, uint32_t off) { return (int16_t) code_u16(c, off); }
+static __device__ __forceinline__ int32_t code_i32(const Ctx& c, uint32_t off)
+{ return (int32_t) (code_u16(c, off) | (code_u16(c, off + 2) << 16)); }
+
+// ---------------------------------------------------------- fast hex VM (a8)
+
+#define FAST_POS_CAP 4608
+
+struct FastPos
+{
+  int32_t input;   // relative to the exec's input position
+  int32_t round;
+  int16_t prev, next;
+};
+
+struct FastWs
+{
+  FastPos v[FAST_POS_CAP];
+};
+
+size_t fast_ws_bytes_per_thread() { return sizeof(FastWs); }
+
+// re.c:2150-2477.  Returns an ERROR_* code.  `pos` = block position of input_data.
+static __device__ int re_fast_exec(
+    Ctx& c, FastWs* ws, uint32_t code_off, int64_t pos, int64_t input_forwards_size, int64_t input_backwards_size,
+    int flags, const CbArgs* cb, int* matches)
+{
+  FastPos* P = ws->v;
+  int n_used = 0;      // bump allocator
+  int free_head = -1;  // recycled entries, linked through .next
+
+  const int input_incr = (flags & RE_FLAGS_BACKWARDS) ? -1 : 1;
+  int bytes_matched;
+  int max_bytes_matched;
+
+  if (flags & RE_FLAGS_BACKWARDS)
+    max_bytes_matched = (int) (input_backwards_size < YRB_RE_SCAN_LIMIT ? input_backwards_size : YRB_RE_SCAN_LIMIT);
+  else
+    max_bytes_matched = (int) (input_forwards_size < YRB_RE_SCAN_LIMIT ? input_forwards_size : YRB_RE_SCAN_LIMIT);
+
+  uint32_t ip = code_off;
+
+  int first = n_used++;
+  P[first].input = (flags & RE_FLAGS_BACKWARDS) ? -1 : 0;
+  P[first].round = 0;
+  P[first].prev = P[first].next = -1;
+
+  int last = first;
+  int round = 0;
+
+  if (matches) *matches = -1;
+
+  while (first >= 0)
+  {
+    int current = first;
+    const uint32_t op = code_u8(c, ip);
+
+    while (current >= 0)
+    {
+      const int next = P[current].next;
+
+      if (P[current].round != round)
+      {
+        current = next;
+        continue;
+      }
+
+      const int cin = P[current].input;
+      bytes_matched = (flags & RE_FLAGS_BACKWARDS) ? (-cin - 1) : cin;
+
+      bool match = false;
+
+      switch (op)
+      {
+      case OP_ANY:
+        if (bytes_matched >= max_bytes_matched) break;
+        match = true;
+        P[current].input += input_incr;
+        break;
+
+      case OP_LITERAL:
+        if (bytes_matched >= max_bytes_matched) break;
+        if (byte_at(c, pos + cin) == code_u8(c, ip + 1)) { match = true; P[current].input += input_incr; }
+        break;
+
+      case OP_NOT_LITERAL:
+        if (bytes_matched >= max_bytes_matched) break;
+        if (byte_at(c, pos + cin) != code_u8(c, ip + 1)) { match = true; P[current].input += input_incr; }
+        break;
+
+      case OP_MASKED_LITERAL:
+      {
+        if (bytes_matched >= max_bytes_matched) break;
+        const uint32_t args = code_u16(c, ip + 1);
+        if ((byte_at(c, pos + cin) & (args >> 8)) == (args & 0xFF)) { match = true; P[current].input += input_incr; }
+        break;
+      }
+
+      case OP_MASKED_NOT_LITERAL:
+      {
+        if (bytes_matched >= max_bytes_matched) break;
+        const uint32_t args = code_u16(c, ip + 1);
+        if ((byte_at(c, pos + cin) & (args >> 8)) != (args & 0xFF)) { match = true; P[current].input += input_incr; }
+        break;
+      }
+
+      case OP_REPEAT_ANY_UNGREEDY:
+      {
+        if (bytes_matched >= max_bytes_matched) break;
+
+        const int rmin = (int) code_u16(c, ip + 1);
+        const int rmax = (int) code_u16(c, ip + 3);
+        const uint32_t next_op = code_u8(c, ip + 5);
+        const uint32_t next_lit = code_u8(c, ip + 6);
+        int insertion_point = current;
+
+        match = true;
+
+        for (int j = rmin + 1; j <= rmax; j++)
+        {
+          if (bytes_matched + j >= max_bytes_matched)
+            break;
+
+          const int next_input = cin + j * input_incr;
+
+          while (P[insertion_point].next >= 0 && next_input >= P[P[insertion_point].next].input)
+            insertion_point = P[insertion_point].next;
+
+          if (next_input == P[insertion_point].input)
+            continue;
+
+          if (next_op == OP_LITERAL && next_lit != byte_at(c, pos + next_input))
+            continue;
+
+          int ni;
+          if (free_head >= 0)
+          {
+            ni = free_head;
+            free_head = P[ni].next;
+          }
+          else if (n_used < FAST_POS_CAP)
+          {
+            ni = n_used++;
+          }
+          else
+          {
+            atomicExch(&c.out.st->ws_overflow, 1u);
+            return YRB_ERROR_INSUFFICIENT_MEMORY;
+          }
+
+          P[ni].input = next_input;
+          P[ni].round = round + 1;
+          P[ni].prev = (int16_t) insertion_point;
+          P[ni].next = P[insertion_point].next;
+          P[insertion_point].next = (int16_t) ni;
+          if (P[ni].next >= 0) P[P[ni].next].prev = (int16_t) ni;
+          if (insertion_point == last) last = ni;
+        }
+
+        P[current].input += input_incr * rmin;
+        break;
+      }
+
+      case OP_MATCH:
+        if (flags & RE_FLAGS_EXHAUSTIVE)
+        {
+          int64_t mpos;
+          if (flags & RE_FLAGS_BACKWARDS)
+          {
+            const int64_t lo = pos - input_backwards_size;
+            mpos = (pos + cin + 1 > lo) ? pos + cin + 1 : lo;
+          }
+          else
+          {
+            mpos = pos;
+          }
+          match_callback(c, mpos, bytes_matched < max_bytes_matched ? bytes_matched : max_bytes_matched, flags, *cb);
+        }
+        else
+        {
+          if (matches) *matches = bytes_matched;
+          return YRB_SUCCESS;
+        }
+        break;
+
+      default:
+        return YRB_ERROR_INTERNAL_FATAL;
+      }
+
+      if (match)
+      {
+        P[current].round = round + 1;
+      }
+      else
+      {
+        if (current == first) first = P[current].next;
+        if (current == last) last = P[current].prev;
+        if (P[current].prev >= 0) P[P[current].prev].next = P[current].next;
+        if (P[current].next >= 0) P[P[current].next].prev = P[current].prev;
+        P[current].next = (int16_t) free_head;
+        free_head = current;
+      }
+
+      current = next;
+    }
+
+    switch (op)
+    {
+    case OP_ANY: ip += 1; break;
+    case OP_LITERAL: case OP_NOT_LITERAL: ip += 2; break;
+    case OP_MASKED_LITERAL: case OP_MASKED_NOT_LITERAL: ip += 3; break;
+    case OP_REPEAT_ANY_UNGREEDY: ip += 5; break;
+    default: break;
+    }
+
+    round++;
+  }
+
+  return YRB_SUCCESS;
+}
+
+// ------------------------------------------------------------- fiber VM (a7)
+
+struct Fiber
+{
+  uint32_t ip;
+  int32_t rc;
+  int16_t sp;
+  int16_t prev, next;
+  int16_t pad;
+};
+
+struct FiberPool
+{
+  Fiber* f;          // YRB_RE_MAX_FIBERS entries
+  uint16_t* stacks;  // YRB_RE_MAX_FIBERS * stack_words
+  int stack_words;
+  int free_head;
+  int head, tail;
+};
+
+size_t re_ws_bytes_per_thread(uint32_t stack_words)
+{
+  size_t b = (size_t) YRB_RE_MAX_FIBERS * (sizeof(Fiber) + sizeof(uint16_t) * stack_words);
+  return (b + 15) & ~(size_t) 15;
+}
+
+static __device__ __forceinline__ uint16_t* fstack(FiberPool& p, int f) { return p.stacks + (size_t) f * p.stack_words; }
+
+// re.c:1214-1248: at most RE_MAX_FIBERS live fibers
+static __device__ int fiber_create(FiberPool& p, int* out)
+{
+  if (p.free_head < 0)
+    return YRB_ERROR_TOO_MANY_RE_FIBERS;
+
+  const int f = p.free_head;
+  p.free_head = p.f[f].next;
+  p.f[f].ip = 0;
+  p.f[f].sp = -1;
+  p.f[f].rc = -1;
+  p.f[f].next = -1;
+  p.f[f].prev = -1;
+  *out = f;
+  return YRB_SUCCESS;
+}
+
+static __device__ __forceinline__ void fiber_release(FiberPool& p, int f)
+{
+  p.f[f].next = (int16_t) p.free_head;
+  p.free_head = f;
+}
+
+// re.c:1278-1315
+static __device__ bool fiber_exists(FiberPool& p, int target, int last)
+{
+  if (last < 0)
+    return false;
+
+  const Fiber t = p.f[target];
+  const uint16_t* ts = fstack(p, target);
+  const int stop = p.f[last].next;
+
+  for (int f = p.head; f != stop; f = p.f[f].next)
+  {
+    const Fiber x = p.f[f];
+    if (x.ip == t.ip && x.sp == t.sp && x.rc == t.rc)
+    {
+      bool equal = true;
+      const uint16_t* xs = fstack(p, f);
+      for (int i = 0; i <= x.sp; i++)
+        if (xs[i] != ts[i]) { equal = false; break; }
+      if (equal)
+        return true;
+    }
+  }
+  return false;
+}
+
+// re.c:1327-1358: the clone goes right after the original
+static __device__ int fiber_split(FiberPool& p, int f, int* out)
+{
+  int n;
+  const int rc = fiber_create(p, &n);
+  if (rc != YRB_SUCCESS)
+    return rc;
+
+  p.f[n].sp = p.f[f].sp;
+  p.f[n].ip = p.f[f].ip;
+  p.f[n].rc = p.f[f].rc;
+
+  const uint16_t* src = fstack(p, f);
+  uint16_t* dst = fstack(p, n);
+  for (int i = 0; i <= p.f[f].sp; i++) dst[i] = src[i];
+
+  p.f[n].next = p.f[f].next;
+  p.f[n].prev = (int16_t) f;
+  if (p.f[f].next >= 0) p.f[p.f[f].next].prev = (int16_t) n;
+  p.f[f].next = (int16_t) n;
+  if (p.tail == f) p.tail = n;
+
+  *out = n;
+  return YRB_SUCCESS;
+}
+
+// re.c:1364-1394
+static __device__ int fiber_kill(FiberPool& p, int f)
+{
+  const int next = p.f[f].next;
+  const int prev = p.f[f].prev;
+
+  if (prev >= 0) p.f[prev].next = (int16_t) next;
+  if (next >= 0) p.f[next].prev = (int16_t) prev;
+  if (p.tail == f) p.tail = prev;
+  if (p.head == f) p.head = next;
+
+  fiber_release(p, f);
+  return next;
+}
+
+// re.c:1399-1433
+static __device__ void fiber_kill_tail(FiberPool& p, int f)
+{
+  const int prev = p.f[f].prev;
+
+  if (prev >= 0) p.f[prev].next = -1;
+  p.tail = prev;
+  if (p.head == f) p.head = -1;
+
+  while (f >= 0)
+  {
+    const int n = p.f[f].next;
+    fiber_release(p, f);
+    f = n;
+  }
+}
+
+static __device__ __forceinline__ void fiber_kill_all(FiberPool& p)
+{
+  if (p.head >= 0)
+    fiber_kill_tail(p, p.head);
+}
+
+// re.c:1441-1654 _yr_re_fiber_sync.  The reference recurses for REPEAT_ANY
+// (re.c:1626); here the recursion is an explicit frame stack.  The set of
+// already-executed split ids (ids < RE_MAX_SPLIT_ID = 128) is a 128-bit mask.
+#define SYNC_MAX_DEPTH 24
+
+struct SyncFrame
+{
+  int last;
+  int resume;
+  uint32_t mask[4];
+};
+
+static __device__ int fiber_sync(Ctx& c, FiberPool& p, int fiber_to_sync)
+{
+  SyncFrame frames[SYNC_MAX_DEPTH];
+  int depth = 0;
+
+  uint32_t mask[4] = {0, 0, 0, 0};
+  int fiber = fiber_to_sync;
+  int last = p.f[fiber_to_sync].next;
+  int branch_a, branch_b, rc;
+
+  for (;;)
+  {
+    if (fiber == last)
+    {
+      if (depth == 0)
+        return YRB_SUCCESS;
+      depth--;
+      fiber = frames[depth].resume;
+      last = frames[depth].last;
+      mask[0] = frames[depth].mask[0]; mask[1] = frames[depth].mask[1];
+      mask[2] = frames[depth].mask[2]; mask[3] = frames[depth].mask[3];
+      continue;
+    }
+
+    const uint32_t ip = p.f[fiber].ip;
+    const uint32_t opcode = code_u8(c, ip);
+
+    switch (opcode)
+    {
+    case OP_SPLIT_A:
+    case OP_SPLIT_B:
+    {
+      const uint32_t split_id = code_u8(c, ip + 1) & 127;
+
+      if (mask[split_id >> 5] & (1u << (split_id & 31)))
+      {
+        fiber = fiber_kill(p, fiber);
+      }
+      else
+      {
+        branch_a = fiber;
+        rc = fiber_split(p, branch_a, &branch_b);
+        if (rc != YRB_SUCCESS) return rc;
+
+        if (opcode == OP_SPLIT_B) { const int t = branch_a; branch_a = branch_b; branch_b = t; }
+
+        p.f[branch_a].ip += 4;
+        p.f[branch_b].ip += code_i16(c, p.f[branch_b].ip + 2);
+        mask[split_id >> 5] |= (1u << (split_id & 31));
+      }
+      break;
+    }
+
+    case OP_REPEAT_START_GREEDY:
+    case OP_REPEAT_START_UNGREEDY:
+    {
+      const uint32_t rmin = code_u16(c, ip + 1);
+      const int32_t roff = code_i32(c, ip + 5);
+      branch_a = fiber;
+
+      if (rmin == 0)
+      {
+        rc = fiber_split(p, branch_a, &branch_b);
+        if (rc != YRB_SUCCESS) return rc;
+        if (opcode == OP_REPEAT_START_UNGREEDY) { const int t = branch_a; branch_a = branch_b; branch_b = t; }
+        p.f[branch_b].ip += roff;
+      }
+
+      p.f[branch_a].sp++;
+      if (p.f[branch_a].sp < p.stack_words)
+        fstack(p, branch_a)[p.f[branch_a].sp] = 0;
+      p.f[branch_a].ip += 9;
+      break;
+    }
+
+    case OP_REPEAT_END_GREEDY:
+    case OP_REPEAT_END_UNGREEDY:
+    {
+      const uint32_t rmin = code_u16(c, ip + 1);
+      const uint32_t rmax = code_u16(c, ip + 3);
+      const int32_t roff = code_i32(c, ip + 5);
+      const int sp = p.f[fiber].sp;
+
+      if (sp < 0 || sp >= p.stack_words)
+        return YRB_ERROR_INTERNAL_FATAL;
+
+      uint16_t* st = fstack(p, fiber);
+      st[sp]++;
+
+      if (st[sp] < rmin)
+      {
+        p.f[fiber].ip += roff;
+        break;
+      }
+
+      branch_a = fiber;
+
+      if (st[sp] < rmax)
+      {
+        rc = fiber_split(p, branch_a, &branch_b);
+        if (rc != YRB_SUCCESS) return rc;
+        if (opcode == OP_REPEAT_END_GREEDY) { const int t = branch_a; branch_a = branch_b; branch_b = t; }
+        p.f[branch_b].ip += roff;
+      }
+
+      p.f[branch_a].sp--;
+      p.f[branch_a].ip += 9;
+      break;
+    }
+
+    case OP_REPEAT_ANY_GREEDY:
+    case OP_REPEAT_ANY_UNGREEDY:
+    {
+      const int rmin = (int) code_u16(c, ip + 1);
+      const int rmax = (int) code_u16(c, ip + 3);
+
+      if (p.f[fiber].rc == -1)
+        p.f[fiber].rc = 0;
+
+      if (p.f[fiber].rc < rmin)
+      {
+        p.f[fiber].rc++;
+        fiber = p.f[fiber].next;
+      }
+      else if (p.f[fiber].rc < rmax)
+      {
+        const int next = p.f[fiber].next;
+        branch_a = fiber;
+        rc = fiber_split(p, branch_a, &branch_b);
+        if (rc != YRB_SUCCESS) return rc;
+        if (opcode == OP_REPEAT_ANY_UNGREEDY) { const int t = branch_a; branch_a = branch_b; branch_b = t; }
+
+        p.f[branch_a].rc++;
+        p.f[branch_b].ip += 5;
+        p.f[branch_b].rc = -1;
+
+        // recursive _yr_re_fiber_sync(branch_b), then continue at `next`
+        if (depth == SYNC_MAX_DEPTH)
+          return YRB_ERROR_INTERNAL_FATAL;
+        frames[depth].last = last;
+        frames[depth].resume = next;
+        frames[depth].mask[0] = mask[0]; frames[depth].mask[1] = mask[1];
+        frames[depth].mask[2] = mask[2]; frames[depth].mask[3] = mask[3];
+        depth++;
+        fiber = branch_b;
+        last = p.f[branch_b].next;
+        mask[0] = mask[1] = mask[2] = mask[3] = 0;
+      }
+      else
+      {
+        p.f[fiber].ip += 5;
+        p.f[fiber].rc = -1;
+      }
+      break;
+    }
+
+    case OP_JUMP:
+      p.f[fiber].ip += code_i16(c, ip + 1);
+      break;
+
+    default:
+      fiber = p.f[fiber].next;
+    }
+  }
+}
+
+static __device__ __forceinline__ bool is_word_char(Ctx& c, int64_t p, int character_size)
+{
+  const uint8_t b = byte_at(c, p);
+  bool result = is_alnum(b) || b == '_';
+  if (character_size == 2)
+    result = result && (byte_at(c, p + 1) == 0);
+  return result;
+}
+
+// re.c:1693-2068 yr_re_exec
+static __device__ int re_exec(
+    Ctx& c, FiberPool& p, uint32_t code_off, int64_t pos, int64_t input_forwards_size, int64_t input_backwards_size,
+    int flags, const CbArgs* cb, int* matches)
+{
+  const int character_size = (flags & RE_FLAGS_WIDE) ? 2 : 1;
+  int input_incr = character_size;
+  int64_t input = pos;
+  int bytes_matched, max_bytes_matched;
+  int fiber, next_fiber, rc;
+
+  if (matches) *matches = -1;
+
+  if (flags & RE_FLAGS_BACKWARDS)
+  {
+    max_bytes_matched = (int) (input_backwards_size < YRB_RE_SCAN_LIMIT ? input_backwards_size : YRB_RE_SCAN_LIMIT);
+    input -= character_size;
+    input_incr = -input_incr;
+  }
+  else
+  {
+    max_bytes_matched = (int) (input_forwards_size < YRB_RE_SCAN_LIMIT ? input_forwards_size : YRB_RE_SCAN_LIMIT);
+  }
+
+  max_bytes_matched = max_bytes_matched - max_bytes_matched % character_size;
+  bytes_matched = 0;
+
+  p.head = p.tail = -1;
+  rc = fiber_create(p, &fiber);
+  if (rc != YRB_SUCCESS) return rc;
+
+  p.f[fiber].ip = code_off;
+  p.head = p.tail = fiber;
+
+  rc = fiber_sync(c, p, fiber);
+  if (rc != YRB_SUCCESS) { fiber_kill_all(p); return rc; }
+
+  while (p.head >= 0)
+  {
+    fiber = p.head;
+
+    while (fiber >= 0)
+    {
+      next_fiber = p.f[fiber].next;
+      if (fiber_exists(p, fiber, p.f[fiber].prev))
+        fiber_kill(p, fiber);
+      fiber = next_fiber;
+    }
+
+    fiber = p.head;
+
+    while (fiber >= 0)
+    {
+      const uint32_t ip = p.f[fiber].ip;
+      const uint32_t op = code_u8(c, ip);
+      int action = 0; // 0 none, 1 continue, 2 kill, 3 kill tail
+      bool match, kill;
+
+#define PROLOG                                                                                        \
+  if ((bytes_matched >= max_bytes_matched) || (character_size == 2 && byte_at(c, input + 1) != 0))    \
+  {                                                                                                   \
+    action = 2;                                                                                       \
+    break;                                                                                            \
+  }
+
+      switch (op)
+      {
+      case OP_ANY:
+        PROLOG;
+        match = (flags & RE_FLAGS_DOT_ALL) || (byte_at(c, input) != 0x0A);
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 1;
+        break;
+
+      case OP_REPEAT_ANY_GREEDY:
+      case OP_REPEAT_ANY_UNGREEDY:
+        PROLOG;
+        match = (flags & RE_FLAGS_DOT_ALL) || (byte_at(c, input) != 0x0A);
+        action = match ? 0 : 2;
+        break;
+
+      case OP_LITERAL:
+        PROLOG;
+        if (flags & RE_FLAGS_NO_CASE)
+          match = __ldg(c.R->lower + byte_at(c, input)) == __ldg(c.R->lower + code_u8(c, ip + 1));
+        else
+          match = (byte_at(c, input) == code_u8(c, ip + 1));
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 2;
+        break;
+
+      case OP_NOT_LITERAL:
+        PROLOG;
+        match = (byte_at(c, input) != code_u8(c, ip + 1));
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 2;
+        break;
+
+      case OP_MASKED_LITERAL:
+      {
+        PROLOG;
+        const uint32_t args = code_u16(c, ip + 1);
+        match = ((byte_at(c, input) & (args >> 8)) == (args & 0xFF));
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 3;
+        break;
+      }
+
+      case OP_MASKED_NOT_LITERAL:
+      {
+        PROLOG;
+        const uint32_t args = code_u16(c, ip + 1);
+        match = ((byte_at(c, input) & (args >> 8)) != (args & 0xFF));
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 3;
+        break;
+      }
+
+      case OP_CLASS:
+      {
+        PROLOG;
+        // re.c:98-112 _yr_re_is_char_in_class; RE_CLASS = negated u8 + bitmap[32]
+        const uint32_t chr = byte_at(c, input);
+        uint32_t r = code_u8(c, ip + 2 + chr / 8) & (1u << (chr % 8));
+        if (flags & RE_FLAGS_NO_CASE)
+        {
+          const uint32_t alt = __ldg(c.R->alter + chr);
+          r |= code_u8(c, ip + 2 + alt / 8) & (1u << (alt % 8));
+        }
+        match = (r != 0);
+        if (code_u8(c, ip + 1)) match = !match;
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 34;
+        break;
+      }
+
+      case OP_WORD_CHAR:
+        PROLOG;
+        match = is_word_char(c, input, character_size);
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 1;
+        break;
+
+      case OP_NON_WORD_CHAR:
+        PROLOG;
+        match = !is_word_char(c, input, character_size);
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 1;
+        break;
+
+      case OP_SPACE:
+      case OP_NON_SPACE:
+      {
+        PROLOG;
+        const uint8_t b = byte_at(c, input);
+        match = (b == ' ' || b == '\t' || b == '\r' || b == '\n' || b == '\v' || b == '\f');
+        if (op == OP_NON_SPACE) match = !match;
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 1;
+        break;
+      }
+
+      case OP_DIGIT:
+      {
+        PROLOG;
+        const uint8_t b = byte_at(c, input);
+        match = (b >= '0' && b <= '9');
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 1;
+        break;
+      }
+
+      case OP_NON_DIGIT:
+      {
+        PROLOG;
+        const uint8_t b = byte_at(c, input);
+        match = !(b >= '0' && b <= '9');
+        action = match ? 0 : 2;
+        p.f[fiber].ip += 1;
+        break;
+      }
+
+      case OP_WORD_BOUNDARY:
+      case OP_NON_WORD_BOUNDARY:
+        if (bytes_matched == 0 && input_backwards_size < character_size)
+          match = true;
+        else if (bytes_matched >= max_bytes_matched)
+          match = true;
+        else
+          match = is_word_char(c, input, character_size) != is_word_char(c, input - input_incr, character_size);
+
+        if (op == OP_NON_WORD_BOUNDARY) match = !match;
+        action = match ? 1 : 2;
+        p.f[fiber].ip += 1;
+        break;
+
+      case OP_MATCH_AT_START:
+        if (flags & RE_FLAGS_BACKWARDS)
+          kill = input_backwards_size > (int64_t) bytes_matched;
+        else
+          kill = input_backwards_size > 0 || (bytes_matched != 0);
+        action = kill ? 2 : 1;
+        p.f[fiber].ip += 1;
+        break;
+
+      case OP_MATCH_AT_END:
+        kill = (flags & RE_FLAGS_BACKWARDS) || input_forwards_size > (int64_t) bytes_matched;
+        action = kill ? 2 : 1;
+        p.f[fiber].ip += 1;
+        break;
+
+      case OP_MATCH:
+        if (matches) *matches = bytes_matched;
+
+        if (flags & RE_FLAGS_EXHAUSTIVE)
+        {
+          if (cb != nullptr)
+            match_callback(c, (flags & RE_FLAGS_BACKWARDS) ? input + character_size : pos, bytes_matched, flags, *cb);
+          action = 2;
+        }
+        else
+        {
+          action = 3;
+        }
+        break;
+
+      default:
+        fiber_kill_all(p);
+        return YRB_ERROR_INTERNAL_FATAL;
+      }
+#undef PROLOG
+
+      switch (action)
+      {
+      case 2:
+        fiber = fiber_kill(p, fiber);
+        break;
+      case 3:
+        fiber_kill_tail(p, fiber);
+        fiber = -1;
+        break;
+      case 1:
+        rc = fiber_sync(c, p, fiber);
+        if (rc != YRB_SUCCESS) { fiber_kill_all(p); return rc; }
+        break;
+      default:
+        next_fiber = p.f[fiber].next;
+        rc = fiber_sync(c, p, fiber);
+        if (rc != YRB_SUCCESS) { fiber_kill_all(p); return rc; }
+        fiber = next_fiber;
+      }
+    }
+
+    input += input_incr;
+    bytes_matched += character_size;
+  }
+
+  return YRB_SUCCESS;
+}
+
+// ------------------------------------------------------- literal verifier (a5)
+
+static __device__ void verify_literal(Ctx& c, const yrb_acm& m, const yrb_string& s, int64_t offset)
+{
+  const uint8_t* __restrict__ str = c.R->lit + s.lit_off;
+  const uint8_t* __restrict__ lower = c.R->lower;
+  const int64_t avail = c.gsize - offset;
+  const int64_t len = s.length;
+  int forward_matches = 0, flags = 0;
+  uint32_t xor_key = 0;
+  int64_t i;
+
+  if (s.flags & YRB_SF_FITS_IN_ATOM)
+  {
+    forward_matches = (int) m.backtrack;
+  }
+  else if (s.flags & YRB_SF_NO_CASE)
+  {
+    if ((s.flags & YRB_SF_ASCII) && avail >= len)
+    {
+      for (i = 0; i < len && __ldg(lower + byte_at(c, offset + i)) == __ldg(lower + __ldg(str + i)); i++) {}
+      forward_matches = (i == len) ? (int) i : 0;
+    }
+    if ((s.flags & YRB_SF_WIDE) && forward_matches == 0 && avail >= len * 2)
+    {
+      for (i = 0; i < len && __ldg(lower + byte_at(c, offset + 2 * i)) == __ldg(lower + __ldg(str + i)) &&
+                  byte_at(c, offset + 2 * i + 1) == 0; i++) {}
+      forward_matches = (i == len) ? (int) (i * 2) : 0;
+    }
+  }
+  else
+  {
+    if ((s.flags & YRB_SF_ASCII) && avail >= len)
+    {
+      for (i = 0; i < len && byte_at(c, offset + i) == __ldg(str + i); i++) {}
+      forward_matches = (i == len) ? (int) i : 0;
+    }
+    if ((s.flags & YRB_SF_WIDE) && forward_matches == 0 && avail >= len * 2)
+    {
+      for (i = 0; i < len && byte_at(c, offset + 2 * i) == __ldg(str + i) && byte_at(c, offset + 2 * i + 1) == 0; i++) {}
+      forward_matches = (i == len) ? (int) (i * 2) : 0;
+    }
+    if ((s.flags & YRB_SF_XOR) && forward_matches == 0)
+    {
+      if ((s.flags & YRB_SF_WIDE) && avail >= len * 2)
+      {
+        const uint32_t k = byte_at(c, offset) ^ __ldg(str);
+        for (i = 0; i < len && byte_at(c, offset + 2 * i) == (__ldg(str + i) ^ k) &&
+                    (byte_at(c, offset + 2 * i + 1) ^ k) == 0; i++) {}
+        forward_matches = (i == len) ? (int) (i * 2) : 0;
+        if (forward_matches > 0) xor_key = k;
+      }
+      if (forward_matches == 0 && avail >= len)
+      {
+        const uint32_t k = byte_at(c, offset) ^ __ldg(str);
+        for (i = 0; i < len && byte_at(c, offset + i) == (__ldg(str + i) ^ k); i++) {}
+        forward_matches = (i == len) ? (int) i : 0;
+        if (forward_matches > 0) xor_key = k;
+      }
+    }
+  }
+
+  if (forward_matches == 0)
+    return;
+
+  if (forward_matches == s.length * 2)
+    flags |= RE_FLAGS_WIDE;
+  if (s.flags & YRB_SF_NO_CASE)
+    flags |= RE_FLAGS_NO_CASE;
+
+  CbArgs a;
+  a.sidx = m.string_idx;
+  a.forward_matches = forward_matches;
+  a.full_word = (s.flags & YRB_SF_FULL_WORD) != 0;
+  a.xor_key = xor_key;
+  a.group = s.chain_head;
+
+  match_callback(c, offset, 0, flags, a);
+}
+
+// ------------------------------------------------------------ RE verifier (a6)
+
+template <bool FAST>
+static __device__ int verify_re(Ctx& c, FastWs* fws, FiberPool* fp, const yrb_acm& m, const yrb_string& s, int64_t offset)
+{
+  int forward_matches = -1, backward_matches = -1;
+  int flags = 0, rc;
+
+  if (s.flags & YRB_SF_GREEDY_REGEXP) flags |= RE_FLAGS_GREEDY;
+  if (s.flags & YRB_SF_NO_CASE) flags |= RE_FLAGS_NO_CASE;
+  if (s.flags & YRB_SF_DOT_ALL) flags |= RE_FLAGS_DOT_ALL;
+
+  const int64_t fwd = c.gsize - offset;
+  const int64_t bwd = offset;
+
+#define EXEC(code, fl, cb, mt) \
+  (FAST ? re_fast_exec(c, fws, (code), offset, fwd, bwd, (fl), (cb), (mt)) : re_exec(c, *fp, (code), offset, fwd, bwd, (fl), (cb), (mt)))
+
+  if (s.flags & (YRB_SF_ASCII | YRB_SF_BASE64 | YRB_SF_BASE64_WIDE))
+  {
+    rc = EXEC(m.fwd_code, flags, nullptr, &forward_matches);
+    if (rc != YRB_SUCCESS) return rc;
+  }
+
+  if (forward_matches == -1 && (s.flags & YRB_SF_WIDE) && !(s.flags & (YRB_SF_BASE64 | YRB_SF_BASE64_WIDE)))
+  {
+    flags |= RE_FLAGS_WIDE;
+    rc = EXEC(m.fwd_code, flags, nullptr, &forward_matches);
+    if (rc != YRB_SUCCESS) return rc;
+  }
+
+  if (forward_matches == -1)
+    return YRB_SUCCESS;
+
+  if (forward_matches == 0 && m.bwd_code == YRB_NONE)
+    return YRB_SUCCESS;
+
+  CbArgs a;
+  a.sidx = m.string_idx;
+  a.forward_matches = forward_matches;
+  a.full_word = (s.flags & YRB_SF_FULL_WORD) != 0;
+  a.xor_key = 0;
+  a.group = s.chain_head;
+
+  if (m.bwd_code != YRB_NONE)
+    return EXEC(m.bwd_code, flags | RE_FLAGS_BACKWARDS | RE_FLAGS_EXHAUSTIVE, &a, &backward_matches);
+
+  match_callback(c, offset, 0, flags, a);
+  return YRB_SUCCESS;
+#undef EXEC
+}
+
+// -------------------------------------------------------------------- kernels
+
+static __device__ __forceinline__ void ctx_init(Ctx& c, const DevRules& R, const ScanView& V, const RawOut& out, const Cand& cd)
+{
+  c.R = &R;
+  c.d = V.d - V.g0;
+  c.g0 = V.g0;
+  c.g1 = V.g1;
+  c.gsize = V.gsize;
+  c.out = out;
+  c.cand_key = cd.key;
+  c.seq = 0;
+}
+
+__global__ void __launch_bounds__(128)
+verify_literal_kernel(DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out)
+{
+  const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+
+  for (unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+  {
+    const Cand cd = cands[t];
+    const yrb_acm m = R.acm[cd.acm_idx];
+    const yrb_string s = R.S[m.string_idx];
+    Ctx c;
+    ctx_init(c, R, V, out, cd);
+    verify_literal(c, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+verify_fast_kernel(DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out, FastWs* ws)
+{
+  const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+  FastWs* my = ws + tid;
+
+  for (unsigned long long t = tid; t < n; t += stride)
+  {
+    const Cand cd = cands[t];
+    const yrb_acm m = R.acm[cd.acm_idx];
+    const yrb_string s = R.S[m.string_idx];
+    Ctx c;
+    ctx_init(c, R, V, out, cd);
+    const int rc = verify_re<true>(c, my, nullptr, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
+    if (rc != YRB_SUCCESS)
+      report_error(out.st, cd.key, rc);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+verify_re_kernel(
+    DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out, uint8_t* ws, size_t ws_per_thread)
+{
+  const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+
+  FiberPool p;
+  p.f = reinterpret_cast<Fiber*>(ws + tid * ws_per_thread);
+  p.stacks = reinterpret_cast<uint16_t*>(p.f + YRB_RE_MAX_FIBERS);
+  p.stack_words = (int) R.stack_words;
+
+  // free list over all YRB_RE_MAX_FIBERS entries (kept consistent across candidates:
+  // every exec returns all of its fibers)
+  for (int f = 0; f < YRB_RE_MAX_FIBERS; f++)
+    p.f[f].next = (int16_t) ((f + 1 < YRB_RE_MAX_FIBERS) ? f + 1 : -1);
+  p.free_head = 0;
+  p.head = p.tail = -1;
+
+  for (unsigned long long t = tid; t < n; t += stride)
+  {
+    const Cand cd = cands[t];
+    const yrb_acm m = R.acm[cd.acm_idx];
+    const yrb_string s = R.S[m.string_idx];
+    Ctx c;
+    ctx_init(c, R, V, out, cd);
+    const int rc = verify_re<false>(c, nullptr, &p, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
+    if (rc != YRB_SUCCESS)
+      report_error(out.st, cd.key, rc);
+  }
+}
+
+void launch_verify(
+    const DevRules& R, const ScanView& V, const CandOut& cands, const unsigned long long n_cand[NUM_CLS],
+    const RawOut& out, void* ws_fast, size_t ws_fast_threads, void* ws_re, size_t ws_re_threads, cudaStream_t s,
+    unsigned* launches)
+{
+  const int T = 128;
+
+  if (n_cand[CLS_LITERAL] > 0)
+  {
+    unsigned long long blocks = (n_cand[CLS_LITERAL] + T - 1) / T;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    verify_literal_kernel<<<(unsigned) blocks, T, 0, s>>>(R, V, cands.cand[CLS_LITERAL], n_cand[CLS_LITERAL], out);
+    (*launches)++;
+  }
+
+  if (n_cand[CLS_FAST] > 0)
+  {
+    unsigned long long threads = n_cand[CLS_FAST] < ws_fast_threads ? n_cand[CLS_FAST] : ws_fast_threads;
+    unsigned blocks = (unsigned) ((threads + T - 1) / T);
+    if ((unsigned long long) blocks * T > ws_fast_threads) blocks = (unsigned) (ws_fast_threads / T);
+    if (blocks == 0) blocks = 1;
+    verify_fast_kernel<<<blocks, T, 0, s>>>(R, V, cands.cand[CLS_FAST], n_cand[CLS_FAST], out, (FastWs*) ws_fast);
+    (*launches)++;
+  }
+
+  if (n_cand[CLS_RE] > 0)
+  {
+    unsigned long long threads = n_cand[CLS_RE] < ws_re_threads ? n_cand[CLS_RE] : ws_re_threads;
+    unsigned blocks = (unsigned) ((threads + T - 1) / T);
+    if ((unsigned long long) blocks * T > ws_re_threads) blocks = (unsigned) (ws_re_threads / T);
+    if (blocks == 0) blocks = 1;
+    verify_re_kernel<<<blocks, T, 0, s>>>(
+        R, V, cands.cand[CLS_RE], n_cand[CLS_RE], out, (uint8_t*) ws_re, re_ws_bytes_per_thread(R.stack_words));
+    (*launches)++;
+  }
+}

@@ -1,0 +1,382 @@
+/*
+ * yr_b200_glue.c -- libyara-side glue of the B200 scan path ("libyara/cuda" of
+ * BASELINE.json's north star).  It is the ONLY code that knows both worlds:
+ * YR_SCANNER / YR_RULES / YR_MATCH on one side, the plain C ABI of
+ * include/yara_b200.h on the other.
+ *
+ *   yr_b200_scan_mem_block   replaces _yr_scanner_scan_mem_block (scanner.c:45-176)
+ *                            at its single call site (scanner.c:493-496)
+ *   materialise()            builds the YR_MATCH nodes scan.c:714-756 would have
+ *                            built, from the notebook, and links them into
+ *                            scanner->matches[] with _yr_scan_add_match_to_list's
+ *                            ordering (scan.c:290-368) so that multi-block scans
+ *                            dedup by base+offset exactly like the reference
+ *   CALLBACK_MSG_TOO_MANY_MATCHES protocol of scan.c:1054-1073, on the caller's thread
+ *
+ * There is no CPU fallback: if the CUDA engine cannot be used the block scan
+ * fails with ERROR_INTERNAL_FATAL_ERROR and says why on stderr.
+ */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <yara.h>
+#include <yara/bitmask.h>
+#include <yara/notebook.h>
+#include <yara/stopwatch.h>
+
+#include "yara_b200.h"
+#include "yr_b200.h"
+
+typedef struct rules_entry
+{
+  YR_RULES* rules;
+  yrb_rules* dev;
+  int device;
+  struct rules_entry* next;
+} rules_entry;
+
+typedef struct scanner_entry
+{
+  YR_SCANNER* scanner;
+  yrb_scanner* dev;
+  struct scanner_entry* next;
+} scanner_entry;
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static rules_entry* g_rules = NULL;
+static scanner_entry* g_scanners = NULL;
+static int g_device = -1;
+
+void yr_b200_set_device(int device) { g_device = device; }
+
+static int current_device(void)
+{
+  if (g_device >= 0)
+    return g_device;
+  const char* e = getenv("YR_B200_DEVICE");
+  return e ? atoi(e) : 0;
+}
+
+static int fail_loudly(const char* what, int rc)
+{
+  fprintf(stderr, "yara_b200: %s failed (code %d); the B200 scan path has no CPU fallback\n", what, rc);
+  return ERROR_INTERNAL_FATAL_ERROR;
+}
+
+/* rules upload, lazily on first scan, shared by all scanners of this YR_RULES */
+static int get_rules(YR_RULES* rules, yrb_rules** out)
+{
+  int device = current_device();
+  rules_entry* e;
+
+  for (e = g_rules; e != NULL; e = e->next)
+  {
+    if (e->rules == rules && e->device == device)
+    {
+      *out = e->dev;
+      return ERROR_SUCCESS;
+    }
+  }
+
+  void* image = NULL;
+  size_t image_size = 0;
+  int rc = yr_b200_rules_flatten(rules, &image, &image_size);
+  if (rc != ERROR_SUCCESS)
+    return rc;
+
+  yrb_rules* dev = NULL;
+  rc = yrb_rules_create(image, image_size, device, &dev);
+  yr_b200_image_free(image);
+  if (rc != YRB_SUCCESS)
+    return fail_loudly("rules upload (yrb_rules_create)", rc);
+
+  e = (rules_entry*) calloc(1, sizeof(*e));
+  if (e == NULL)
+  {
+    yrb_rules_release(dev);
+    return ERROR_INSUFFICIENT_MEMORY;
+  }
+  e->rules = rules;
+  e->dev = dev;
+  e->device = device;
+  e->next = g_rules;
+  g_rules = e;
+  *out = dev;
+  return ERROR_SUCCESS;
+}
+
+static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out)
+{
+  scanner_entry* e;
+  int rc = ERROR_SUCCESS;
+
+  pthread_mutex_lock(&g_lock);
+
+  for (e = g_scanners; e != NULL; e = e->next)
+  {
+    if (e->scanner == scanner)
+    {
+      *out = e->dev;
+      pthread_mutex_unlock(&g_lock);
+      return ERROR_SUCCESS;
+    }
+  }
+
+  yrb_rules* dev_rules = NULL;
+  rc = get_rules(scanner->rules, &dev_rules);
+
+  if (rc == ERROR_SUCCESS)
+  {
+    yrb_scanner* dev = NULL;
+    int r2 = yrb_scanner_create(dev_rules, &dev);
+    if (r2 != YRB_SUCCESS)
+    {
+      rc = fail_loudly("yrb_scanner_create", r2);
+    }
+    else
+    {
+      e = (scanner_entry*) calloc(1, sizeof(*e));
+      e->scanner = scanner;
+      e->dev = dev;
+      e->next = g_scanners;
+      g_scanners = e;
+      *out = dev;
+    }
+  }
+
+  pthread_mutex_unlock(&g_lock);
+  return rc;
+}
+
+void yr_b200_scanner_release(YR_SCANNER* scanner)
+{
+  pthread_mutex_lock(&g_lock);
+  scanner_entry** pp = &g_scanners;
+  while (*pp != NULL)
+  {
+    if ((*pp)->scanner == scanner)
+    {
+      scanner_entry* e = *pp;
+      *pp = e->next;
+      yrb_scanner_destroy(e->dev);
+      free(e);
+      break;
+    }
+    pp = &(*pp)->next;
+  }
+  pthread_mutex_unlock(&g_lock);
+}
+
+void yr_b200_rules_release(YR_RULES* rules)
+{
+  pthread_mutex_lock(&g_lock);
+  rules_entry** pp = &g_rules;
+  while (*pp != NULL)
+  {
+    if ((*pp)->rules == rules)
+    {
+      rules_entry* e = *pp;
+      *pp = e->next;
+      yrb_rules_release(e->dev);
+      free(e);
+      continue;
+    }
+    pp = &(*pp)->next;
+  }
+  pthread_mutex_unlock(&g_lock);
+}
+
+/* scan.c:290-368 over real YR_MATCH nodes */
+static int add_match_to_list(YR_MATCH* match, YR_MATCHES* list, int replace_if_exists)
+{
+  YR_MATCH* ip = list->tail;
+
+  if (list->count == YR_MAX_STRING_MATCHES)
+    return ERROR_TOO_MANY_MATCHES;
+
+  while (ip != NULL)
+  {
+    if ((match->base + match->offset) == (ip->base + ip->offset))
+    {
+      if (replace_if_exists)
+      {
+        ip->match_length = match->match_length;
+        ip->data_length = match->data_length;
+        ip->data = match->data;
+      }
+      return ERROR_SUCCESS;
+    }
+    if ((match->base + match->offset) > (ip->base + ip->offset))
+      break;
+    ip = ip->prev;
+  }
+
+  match->prev = ip;
+
+  if (ip != NULL)
+  {
+    match->next = ip->next;
+    ip->next = match;
+  }
+  else
+  {
+    match->next = list->head;
+    list->head = match;
+  }
+
+  list->count++;
+
+  if (match->next != NULL)
+    match->next->prev = match;
+  else
+    list->tail = match;
+
+  return ERROR_SUCCESS;
+}
+
+/* scan.c:1054-1073 */
+static int too_many_protocol(YR_SCANNER* scanner, YR_STRING* string)
+{
+  int r = scanner->callback(scanner, CALLBACK_MSG_TOO_MANY_MATCHES, (void*) string, scanner->user_data);
+
+  if (r == CALLBACK_CONTINUE)
+  {
+    yr_bitmask_set(scanner->strings_temp_disabled, string->idx);
+    return ERROR_SUCCESS;
+  }
+
+  scanner->last_error_string = string;
+  return ERROR_TOO_MANY_MATCHES;
+}
+
+static int materialise(
+    YR_SCANNER* scanner, const uint8_t* block_data, YR_MEMORY_BLOCK* block, const yrb_match* recs, size_t n,
+    YR_MATCHES* lists, int confirmed, uint32_t max_match_data)
+{
+  YR_RULES* rules = scanner->rules;
+
+  for (size_t i = 0; i < n; i++)
+  {
+    const yrb_match* r = &recs[i];
+    YR_STRING* string = &rules->strings_table[r->string_idx];
+
+    if (yr_bitmask_is_set(scanner->strings_temp_disabled, string->idx))
+      continue; /* disabled in an earlier block of this scan (scan.c:1018) */
+
+    YR_MATCH* m = (YR_MATCH*) yr_notebook_alloc(scanner->matches_notebook, sizeof(YR_MATCH));
+    if (m == NULL)
+      return ERROR_INSUFFICIENT_MEMORY;
+
+    m->base = block->base;
+    m->offset = r->offset;
+    m->match_length = r->match_length;
+    m->data_length = r->match_length < (int32_t) max_match_data ? r->match_length : (int32_t) max_match_data;
+    m->prev = NULL;
+    m->next = NULL;
+    m->chain_length = r->chain_length;
+    m->is_private = STRING_IS_PRIVATE(string);
+    m->xor_key = r->xor_key;
+    m->data = NULL;
+
+    if (m->data_length > 0)
+    {
+      uint8_t* d = (uint8_t*) yr_notebook_alloc(scanner->matches_notebook, m->data_length);
+      if (d == NULL)
+        return ERROR_INSUFFICIENT_MEMORY;
+      memcpy(d, block_data + r->offset, m->data_length);
+      m->data = d;
+    }
+    else if (m->data_length < 0)
+    {
+      m->data_length = 0;
+    }
+
+    int rc = add_match_to_list(m, &lists[string->idx], confirmed && STRING_IS_GREEDY_REGEXP(string));
+
+    if (rc == ERROR_TOO_MANY_MATCHES)
+    {
+      /* only reachable when earlier blocks already filled the list */
+      rc = too_many_protocol(scanner, string);
+      if (rc != ERROR_SUCCESS)
+        return rc;
+    }
+  }
+
+  return ERROR_SUCCESS;
+}
+
+int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_MEMORY_BLOCK* block)
+{
+  yrb_scanner* dev = NULL;
+  uint32_t max_match_data;
+  int rc;
+
+  if (scanner->timeout > 0 && yr_stopwatch_elapsed_ns(&scanner->stopwatch) > scanner->timeout)
+    return ERROR_SCAN_TIMEOUT;
+
+  rc = get_scanner(scanner, &dev);
+  if (rc != ERROR_SUCCESS)
+    return rc;
+
+  FAIL_ON_ERROR(yr_get_configuration_uint32(YR_CONFIG_MAX_MATCH_DATA, &max_match_data));
+
+  yrb_scan_params params;
+  memset(&params, 0, sizeof(params));
+  params.base = block->base;
+  params.scan_flags = scanner->flags;
+  params.too_many_action = 0; /* the user's answer is only known after asking: see below */
+
+  yrb_scan_result res;
+  rc = yrb_scan_host(dev, block_data, block->size, &params, &res);
+  if (rc != YRB_SUCCESS)
+    return rc < 1000 ? rc : fail_loudly("yrb_scan_host", rc);
+
+  if (res.error != 0)
+  {
+    if (res.error_string != YRB_NONE)
+      scanner->last_error_string = &scanner->rules->strings_table[res.error_string];
+    return res.error;
+  }
+
+  /* In fast mode a SINGLE_MATCH string that already matched in an earlier block is
+     not verified again (scan.c:1021-1023): drop this block's records for it. */
+  if (scanner->flags & SCAN_FLAGS_FAST_MODE)
+  {
+    yrb_match* recs = (yrb_match*) res.matches;
+    size_t k = 0;
+    for (size_t i = 0; i < res.n_matches; i++)
+    {
+      YR_STRING* string = &scanner->rules->strings_table[recs[i].string_idx];
+      if (STRING_IS_SINGLE_MATCH(string) && scanner->matches[string->idx].head != NULL)
+        continue;
+      recs[k++] = recs[i];
+    }
+    res.n_matches = k;
+  }
+
+  rc = materialise(scanner, block_data, block, res.matches, res.n_matches, scanner->matches, 1, max_match_data);
+  if (rc != ERROR_SUCCESS)
+    return rc;
+
+  rc = materialise(
+      scanner, block_data, block, res.unconfirmed, res.n_unconfirmed, scanner->unconfirmed_matches, 0, max_match_data);
+  if (rc != ERROR_SUCCESS)
+    return rc;
+
+  /* strings that hit YR_MAX_STRING_MATCHES inside this block, in firing order */
+  for (uint32_t i = 0; i < res.n_too_many; i++)
+  {
+    YR_STRING* string = &scanner->rules->strings_table[res.too_many[i]];
+    if (yr_bitmask_is_set(scanner->strings_temp_disabled, string->idx))
+      continue;
+    rc = too_many_protocol(scanner, string);
+    if (rc != ERROR_SUCCESS)
+      return rc;
+  }
+
+  if (scanner->timeout > 0 && yr_stopwatch_elapsed_ns(&scanner->stopwatch) > scanner->timeout)
+    return ERROR_SCAN_TIMEOUT;
+
+  return ERROR_SUCCESS;
+}
