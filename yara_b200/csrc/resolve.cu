@@ -355,7 +355,7 @@ __global__ void chain_init_kernel(ChainLists L, uint32_t num_strings)
 
 __global__ void chain_resolve_kernel(
     const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, DevRules R, ChainLists L, uint64_t* kF,
-    yrb_match* outU, yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap)
+    yrb_match* outU, yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap, int scan_flags)
 {
   const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (j0 >= n) return;
@@ -374,6 +374,8 @@ __global__ void chain_resolve_kernel(
   uint32_t j = j0;
   uint64_t prev_key = ~0ULL;
   uint32_t disabled_string = YRB_NONE; // strings_temp_disabled after a TOO_MANY (at most one tracked per chain)
+  uint64_t cur_cand = ~0ULL;
+  bool skip_cand = false;
 
   for (; j < n && kA[j] == a; j++)
   {
@@ -385,6 +387,17 @@ __global__ void chain_resolve_kernel(
     prev_key = r.key;
 
     if (r.string_idx == disabled_string) continue;
+
+    // scan.c:1021-1023: the FAST_MODE / SINGLE_MATCH guard is evaluated once per
+    // candidate, before verification, against matches[string->idx] (only ever
+    // non-empty for the chain's head string)
+    if ((r.key >> KEY_SEQ_BITS) != cur_cand)
+    {
+      cur_cand = r.key >> KEY_SEQ_BITS;
+      skip_cand = (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) &&
+                  L.mcnt[r.string_idx] > 0;
+    }
+    if (skip_cand) continue;
 
     if (verify_chained(c, (int32_t) j) == 2)
     {
@@ -550,7 +563,7 @@ void launch_resolve_chains_and_order(ResolveWork& w, cudaStream_t s, unsigned* l
     L.mhead = w.s_lists + 3 * (size_t) w.R.num_strings; L.mtail = w.s_lists + 4 * (size_t) w.R.num_strings;
     L.mcnt = w.s_lists + 5 * (size_t) w.R.num_strings;
     chain_init_kernel<<<GRID(w.R.num_strings), 0, s>>>(L, w.R.num_strings);
-    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix0, w.k1, n, w.R, L, w.kF, w.outU, w.unconf, w.st, w.too_many, w.too_many_cap);
+    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix0, w.k1, n, w.R, L, w.kF, w.outU, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags);
     (*launches) += 2;
   }
 
