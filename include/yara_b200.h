@@ -168,6 +168,13 @@ int yrb_dev_fill_random(int device, void* d_ptr, size_t bytes, uint64_t seed, ui
 int yrb_dev_write(int device, void* d_ptr, size_t d_offset, const void* src, size_t bytes);
 int yrb_dev_read(int device, const void* d_ptr, size_t d_offset, void* dst, size_t bytes);
 int yrb_dev_flush_l2(int device);
+/* n byte strings, string k = bytes[starts[k] .. starts[k+1]), written at d_ptr + offsets[k] */
+int yrb_dev_scatter(
+    int device, void* d_ptr, size_t d_size, uint32_t n, const uint64_t* offsets, const uint64_t* starts,
+    const uint8_t* bytes);
+/* pinned host memory (cudaHostAlloc) for end-to-end measurements */
+int yrb_host_alloc(size_t bytes, void** h_ptr);
+int yrb_host_free(void* h_ptr);
 
 #ifdef __cplusplus
 }

@@ -814,6 +814,51 @@ extern "C" int yrb_dev_fill_random(int device, void* d_ptr, size_t bytes, uint64
   return YRB_SUCCESS;
 }
 
+// plants: n byte strings (concatenated in `bytes`, string k = [starts[k], starts[k+1])) written at d_ptr + offsets[k]
+__global__ void scatter_kernel(uint8_t* dst, size_t dst_size, uint32_t n, const uint64_t* offsets, const uint64_t* starts, const uint8_t* bytes)
+{
+  const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (k >= n) return;
+  const uint64_t s0 = starts[k], s1 = starts[k + 1], o = offsets[k];
+  for (uint64_t j = lane; j < s1 - s0; j += 32)
+    if (o + j < dst_size) dst[o + j] = bytes[s0 + j];
+}
+
+extern "C" int yrb_dev_scatter(
+    int device, void* d_ptr, size_t d_size, uint32_t n, const uint64_t* offsets, const uint64_t* starts, const uint8_t* bytes)
+{
+  if (device < 0 || device >= yrb_device_count()) return YRB_ERROR_NO_DEVICE;
+  CK(cudaSetDevice(device));
+  if (n == 0) return YRB_SUCCESS;
+  uint64_t *d_off = nullptr, *d_st = nullptr;
+  uint8_t* d_b = nullptr;
+  const size_t nb = (size_t) starts[n];
+  CK(cudaMalloc((void**) &d_off, sizeof(uint64_t) * n));
+  CK(cudaMalloc((void**) &d_st, sizeof(uint64_t) * ((size_t) n + 1)));
+  CK(cudaMalloc((void**) &d_b, nb ? nb : 1));
+  CK(cudaMemcpy(d_off, offsets, sizeof(uint64_t) * n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_st, starts, sizeof(uint64_t) * ((size_t) n + 1), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_b, bytes, nb, cudaMemcpyHostToDevice));
+  scatter_kernel<<<(unsigned) (((uint64_t) n * 32 + 255) / 256), 256>>>((uint8_t*) d_ptr, d_size, n, d_off, d_st, d_b);
+  CK(cudaDeviceSynchronize());
+  cudaFree(d_off); cudaFree(d_st); cudaFree(d_b);
+  return YRB_SUCCESS;
+}
+
+extern "C" int yrb_host_alloc(size_t bytes, void** h_ptr)
+{
+  if (yrb_device_count() < 1) return YRB_ERROR_NO_DEVICE;
+  CK(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return YRB_SUCCESS;
+}
+
+extern "C" int yrb_host_free(void* h_ptr)
+{
+  CK(cudaFreeHost(h_ptr));
+  return YRB_SUCCESS;
+}
+
 extern "C" int yrb_dev_write(int device, void* d_ptr, size_t d_offset, const void* src, size_t bytes)
 {
   if (device < 0 || device >= yrb_device_count()) return YRB_ERROR_NO_DEVICE;
