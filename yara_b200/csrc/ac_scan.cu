@@ -105,20 +105,353 @@ void launch_ac_scan_walk(
 }
 
 // ---------------------------------------------------------------- filter kernel
-// (placeholder until the prefilter kernel lands: reports "not usable" so that the
-// engine picks the walk kernel)
-int build_filter_tables(const void* host_image, int device, FilterTables* out, void** d_storage)
+//
+// Why: the table walk needs >= 2 dependent 4-byte gathers per input byte
+// (T[state+index], match_table[state]); at 50 % of HBM bandwidth that would be
+// ~26 TB/s of bank-conflicting on-chip gathers (SURVEY.md section 7 "Hard
+// parts").  But the walk's OUTPUT is sparse: position i has an event iff
+// match_table[S(i)] != 0, and S(i) depends only on the 4-byte window
+// W(p) = data[p-3..p], p = i-1.  So the kernel filters windows instead of
+// walking states:
+//
+//   level 1  B3: 2^20-bit bitmap in shared memory, probed ONCE PER TWO
+//            POSITIONS with the 3 bytes data[p-2..p] the windows W(p) and W(p+1)
+//            have in common; set for the suffix3 and the prefix3 of every hit
+//            window.  Branch-free: one IMAD hash, one LDS, the bit lands in a
+//            per-thread mask.
+//   level 2  B4: 2^19-bit bitmap in shared memory over the hashed 4-byte window,
+//            only for positions of pairs that passed level 1.
+//   level 3  exact: open-addressed hash table (window -> match_table value of
+//            the state the reference walk would be in), L2-resident; then
+//            emit_events() exactly as the walk kernel does.
+//
+// "Hit windows" are enumerated on the host from the compiled automaton
+// (build_filter_tables): every AC state with a non-empty match list and depth
+// 3 or 4 contributes the 4-byte windows that end in its path.  Rulesets with hit
+// states of depth <= 2 (1-2 byte atoms, or strings with no atom at all, quirk 7)
+// would saturate the bitmaps: they are scanned by the walk kernel instead.
+
+#define FT_THREADS 1024
+#define FT_U 4
+#define FT_TILE (FT_THREADS * 16 * FT_U)
+#define HT_MUL 0xC2B2AE35u
+
+struct FilterDev
 {
-  (void) host_image; (void) device;
+  const uint32_t* b3;
+  const uint32_t* b4;
+  const uint2* ht;     // {window, match_table value}; .y == 0 means empty
+  uint32_t ht_bits;
+};
+
+static __device__ __forceinline__ uint32_t ht_lookup(const FilterDev& F, uint32_t w)
+{
+  const uint32_t mask = (1u << F.ht_bits) - 1;
+  uint32_t slot = (w * HT_MUL) >> (32 - F.ht_bits);
+  for (;;)
+  {
+    const uint2 e = __ldg(&F.ht[slot]);
+    if (e.y == 0) return 0;
+    if (e.x == w) return e.y;
+    slot = (slot + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, int64_t hi)
+{
+  extern __shared__ uint32_t smem[];
+  uint32_t* sB3 = smem;
+  uint32_t* sB4 = smem + B3_WORDS;
+
+  {
+    const uint4* g3 = reinterpret_cast<const uint4*>(F.b3);
+    const uint4* g4 = reinterpret_cast<const uint4*>(F.b4);
+    uint4* s3 = reinterpret_cast<uint4*>(sB3);
+    uint4* s4 = reinterpret_cast<uint4*>(sB4);
+    for (uint32_t i = threadIdx.x; i < B3_WORDS / 4; i += FT_THREADS) s3[i] = __ldg(&g3[i]);
+    for (uint32_t i = threadIdx.x; i < B4_WORDS / 4; i += FT_THREADS) s4[i] = __ldg(&g4[i]);
+  }
+  __syncthreads();
+
+  const uint8_t* __restrict__ d = V.d - V.g0; // d[p] = block byte p; (d + lo) is 16-byte aligned
+  const int64_t ntiles = (hi - lo + FT_TILE - 1) / FT_TILE;
+  const uint32_t H3 = HASH3_MUL << 8;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+  {
+    const int64_t base = lo + tile * FT_TILE + (int64_t) threadIdx.x * 16;
+
+    uint4 v[FT_U];
+    uint32_t pv[FT_U];
+
+#pragma unroll
+    for (int u = 0; u < FT_U; u++)
+    {
+      const int64_t a = base + (int64_t) u * (FT_THREADS * 16);
+      if (a < hi)
+      {
+        v[u] = *reinterpret_cast<const uint4*>(d + a);
+        pv[u] = *reinterpret_cast<const uint32_t*>(d + a - 4);
+      }
+      else
+      {
+        v[u] = make_uint4(0, 0, 0, 0);
+        pv[u] = 0;
+      }
+    }
+
+    // ---- level 1: one B3 probe per pair of positions, branch-free
+    uint32_t mask = 0;
+
+#define PROBE3(x)                                                  \
+  {                                                                \
+    const uint32_t h_ = (x) * H3;                                  \
+    const uint32_t w_ = sB3[h_ >> 17];                             \
+    mask = (mask << 1) | ((w_ >> ((h_ >> 12) & 31)) & 1u);         \
+  }
+
+#pragma unroll
+    for (int u = 0; u < FT_U; u++)
+    {
+      const uint32_t m = pv[u], w0 = v[u].x, w1 = v[u].y, w2 = v[u].z, w3 = v[u].w;
+      PROBE3(__funnelshift_r(m, w0, 16));
+      PROBE3(w0);
+      PROBE3(__funnelshift_r(w0, w1, 16));
+      PROBE3(w1);
+      PROBE3(__funnelshift_r(w1, w2, 16));
+      PROBE3(w2);
+      PROBE3(__funnelshift_r(w2, w3, 16));
+      PROBE3(w3);
+    }
+#undef PROBE3
+
+    // chunks past the end of the range were zero-filled: drop their bits
+#pragma unroll
+    for (int u = 0; u < FT_U; u++)
+      if (base + (int64_t) u * (FT_THREADS * 16) >= hi)
+        mask &= ~(0xFF000000u >> (8 * u));
+
+    // ---- levels 2 and 3 for the pairs that passed
+    while (mask != 0)
+    {
+      const int s = __clz(mask);
+      mask &= ~(0x80000000u >> s);
+
+      const int u = s >> 3;
+      const int k = (s & 7) * 2;
+      const int64_t p = base + (int64_t) u * (FT_THREADS * 16) + k; // first position of the pair
+
+      // bytes p-3 .. p+1, re-read through L1
+      const int64_t q = (p - 3) & ~(int64_t) 3;
+      const uint32_t sh = (uint32_t) ((p - 3) & 3) * 8;
+      const uint32_t x0 = *reinterpret_cast<const uint32_t*>(d + q);
+      const uint32_t x1 = *reinterpret_cast<const uint32_t*>(d + q + 4);
+      const uint64_t x = ((uint64_t) x1 << 32) | x0;
+
+#pragma unroll
+      for (int e = 0; e < 2; e++)
+      {
+        const uint32_t w = (uint32_t) (x >> (sh + 8 * e));   // W(p + e)
+        const uint32_t i4 = hash4(w);
+        if ((sB4[i4 >> 5] >> (i4 & 31)) & 1u)
+        {
+          const uint32_t mv = ht_lookup(F, w);
+          if (mv != 0)
+            emit_events(R, V, out, p + e + 1, mv);
+        }
+      }
+    }
+  }
+}
+
+// ---- host: enumerate hit windows of the compiled automaton, build B3 / B4 / hash table
+
+struct FilterStorage
+{
+  uint32_t b3[B3_WORDS];
+  uint32_t b4[B4_WORDS];
+};
+
+static uint32_t host_ac_step(const uint32_t* T, uint32_t state, uint32_t byte)
+{
+  const uint32_t index = byte + 1;
+  uint32_t t = T[state + index];
+  while ((t & 0x1FF) != index)
+  {
+    if (state != 0) { state = T[state] >> 9; t = T[state + index]; }
+    else { t = 0; break; }
+  }
+  return t >> 9;
+}
+
+#include <vector>
+
+int build_filter_tables(const void* image, int device, FilterTables* out, void** d_storage)
+{
+  (void) device;
   memset(out, 0, sizeof(*out));
   *d_storage = nullptr;
+
+  const yrb_image_header* h = (const yrb_image_header*) image;
+  const uint32_t* T = yrb_img_trans(image);
+  const uint32_t* M = yrb_img_match(image);
+
+  if (h->tables_size < 257)
+    return YRB_SUCCESS;
+
+  if (M[0] != 0)
+  {
+    out->root_match = 1; // every position is an event: nothing to filter
+    return YRB_SUCCESS;
+  }
+
+  // breadth-first over the trie (depth <= YR_MAX_ATOM_LENGTH), remembering each state's path
+  struct Node { uint32_t state; uint32_t path; int depth; };
+  std::vector<Node> level, next;
+  std::vector<uint32_t> windows; // hit windows, little-endian: data[p-3] in bits 0-7
+  level.push_back({0, 0, 0});
+  size_t n_d3 = 0;
+
+  while (!level.empty())
+  {
+    next.clear();
+    for (const Node& n : level)
+    {
+      if (n.depth > 0 && M[n.state] != 0)
+      {
+        if (n.depth <= 2)
+        {
+          if (n.depth == 1) out->has_d1 = 1; else out->has_d2 = 1;
+        }
+        else if (n.depth == 3)
+        {
+          n_d3++;
+          for (uint32_t x = 0; x < 256; x++) windows.push_back(x | (n.path << 8));
+        }
+        else
+        {
+          windows.push_back(n.path);
+        }
+      }
+      if (n.depth < YRB_MAX_ATOM_LENGTH)
+      {
+        for (uint32_t b = 0; b < 256; b++)
+        {
+          const uint32_t t = T[n.state + b + 1];
+          if ((t & 0x1FF) == b + 1)
+            next.push_back({t >> 9, n.path | (b << (8 * n.depth)), n.depth + 1});
+        }
+      }
+    }
+    level.swap(next);
+  }
+
+  if (out->has_d1 || out->has_d2 || windows.empty() || n_d3 > 512)
+    return YRB_SUCCESS; // not usable: the engine falls back to the walk kernel
+
+  FilterStorage* fs = new FilterStorage();
+  memset(fs, 0, sizeof(*fs));
+
+  uint32_t ht_bits = 4;
+  while ((1ull << ht_bits) < windows.size() * 2) ht_bits++;
+  std::vector<uint2> ht((size_t) 1 << ht_bits, make_uint2(0, 0));
+  const uint32_t ht_mask = (1u << ht_bits) - 1;
+
+  for (uint32_t w : windows)
+  {
+    // the state the reference walk is in after these 4 bytes (ROOT restart is exact: depth <= 4)
+    uint32_t st = 0;
+    for (int j = 0; j < 4; j++) st = host_ac_step(T, st, (w >> (8 * j)) & 0xFF);
+    const uint32_t mv = M[st];
+    if (mv == 0) continue;
+
+    const uint32_t k_suffix = w >> 8, k_prefix = w & 0xFFFFFF;
+    uint32_t i3 = hash3(k_suffix);
+    fs->b3[i3 >> 5] |= 1u << (i3 & 31);
+    i3 = hash3(k_prefix);
+    fs->b3[i3 >> 5] |= 1u << (i3 & 31);
+    const uint32_t i4 = hash4(w);
+    fs->b4[i4 >> 5] |= 1u << (i4 & 31);
+
+    uint32_t slot = (w * HT_MUL) >> (32 - ht_bits);
+    while (ht[slot].y != 0 && ht[slot].x != w) slot = (slot + 1) & ht_mask;
+    ht[slot] = make_uint2(w, mv);
+  }
+
+  size_t pop3 = 0;
+  for (uint32_t i = 0; i < B3_WORDS; i++) pop3 += (size_t) __builtin_popcount(fs->b3[i]);
+  const double fill3 = (double) pop3 / (double) (1u << B3_BITS);
+
+  if (fill3 > 0.45)
+  {
+    delete fs;
+    return YRB_SUCCESS; // too dense to filter anything
+  }
+
+  uint8_t* dptr = nullptr;
+  const size_t ht_bytes = ht.size() * sizeof(uint2);
+  const size_t total = sizeof(FilterStorage) + ht_bytes;
+  if (cudaMalloc((void**) &dptr, total) != cudaSuccess) { cudaGetLastError(); delete fs; return YRB_ERROR_INSUFFICIENT_MEMORY; }
+  cudaMemcpy(dptr, fs, sizeof(FilterStorage), cudaMemcpyHostToDevice);
+  cudaMemcpy(dptr + sizeof(FilterStorage), ht.data(), ht_bytes, cudaMemcpyHostToDevice);
+  delete fs;
+
+  out->b3 = reinterpret_cast<const uint32_t*>(dptr);
+  out->b4 = reinterpret_cast<const uint32_t*>(dptr + sizeof(uint32_t) * B3_WORDS);
+  out->ht = reinterpret_cast<const void*>(dptr + sizeof(FilterStorage));
+  out->ht_bits = ht_bits;
+  out->n_windows = (uint32_t) windows.size();
+  out->fill3 = (float) fill3;
+  out->usable = 1;
+  *d_storage = dptr;
+
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev])
+  {
+    cudaFuncSetAttribute(ac_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int) ((B3_WORDS + B4_WORDS) * sizeof(uint32_t)));
+    attr_set[dev] = true;
+  }
   return YRB_SUCCESS;
 }
 
+// Bytes [lo, hi) in block coordinates.  The filter kernel takes the 16-byte
+// aligned middle; the head (which also covers the first bytes of the block, where
+// a window would reach before byte 0) and the tail go to the walk kernel.
 void launch_ac_scan_filter(
     const DevRules& R, const FilterTables& F, const ScanView& V, const CandOut& out, int64_t lo, int64_t hi,
     int num_sms, cudaStream_t s)
 {
-  (void) F; (void) num_sms;
-  launch_ac_scan_walk(R, V, out, lo, hi, s);
+  if (hi <= lo)
+    return;
+
+  const uint8_t* d = V.d - V.g0;
+  int64_t flo = lo;
+  if (flo < 16) flo = 16;
+  if (flo < V.g0 + 16) flo = V.g0 + 16;
+  flo += (int64_t) ((16 - ((uintptr_t) (d + flo) & 15)) & 15);
+  int64_t fhi = hi - (int64_t) ((uintptr_t) (d + hi) & 15);
+
+  if (fhi - flo < 4096)
+  {
+    launch_ac_scan_walk(R, V, out, lo, hi, s);
+    return;
+  }
+
+  launch_ac_scan_walk(R, V, out, lo, flo, s);
+
+  FilterDev fd;
+  fd.b3 = F.b3;
+  fd.b4 = F.b4;
+  fd.ht = reinterpret_cast<const uint2*>(F.ht);
+  fd.ht_bits = F.ht_bits;
+
+  const int64_t ntiles = (fhi - flo + FT_TILE - 1) / FT_TILE;
+  const unsigned grid = (unsigned) (ntiles < num_sms ? ntiles : num_sms);
+  ac_filter_kernel<<<grid, FT_THREADS, (B3_WORDS + B4_WORDS) * sizeof(uint32_t), s>>>(R, fd, V, out, flo, fhi);
+
+  launch_ac_scan_walk(R, V, out, fhi, hi, s);
 }

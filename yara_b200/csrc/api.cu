@@ -225,6 +225,8 @@ extern "C" int yrb_scanner_create(yrb_rules* rules, yrb_scanner** out)
   s->rules = rules;
   s->device = rules->device;
   yrb_rules_retain(rules);
+  if (const char* e = getenv("YRB_SCAN_KERNEL")) // test hook: 1 = walk, 2 = filter
+    s->opt_kernel = atoi(e);
 
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
@@ -283,6 +285,9 @@ extern "C" int yrb_scanner_set_option(yrb_scanner* s, int option, uint64_t value
 static int pick_kernel(const yrb_scanner* s)
 {
   if (s->opt_kernel == YRB_KERNEL_WALK) return YRB_KERNEL_WALK;
+  if (getenv("YRB_DEBUG") && !s->rules->F.usable)
+    fprintf(stderr, "yrb200: prefilter not usable (root_match=%d d1=%d d2=%d), using the walk kernel\n",
+            s->rules->F.root_match, s->rules->F.has_d1, s->rules->F.has_d2);
   if (s->rules->F.usable) return YRB_KERNEL_FILTER;
   return YRB_KERNEL_WALK;
 }

@@ -121,8 +121,10 @@ struct FilterTables
 {
   const uint32_t* b3;     // 2^20-bit bitmap over hashed 3-byte keys (pair probe)
   const uint32_t* b4;     // 2^19-bit bitmap over hashed 4-byte windows
-  const uint32_t* b2;     // 2^16-bit direct bitmap over 2-byte suffixes (depth-2 states)
-  uint32_t b1[8];         // 256-bit direct bitmap over 1-byte suffixes (depth-1 states)
+  const void* ht;         // open-addressed {window, match_table value} table
+  uint32_t ht_bits;
+  uint32_t n_windows;
+  float fill3;
   int has_d1, has_d2, root_match, usable;
 };
 
