@@ -119,7 +119,7 @@ void launch_ac_scan_walk(
 //            have in common; set for the suffix3 and the prefix3 of every hit
 //            window.  Branch-free: one IMAD hash, one LDS, the bit lands in a
 //            per-thread mask.
-//   level 2  B4: 2^19-bit bitmap in shared memory over the hashed 4-byte window,
+//   level 2  B4: 2^19-bit Bloom filter (k = 4) in shared memory over the 4-byte window,
 //            only for positions of pairs that passed level 1.
 //   level 3  exact: open-addressed hash table (window -> match_table value of
 //            the state the reference walk would be in), L2-resident; then
@@ -131,10 +131,16 @@ void launch_ac_scan_walk(
 // states of depth <= 2 (1-2 byte atoms, or strings with no atom at all, quirk 7)
 // would saturate the bitmaps: they are scanned by the walk kernel instead.
 
-#define FT_THREADS 1024
-#define FT_U 4
-#define FT_TILE (FT_THREADS * 16 * FT_U)
+#define FT_ROW 528                       // per warp, per u: 12 B pad | 4 B halo | 512 B data
 #define HT_MUL 0xC2B2AE35u
+
+// Kernel variants (threads per CTA, 16-byte chunks per thread per tile, log2 of the
+// B4 Bloom filter size); all three fit the 227 KB of shared memory with B3.
+struct FtVariant { int threads, u, b4_bits, prefetch; };
+static const FtVariant kVariants[] = {{1024, 4, 18, 0}, {512, 4, 19, 0}, {1024, 2, 19, 1}, {512, 4, 19, 1}, {1024, 2, 19, 0}};
+#define FT_NUM_VARIANTS 5
+static inline size_t ft_smem_bytes(const FtVariant& v)
+{ return (size_t) B3_WORDS * 4 + ((size_t) 1 << (v.b4_bits - 3)) + (size_t) (v.threads / 32) * v.u * FT_ROW; }
 
 struct FilterDev
 {
@@ -157,12 +163,40 @@ static __device__ __forceinline__ uint32_t ht_lookup(const FilterDev& F, uint32_
   }
 }
 
+// B4 is a Bloom filter with BLOOM_K probes (Kirsch-Mitzenmacher double hashing):
+// the level-2 test must be selective enough that the L2-resident exact lookup
+// (hundreds of cycles of latency for the whole warp) is reached almost only by
+// real hits: 2^19 bits for ~36k windows and k = 4 gives ~0.3 % false positives.
+template <int B4BITS>
+static __device__ __forceinline__ bool bloom4_test(const uint32_t* sB4, uint32_t w)
+{
+  const uint32_t g1 = w * HASH4_MUL, g2 = (w * HASH4_MUL2) | 1u;
+  uint32_t g = g1;
+#pragma unroll
+  for (int k = 0; k < BLOOM_K; k++)
+  {
+    const uint32_t i4 = g >> (32 - B4BITS);
+    if (!((sB4[i4 >> 5] << (i4 & 31)) & 0x80000000u))
+      return false;
+    g += g2;
+  }
+  return true;
+}
+
+// Bit layout: bits are numbered MSB-first, so that `word << n` brings bit n to bit
+// 31 and one funnel shift appends it to the per-thread mask.  B3: word = top 15
+// bits of hash3(key), n = key & 31 (the shift instruction takes the low 5 bits of
+// the key register for free).  B4: word = idx >> 5, n = idx & 31.
+template <int FT_THREADS, int FT_U, int B4BITS, bool PREFETCH>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, int64_t hi)
 {
-  extern __shared__ uint32_t smem[];
-  uint32_t* sB3 = smem;
-  uint32_t* sB4 = smem + B3_WORDS;
+  constexpr int FT_TILE = FT_THREADS * 16 * FT_U;
+  constexpr uint32_t B4_WORDS = 1u << (B4BITS - 5);
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint32_t* sB3 = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* sB4 = sB3 + B3_WORDS;
+  uint8_t* stage = smem_raw + (B3_WORDS + B4_WORDS) * 4;
 
   {
     const uint4* g3 = reinterpret_cast<const uint4*>(F.b3);
@@ -174,47 +208,65 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
   }
   __syncthreads();
 
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  uint8_t* wstage = stage + warp * (FT_U * FT_ROW);   // this warp's private rows
+
   const uint8_t* __restrict__ d = V.d - V.g0; // d[p] = block byte p; (d + lo) is 16-byte aligned
   const int64_t ntiles = (hi - lo + FT_TILE - 1) / FT_TILE;
   const uint32_t H3 = HASH3_MUL << 8;
+  const uint8_t* sB3b = reinterpret_cast<const uint8_t*>(sB3);
+
+  uint4 v[FT_U], vn[FT_U];
+  uint32_t halo[FT_U], halon[FT_U];
+
+#define LOAD_TILE(T_, V_, H_)                                                       \
+  {                                                                                 \
+    const int64_t b_ = lo + (T_) * FT_TILE + (int64_t) threadIdx.x * 16;            \
+    _Pragma("unroll") for (int u = 0; u < FT_U; u++)                                \
+    {                                                                               \
+      const int64_t a_ = b_ + (int64_t) u * (FT_THREADS * 16);                      \
+      V_[u] = make_uint4(0, 0, 0, 0);                                               \
+      H_[u] = 0;                                                                    \
+      if ((T_) < ntiles && a_ < hi)                                                 \
+      {                                                                             \
+        V_[u] = *reinterpret_cast<const uint4*>(d + a_);                            \
+        if (lane == 0) H_[u] = *reinterpret_cast<const uint32_t*>(d + a_ - 4);      \
+      }                                                                             \
+    }                                                                               \
+  }
+
+  if (PREFETCH) LOAD_TILE((int64_t) blockIdx.x, v, halo);
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
   {
     const int64_t base = lo + tile * FT_TILE + (int64_t) threadIdx.x * 16;
 
-    uint4 v[FT_U];
-    uint32_t pv[FT_U];
-
-#pragma unroll
-    for (int u = 0; u < FT_U; u++)
-    {
-      const int64_t a = base + (int64_t) u * (FT_THREADS * 16);
-      if (a < hi)
-      {
-        v[u] = *reinterpret_cast<const uint4*>(d + a);
-        pv[u] = *reinterpret_cast<const uint32_t*>(d + a - 4);
-      }
-      else
-      {
-        v[u] = make_uint4(0, 0, 0, 0);
-        pv[u] = 0;
-      }
-    }
+    // software pipeline: the next tile's bytes are in flight while this one is probed
+    if (PREFETCH) { LOAD_TILE(tile + gridDim.x, vn, halon); }
+    else { LOAD_TILE(tile, v, halo); }
 
     // ---- level 1: one B3 probe per pair of positions, branch-free
     uint32_t mask = 0;
 
-#define PROBE3(x)                                                  \
-  {                                                                \
-    const uint32_t h_ = (x) * H3;                                  \
-    const uint32_t w_ = sB3[h_ >> 17];                             \
-    mask = (mask << 1) | ((w_ >> ((h_ >> 12) & 31)) & 1u);         \
+#define PROBE3(x)                                                                   \
+  {                                                                                 \
+    const uint32_t h_ = (x) * H3;                                                   \
+    const uint32_t w_ = *reinterpret_cast<const uint32_t*>(sB3b + ((h_ >> 15) & 0x1FFFCu)); \
+    mask = __funnelshift_l(__funnelshift_l(0u, w_, (x)), mask, 1);                  \
   }
 
 #pragma unroll
     for (int u = 0; u < FT_U; u++)
     {
-      const uint32_t m = pv[u], w0 = v[u].x, w1 = v[u].y, w2 = v[u].z, w3 = v[u].w;
+      uint32_t m = __shfl_up_sync(0xFFFFFFFFu, v[u].w, 1);
+      if (lane == 0) m = halo[u];
+      const uint32_t w0 = v[u].x, w1 = v[u].y, w2 = v[u].z, w3 = v[u].w;
+
+      // stage the chunk (and the warp's halo word) for level 2
+      *reinterpret_cast<uint4*>(wstage + u * FT_ROW + 16 + lane * 16) = v[u];
+      if (lane == 0) *reinterpret_cast<uint32_t*>(wstage + u * FT_ROW + 12) = m;
+
       PROBE3(__funnelshift_r(m, w0, 16));
       PROBE3(w0);
       PROBE3(__funnelshift_r(w0, w1, 16));
@@ -226,43 +278,54 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
     }
 #undef PROBE3
 
-    // chunks past the end of the range were zero-filled: drop their bits
+    // mask bit (8*FT_U - 1 - slot) belongs to slot = u*8 + pair; chunks past the end
+    // of the range were zero-filled: drop their bits
 #pragma unroll
     for (int u = 0; u < FT_U; u++)
       if (base + (int64_t) u * (FT_THREADS * 16) >= hi)
-        mask &= ~(0xFF000000u >> (8 * u));
+        mask &= ~(0xFFu << (8 * (FT_U - 1 - u)));
+
+    __syncwarp();
 
     // ---- levels 2 and 3 for the pairs that passed
     while (mask != 0)
     {
-      const int s = __clz(mask);
-      mask &= ~(0x80000000u >> s);
+      const int s = __clz(mask) - (32 - 8 * FT_U);
+      mask &= ~(0x80000000u >> (s + 32 - 8 * FT_U));
 
       const int u = s >> 3;
       const int k = (s & 7) * 2;
-      const int64_t p = base + (int64_t) u * (FT_THREADS * 16) + k; // first position of the pair
 
-      // bytes p-3 .. p+1, re-read through L1
-      const int64_t q = (p - 3) & ~(int64_t) 3;
-      const uint32_t sh = (uint32_t) ((p - 3) & 3) * 8;
-      const uint32_t x0 = *reinterpret_cast<const uint32_t*>(d + q);
-      const uint32_t x1 = *reinterpret_cast<const uint32_t*>(d + q + 4);
+      // bytes p-3 .. p+1 of the pair's first position p, from this warp's staged row
+      const uint32_t off = 16 + lane * 16 + k - 3;
+      const uint8_t* row = wstage + u * FT_ROW;
+      const uint32_t x0 = *reinterpret_cast<const uint32_t*>(row + (off & ~3u));
+      const uint32_t x1 = *reinterpret_cast<const uint32_t*>(row + (off & ~3u) + 4);
       const uint64_t x = ((uint64_t) x1 << 32) | x0;
+      const uint32_t sh = (off & 3u) * 8;
 
 #pragma unroll
       for (int e = 0; e < 2; e++)
       {
         const uint32_t w = (uint32_t) (x >> (sh + 8 * e));   // W(p + e)
-        const uint32_t i4 = hash4(w);
-        if ((sB4[i4 >> 5] >> (i4 & 31)) & 1u)
+        if (bloom4_test<B4BITS>(sB4, w))
         {
           const uint32_t mv = ht_lookup(F, w);
           if (mv != 0)
-            emit_events(R, V, out, p + e + 1, mv);
+            emit_events(R, V, out, base + (int64_t) u * (FT_THREADS * 16) + k + e + 1, mv);
         }
       }
     }
+
+    __syncwarp();
+
+    if (PREFETCH)
+    {
+#pragma unroll
+      for (int u = 0; u < FT_U; u++) { v[u] = vn[u]; halo[u] = halon[u]; }
+    }
   }
+#undef LOAD_TILE
 }
 
 // ---- host: enumerate hit windows of the compiled automaton, build B3 / B4 / hash table
@@ -270,8 +333,15 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
 struct FilterStorage
 {
   uint32_t b3[B3_WORDS];
-  uint32_t b4[B4_WORDS];
+  uint32_t b4[1u << (19 - 5)];   // sized for the largest variant
 };
+
+static int ft_variant_index()
+{
+  const char* e = getenv("YRB_FILTER_VARIANT");
+  int v = e ? atoi(e) : 0;
+  return (v < 0 || v >= FT_NUM_VARIANTS) ? 0 : v;
+}
 
 static uint32_t host_ac_step(const uint32_t* T, uint32_t state, uint32_t byte)
 {
@@ -352,6 +422,8 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
 
   FilterStorage* fs = new FilterStorage();
   memset(fs, 0, sizeof(*fs));
+  const int variant = ft_variant_index();
+  const int b4_bits = kVariants[variant].b4_bits;
 
   uint32_t ht_bits = 4;
   while ((1ull << ht_bits) < windows.size() * 2) ht_bits++;
@@ -367,12 +439,19 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
     if (mv == 0) continue;
 
     const uint32_t k_suffix = w >> 8, k_prefix = w & 0xFFFFFF;
-    uint32_t i3 = hash3(k_suffix);
-    fs->b3[i3 >> 5] |= 1u << (i3 & 31);
-    i3 = hash3(k_prefix);
-    fs->b3[i3 >> 5] |= 1u << (i3 & 31);
-    const uint32_t i4 = hash4(w);
-    fs->b4[i4 >> 5] |= 1u << (i4 & 31);
+    // B3 entry of a 3-byte key: word = top 15 bits of the hash, bit = low 5 bits of the key itself
+    fs->b3[hash3(k_suffix) >> 5] |= 0x80000000u >> (k_suffix & 31);
+    fs->b3[hash3(k_prefix) >> 5] |= 0x80000000u >> (k_prefix & 31);
+    {
+      const uint32_t g1 = w * HASH4_MUL, g2 = (w * HASH4_MUL2) | 1u;
+      uint32_t g = g1;
+      for (int k = 0; k < BLOOM_K; k++)
+      {
+        const uint32_t i4 = g >> (32 - b4_bits);
+        fs->b4[i4 >> 5] |= 0x80000000u >> (i4 & 31);
+        g += g2;
+      }
+    }
 
     uint32_t slot = (w * HT_MUL) >> (32 - ht_bits);
     while (ht[slot].y != 0 && ht[slot].x != w) slot = (slot + 1) & ht_mask;
@@ -404,6 +483,7 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
   out->n_windows = (uint32_t) windows.size();
   out->fill3 = (float) fill3;
   out->usable = 1;
+  out->variant = variant;
   *d_storage = dptr;
 
   static bool attr_set[64] = {false};
@@ -411,8 +491,11 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev])
   {
-    cudaFuncSetAttribute(ac_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int) ((B3_WORDS + B4_WORDS) * sizeof(uint32_t)));
+    cudaFuncSetAttribute(ac_filter_kernel<1024, 4, 18, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[0]));
+    cudaFuncSetAttribute(ac_filter_kernel<512, 4, 19, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[1]));
+    cudaFuncSetAttribute(ac_filter_kernel<1024, 2, 19, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[2]));
+    cudaFuncSetAttribute(ac_filter_kernel<512, 4, 19, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[3]));
+    cudaFuncSetAttribute(ac_filter_kernel<1024, 2, 19, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[4]));
     attr_set[dev] = true;
   }
   return YRB_SUCCESS;
@@ -449,9 +532,19 @@ void launch_ac_scan_filter(
   fd.ht = reinterpret_cast<const uint2*>(F.ht);
   fd.ht_bits = F.ht_bits;
 
-  const int64_t ntiles = (fhi - flo + FT_TILE - 1) / FT_TILE;
+  const FtVariant& fv = kVariants[F.variant];
+  const int64_t tile_bytes = (int64_t) fv.threads * 16 * fv.u;
+  const int64_t ntiles = (fhi - flo + tile_bytes - 1) / tile_bytes;
   const unsigned grid = (unsigned) (ntiles < num_sms ? ntiles : num_sms);
-  ac_filter_kernel<<<grid, FT_THREADS, (B3_WORDS + B4_WORDS) * sizeof(uint32_t), s>>>(R, fd, V, out, flo, fhi);
+  const size_t smem = ft_smem_bytes(fv);
+  switch (F.variant)
+  {
+  case 0: ac_filter_kernel<1024, 4, 18, false><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  case 1: ac_filter_kernel<512, 4, 19, false><<<grid, 512, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  case 2: ac_filter_kernel<1024, 2, 19, true><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  case 3: ac_filter_kernel<512, 4, 19, true><<<grid, 512, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  default: ac_filter_kernel<1024, 2, 19, false><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  }
 
   launch_ac_scan_walk(R, V, out, fhi, hi, s);
 }

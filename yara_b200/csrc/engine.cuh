@@ -120,24 +120,23 @@ struct RawOut
 struct FilterTables
 {
   const uint32_t* b3;     // 2^20-bit bitmap over hashed 3-byte keys (pair probe)
-  const uint32_t* b4;     // 2^19-bit bitmap over hashed 4-byte windows
+  const uint32_t* b4;     // 2^19-bit Bloom filter (BLOOM_K probes) over 4-byte windows
   const void* ht;         // open-addressed {window, match_table value} table
   uint32_t ht_bits;
   uint32_t n_windows;
   float fill3;
-  int has_d1, has_d2, root_match, usable;
+  int has_d1, has_d2, root_match, usable, variant;
 };
 
 #define B3_BITS 20
-#define B4_BITS 19
 #define B3_WORDS (1u << (B3_BITS - 5))
-#define B4_WORDS (1u << (B4_BITS - 5))
 #define B2_WORDS (1u << (16 - 5))
 #define HASH3_MUL 0x9E3779B1u
 #define HASH4_MUL 0x85EBCA6Bu
+#define HASH4_MUL2 0x27D4EB2Fu
+#define BLOOM_K 4
 
 __host__ __device__ static inline uint32_t hash3(uint32_t key3) { return ((key3 << 8) * HASH3_MUL) >> (32 - B3_BITS); }
-__host__ __device__ static inline uint32_t hash4(uint32_t w) { return (w * HASH4_MUL) >> (32 - B4_BITS); }
 
 static __device__ __forceinline__ void report_error(ScanStatus* st, uint64_t cand_key, int code)
 {
