@@ -197,12 +197,14 @@ def main():
         assert r.rc == 0 and r.error == 0, (r.rc, r.error)
     barrier()
     clocks = ClockSampler(device)
-    ms_total, ms_scan, launches, wall0 = [], [], 0, time.time()
+    ms_total, ms_scan, ms_verify, ms_resolve, launches, wall0 = [], [], [], [], 0, time.time()
     for _ in range(args.steps):
         r = eng.scan_device(dbuf, copy=False, **kw)
         assert r.rc == 0 and r.error == 0, (r.rc, r.error)
         ms_total.append(r.stats["ms_total"])
         ms_scan.append(r.stats["ms_scan"])
+        ms_verify.append(r.stats["ms_verify"])
+        ms_resolve.append(r.stats["ms_resolve"])
         launches += r.stats["kernel_launches"]
     wall = time.time() - wall0
     barrier()
@@ -259,6 +261,8 @@ def main():
             "l2_policy": "input (%.3g GiB) is larger than L2 (126 MB); no flush needed" % (S / 2**30),
             "timing": "CUDA events on the scanner stream per step (sum over steps), max over ranks; wall-clock %.4f s" % wall,
             "setup_s": {"compile_upload": round(t_compile, 2), "corpus": round(t_corpus, 2)},
+            "ms_breakdown": {"scan": round(float(np.mean(ms_scan)), 3), "verify": round(float(np.mean(ms_verify)), 3),
+                             "resolve_and_d2h": round(float(np.mean(ms_resolve)), 3)},
         },
         "clocks": clk,
         "gpu_launches": int(launches),

@@ -167,6 +167,22 @@ static __device__ __forceinline__ uint32_t ht_lookup(const FilterDev& F, uint32_
 // the level-2 test must be selective enough that the L2-resident exact lookup
 // (hundreds of cycles of latency for the whole warp) is reached almost only by
 // real hits: 2^19 bits for ~36k windows and k = 4 gives ~0.3 % false positives.
+// Integer multiplies run on the FMA pipe; shifts/logic on the (saturated) ALU pipe.
+// Inline PTX keeps ptxas from strength-reducing them back into shifts.
+static __device__ __forceinline__ uint32_t mulhi_u32(uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+static __device__ __forceinline__ uint32_t fshr16_fma(uint32_t lo, uint32_t hi)
+{
+  uint32_t r;
+  asm("{ .reg .u32 t; mul.hi.u32 t, %1, 65536; mad.lo.u32 %0, %2, 65536, t; }" : "=r"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+
 template <int B4BITS>
 static __device__ __forceinline__ bool bloom4_test(const uint32_t* sB4, uint32_t w)
 {
@@ -184,9 +200,13 @@ static __device__ __forceinline__ bool bloom4_test(const uint32_t* sB4, uint32_t
 }
 
 // Bit layout: bits are numbered MSB-first, so that `word << n` brings bit n to bit
-// 31 and one funnel shift appends it to the per-thread mask.  B3: word = top 15
-// bits of hash3(key), n = key & 31 (the shift instruction takes the low 5 bits of
-// the key register for free).  B4: word = idx >> 5, n = idx & 31.
+// 31 and one funnel shift appends it to a per-thread mask.  B3 is a blocked Bloom
+// filter with two bits per key inside ONE 32-bit word (one LDS per probe): word =
+// top 15 bits of hash3(key), n1 = low 5 bits of the key's first byte, n2 = low 5
+// bits of its third byte -- both are the low bits of registers the probe already
+// holds, and the shift instruction masks its count to 5 bits for free.  The two
+// tests are accumulated in two masks that are ANDed once per tile.
+// B4: word = idx >> 5, n = idx & 31.
 template <int FT_THREADS, int FT_U, int B4BITS, bool PREFETCH>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, int64_t hi)
@@ -247,13 +267,14 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
     else { LOAD_TILE(tile, v, halo); }
 
     // ---- level 1: one B3 probe per pair of positions, branch-free
-    uint32_t mask = 0;
+    uint32_t maskA = 0, maskB = 0;
 
-#define PROBE3(x)                                                                   \
+#define PROBE3(x, y)                                                                \
   {                                                                                 \
     const uint32_t h_ = (x) * H3;                                                   \
-    const uint32_t w_ = *reinterpret_cast<const uint32_t*>(sB3b + ((h_ >> 15) & 0x1FFFCu)); \
-    mask = __funnelshift_l(__funnelshift_l(0u, w_, (x)), mask, 1);                  \
+    const uint32_t w_ = sB3[h_ >> 17];                                              \
+    maskA = __funnelshift_l(__funnelshift_l(0u, w_, (x)), maskA, 1);                \
+    maskB = __funnelshift_l(__funnelshift_l(0u, w_, (y)), maskB, 1);                \
   }
 
 #pragma unroll
@@ -267,16 +288,21 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
       *reinterpret_cast<uint4*>(wstage + u * FT_ROW + 16 + lane * 16) = v[u];
       if (lane == 0) *reinterpret_cast<uint32_t*>(wstage + u * FT_ROW + 12) = m;
 
-      PROBE3(__funnelshift_r(m, w0, 16));
-      PROBE3(w0);
-      PROBE3(__funnelshift_r(w0, w1, 16));
-      PROBE3(w1);
-      PROBE3(__funnelshift_r(w1, w2, 16));
-      PROBE3(w2);
-      PROBE3(__funnelshift_r(w2, w3, 16));
-      PROBE3(w3);
+      // key = 3 bytes; x holds them in its low 24 bits, y is any register whose low
+      // byte is the key's third byte (both bit indices come for free as shift counts)
+      const uint32_t f0 = __funnelshift_r(m, w0, 16), f1 = __funnelshift_r(w0, w1, 16);
+      const uint32_t f2 = __funnelshift_r(w1, w2, 16), f3 = __funnelshift_r(w2, w3, 16);
+      PROBE3(f0, w0);
+      PROBE3(w0, f1);
+      PROBE3(f1, w1);
+      PROBE3(w1, f2);
+      PROBE3(f2, w2);
+      PROBE3(w2, f3);
+      PROBE3(f3, w3);
+      PROBE3(w3, w3 >> 16);
     }
 #undef PROBE3
+    uint32_t mask = maskA & maskB;
 
     // mask bit (8*FT_U - 1 - slot) belongs to slot = u*8 + pair; chunks past the end
     // of the range were zero-filled: drop their bits
@@ -439,9 +465,10 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
     if (mv == 0) continue;
 
     const uint32_t k_suffix = w >> 8, k_prefix = w & 0xFFFFFF;
-    // B3 entry of a 3-byte key: word = top 15 bits of the hash, bit = low 5 bits of the key itself
-    fs->b3[hash3(k_suffix) >> 5] |= 0x80000000u >> (k_suffix & 31);
-    fs->b3[hash3(k_prefix) >> 5] |= 0x80000000u >> (k_prefix & 31);
+    // B3 entry of a 3-byte key: word = top 15 bits of the hash; TWO bits per key, numbered
+    // MSB-first: low 5 bits of the key's first byte and low 5 bits of its third byte
+    fs->b3[hash3(k_suffix) >> 5] |= (0x80000000u >> (k_suffix & 31)) | (0x80000000u >> ((k_suffix >> 16) & 31));
+    fs->b3[hash3(k_prefix) >> 5] |= (0x80000000u >> (k_prefix & 31)) | (0x80000000u >> ((k_prefix >> 16) & 31));
     {
       const uint32_t g1 = w * HASH4_MUL, g2 = (w * HASH4_MUL2) | 1u;
       uint32_t g = g1;
