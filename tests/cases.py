@@ -65,4 +65,8 @@ CASES = [
     (R("$a = /(a|ab)(c|bcd)(d*)/"), b"abcd abcdd acd"),
     (R("$a = /a*b/ $b = /(a*)*b/"), b"aaab b ab"),
     (R("$a = /abc/ fullword $b = /abc/ wide fullword"), b"abc xabc abc a\0b\0c\0 x\0a\0b\0c\0"),
+    # work-area tiers of the GPU verifiers: > 96 live positions in the fast hex VM, > 64 live fibers in the fiber VM
+    (R("$a = { 31 32 33 34 [0-180] 35 ?? [0-180] 36 37 38 39 }"), b"1234" + b"5" * 170 + b"x" * 20 + b"6789" + b"5z" * 40 + b"6789"),
+    (R("$a = /abcd.{0,150}e.{0,150}fgh/s"), b"abcd" + b"e" * 140 + b"zz" + b"fgh" + b"e" * 30 + b"fgh"),
+    (R("$a = /abcd(x|y|z)+.{0,90}q/"), b"abcd" + b"xyz" * 40 + b"q" + b"x" * 30 + b"q"),
 ]

@@ -103,8 +103,9 @@ struct yrb_scanner
   DevBuf<uint8_t> d_data;
   DevBuf<Cand> d_cand[NUM_CLS];
   DevBuf<Raw> d_raw;
-  DevBuf<uint8_t> ws_fast, ws_re;
-  size_t ws_fast_threads = 0, ws_re_threads = 0;
+  DevBuf<uint8_t> ws_fast1, ws_fast2, ws_re1, ws_re2;
+  DevBuf<uint32_t> retry_fast, retry_re;
+  VerifyWs vws = {};
   ScanStatus* d_status = nullptr;
   ScanStatus* h_status = nullptr;
 
@@ -246,7 +247,8 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   cudaStreamSynchronize(s->copy_stream);
   s->d_data.release();
   for (int c = 0; c < NUM_CLS; c++) s->d_cand[c].release();
-  s->d_raw.release(); s->ws_fast.release(); s->ws_re.release();
+  s->d_raw.release(); s->ws_fast1.release(); s->ws_fast2.release(); s->ws_re1.release(); s->ws_re2.release();
+  s->retry_fast.release(); s->retry_re.release();
   s->k0.release(); s->k1.release(); s->kF.release(); s->ix0.release(); s->ix1.release(); s->scr32.release();
   s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release();
   s->s_lists.release(); s->c_where.release(); s->outU.release(); s->finals.release(); s->unconf.release();
@@ -567,29 +569,35 @@ static int scan_impl(
   for (int c = 0; c < NUM_CLS; c++) { n_cand[c] = hs->n_cand[c]; total_cand += n_cand[c]; }
   res->stats.n_candidates = total_cand;
 
-  // ---- verification
+  // ---- verification work areas: tier 1 sized by the candidate count, tier 2 fixed
   if (n_cand[CLS_FAST] > 0)
   {
     size_t want = (size_t) ((n_cand[CLS_FAST] + 127) / 128) * 128;
-    const size_t maxt = (size_t) s->rules->num_sms * 256; // bounds the work area (55 KB per thread)
+    const size_t maxt = (size_t) s->rules->num_sms * 2048;
     if (want > maxt) want = maxt;
-    if (want > s->ws_fast_threads)
-    {
-      if (s->ws_fast.ensure(want * fast_ws_bytes_per_thread()) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
-      s->ws_fast_threads = want;
-    }
+    const size_t t2 = (size_t) s->rules->num_sms * 128;
+    if (s->ws_fast1.ensure(want * fast_ws_bytes_per_thread(1)) != YRB_SUCCESS ||
+        s->ws_fast2.ensure(t2 * fast_ws_bytes_per_thread(2)) != YRB_SUCCESS ||
+        s->retry_fast.ensure((size_t) n_cand[CLS_FAST]) != YRB_SUCCESS)
+      return YRB_ERROR_INSUFFICIENT_MEMORY;
+    s->vws.fast1 = s->ws_fast1.p; s->vws.fast1_threads = s->ws_fast1.cap / fast_ws_bytes_per_thread(1) / 128 * 128;
+    s->vws.fast2 = s->ws_fast2.p; s->vws.fast2_threads = t2;
+    s->vws.retry_fast = s->retry_fast.p;
   }
   if (n_cand[CLS_RE] > 0)
   {
+    const uint32_t sw = s->rules->R.stack_words;
     size_t want = (size_t) ((n_cand[CLS_RE] + 127) / 128) * 128;
-    const size_t maxt = (size_t) s->rules->num_sms * 512;
+    const size_t maxt = (size_t) s->rules->num_sms * 2048;
     if (want > maxt) want = maxt;
-    if (want > s->ws_re_threads)
-    {
-      if (s->ws_re.ensure(want * re_ws_bytes_per_thread(s->rules->R.stack_words)) != YRB_SUCCESS)
-        return YRB_ERROR_INSUFFICIENT_MEMORY;
-      s->ws_re_threads = want;
-    }
+    const size_t t2 = (size_t) s->rules->num_sms * 128;
+    if (s->ws_re1.ensure(want * re_ws_bytes_per_thread(sw, 1)) != YRB_SUCCESS ||
+        s->ws_re2.ensure(t2 * re_ws_bytes_per_thread(sw, 2)) != YRB_SUCCESS ||
+        s->retry_re.ensure((size_t) n_cand[CLS_RE]) != YRB_SUCCESS)
+      return YRB_ERROR_INSUFFICIENT_MEMORY;
+    s->vws.re1 = s->ws_re1.p; s->vws.re1_threads = s->ws_re1.cap / re_ws_bytes_per_thread(sw, 1) / 128 * 128;
+    s->vws.re2 = s->ws_re2.p; s->vws.re2_threads = t2;
+    s->vws.retry_re = s->retry_re.p;
   }
 
   if (s->d_raw.ensure((size_t) total_cand * 2 + 4096) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
@@ -604,8 +612,7 @@ static int scan_impl(
     ro.cap = s->d_raw.cap;
     ro.st = s->d_status;
 
-    launch_verify(s->rules->R, V, co, n_cand, ro, s->ws_fast.p, s->ws_fast_threads, s->ws_re.p, s->ws_re_threads,
-                  s->stream, &launches);
+    launch_verify(s->rules->R, V, co, n_cand, ro, s->vws, s->stream, &launches);
     CK(cudaEventRecord(s->ev[2], s->stream));
     int rc = read_status(s);
     if (rc != YRB_SUCCESS) return rc;
@@ -615,6 +622,7 @@ static int scan_impl(
     if (s->d_raw.ensure((size_t) hs->n_raw + 1024) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
     CK(cudaMemsetAsync(&s->d_status->n_raw, 0, sizeof(unsigned long long), s->stream));
     CK(cudaMemsetAsync(&s->d_status->err_key, 0xFF, sizeof(unsigned long long), s->stream));
+    CK(cudaMemsetAsync(&s->d_status->n_retry[0], 0, 2 * sizeof(unsigned int), s->stream));
   }
 
   if (hs->margin_fault)

@@ -99,7 +99,8 @@ struct ScanStatus
   unsigned int over_cap;        // some plain string has more than YR_MAX_STRING_MATCHES distinct offsets
   unsigned int ws_overflow;     // a per-candidate work area was too small
   unsigned int survivors;       // filter kernel statistics
-  unsigned int pad[3];
+  unsigned int n_retry[2];      // candidates queued for the tier-2 verifiers (fast VM, fiber VM)
+  unsigned int pad[1];
 };
 
 struct CandOut
@@ -151,9 +152,18 @@ void launch_ac_scan_filter(
     int num_sms, cudaStream_t s);
 int build_filter_tables(const void* host_image, int device, FilterTables* out, void** d_storage);
 
+struct VerifyWs
+{
+  void* fast1; size_t fast1_threads;   // tier 1 work areas (small, many threads)
+  void* fast2; size_t fast2_threads;   // tier 2 (full limits, few threads)
+  void* re1;   size_t re1_threads;
+  void* re2;   size_t re2_threads;
+  uint32_t* retry_fast;
+  uint32_t* retry_re;
+};
+
 void launch_verify(
     const DevRules& R, const ScanView& V, const CandOut& cands, const unsigned long long n_cand[NUM_CLS],
-    const RawOut& out, void* ws_fast, size_t ws_fast_threads, void* ws_re, size_t ws_re_threads, cudaStream_t s,
-    unsigned* launches);
-size_t fast_ws_bytes_per_thread();
-size_t re_ws_bytes_per_thread(uint32_t stack_words);
+    const RawOut& out, const VerifyWs& W, cudaStream_t s, unsigned* launches);
+size_t fast_ws_bytes_per_thread(int tier);
+size_t re_ws_bytes_per_thread(uint32_t stack_words, int tier);

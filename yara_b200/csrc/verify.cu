@@ -116,7 +116,9 @@ static __device__ __forceinline__ int32_t code_i32(const Ctx& c, uint32_t off)
 
 // ---------------------------------------------------------- fast hex VM (a8)
 
-#define FAST_POS_CAP 4608
+#define FAST_POS_CAP 4608       // tier 2: more than any forward-mode list can hold (<= 4097 distinct positions)
+#define FAST_POS_CAP_SMALL 96   // tier 1: what almost every candidate needs
+#define WS_RETRY (-2)           // internal: the small work area overflowed, verify again in tier 2
 
 struct FastPos
 {
@@ -127,10 +129,11 @@ struct FastPos
 
 struct FastWs
 {
-  FastPos v[FAST_POS_CAP];
+  FastPos* v;
+  int cap;
 };
 
-size_t fast_ws_bytes_per_thread() { return sizeof(FastWs); }
+size_t fast_ws_bytes_per_thread(int tier) { return sizeof(FastPos) * (size_t) (tier == 1 ? FAST_POS_CAP_SMALL : FAST_POS_CAP); }
 
 // re.c:2150-2477.  Returns an ERROR_* code.  `pos` = block position of input_data.
 static __device__ int re_fast_exec(
@@ -250,14 +253,13 @@ static __device__ int re_fast_exec(
             ni = free_head;
             free_head = P[ni].next;
           }
-          else if (n_used < FAST_POS_CAP)
+          else if (n_used < ws->cap)
           {
             ni = n_used++;
           }
           else
           {
-            atomicExch(&c.out.st->ws_overflow, 1u);
-            return YRB_ERROR_INSUFFICIENT_MEMORY;
+            return WS_RETRY;
           }
 
           P[ni].input = next_input;
@@ -342,18 +344,21 @@ struct Fiber
   int16_t pad;
 };
 
+#define RE_FIBERS_SMALL 64      // tier 1 pool; tier 2 has the reference's RE_MAX_FIBERS = 1024
+
 struct FiberPool
 {
-  Fiber* f;          // YRB_RE_MAX_FIBERS entries
-  uint16_t* stacks;  // YRB_RE_MAX_FIBERS * stack_words
+  Fiber* f;          // cap entries
+  uint16_t* stacks;  // cap * stack_words
+  int cap;
   int stack_words;
   int free_head;
   int head, tail;
 };
 
-size_t re_ws_bytes_per_thread(uint32_t stack_words)
+size_t re_ws_bytes_per_thread(uint32_t stack_words, int tier)
 {
-  size_t b = (size_t) YRB_RE_MAX_FIBERS * (sizeof(Fiber) + sizeof(uint16_t) * stack_words);
+  size_t b = (size_t) (tier == 1 ? RE_FIBERS_SMALL : YRB_RE_MAX_FIBERS) * (sizeof(Fiber) + sizeof(uint16_t) * stack_words);
   return (b + 15) & ~(size_t) 15;
 }
 
@@ -363,7 +368,7 @@ static __device__ __forceinline__ uint16_t* fstack(FiberPool& p, int f) { return
 static __device__ int fiber_create(FiberPool& p, int* out)
 {
   if (p.free_head < 0)
-    return YRB_ERROR_TOO_MANY_RE_FIBERS;
+    return p.cap < YRB_RE_MAX_FIBERS ? WS_RETRY : YRB_ERROR_TOO_MANY_RE_FIBERS;
 
   const int f = p.free_head;
   p.free_head = p.f[f].next;
@@ -1081,53 +1086,92 @@ verify_literal_kernel(DevRules R, ScanView V, const Cand* cands, unsigned long l
   }
 }
 
+// Two tiers per VM class.  Tier 1 verifies every candidate with a small work area
+// (1-2 KB per thread, so hundreds of thousands of candidates are in flight and
+// the lists stay cache resident); a candidate whose lists outgrow it is queued
+// and verified again from scratch by tier 2 with the reference's full limits.
+// Records a candidate emitted before overflowing are emitted again with the same
+// discovery keys; resolve.cu treats equal keys as one record.
+template <bool TIER2>
 __global__ void __launch_bounds__(128)
-verify_fast_kernel(DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out, FastWs* ws)
+verify_fast_kernel(
+    DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out, uint8_t* ws, size_t ws_per_thread,
+    int cap, uint32_t* retry)
 {
   const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
-  FastWs* my = ws + tid;
+  FastWs my;
+  my.v = reinterpret_cast<FastPos*>(ws + tid * ws_per_thread);
+  my.cap = cap;
+
+  if (TIER2) n = out.st->n_retry[0];
 
   for (unsigned long long t = tid; t < n; t += stride)
   {
-    const Cand cd = cands[t];
+    const unsigned long long ci = TIER2 ? retry[t] : t;
+    const Cand cd = cands[ci];
     const yrb_acm m = R.acm[cd.acm_idx];
     const yrb_string s = R.S[m.string_idx];
     Ctx c;
     ctx_init(c, R, V, out, cd);
-    const int rc = verify_re<true>(c, my, nullptr, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
+    int rc = verify_re<true>(c, &my, nullptr, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
+    if (rc == WS_RETRY)
+    {
+      if (!TIER2)
+      {
+        retry[atomicAdd(&out.st->n_retry[0], 1u)] = (uint32_t) ci;
+        continue;
+      }
+      atomicExch(&out.st->ws_overflow, 1u);
+      rc = YRB_ERROR_INSUFFICIENT_MEMORY;
+    }
     if (rc != YRB_SUCCESS)
       report_error(out.st, cd.key, rc);
   }
 }
 
+template <bool TIER2>
 __global__ void __launch_bounds__(128)
 verify_re_kernel(
-    DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out, uint8_t* ws, size_t ws_per_thread)
+    DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out, uint8_t* ws, size_t ws_per_thread,
+    int cap, uint32_t* retry)
 {
   const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
 
+  if (TIER2) n = out.st->n_retry[1];
+  if (tid >= n) return;
+
   FiberPool p;
   p.f = reinterpret_cast<Fiber*>(ws + tid * ws_per_thread);
-  p.stacks = reinterpret_cast<uint16_t*>(p.f + YRB_RE_MAX_FIBERS);
+  p.stacks = reinterpret_cast<uint16_t*>(p.f + cap);
+  p.cap = cap;
   p.stack_words = (int) R.stack_words;
 
-  // free list over all YRB_RE_MAX_FIBERS entries (kept consistent across candidates:
-  // every exec returns all of its fibers)
-  for (int f = 0; f < YRB_RE_MAX_FIBERS; f++)
-    p.f[f].next = (int16_t) ((f + 1 < YRB_RE_MAX_FIBERS) ? f + 1 : -1);
+  // free list over the pool (kept consistent across candidates: every exec returns all of its fibers)
+  for (int f = 0; f < cap; f++)
+    p.f[f].next = (int16_t) ((f + 1 < cap) ? f + 1 : -1);
   p.free_head = 0;
   p.head = p.tail = -1;
 
   for (unsigned long long t = tid; t < n; t += stride)
   {
-    const Cand cd = cands[t];
+    const unsigned long long ci = TIER2 ? retry[t] : t;
+    const Cand cd = cands[ci];
     const yrb_acm m = R.acm[cd.acm_idx];
     const yrb_string s = R.S[m.string_idx];
     Ctx c;
     ctx_init(c, R, V, out, cd);
-    const int rc = verify_re<false>(c, nullptr, &p, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
+    int rc = verify_re<false>(c, nullptr, &p, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
+    if (rc == WS_RETRY)
+    {
+      if (!TIER2)
+      {
+        retry[atomicAdd(&out.st->n_retry[1], 1u)] = (uint32_t) ci;
+        continue;
+      }
+      rc = YRB_ERROR_INTERNAL_FATAL;
+    }
     if (rc != YRB_SUCCESS)
       report_error(out.st, cd.key, rc);
   }
@@ -1135,37 +1179,44 @@ verify_re_kernel(
 
 void launch_verify(
     const DevRules& R, const ScanView& V, const CandOut& cands, const unsigned long long n_cand[NUM_CLS],
-    const RawOut& out, void* ws_fast, size_t ws_fast_threads, void* ws_re, size_t ws_re_threads, cudaStream_t s,
-    unsigned* launches)
+    const RawOut& out, const VerifyWs& W, cudaStream_t s, unsigned* launches)
 {
   const int T = 128;
 
   if (n_cand[CLS_LITERAL] > 0)
   {
     unsigned long long blocks = (n_cand[CLS_LITERAL] + T - 1) / T;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > 148 * 64) blocks = 148 * 64;
     verify_literal_kernel<<<(unsigned) blocks, T, 0, s>>>(R, V, cands.cand[CLS_LITERAL], n_cand[CLS_LITERAL], out);
     (*launches)++;
   }
 
   if (n_cand[CLS_FAST] > 0)
   {
-    unsigned long long threads = n_cand[CLS_FAST] < ws_fast_threads ? n_cand[CLS_FAST] : ws_fast_threads;
+    unsigned long long threads = n_cand[CLS_FAST] < W.fast1_threads ? n_cand[CLS_FAST] : W.fast1_threads;
     unsigned blocks = (unsigned) ((threads + T - 1) / T);
-    if ((unsigned long long) blocks * T > ws_fast_threads) blocks = (unsigned) (ws_fast_threads / T);
+    if ((unsigned long long) blocks * T > W.fast1_threads) blocks = (unsigned) (W.fast1_threads / T);
     if (blocks == 0) blocks = 1;
-    verify_fast_kernel<<<blocks, T, 0, s>>>(R, V, cands.cand[CLS_FAST], n_cand[CLS_FAST], out, (FastWs*) ws_fast);
-    (*launches)++;
+    verify_fast_kernel<false><<<blocks, T, 0, s>>>(
+        R, V, cands.cand[CLS_FAST], n_cand[CLS_FAST], out, (uint8_t*) W.fast1, fast_ws_bytes_per_thread(1),
+        FAST_POS_CAP_SMALL, W.retry_fast);
+    verify_fast_kernel<true><<<(unsigned) (W.fast2_threads / T), T, 0, s>>>(
+        R, V, cands.cand[CLS_FAST], 0, out, (uint8_t*) W.fast2, fast_ws_bytes_per_thread(2), FAST_POS_CAP, W.retry_fast);
+    (*launches) += 2;
   }
 
   if (n_cand[CLS_RE] > 0)
   {
-    unsigned long long threads = n_cand[CLS_RE] < ws_re_threads ? n_cand[CLS_RE] : ws_re_threads;
+    unsigned long long threads = n_cand[CLS_RE] < W.re1_threads ? n_cand[CLS_RE] : W.re1_threads;
     unsigned blocks = (unsigned) ((threads + T - 1) / T);
-    if ((unsigned long long) blocks * T > ws_re_threads) blocks = (unsigned) (ws_re_threads / T);
+    if ((unsigned long long) blocks * T > W.re1_threads) blocks = (unsigned) (W.re1_threads / T);
     if (blocks == 0) blocks = 1;
-    verify_re_kernel<<<blocks, T, 0, s>>>(
-        R, V, cands.cand[CLS_RE], n_cand[CLS_RE], out, (uint8_t*) ws_re, re_ws_bytes_per_thread(R.stack_words));
-    (*launches)++;
+    verify_re_kernel<false><<<blocks, T, 0, s>>>(
+        R, V, cands.cand[CLS_RE], n_cand[CLS_RE], out, (uint8_t*) W.re1, re_ws_bytes_per_thread(R.stack_words, 1),
+        RE_FIBERS_SMALL, W.retry_re);
+    verify_re_kernel<true><<<(unsigned) (W.re2_threads / T), T, 0, s>>>(
+        R, V, cands.cand[CLS_RE], 0, out, (uint8_t*) W.re2, re_ws_bytes_per_thread(R.stack_words, 2),
+        YRB_RE_MAX_FIBERS, W.retry_re);
+    (*launches) += 2;
   }
 }
