@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <yara.h>
 #include <yara/bitmask.h>
 #include <yara/notebook.h>
@@ -40,8 +41,22 @@ typedef struct scanner_entry
 {
   YR_SCANNER* scanner;
   yrb_scanner* dev;
+  yrb_rules* dev_rules;
   struct scanner_entry* next;
 } scanner_entry;
+
+/* Device scanners (stream, block buffer, work areas, pinned result buffers) are
+   expensive to create and yr_rules_scan_mem creates a YR_SCANNER per call
+   (rules.c:196): released ones are parked here and handed to the next scanner of
+   the same rules. */
+#define YR_B200_POOL_MAX 32
+typedef struct pool_entry
+{
+  yrb_scanner* dev;
+  yrb_rules* dev_rules;
+} pool_entry;
+static pool_entry g_pool[YR_B200_POOL_MAX];
+static int g_pool_n = 0;
 
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static rules_entry* g_rules = NULL;
@@ -129,7 +144,21 @@ static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out)
   if (rc == ERROR_SUCCESS)
   {
     yrb_scanner* dev = NULL;
-    int r2 = yrb_scanner_create(dev_rules, &dev);
+    int r2 = YRB_SUCCESS;
+
+    for (int i = 0; i < g_pool_n; i++)
+    {
+      if (g_pool[i].dev_rules == dev_rules)
+      {
+        dev = g_pool[i].dev;
+        g_pool[i] = g_pool[--g_pool_n];
+        break;
+      }
+    }
+
+    if (dev == NULL)
+      r2 = yrb_scanner_create(dev_rules, &dev);
+
     if (r2 != YRB_SUCCESS)
     {
       rc = fail_loudly("yrb_scanner_create", r2);
@@ -139,6 +168,7 @@ static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out)
       e = (scanner_entry*) calloc(1, sizeof(*e));
       e->scanner = scanner;
       e->dev = dev;
+      e->dev_rules = dev_rules;
       e->next = g_scanners;
       g_scanners = e;
       *out = dev;
@@ -159,7 +189,16 @@ void yr_b200_scanner_release(YR_SCANNER* scanner)
     {
       scanner_entry* e = *pp;
       *pp = e->next;
-      yrb_scanner_destroy(e->dev);
+      if (g_pool_n < YR_B200_POOL_MAX)
+      {
+        g_pool[g_pool_n].dev = e->dev;
+        g_pool[g_pool_n].dev_rules = e->dev_rules;
+        g_pool_n++;
+      }
+      else
+      {
+        yrb_scanner_destroy(e->dev);
+      }
       free(e);
       break;
     }
@@ -178,6 +217,18 @@ void yr_b200_rules_release(YR_RULES* rules)
     {
       rules_entry* e = *pp;
       *pp = e->next;
+      for (int i = 0; i < g_pool_n;)
+      {
+        if (g_pool[i].dev_rules == e->dev)
+        {
+          yrb_scanner_destroy(g_pool[i].dev);
+          g_pool[i] = g_pool[--g_pool_n];
+        }
+        else
+        {
+          i++;
+        }
+      }
       yrb_rules_release(e->dev);
       free(e);
       continue;
@@ -327,8 +378,14 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
   params.scan_flags = scanner->flags;
   params.too_many_action = 0; /* the user's answer is only known after asking: see below */
 
+  static int timing = -1;
+  if (timing < 0) timing = getenv("YRB_TIMING") != NULL;
+  struct timespec t0, t1, t2;
+  if (timing) clock_gettime(CLOCK_MONOTONIC, &t0);
+
   yrb_scan_result res;
   rc = yrb_scan_host(dev, block_data, block->size, &params, &res);
+  if (timing) clock_gettime(CLOCK_MONOTONIC, &t1);
   if (rc != YRB_SUCCESS)
     return rc < 1000 ? rc : fail_loudly("yrb_scan_host", rc);
 
@@ -373,6 +430,17 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
     rc = too_many_protocol(scanner, string);
     if (rc != ERROR_SUCCESS)
       return rc;
+  }
+
+  if (timing)
+  {
+    clock_gettime(CLOCK_MONOTONIC, &t2);
+    fprintf(stderr,
+            "yara_b200: block %zu B: engine %.3f ms (scan+h2d %.3f verify %.3f resolve %.3f), materialise %.3f ms, "
+            "%zu matches, %llu candidates, %u launches\n",
+            block->size, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6, res.stats.ms_scan,
+            res.stats.ms_verify, res.stats.ms_resolve, (t2.tv_sec - t1.tv_sec) * 1e3 + (t2.tv_nsec - t1.tv_nsec) * 1e-6,
+            res.n_matches, (unsigned long long) res.stats.n_candidates, res.stats.kernel_launches);
   }
 
   if (scanner->timeout > 0 && yr_stopwatch_elapsed_ns(&scanner->stopwatch) > scanner->timeout)
