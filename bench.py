@@ -102,7 +102,7 @@ def reference_arm(args):
     from yara_b200 import synth
 
     ncores = os.cpu_count() or 1
-    rs = synth.ruleset(3, args.strings)
+    rs = synth.ruleset(args.config, args.strings)
     rules = yrh.ref().compile(rs.source)
     sample = int(args.ref_sample_mib) << 20
     data = synth.corpus(rs, sample, 65536, tail_plant=False)
@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--size-gib", type=float, default=16.0, help="bytes owned per GPU")
     ap.add_argument("--strings", type=int, default=20000)
+    ap.add_argument("--config", type=int, default=3, help="synthetic ruleset shape (BASELINE configs): 2, 3 (headline), 4, 5")
     ap.add_argument("--every", type=int, default=65536, help="one planted instance per this many bytes")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 walk, 2 filter")
     ap.add_argument("--ref-sample-mib", type=int, default=2048)
@@ -168,7 +169,7 @@ def main():
     t0 = time.time()
     ly = LibYara()
     ly.set_device(device)
-    rs = synth.ruleset(3, args.strings)
+    rs = synth.ruleset(args.config, args.strings)
     rules = ly.compile(rs.source)
     image = ly.flatten(rules)
     hdr = np.frombuffer(image[:64], dtype=np.uint32)
@@ -253,8 +254,9 @@ def main():
         "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {
-            "workload": "configs[2]: 20,000 hex strings with wildcards/jumps + nocase/wide text over %.3g GiB per GPU, "
-                        "byte-range sharded with %d-byte read margins" % (S / 2**30, MARGIN),
+            "workload": ("configs[2]: 20,000 hex strings with wildcards/jumps + nocase/wide text over %.3g GiB per GPU, "
+                         "byte-range sharded with %d-byte read margins" % (S / 2**30, MARGIN)) if args.config == 3 and args.strings == 20000
+                        else "synthetic ruleset shape %d, %d declared strings, %.3g GiB per GPU" % (args.config, args.strings, S / 2**30),
             "strings_declared": args.strings, "strings_compiled": int(hdr[6]), "ac_slots": int(hdr[4]),
             "bytes_per_gpu": S, "plants_per_gpu": n_plants, "matches_rank0": int(n_matches), "candidates_rank0": int(n_cand),
             "scan_kernel": {1: "walk", 2: "filter"}.get(scan_kernel, "?"),

@@ -110,7 +110,9 @@ typedef struct yrb_scan_result
 {
   int32_t error;           /* ERROR_* of the block scan */
   uint32_t error_string;   /* idx for scanner->last_error_string, YRB_NONE if none */
-  size_t n_matches;        /* confirmed matches: by string_idx asc, YR_MATCHES list order inside */
+  size_t n_matches;        /* confirmed matches: the records of one string are contiguous and in
+                              YR_MATCHES list order (ascending offset); plain strings come string-major,
+                              the lists of chained strings' heads after them */
   const yrb_match* matches;
   size_t n_unconfirmed;    /* unconfirmed chain-part matches left at end of block */
   const yrb_match* unconfirmed;

@@ -144,9 +144,9 @@ static inline const uint8_t* yrb_img_alter(const void* img)
 /*
  * One resolved match, as the engine (and the oracle restatement) hand it back:
  * exactly the fields scan.c:714-756 would have put into a YR_MATCH, minus the
- * data copy, which the caller takes from its own block buffer.  Lists come back
- * grouped by string_idx ascending and, inside one string, in YR_MATCHES list
- * order (ascending offset, unique offsets; scan.c:290-368).
+ * data copy, which the caller takes from its own block buffer.  The records of
+ * one string are contiguous and in YR_MATCHES list order (ascending offset,
+ * unique offsets; scan.c:290-368).
  */
 typedef struct yrb_match
 {

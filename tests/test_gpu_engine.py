@@ -12,7 +12,15 @@ pytestmark = pytest.mark.gpu
 
 
 def as_tuples(m):
-    return [(int(x["string_idx"]), int(x["offset"]), int(x["match_length"]), int(x["xor_key"])) for x in m]
+    """records in canonical (string, offset) order: the engine returns plain strings' lists string-major and the
+    lists of chain heads after them; inside one string the order is always the YR_MATCHES list order"""
+    t = [(int(x["string_idx"]), int(x["offset"]), int(x["match_length"]), int(x["xor_key"])) for x in m]
+    # list order inside a string must already be ascending offset
+    last = {}
+    for s_, o, _, _ in t:
+        assert last.get(s_, -1) < o
+        last[s_] = o
+    return sorted(t)
 
 
 @pytest.fixture(scope="module")

@@ -13,6 +13,7 @@
 //   ac_filter_kernel  shared-memory atom prefilter over 16-byte vector loads;
 //                     only the (rare) survivors are resolved exactly through the
 //                     transition table (see the comment above the kernel)
+#include <cstdlib>
 #include <cstring>
 
 #include "emit.cuh"
@@ -489,7 +490,7 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
   for (uint32_t i = 0; i < B3_WORDS; i++) pop3 += (size_t) __builtin_popcount(fs->b3[i]);
   const double fill3 = (double) pop3 / (double) (1u << B3_BITS);
 
-  if (fill3 > 0.45)
+  if (fill3 > (getenv("YRB_FILTER_MAX_FILL") ? atof(getenv("YRB_FILTER_MAX_FILL")) : 0.45))
   {
     delete fs;
     return YRB_SUCCESS; // too dense to filter anything

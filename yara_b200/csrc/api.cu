@@ -114,8 +114,8 @@ struct yrb_scanner
   DevBuf<uint32_t> ix0, ix1, scr32;
   DevBuf<uint8_t> cub_tmp;
   DevBuf<int32_t> c_nxt, c_prv, c_clen, c_mlen, s_lists;
-  DevBuf<uint8_t> c_where;
-  DevBuf<yrb_match> outU, finals, unconf;
+  DevBuf<uint8_t> c_where, flags8;
+  DevBuf<yrb_match> finals, unconf;
   DevBuf<unsigned long long> str_min_key, str_cut_key;
   DevBuf<uint32_t> str_count, too_many;
   bool cut_dirty = true;
@@ -251,7 +251,7 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   s->retry_fast.release(); s->retry_re.release();
   s->k0.release(); s->k1.release(); s->kF.release(); s->ix0.release(); s->ix1.release(); s->scr32.release();
   s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release();
-  s->s_lists.release(); s->c_where.release(); s->outU.release(); s->finals.release(); s->unconf.release();
+  s->s_lists.release(); s->c_where.release(); s->flags8.release(); s->finals.release(); s->unconf.release();
   s->str_min_key.release(); s->str_cut_key.release(); s->str_count.release(); s->too_many.release();
   s->g_offsets.release(); s->g_data.release();
   s->h_finals.release(); s->h_unconf.release(); s->h_too_many.release(); s->h_str_count.release(); s->h_raw.release();
@@ -315,7 +315,7 @@ static int ensure_resolve_scratch(yrb_scanner* s, uint32_t n)
   int rc = 0;
   rc |= s->k0.ensure(n); rc |= s->k1.ensure(n); rc |= s->kF.ensure(n);
   rc |= s->ix0.ensure(n); rc |= s->ix1.ensure(n); rc |= s->scr32.ensure(n);
-  rc |= s->outU.ensure(n); rc |= s->finals.ensure(n); rc |= s->unconf.ensure(n);
+  rc |= s->flags8.ensure(n); rc |= s->finals.ensure(n); rc |= s->unconf.ensure(n);
   rc |= s->cub_tmp.ensure(resolve_cub_temp_bytes(n));
   if (s->rules->h.num_chains > 0)
   {
@@ -338,7 +338,7 @@ static void fill_work(yrb_scanner* s, ResolveWork& w, const Raw* raw, uint32_t n
   w.k0 = s->k0.p; w.k1 = s->k1.p; w.kF = s->kF.p; w.ix0 = s->ix0.p; w.ix1 = s->ix1.p; w.c_scratch_u32 = s->scr32.p;
   w.cub_tmp = s->cub_tmp.p; w.cub_tmp_bytes = s->cub_tmp.cap;
   w.c_nxt = s->c_nxt.p; w.c_prv = s->c_prv.p; w.c_clen = s->c_clen.p; w.c_mlen = s->c_mlen.p; w.c_where = s->c_where.p;
-  w.outU = s->outU.p;
+  w.flags = s->flags8.p;
   w.str_min_key = s->str_min_key.p; w.str_cut_key = s->str_cut_key.p; w.str_count = s->str_count.p;
   w.s_lists = s->s_lists.p;
   w.finals = s->finals.p; w.unconf = s->unconf.p;
@@ -359,18 +359,21 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
   {
     int rc = ensure_resolve_scratch(s, n);
     if (rc != YRB_SUCCESS) return rc;
+    if (s->h_finals.ensure(n) || s->h_too_many.ensure(2048)) return YRB_ERROR_INSUFFICIENT_MEMORY;
 
     ResolveWork w;
     fill_work(s, w, d_raw, n, params->scan_flags);
 
-    launch_resolve_sorts(w, s->stream, launches);
-    launch_resolve_select(w, s->stream, launches);
-    rc = read_status(s);
-    if (rc != YRB_SUCCESS) return rc;
-
-    if (hs->over_cap)
+    for (int pass = 0;; pass++)
     {
-      // rare, exact path: find each over-cap string's cut key, then redo sort+select without the cut records
+      // one queue of kernels, the result records (at most n) and the status come back with ONE synchronisation
+      launch_resolve(w, s->stream, launches);
+      CK(cudaMemcpyAsync(s->h_finals.p, s->finals.p, (size_t) n * sizeof(yrb_match), cudaMemcpyDeviceToHost, s->stream));
+      rc = read_status(s);
+      if (rc != YRB_SUCCESS) return rc;
+      if (!hs->over_cap || pass == 1) break;
+
+      // rare, exact path: find each over-cap string's cut key, then resolve again without the cut records
       const uint32_t ns = s->rules->R.num_strings;
       if (s->h_str_count.ensure(ns) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
       CK(cudaMemsetAsync(s->str_cut_key.p, 0xFF, sizeof(unsigned long long) * ns, s->stream));
@@ -387,30 +390,26 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
         }
       }
       w.use_cut = 1;
-      CK(cudaMemsetAsync(&s->d_status->n_final, 0, sizeof(unsigned long long), s->stream));
+      CK(cudaMemsetAsync(&s->d_status->n_chain_out, 0, sizeof(unsigned long long), s->stream));
+      CK(cudaMemsetAsync(&s->d_status->n_unconf, 0, sizeof(unsigned long long), s->stream));
+      CK(cudaMemsetAsync(&s->d_status->n_too_many, 0, sizeof(unsigned int), s->stream));
       CK(cudaMemsetAsync(&s->d_status->over_cap, 0, sizeof(unsigned int), s->stream));
-      launch_resolve_sorts(w, s->stream, launches);
-      launch_resolve_select(w, s->stream, launches);
     }
 
-    launch_resolve_chains_and_order(w, s->stream, launches);
-    rc = read_status(s);
-    if (rc != YRB_SUCCESS) return rc;
-
-    const size_t nf = (size_t) hs->n_final, nu = (size_t) hs->n_unconf;
+    const size_t nf = (size_t) hs->n_sel + (size_t) hs->n_chain_out, nu = (size_t) hs->n_unconf;
     uint32_t ntm = hs->n_too_many > 1024 ? 1024 : hs->n_too_many;
 
-    if (s->h_finals.ensure(nf ? nf : 1) || s->h_unconf.ensure(nu ? nu : 1) || s->h_too_many.ensure(1024 + cuts.size() + 1))
-      return YRB_ERROR_INSUFFICIENT_MEMORY;
-
-    if (nf) CK(cudaMemcpyAsync(s->h_finals.p, s->finals.p, nf * sizeof(yrb_match), cudaMemcpyDeviceToHost, s->stream));
-    if (nu) CK(cudaMemcpyAsync(s->h_unconf.p, s->unconf.p, nu * sizeof(yrb_match), cudaMemcpyDeviceToHost, s->stream));
-    if (ntm) CK(cudaMemcpyAsync(s->h_too_many.p, s->too_many.p, ntm * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
+    if (nu || ntm)
+    {
+      if (s->h_unconf.ensure(nu ? nu : 1)) return YRB_ERROR_INSUFFICIENT_MEMORY;
+      if (nu) CK(cudaMemcpyAsync(s->h_unconf.p, s->unconf.p, nu * sizeof(yrb_match), cudaMemcpyDeviceToHost, s->stream));
+      if (ntm) CK(cudaMemcpyAsync(s->h_too_many.p, s->too_many.p, ntm * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+      CK(cudaStreamSynchronize(s->stream));
+    }
 
     // cut strings fire their TOO_MANY callback in discovery order of the cut
     std::sort(cuts.begin(), cuts.end());
-    for (auto& c : cuts) s->h_too_many.p[ntm++] = c.second;
+    for (auto& c : cuts) if (ntm < 2048) s->h_too_many.p[ntm++] = c.second;
 
     res->n_matches = nf;
     res->n_unconfirmed = nu;

@@ -100,7 +100,7 @@ struct ScanStatus
   unsigned int ws_overflow;     // a per-candidate work area was too small
   unsigned int survivors;       // filter kernel statistics
   unsigned int n_retry[2];      // candidates queued for the tier-2 verifiers (fast VM, fiber VM)
-  unsigned int pad[1];
+  int n_sel;                    // surviving records of plain strings (ordered compaction)
 };
 
 struct CandOut

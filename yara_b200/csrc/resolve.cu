@@ -7,10 +7,12 @@
 //
 // The reference applies these one candidate at a time in discovery order.  Here
 // every record carries its discovery key, so the same result is computed as:
-//   plain strings   stable radix sort by (string, offset, key); of each
-//                   (string, offset) group the first discovered record survives,
-//                   or the last one for GREEDY_REGEXP strings (replace_if_exists)
-//   chained strings records of one chain sorted by key and replayed by ONE thread
+//   plain strings   ONE radix sort by (string, offset); of each (string, offset)
+//                   group the record with the smallest discovery key survives, or
+//                   the one with the largest for GREEDY_REGEXP (replace_if_exists);
+//                   ordered compaction keeps the lists in YR_MATCHES order
+//   chained strings sorted by (chain, input position) by the same sort, ties put
+//                   in key order locally, then replayed by ONE thread per chain
 //                   through a verbatim restatement of the list logic (chains are
 //                   independent of each other; quirk 10 of SURVEY.md 8(a) rules
 //                   out a relational formulation)
@@ -34,29 +36,23 @@ __global__ void fastmode_min_kernel(const Raw* raw, uint32_t n, DevRules R, unsi
     atomicMin(&str_min_key[r.string_idx], (unsigned long long) (r.key >> KEY_SEQ_BITS));
 }
 
-__global__ void build_key_b_kernel(const Raw* raw, uint32_t n, uint64_t* kB, uint32_t* ix)
-{
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  kB[j] = raw[j].key;
-  ix[j] = j;
-}
-
-// After the sort by discovery key: the (string, offset) key for plain strings,
-// the chain key for chain parts.
+// The sort key: (string, offset) for plain strings; (chain, input position of the
+// candidate) for chain parts -- records of one chain must be replayed in discovery
+// order, and the few records that share a position are ordered locally by the
+// chain kernel.
 __global__ void build_key_a_kernel(
-    const Raw* raw, const uint32_t* ix, uint32_t n, DevRules R, int scan_flags, const unsigned long long* str_min_key,
-    const unsigned long long* str_cut_key, uint64_t* kA)
+    const Raw* raw, uint32_t n, DevRules R, int scan_flags, const unsigned long long* str_min_key,
+    const unsigned long long* str_cut_key, uint64_t* kA, uint32_t* ix)
 {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
 
-  const Raw r = raw[ix[j]];
+  const Raw r = raw[j];
   const uint32_t sflags = R.S[r.string_idx].flags;
   uint64_t a;
 
   if (r.group != YRB_NONE)
-    a = A_CHAIN_BIT | ((uint64_t) r.group << 24);
+    a = A_CHAIN_BIT | ((uint64_t) (r.group & 0x7FFFFF) << OFFSET_BITS) | (r.key >> KEY_I_SHIFT);
   else
     a = ((uint64_t) r.string_idx << OFFSET_BITS) | (uint64_t) r.offset;
 
@@ -71,35 +67,69 @@ __global__ void build_key_a_kernel(
     a = A_DROPPED;
 
   kA[j] = a;
+  ix[j] = j;
 }
 
 // --------------------------------------------------------------- plain strings
 
+// Is sorted record j the one of its (string, offset) group that survives?  The
+// group is a run of equal keys in kA; its members are in no particular order.
+// first discovered = smallest discovery key (ties, which are re-emissions of the
+// same callback by the tier-2 verifier, go to the lowest position).
+static __device__ __forceinline__ bool group_pick(
+    const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, uint32_t j, bool want_last)
+{
+  const uint64_t a = kA[j];
+  if ((j == 0 || kA[j - 1] != a) && (j + 1 == n || kA[j + 1] != a))
+    return true; // singleton group: the common case
+
+  const uint64_t my = raw[ix[j]].key;
+  for (uint32_t k = j; k-- > 0 && kA[k] == a;)
+  {
+    const uint64_t o = raw[ix[k]].key;
+    if (want_last ? (o > my) : (o <= my)) return false;
+  }
+  for (uint32_t k = j + 1; k < n && kA[k] == a; k++)
+  {
+    const uint64_t o = raw[ix[k]].key;
+    if (want_last ? (o >= my) : (o < my)) return false;
+  }
+  return true;
+}
+
 __global__ void select_plain_kernel(
-    const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, DevRules R, uint32_t* str_count,
-    uint64_t* kF, yrb_match* outU, ScanStatus* st)
+    const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, DevRules R, uint32_t* str_count, uint8_t* flags)
 {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
 
+  uint8_t f = 0;
   const uint64_t a = kA[j];
-  if (a & A_CHAIN_BIT) return; // chain record or dropped
 
-  const bool is_first = (j == 0) || (kA[j - 1] != a);
-  const bool is_last = (j + 1 == n) || (kA[j + 1] != a);
+  if (!(a & A_CHAIN_BIT)) // plain, not dropped
+  {
+    const uint32_t sidx = (uint32_t) (a >> OFFSET_BITS);
+    // replace_if_exists (scan.c:314-319) rewrites length/data of the node that was
+    // inserted first; xor_key of a greedy regexp is always 0, so "last record" is
+    // the same thing.
+    const bool greedy = (R.S[sidx].flags & YRB_SF_GREEDY_REGEXP) != 0;
+    if (group_pick(raw, ix, kA, n, j, greedy))
+    {
+      f = 1;
+      atomicAdd(&str_count[sidx], 1u);
+    }
+  }
 
-  const Raw r = raw[ix[j]];
-  const bool greedy = (R.S[r.string_idx].flags & YRB_SF_GREEDY_REGEXP) != 0;
+  flags[j] = f;
+}
 
-  // replace_if_exists (scan.c:314-319) rewrites length/data of the node that was
-  // inserted first; xor_key of a greedy regexp is always 0, so "last record" is
-  // the same thing.
-  if (greedy ? !is_last : !is_first)
-    return;
-
-  atomicAdd(&str_count[r.string_idx], 1u);
-
-  const unsigned long long slot = atomicAdd(&st->n_final, 1ULL);
+// sel[k] = sorted position of the k-th surviving plain record (ordered compaction)
+__global__ void write_plain_kernel(
+    const Raw* raw, const uint32_t* ix, const uint32_t* sel, const ScanStatus* st, uint32_t n, yrb_match* out)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n || (int) k >= st->n_sel) return;
+  const Raw r = raw[ix[sel[k]]];
   yrb_match m;
   m.offset = r.offset;
   m.string_idx = r.string_idx;
@@ -108,8 +138,7 @@ __global__ void select_plain_kernel(
   m.flags = 0;
   m.reserved = 0;
   m.chain_length = 0;
-  outU[slot] = m;
-  kF[slot] = a;
+  out[k] = m;
 }
 
 __global__ void check_cap_kernel(const uint32_t* str_count, uint32_t num_strings, ScanStatus* st)
@@ -354,15 +383,16 @@ __global__ void chain_init_kernel(ChainLists L, uint32_t num_strings)
 }
 
 __global__ void chain_resolve_kernel(
-    const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, DevRules R, ChainLists L, uint64_t* kF,
-    yrb_match* outU, yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap, int scan_flags)
+    const Raw* raw, uint32_t* ix, const uint64_t* kA, uint32_t n, DevRules R, ChainLists L, yrb_match* finals,
+    yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap, int scan_flags)
 {
   const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (j0 >= n) return;
 
-  const uint64_t a = kA[j0];
-  if (!(a & A_CHAIN_BIT) || a == A_DROPPED) return;
-  if (j0 > 0 && kA[j0 - 1] == a) return; // not the first record of its chain
+  const uint64_t a0 = kA[j0];
+  if (!(a0 & A_CHAIN_BIT) || a0 == A_DROPPED) return;
+  const uint64_t chain = a0 >> OFFSET_BITS;
+  if (j0 > 0 && (kA[j0 - 1] >> OFFSET_BITS) == chain) return; // not the first record of its chain
 
   ChainCtx c;
   c.raw = raw;
@@ -377,41 +407,56 @@ __global__ void chain_resolve_kernel(
   uint64_t cur_cand = ~0ULL;
   bool skip_cand = false;
 
-  for (; j < n && kA[j] == a; j++)
+  while (j < n && (kA[j] >> OFFSET_BITS) == chain)
   {
-    L.nxt[j] = L.prv[j] = -1;
-    L.where[j] = 0;
-
-    const Raw r = raw[ix[j]];
-    if (r.key == prev_key) continue; // idempotent re-emission of the same callback
-    prev_key = r.key;
-
-    if (r.string_idx == disabled_string) continue;
-
-    // scan.c:1021-1023: the FAST_MODE / SINGLE_MATCH guard is evaluated once per
-    // candidate, before verification, against matches[string->idx] (only ever
-    // non-empty for the chain's head string)
-    if ((r.key >> KEY_SEQ_BITS) != cur_cand)
+    // records of this chain that share the input position: put them in discovery-key order
+    uint32_t r_end = j + 1;
+    while (r_end < n && kA[r_end] == kA[j]) r_end++;
+    for (uint32_t x = j + 1; x < r_end; x++)
     {
-      cur_cand = r.key >> KEY_SEQ_BITS;
-      skip_cand = (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) &&
-                  L.mcnt[r.string_idx] > 0;
+      const uint32_t vx = ix[x];
+      const uint64_t kx = raw[vx].key;
+      uint32_t y = x;
+      while (y > j && raw[ix[y - 1]].key > kx) { ix[y] = ix[y - 1]; y--; }
+      ix[y] = vx;
     }
-    if (skip_cand) continue;
 
-    if (verify_chained(c, (int32_t) j) == 2)
+    for (; j < r_end; j++)
     {
-      const uint32_t slot = atomicAdd(&st->n_too_many, 1u);
-      if (slot < too_many_cap) too_many[slot] = r.string_idx;
-      disabled_string = r.string_idx;
+      L.nxt[j] = L.prv[j] = -1;
+      L.where[j] = 0;
+
+      const Raw r = raw[ix[j]];
+      if (r.key == prev_key) continue; // re-emission of the same callback by the tier-2 verifier
+      prev_key = r.key;
+
+      if (r.string_idx == disabled_string) continue;
+
+      // scan.c:1021-1023: the FAST_MODE / SINGLE_MATCH guard is evaluated once per
+      // candidate, before verification, against matches[string->idx] (only ever
+      // non-empty for the chain's head string)
+      if ((r.key >> KEY_SEQ_BITS) != cur_cand)
+      {
+        cur_cand = r.key >> KEY_SEQ_BITS;
+        skip_cand = (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) &&
+                    L.mcnt[r.string_idx] > 0;
+      }
+      if (skip_cand) continue;
+
+      if (verify_chained(c, (int32_t) j) == 2)
+      {
+        const uint32_t slot = atomicAdd(&st->n_too_many, 1u);
+        if (slot < too_many_cap) too_many[slot] = r.string_idx;
+        disabled_string = r.string_idx;
+      }
     }
   }
 
-  // confirmed matches of the chain's head string, in list order
+  // confirmed matches of the chain's head string, in list order, after the plain strings' records
   const int32_t cnt = L.mcnt[head_string];
   if (cnt > 0)
   {
-    unsigned long long slot = atomicAdd(&st->n_final, (unsigned long long) cnt);
+    unsigned long long slot = (unsigned long long) st->n_sel + atomicAdd(&st->n_chain_out, (unsigned long long) cnt);
     for (int32_t k = L.mhead[head_string]; k >= 0; k = L.nxt[k])
     {
       const Raw r = raw[ix[k]];
@@ -423,9 +468,7 @@ __global__ void chain_resolve_kernel(
       m.flags = 0;
       m.reserved = 0;
       m.chain_length = L.clen[k];
-      outU[slot] = m;
-      kF[slot] = ((uint64_t) head_string << OFFSET_BITS) | (uint64_t) r.offset;
-      slot++;
+      finals[slot++] = m;
     }
   }
 
@@ -449,25 +492,10 @@ __global__ void chain_resolve_kernel(
   }
 }
 
-// ------------------------------------------------------------------ final order
-
-__global__ void fill_u64_kernel(uint64_t* p, uint32_t n, uint64_t v)
-{
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) p[j] = v;
-}
-
 __global__ void iota_kernel(uint32_t* p, uint32_t n)
 {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) p[j] = j;
-}
-
-__global__ void gather_final_kernel(const yrb_match* outU, const uint32_t* ix, const ScanStatus* st, uint32_t n, yrb_match* out)
-{
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n || (unsigned long long) j >= st->n_final) return;
-  out[j] = outU[ix[j]];
 }
 
 // ---------------------------------------------------------------- 1M cap (a10)
@@ -480,15 +508,15 @@ __global__ void gather_final_kernel(const yrb_match* outU, const uint32_t* ix, c
 // the list (the callback disables the string, scan.c:1064-1067).
 
 __global__ void cap_mark_first_kernel(
-    const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, const uint32_t* str_count, uint64_t* keys_out,
-    uint32_t target, unsigned int* n_out)
+    const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, uint64_t* keys_out, uint32_t target,
+    unsigned int* n_out)
 {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const uint64_t a = kA[j];
   if (a & A_CHAIN_BIT) return;
   if ((uint32_t) (a >> OFFSET_BITS) != target) return;
-  if (j > 0 && kA[j - 1] == a) return; // not the first discovered of its offset
+  if (!group_pick(raw, ix, kA, n, j, false)) return; // not the first discovered of its offset
   keys_out[atomicAdd(n_out, 1u)] = raw[ix[j]].key;
 }
 
@@ -508,21 +536,21 @@ __global__ void cap_cut_kernel(
 
 size_t resolve_cub_temp_bytes(uint32_t n)
 {
-  size_t b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, b, (uint64_t*) nullptr, (uint64_t*) nullptr, (uint32_t*) nullptr,
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b1, (uint64_t*) nullptr, (uint64_t*) nullptr, (uint32_t*) nullptr,
                                   (uint32_t*) nullptr, (int) n);
-  return b + 256;
+  cub::DeviceSelect::Flagged(nullptr, b2, cub::CountingInputIterator<uint32_t>(0), (uint8_t*) nullptr, (uint32_t*) nullptr,
+                             (int*) nullptr, (int) n);
+  return (b1 > b2 ? b1 : b2) + 256;
 }
 
 #define GRID(n) (unsigned) (((n) + 255) / 256), 256
 
-static void sort_pairs(ResolveWork& w, uint64_t* kin, uint64_t* kout, uint32_t* vin, uint32_t* vout, uint32_t n, cudaStream_t s)
-{
-  size_t b = w.cub_tmp_bytes;
-  cub::DeviceRadixSort::SortPairs(w.cub_tmp, b, kin, kout, vin, vout, (int) n, 0, 64, s);
-}
-
-void launch_resolve_sorts(ResolveWork& w, cudaStream_t s, unsigned* launches)
+// Everything from Raw records to final records, queued on the stream without any
+// host synchronisation; the caller reads ScanStatus (n_sel, n_chain_out, n_unconf,
+// over_cap) afterwards.  With w.use_cut the records at or after each string's cut
+// key are dropped (1M cap, second pass).
+void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches)
 {
   const uint32_t n = w.n_raw;
 
@@ -533,27 +561,17 @@ void launch_resolve_sorts(ResolveWork& w, cudaStream_t s, unsigned* launches)
     (*launches)++;
   }
 
-  build_key_b_kernel<<<GRID(n), 0, s>>>(w.raw, n, w.k0, w.ix0);
-  sort_pairs(w, w.k0, w.k1, w.ix0, w.ix1, n, s);                       // by discovery key -> ix1
-  build_key_a_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, n, w.R, w.scan_flags, w.str_min_key, w.use_cut ? w.str_cut_key : nullptr, w.k0);
-  sort_pairs(w, w.k0, w.k1, w.ix1, w.ix0, n, s);                       // stable by (string, offset) / chain -> k1, ix0
-  (*launches) += 2 + 2 * 9;
-}
-
-void launch_resolve_select(ResolveWork& w, cudaStream_t s, unsigned* launches)
-{
-  const uint32_t n = w.n_raw;
+  build_key_a_kernel<<<GRID(n), 0, s>>>(w.raw, n, w.R, w.scan_flags, w.str_min_key, w.use_cut ? w.str_cut_key : nullptr, w.k0, w.ix0);
+  size_t b = w.cub_tmp_bytes;
+  cub::DeviceRadixSort::SortPairs(w.cub_tmp, b, w.k0, w.k1, w.ix0, w.ix1, (int) n, 0, 64, s); // -> k1, ix1
 
   cudaMemsetAsync(w.str_count, 0, sizeof(uint32_t) * w.R.num_strings, s);
-  fill_u64_kernel<<<GRID(n), 0, s>>>(w.kF, n, ~0ULL);
-  select_plain_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix0, w.k1, n, w.R, w.str_count, w.kF, w.outU, w.st);
+  select_plain_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.R, w.str_count, w.flags);
   check_cap_kernel<<<GRID(w.R.num_strings), 0, s>>>(w.str_count, w.R.num_strings, w.st);
-  (*launches) += 3;
-}
-
-void launch_resolve_chains_and_order(ResolveWork& w, cudaStream_t s, unsigned* launches)
-{
-  const uint32_t n = w.n_raw;
+  b = w.cub_tmp_bytes;
+  cub::DeviceSelect::Flagged(w.cub_tmp, b, cub::CountingInputIterator<uint32_t>(0), w.flags, w.ix0, &w.st->n_sel, (int) n, s);
+  write_plain_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.ix0, w.st, n, w.finals);
+  (*launches) += 4 + 10 + 3;
 
   if (w.has_chains)
   {
@@ -563,15 +581,9 @@ void launch_resolve_chains_and_order(ResolveWork& w, cudaStream_t s, unsigned* l
     L.mhead = w.s_lists + 3 * (size_t) w.R.num_strings; L.mtail = w.s_lists + 4 * (size_t) w.R.num_strings;
     L.mcnt = w.s_lists + 5 * (size_t) w.R.num_strings;
     chain_init_kernel<<<GRID(w.R.num_strings), 0, s>>>(L, w.R.num_strings);
-    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix0, w.k1, n, w.R, L, w.kF, w.outU, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags);
+    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags);
     (*launches) += 2;
   }
-
-  // final order: (string, offset); unused slots carry ~0 and sort to the end
-  iota_kernel<<<GRID(n), 0, s>>>(w.ix1, n);
-  sort_pairs(w, w.kF, w.k0, w.ix1, w.ix0, n, s);
-  gather_final_kernel<<<GRID(n), 0, s>>>(w.outU, w.ix0, w.st, n, w.finals);
-  (*launches) += 2 + 9;
 }
 
 // Computes the cut key of one over-cap string (see above).  Synchronises.
@@ -580,8 +592,8 @@ int resolve_cap_cut(ResolveWork& w, uint32_t target, cudaStream_t s, unsigned lo
   const uint32_t n = w.n_raw;
   unsigned int* d_n = reinterpret_cast<unsigned int*>(w.str_min_key); // scratch, re-initialised by fast mode anyway
   cudaMemsetAsync(d_n, 0, sizeof(unsigned int), s);
-  // first-occurrence keys of the target string (k1/ix0 hold the (string, offset, key) order)
-  cap_mark_first_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix0, w.k1, n, w.str_count, w.kF, target, d_n);
+  // first-occurrence keys of the target string (k1/ix1 hold the (string, offset) order)
+  cap_mark_first_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.kF, target, d_n);
   unsigned int n_first = 0;
   cudaMemcpyAsync(&n_first, d_n, sizeof(n_first), cudaMemcpyDeviceToHost, s);
   if (cudaStreamSynchronize(s) != cudaSuccess) return YRB_ERROR_CUDA;
@@ -590,9 +602,9 @@ int resolve_cap_cut(ResolveWork& w, uint32_t target, cudaStream_t s, unsigned lo
     *cut_out = ~0ULL;
     return YRB_SUCCESS;
   }
-  iota_kernel<<<GRID(n_first), 0, s>>>(w.ix1, n_first);
+  iota_kernel<<<GRID(n_first), 0, s>>>(w.ix0, n_first);
   size_t b = w.cub_tmp_bytes;
-  cub::DeviceRadixSort::SortPairs(w.cub_tmp, b, w.kF, w.k0, w.ix1, w.c_scratch_u32, (int) n_first, 0, 64, s);
+  cub::DeviceRadixSort::SortPairs(w.cub_tmp, b, w.kF, w.k0, w.ix0, w.c_scratch_u32, (int) n_first, 0, 64, s);
   unsigned long long* d_cut = w.str_cut_key + target;
   cap_cut_kernel<<<GRID(n), 0, s>>>(w.raw, n, target, w.k0, d_cut);
   cudaMemcpyAsync(cut_out, d_cut, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);

@@ -27,7 +27,7 @@ struct ResolveWork
   int32_t* c_clen;
   int32_t* c_mlen;
   uint8_t* c_where;
-  yrb_match* outU;
+  uint8_t* flags;
 
   // per string
   unsigned long long* str_min_key; // num_strings
@@ -44,7 +44,5 @@ struct ResolveWork
 };
 
 size_t resolve_cub_temp_bytes(uint32_t n);
-void launch_resolve_sorts(ResolveWork& w, cudaStream_t s, unsigned* launches);
-void launch_resolve_select(ResolveWork& w, cudaStream_t s, unsigned* launches);
-void launch_resolve_chains_and_order(ResolveWork& w, cudaStream_t s, unsigned* launches);
+void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches);
 int resolve_cap_cut(ResolveWork& w, uint32_t target, cudaStream_t s, unsigned long long* cut_out);
