@@ -137,9 +137,9 @@ void launch_ac_scan_walk(
 
 // Kernel variants (threads per CTA, 16-byte chunks per thread per tile, log2 of the
 // B4 Bloom filter size); all three fit the 227 KB of shared memory with B3.
-struct FtVariant { int threads, u, b4_bits, prefetch; };
-static const FtVariant kVariants[] = {{1024, 4, 18, 0}, {512, 4, 19, 0}, {1024, 2, 19, 1}, {512, 4, 19, 1}, {1024, 2, 19, 0}};
-#define FT_NUM_VARIANTS 5
+struct FtVariant { int threads, u, b4_bits; };
+static const FtVariant kVariants[] = {{1024, 4, 18}, {512, 4, 19}, {1024, 2, 19}};
+#define FT_NUM_VARIANTS 3
 static inline size_t ft_smem_bytes(const FtVariant& v)
 { return (size_t) B3_WORDS * 4 + ((size_t) 1 << (v.b4_bits - 3)) + (size_t) (v.threads / 32) * v.u * FT_ROW; }
 
@@ -208,7 +208,7 @@ static __device__ __forceinline__ bool bloom4_test(const uint32_t* sB4, uint32_t
 // holds, and the shift instruction masks its count to 5 bits for free.  The two
 // tests are accumulated in two masks that are ANDed once per tile.
 // B4: word = idx >> 5, n = idx & 31.
-template <int FT_THREADS, int FT_U, int B4BITS, bool PREFETCH>
+template <int FT_THREADS, int FT_U, int B4BITS>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, int64_t hi)
 {
@@ -234,38 +234,27 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
   uint8_t* wstage = stage + warp * (FT_U * FT_ROW);   // this warp's private rows
 
   const uint8_t* __restrict__ d = V.d - V.g0; // d[p] = block byte p; (d + lo) is 16-byte aligned
-  const int64_t ntiles = (hi - lo + FT_TILE - 1) / FT_TILE;
+  const int64_t ntiles = (hi - lo) / FT_TILE;
   const uint32_t H3 = HASH3_MUL << 8;
   const uint8_t* sB3b = reinterpret_cast<const uint8_t*>(sB3);
 
-  uint4 v[FT_U], vn[FT_U];
-  uint32_t halo[FT_U], halon[FT_U];
+  // [lo, hi) is a whole number of tiles (the host gives the remainder to the walk kernel),
+  // so no load needs a bounds check
+  const uint8_t* tp = d + lo + (int64_t) blockIdx.x * FT_TILE + (int64_t) threadIdx.x * 16;
+  const int64_t tstep = (int64_t) gridDim.x * FT_TILE;
 
-#define LOAD_TILE(T_, V_, H_)                                                       \
-  {                                                                                 \
-    const int64_t b_ = lo + (T_) * FT_TILE + (int64_t) threadIdx.x * 16;            \
-    _Pragma("unroll") for (int u = 0; u < FT_U; u++)                                \
-    {                                                                               \
-      const int64_t a_ = b_ + (int64_t) u * (FT_THREADS * 16);                      \
-      V_[u] = make_uint4(0, 0, 0, 0);                                               \
-      H_[u] = 0;                                                                    \
-      if ((T_) < ntiles && a_ < hi)                                                 \
-      {                                                                             \
-        V_[u] = *reinterpret_cast<const uint4*>(d + a_);                            \
-        if (lane == 0) H_[u] = *reinterpret_cast<const uint32_t*>(d + a_ - 4);      \
-      }                                                                             \
-    }                                                                               \
-  }
-
-  if (PREFETCH) LOAD_TILE((int64_t) blockIdx.x, v, halo);
-
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tp += tstep)
   {
-    const int64_t base = lo + tile * FT_TILE + (int64_t) threadIdx.x * 16;
+    uint4 v[FT_U];
+    uint32_t halo[FT_U];
 
-    // software pipeline: the next tile's bytes are in flight while this one is probed
-    if (PREFETCH) { LOAD_TILE(tile + gridDim.x, vn, halon); }
-    else { LOAD_TILE(tile, v, halo); }
+#pragma unroll
+    for (int u = 0; u < FT_U; u++)
+    {
+      v[u] = *reinterpret_cast<const uint4*>(tp + u * (FT_THREADS * 16));
+      halo[u] = 0;
+      if (lane == 0) halo[u] = *reinterpret_cast<const uint32_t*>(tp + u * (FT_THREADS * 16) - 4);
+    }
 
     // ---- level 1: one B3 probe per pair of positions, branch-free
     uint32_t maskA = 0, maskB = 0;
@@ -303,14 +292,8 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
       PROBE3(w3, w3 >> 16);
     }
 #undef PROBE3
+    // mask bit (8*FT_U - 1 - slot) belongs to slot = u*8 + pair
     uint32_t mask = maskA & maskB;
-
-    // mask bit (8*FT_U - 1 - slot) belongs to slot = u*8 + pair; chunks past the end
-    // of the range were zero-filled: drop their bits
-#pragma unroll
-    for (int u = 0; u < FT_U; u++)
-      if (base + (int64_t) u * (FT_THREADS * 16) >= hi)
-        mask &= ~(0xFFu << (8 * (FT_U - 1 - u)));
 
     __syncwarp();
 
@@ -339,21 +322,15 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
         {
           const uint32_t mv = ht_lookup(F, w);
           if (mv != 0)
-            emit_events(R, V, out, base + (int64_t) u * (FT_THREADS * 16) + k + e + 1, mv);
+            emit_events(R, V, out, (int64_t) (tp - d) + (int64_t) u * (FT_THREADS * 16) + k + e + 1, mv);
         }
       }
     }
 
     __syncwarp();
-
-    if (PREFETCH)
-    {
-#pragma unroll
-      for (int u = 0; u < FT_U; u++) { v[u] = vn[u]; halo[u] = halon[u]; }
-    }
   }
-#undef LOAD_TILE
 }
+
 
 // ---- host: enumerate hit windows of the compiled automaton, build B3 / B4 / hash table
 
@@ -519,11 +496,9 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
   cudaGetDevice(&dev);
   if (dev < 64 && !attr_set[dev])
   {
-    cudaFuncSetAttribute(ac_filter_kernel<1024, 4, 18, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[0]));
-    cudaFuncSetAttribute(ac_filter_kernel<512, 4, 19, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[1]));
-    cudaFuncSetAttribute(ac_filter_kernel<1024, 2, 19, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[2]));
-    cudaFuncSetAttribute(ac_filter_kernel<512, 4, 19, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[3]));
-    cudaFuncSetAttribute(ac_filter_kernel<1024, 2, 19, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[4]));
+    cudaFuncSetAttribute(ac_filter_kernel<1024, 4, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[0]));
+    cudaFuncSetAttribute(ac_filter_kernel<512, 4, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[1]));
+    cudaFuncSetAttribute(ac_filter_kernel<1024, 2, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[2]));
     attr_set[dev] = true;
   }
   return YRB_SUCCESS;
@@ -544,9 +519,12 @@ void launch_ac_scan_filter(
   if (flo < 16) flo = 16;
   if (flo < V.g0 + 16) flo = V.g0 + 16;
   flo += (int64_t) ((16 - ((uintptr_t) (d + flo) & 15)) & 15);
-  int64_t fhi = hi - (int64_t) ((uintptr_t) (d + hi) & 15);
+  const FtVariant& fv = kVariants[F.variant];
+  const int64_t tile_bytes = (int64_t) fv.threads * 16 * fv.u;
+  const int64_t ntiles = (hi - flo) / tile_bytes;
+  const int64_t fhi = flo + ntiles * tile_bytes;   // whole tiles only; the rest is walked
 
-  if (fhi - flo < 4096)
+  if (ntiles < 1)
   {
     launch_ac_scan_walk(R, V, out, lo, hi, s);
     return;
@@ -560,18 +538,13 @@ void launch_ac_scan_filter(
   fd.ht = reinterpret_cast<const uint2*>(F.ht);
   fd.ht_bits = F.ht_bits;
 
-  const FtVariant& fv = kVariants[F.variant];
-  const int64_t tile_bytes = (int64_t) fv.threads * 16 * fv.u;
-  const int64_t ntiles = (fhi - flo + tile_bytes - 1) / tile_bytes;
   const unsigned grid = (unsigned) (ntiles < num_sms ? ntiles : num_sms);
   const size_t smem = ft_smem_bytes(fv);
   switch (F.variant)
   {
-  case 0: ac_filter_kernel<1024, 4, 18, false><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
-  case 1: ac_filter_kernel<512, 4, 19, false><<<grid, 512, smem, s>>>(R, fd, V, out, flo, fhi); break;
-  case 2: ac_filter_kernel<1024, 2, 19, true><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
-  case 3: ac_filter_kernel<512, 4, 19, true><<<grid, 512, smem, s>>>(R, fd, V, out, flo, fhi); break;
-  default: ac_filter_kernel<1024, 2, 19, false><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  case 0: ac_filter_kernel<1024, 4, 18><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  case 1: ac_filter_kernel<512, 4, 19><<<grid, 512, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  default: ac_filter_kernel<1024, 2, 19><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   }
 
   launch_ac_scan_walk(R, V, out, fhi, hi, s);
