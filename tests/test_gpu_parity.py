@@ -119,3 +119,25 @@ def test_matches_restatement_oracle():
     assert len(got) == len(b.matches)
     for f in ("offset", "string_idx", "match_length", "xor_key", "data_hash"):
         assert (got[f] == b.matches[f]).all(), f
+
+
+def test_concurrent_scanners_share_rules():
+    """`yara -p N` structure (cli/yara.c:1561-1610): N threads, each with its own
+    scanner over one shared YR_RULES -> one device rules image, N device scanners."""
+    rs = synth.ruleset(3, 2000)
+    rr, rb = both(rs.source)
+    data = synth.corpus(rs, 1 << 23, 2048)
+    secs, rc = rb.scan_mt(data, 8)
+    assert rc == 0
+    # slices are scanned independently: compare one slice against the reference
+    part = data[: len(data) // 8].copy()
+    assert_same(rr.scan(part, cap=1 << 18), rb.scan(part, cap=1 << 18))
+
+
+def test_small_block_latency_smoke():
+    """file-batch shaped input (64 KiB blobs): every scan goes through the whole pipeline"""
+    rs = synth.ruleset(4, 3000)
+    rr, rb = both(rs.source)
+    for k in range(20):
+        data = synth.corpus(rs, 65536 + 4096 * k, 4096, seed=100 + k, plant_seed=k)
+        assert_same(rr.scan(data), rb.scan(data))

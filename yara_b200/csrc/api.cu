@@ -568,6 +568,21 @@ static int scan_impl(
   for (int c = 0; c < NUM_CLS; c++) { n_cand[c] = hs->n_cand[c]; total_cand += n_cand[c]; }
   res->stats.n_candidates = total_cand;
 
+  if (total_cand == 0 && !params->defer_resolve)
+  {
+    // nothing to verify (the common case for small benign blocks): no further launches or syncs
+    s->last_n_final = 0;
+    s->last_view = V;
+    res->matches = s->h_finals.p;
+    res->unconfirmed = s->h_unconf.p;
+    res->too_many = s->h_too_many.p;
+    res->stats.kernel_launches = launches;
+    cudaEventElapsedTime(&res->stats.ms_scan, s->ev[0], s->ev[1]);
+    res->stats.ms_total = res->stats.ms_scan;
+    res->stats.ms_h2d = h_data ? res->stats.ms_scan : 0.f;
+    return YRB_SUCCESS;
+  }
+
   // ---- verification work areas: tier 1 sized by the candidate count, tier 2 fixed
   if (n_cand[CLS_FAST] > 0)
   {
