@@ -245,6 +245,13 @@ def main():
         return
 
     peak, peak_src = peaks()
+    traffic = None
+    try:  # dram__bytes_read+write of the dominant kernel, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if scan_kernel == 2:
+            traffic = float(tj["dram_bytes_per_algorithmic_byte"]) * S
+    except Exception:
+        pass
     total_bytes = float(S) * world * args.steps
     value = total_bytes / dev_s / 1e9
     scan_gbs = float(S) / (float(np.mean(ms_scan)) / 1e3) / 1e9
@@ -269,7 +276,7 @@ def main():
         "clocks": clk,
         "gpu_launches": int(launches),
         "roofline": {
-            "bound": "hbm", "achieved": scan_gbs, "peak": peak, "unit": "GB/s", "frac": scan_gbs / peak, "traffic": None,
+            "bound": "hbm", "achieved": scan_gbs, "peak": peak, "unit": "GB/s", "frac": scan_gbs / peak, "traffic": traffic,
             "kernel": "AC scan kernel (%s)" % {1: "ac_walk_kernel", 2: "ac_filter_kernel"}.get(scan_kernel, "?"),
             "algorithmic_bytes_per_launch": S, "peak_source": peak_src,
         },

@@ -243,21 +243,25 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
   const uint8_t* tp = d + lo + (int64_t) blockIdx.x * FT_TILE + (int64_t) threadIdx.x * 16;
   const int64_t tstep = (int64_t) gridDim.x * FT_TILE;
 
+  uint4 v[FT_U];
+  uint32_t halo[FT_U];
+
+#define LOAD_TILE(P_)                                                                              \
+  _Pragma("unroll") for (int u = 0; u < FT_U; u++)                                                 \
+  {                                                                                                \
+    v[u] = *reinterpret_cast<const uint4*>((P_) + u * (FT_THREADS * 16));                          \
+    halo[u] = 0;                                                                                   \
+    if (lane == 0) halo[u] = *reinterpret_cast<const uint32_t*>((P_) + u * (FT_THREADS * 16) - 4); \
+  }
+
+  if ((int64_t) blockIdx.x < ntiles) { LOAD_TILE(tp); }
+
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tp += tstep)
   {
-    uint4 v[FT_U];
-    uint32_t halo[FT_U];
-
-#pragma unroll
-    for (int u = 0; u < FT_U; u++)
-    {
-      v[u] = *reinterpret_cast<const uint4*>(tp + u * (FT_THREADS * 16));
-      halo[u] = 0;
-      if (lane == 0) halo[u] = *reinterpret_cast<const uint32_t*>(tp + u * (FT_THREADS * 16) - 4);
-    }
 
     // ---- level 1: one B3 probe per pair of positions, branch-free
     uint32_t maskA = 0, maskB = 0;
+    const bool has_next = tile + gridDim.x < ntiles;
 
 #define PROBE3(x, y)                                                                \
   {                                                                                 \
@@ -290,6 +294,15 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
       PROBE3(w2, f3);
       PROBE3(f3, w3);
       PROBE3(w3, w3 >> 16);
+
+      // this chunk's registers are free again (level 2 reads the staged copy): put the next
+      // tile's load in flight now, so that HBM latency hides behind the rest of the tile
+      if (has_next)
+      {
+        v[u] = *reinterpret_cast<const uint4*>(tp + tstep + u * (FT_THREADS * 16));
+        halo[u] = 0;
+        if (lane == 0) halo[u] = *reinterpret_cast<const uint32_t*>(tp + tstep + u * (FT_THREADS * 16) - 4);
+      }
     }
 #undef PROBE3
     // mask bit (8*FT_U - 1 - slot) belongs to slot = u*8 + pair
@@ -329,6 +342,7 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
 
     __syncwarp();
   }
+#undef LOAD_TILE
 }
 
 
