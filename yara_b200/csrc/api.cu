@@ -116,7 +116,7 @@ struct yrb_scanner
   DevBuf<int32_t> c_nxt, c_prv, c_clen, c_mlen, s_lists;
   DevBuf<uint8_t> c_where, flags8;
   DevBuf<yrb_match> finals, unconf;
-  DevBuf<unsigned long long> str_min_key, str_cut_key;
+  DevBuf<unsigned long long> str_min_key, str_cut_key, str_err;
   DevBuf<uint32_t> str_count, too_many;
   bool cut_dirty = true;
 
@@ -252,7 +252,7 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   s->k0.release(); s->k1.release(); s->kF.release(); s->ix0.release(); s->ix1.release(); s->scr32.release();
   s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release();
   s->s_lists.release(); s->c_where.release(); s->flags8.release(); s->finals.release(); s->unconf.release();
-  s->str_min_key.release(); s->str_cut_key.release(); s->str_count.release(); s->too_many.release();
+  s->str_min_key.release(); s->str_cut_key.release(); s->str_err.release(); s->str_count.release(); s->too_many.release();
   s->g_offsets.release(); s->g_data.release();
   s->h_finals.release(); s->h_unconf.release(); s->h_too_many.release(); s->h_str_count.release(); s->h_raw.release();
   if (s->d_status) cudaFree(s->d_status);
@@ -425,6 +425,17 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
   res->unconfirmed = s->h_unconf.p;
   res->too_many = s->h_too_many.p;
 
+  if (hs->any_error)
+  {
+    // rare: pick the earliest failing candidate the reference would really have verified
+    ResolveWork w;
+    fill_work(s, w, d_raw, n, params->scan_flags);
+    w.use_cut = !cuts.empty();
+    launch_error_select(w, s->str_err.p, n > 0, s->stream);
+    int rc = read_status(s);
+    if (rc != YRB_SUCCESS) return rc;
+  }
+
   // error precedence: the earliest failing candidate in discovery order
   // (scanner.c:111 GOTO_EXIT_ON_ERROR) vs. the earliest TOO_MANY abort
   unsigned long long first_abort = ~0ULL;
@@ -503,6 +514,13 @@ static int scan_impl(
   }
 
   ScanStatus* hs = s->h_status;
+
+  {
+    const uint32_t ns = s->rules->R.num_strings ? s->rules->R.num_strings : 1;
+    if (s->str_err.ensure(ns) != YRB_SUCCESS || s->str_min_key.ensure(ns) != YRB_SUCCESS ||
+        s->str_cut_key.ensure(ns) != YRB_SUCCESS || s->str_count.ensure(ns) != YRB_SUCCESS)
+      return YRB_ERROR_INSUFFICIENT_MEMORY;
+  }
 
   for (int attempt = 0;; attempt++)
   {
@@ -625,6 +643,9 @@ static int scan_impl(
     ro.raw = s->d_raw.p;
     ro.cap = s->d_raw.cap;
     ro.st = s->d_status;
+    ro.str_err = s->str_err.p;
+    if (s->rules->h.code_size > 0) // only RE / hex strings can raise verifier errors
+      CK(cudaMemsetAsync(s->str_err.p, 0xFF, sizeof(unsigned long long) * s->rules->R.num_strings, s->stream));
 
     launch_verify(s->rules->R, V, co, n_cand, ro, s->vws, s->stream, &launches);
     CK(cudaEventRecord(s->ev[2], s->stream));
@@ -637,6 +658,7 @@ static int scan_impl(
     CK(cudaMemsetAsync(&s->d_status->n_raw, 0, sizeof(unsigned long long), s->stream));
     CK(cudaMemsetAsync(&s->d_status->err_key, 0xFF, sizeof(unsigned long long), s->stream));
     CK(cudaMemsetAsync(&s->d_status->n_retry[0], 0, 2 * sizeof(unsigned int), s->stream));
+    CK(cudaMemsetAsync(&s->d_status->any_error, 0, sizeof(unsigned int), s->stream));
   }
 
   if (hs->margin_fault)
@@ -653,7 +675,16 @@ static int scan_impl(
     if (s->h_raw.ensure(n_raw ? (size_t) n_raw : 1) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
     if (n_raw) CK(cudaMemcpyAsync(s->h_raw.p, s->d_raw.p, (size_t) n_raw * sizeof(Raw), cudaMemcpyDeviceToHost, s->stream));
     s->h_raw_n = (size_t) n_raw;
-    if (hs->err_key != ~0ULL) res->error = (int32_t) (hs->err_key & KEY_SEQ_MAX);
+    if (hs->any_error)
+    {
+      // shard: report the earliest failing candidate; the global guards are not known here
+      ResolveWork w;
+      fill_work(s, w, s->d_raw.p, (uint32_t) n_raw, 0);
+      launch_error_select(w, s->str_err.p, false, s->stream);
+      int rc2 = read_status(s);
+      if (rc2 != YRB_SUCCESS) return rc2;
+      if (hs->err_key != ~0ULL) res->error = (int32_t) (hs->err_key & KEY_SEQ_MAX);
+    }
     CK(cudaEventRecord(s->ev[3], s->stream));
     CK(cudaStreamSynchronize(s->stream));
   }

@@ -101,6 +101,8 @@ struct ScanStatus
   unsigned int survivors;       // filter kernel statistics
   unsigned int n_retry[2];      // candidates queued for the tier-2 verifiers (fast VM, fiber VM)
   int n_sel;                    // surviving records of plain strings (ordered compaction)
+  unsigned int any_error;       // some verifier reported an error (see report_error)
+  unsigned int pad2[3];
 };
 
 struct CandOut
@@ -115,6 +117,7 @@ struct RawOut
   Raw* raw;
   unsigned long long cap;
   ScanStatus* st;
+  unsigned long long* str_err;  // per string: min over its failing candidates of (candidate key | error code)
 };
 
 // Atom prefilter tables of one ruleset (ac_scan.cu, filter kernel).
@@ -139,9 +142,16 @@ struct FilterTables
 
 __host__ __device__ static inline uint32_t hash3(uint32_t key3) { return ((key3 << 8) * HASH3_MUL) >> (32 - B3_BITS); }
 
-static __device__ __forceinline__ void report_error(ScanStatus* st, uint64_t cand_key, int code)
+// A verifier error (ERROR_TOO_MANY_RE_FIBERS ...) aborts the reference's scan at that
+// candidate -- but only if the reference would have verified the candidate at all
+// (scan.c:1018-1023: not when the string was already disabled by the 1M cap, nor in
+// fast mode once a SINGLE_MATCH string has matched).  Both conditions are "candidate
+// key below a per-string threshold", so the earliest failing candidate per string is
+// all that needs to be kept; resolve.cu decides which of them counts.
+static __device__ __forceinline__ void report_error(const RawOut& out, uint32_t sidx, uint64_t cand_key, int code)
 {
-  atomicMin(&st->err_key, (unsigned long long) ((cand_key & ~(uint64_t) KEY_SEQ_MAX) | (uint64_t) code));
+  atomicMin(&out.str_err[sidx], (unsigned long long) ((cand_key & ~(uint64_t) KEY_SEQ_MAX) | (uint64_t) code));
+  atomicExch(&out.st->any_error, 1u);
 }
 
 // ---- launch helpers implemented across the .cu files -------------------------

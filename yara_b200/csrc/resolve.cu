@@ -498,6 +498,37 @@ __global__ void iota_kernel(uint32_t* p, uint32_t n)
   if (j < n) p[j] = j;
 }
 
+// ------------------------------------------------------------ verifier errors
+
+// The scan's error = the earliest failing candidate, in discovery order, that the
+// reference would actually have verified (see report_error in engine.cuh).
+__global__ void error_select_kernel(
+    const unsigned long long* str_err, const unsigned long long* str_min_key, const unsigned long long* str_cut_key,
+    DevRules R, int scan_flags, ScanStatus* st)
+{
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= R.num_strings) return;
+  const unsigned long long e = str_err[s];
+  if (e == ~0ULL) return;
+  const unsigned long long cand = e >> KEY_SEQ_BITS;
+
+  // scan.c:1021-1023: later candidates of a SINGLE_MATCH string that already matched are not verified
+  if (str_min_key != nullptr && (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[s].flags & YRB_SF_SINGLE_MATCH) &&
+      R.S[s].chain_head == YRB_NONE && str_min_key[s] < cand)
+    return;
+  // scan.c:1018: neither are candidates of a string disabled by the 1M cap
+  if (str_cut_key != nullptr && str_cut_key[s] != ~0ULL && (str_cut_key[s] >> KEY_SEQ_BITS) < cand)
+    return;
+
+  atomicMin(&st->err_key, e);
+}
+
+void launch_error_select(ResolveWork& w, unsigned long long* str_err, bool have_min_key, cudaStream_t s)
+{
+  error_select_kernel<<<(w.R.num_strings + 255) / 256, 256, 0, s>>>(
+      str_err, have_min_key ? w.str_min_key : nullptr, w.use_cut ? w.str_cut_key : nullptr, w.R, w.scan_flags, w.st);
+}
+
 // ---------------------------------------------------------------- 1M cap (a10)
 //
 // scan.c:303-307 tests `count == YR_MAX_STRING_MATCHES` BEFORE dedup, in

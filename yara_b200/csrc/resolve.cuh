@@ -45,4 +45,5 @@ struct ResolveWork
 
 size_t resolve_cub_temp_bytes(uint32_t n);
 void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches);
+void launch_error_select(ResolveWork& w, unsigned long long* str_err, bool have_min_key, cudaStream_t s);
 int resolve_cap_cut(ResolveWork& w, uint32_t target, cudaStream_t s, unsigned long long* cut_out);

@@ -1126,7 +1126,7 @@ verify_fast_kernel(
       rc = YRB_ERROR_INSUFFICIENT_MEMORY;
     }
     if (rc != YRB_SUCCESS)
-      report_error(out.st, cd.key, rc);
+      report_error(out, m.string_idx, cd.key, rc);
   }
 }
 
@@ -1173,7 +1173,7 @@ verify_re_kernel(
       rc = YRB_ERROR_INTERNAL_FATAL;
     }
     if (rc != YRB_SUCCESS)
-      report_error(out.st, cd.key, rc);
+      report_error(out, m.string_idx, cd.key, rc);
   }
 }
 
