@@ -102,7 +102,7 @@ struct ScanStatus
   unsigned int n_retry[2];      // candidates queued for the tier-2 verifiers (fast VM, fiber VM)
   int n_sel;                    // surviving records of plain strings (ordered compaction)
   unsigned int any_error;       // some verifier reported an error (see report_error)
-  unsigned int pad2[3];
+  unsigned int dbg[3];          // chain resolver step counters: list-insert walks, prune-loop steps, unvisited-scan steps
 };
 
 struct CandOut

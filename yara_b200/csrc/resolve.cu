@@ -164,6 +164,8 @@ struct ChainLists
   int32_t* mhead; // per string: matches[s] (only chain heads are used)
   int32_t* mtail;
   int32_t* mcnt;
+  int32_t* uvn;    // per record: next in its string's not-yet-visited list / in the ready list
+  int32_t* uvhead; // per string
 };
 
 struct ChainCtx
@@ -172,6 +174,7 @@ struct ChainCtx
   const uint32_t* ix;
   DevRules R;
   ChainLists L;
+  unsigned int steps[3];
 };
 
 static __device__ __forceinline__ int64_t c_off(const ChainCtx& c, int32_t j) { return c.raw[c.ix[j]].offset; }
@@ -187,6 +190,7 @@ static __device__ int clist_add(ChainCtx& c, int32_t* head, int32_t* tail, int32
 
   while (ip >= 0)
   {
+    c.steps[0]++;
     const int64_t o = c_off(c, ip);
     if (off == o) return 1;
     if (off > o) break;
@@ -224,55 +228,92 @@ static __device__ void clist_remove(ChainCtx& c, int32_t* head, int32_t* tail, i
   c.L.nxt[j] = c.L.prv[j] = -1;
 }
 
-// scan.c:257-288, recursion turned into an explicit stack of (string, node, length, cursor)
+// scan.c:257-288 _yr_scan_update_match_chain_length, recursion turned into an
+// explicit stack.
+//
+// The reference re-scans the whole predecessor list on every call and relies on
+// `if (match_to_update->chain_length == chain_length) return;` to stop early.  A
+// node of a string that sits d links before the chain's tail is only ever
+// updated to the value d, so a node that was updated once ("visited") makes every
+// later call on it a no-op (including the recursion below it: quirk 10).  Keeping,
+// per string, a list of the nodes NOT yet visited and scanning only those visits
+// exactly the same nodes in every call, in O(new nodes) instead of O(all nodes)
+// -- which matters for one GPU thread replaying a chain whose parts match
+// thousands of times.  Head-string nodes that get visited are exactly the ones
+// scan.c:552-583 moves to matches[]: they are collected in a "ready" list.
 #define CHAIN_MAX_DEPTH 48
 
-static __device__ void update_chain_length(ChainCtx& c, uint32_t sidx, int32_t node, int chain_length)
+// unvisited list of string t: singly linked through L.uvn, head in L.uvhead[t]; nodes that
+// left unconfirmed_matches[] in the meantime (where != 1) are unlinked lazily
+static __device__ void update_chain_length(
+    ChainCtx& c, uint32_t sidx, int32_t node, int chain_length, int32_t* ready_head)
 {
-  struct Frame { uint32_t s; int32_t upd; int32_t cur; int len; };
+  struct Frame { uint32_t s; int32_t upd; int32_t prev; int32_t cur; int len; };
   Frame fr[CHAIN_MAX_DEPTH];
   int depth = 0;
 
-  // enter(sidx, node, chain_length)
   uint32_t s = sidx;
   int32_t upd = node;
   int len = chain_length;
 
   for (;;)
   {
-    bool descend = false;
-
-    if (c.L.clen[upd] != len)
+    // "call" update(s, upd, len): upd is an unvisited node of string s
+    c.L.clen[upd] = len;
+    const yrb_string st = c.R.S[s];
+    if (st.chained_to == YRB_NONE)
     {
-      c.L.clen[upd] = len;
-      const yrb_string st = c.R.S[s];
-      if (st.chained_to != YRB_NONE && depth < CHAIN_MAX_DEPTH)
-      {
-        fr[depth].s = s; fr[depth].upd = upd; fr[depth].len = len;
-        fr[depth].cur = c.L.uhead[st.chained_to];
-        depth++;
-        descend = true;
-      }
+      c.L.uvn[upd] = *ready_head; // head string: whole chain confirmed up to here
+      *ready_head = upd;
+    }
+    else if (depth < CHAIN_MAX_DEPTH)
+    {
+      fr[depth].s = s; fr[depth].upd = upd; fr[depth].len = len;
+      fr[depth].prev = -1;
+      fr[depth].cur = c.L.uvhead[st.chained_to];
+      depth++;
     }
 
-    (void) descend;
-
-    // resume the innermost loop that still has predecessors to visit
+    // resume the innermost loop that still has unvisited predecessors to look at
     bool entered = false;
     while (depth > 0 && !entered)
     {
       Frame& f = fr[depth - 1];
-      const yrb_string st = c.R.S[f.s];
+      const yrb_string fs = c.R.S[f.s];
+      const uint32_t t = fs.chained_to;
       const int64_t upd_off = c_off(c, f.upd);
 
       while (f.cur >= 0)
       {
+        c.steps[2]++;
         const int32_t k = f.cur;
-        f.cur = c.L.nxt[k];
-        const int64_t ending = c_off(c, k) + c.L.mlen[k];
-        if (ending + st.chain_gap_max >= upd_off && ending + st.chain_gap_min <= upd_off)
+        const int32_t nk = c.L.uvn[k];
+        bool unlink = false, visit = false;
+
+        if (c.L.where[k] != 1)
         {
-          s = st.chained_to;
+          unlink = true; // pruned or confirmed meanwhile
+        }
+        else
+        {
+          const int64_t ending = c_off(c, k) + c.L.mlen[k];
+          if (ending + fs.chain_gap_max >= upd_off && ending + fs.chain_gap_min <= upd_off)
+            unlink = visit = true;
+        }
+
+        if (unlink)
+        {
+          if (f.prev >= 0) c.L.uvn[f.prev] = nk; else c.L.uvhead[t] = nk;
+        }
+        else
+        {
+          f.prev = k;
+        }
+        f.cur = nk;
+
+        if (visit)
+        {
+          s = t;
           upd = k;
           len = f.len + 1;
           entered = true;
@@ -310,6 +351,7 @@ static __device__ int verify_chained(ChainCtx& c, int32_t j)
 
     while (k >= 0)
     {
+      c.steps[1]++;
       const int32_t next = c.L.nxt[k];
       const int64_t ending = c_off(c, k) + c.L.mlen[k];
 
@@ -332,13 +374,6 @@ static __device__ int verify_chained(ChainCtx& c, int32_t j)
 
   if (ms.flags & YRB_SF_CHAIN_TAIL)
   {
-    for (int32_t k = c.L.uhead[ms.chained_to]; k >= 0; k = c.L.nxt[k])
-    {
-      const int64_t ending = c_off(c, k) + c.L.mlen[k];
-      if (ending + ms.chain_gap_max >= match_offset && ending + ms.chain_gap_min <= match_offset)
-        update_chain_length(c, ms.chained_to, k, 1);
-    }
-
     int32_t full_chain_length = 0;
     uint32_t hs = sidx;
     while (c.R.S[hs].chained_to != YRB_NONE)
@@ -347,11 +382,47 @@ static __device__ int verify_chained(ChainCtx& c, int32_t j)
       hs = c.R.S[hs].chained_to;
     }
 
-    int32_t k = c.L.uhead[hs];
-    while (k >= 0)
+    // scan.c:519-534: every predecessor in range gets chain_length 1 (and recursively
+    // 2, 3 ... up the chain); only not-yet-visited nodes can change anything
+    int32_t ready = -1;
     {
-      const int32_t next = c.L.nxt[k];
-      if (c.L.clen[k] == full_chain_length)
+      const uint32_t t = ms.chained_to;
+      int32_t prev = -1, k = c.L.uvhead[t];
+      while (k >= 0)
+      {
+        c.steps[2]++;
+        const int32_t nk = c.L.uvn[k];
+        bool unlink = false, visit = false;
+        if (c.L.where[k] != 1)
+        {
+          unlink = true;
+        }
+        else
+        {
+          const int64_t ending = c_off(c, k) + c.L.mlen[k];
+          if (ending + ms.chain_gap_max >= match_offset && ending + ms.chain_gap_min <= match_offset)
+            unlink = visit = true;
+        }
+        if (unlink)
+        {
+          if (prev >= 0) c.L.uvn[prev] = nk; else c.L.uvhead[t] = nk;
+        }
+        else
+        {
+          prev = k;
+        }
+        if (visit)
+          update_chain_length(c, t, k, 1, &ready);
+        k = nk;
+      }
+    }
+
+    // scan.c:546-583: head matches whose whole chain is confirmed move to matches[]
+    (void) full_chain_length;
+    for (int32_t k = ready; k >= 0;)
+    {
+      const int32_t next = c.L.uvn[k];
+      if (c.L.where[k] == 1)
       {
         clist_remove(c, c.L.uhead, c.L.utail, c.L.ucnt, hs, k);
         c.L.mlen[k] = (int32_t) (match_offset - c_off(c, k) + match_length);
@@ -368,6 +439,11 @@ static __device__ int verify_chained(ChainCtx& c, int32_t j)
     c.L.mlen[j] = match_length;
     const int rc = clist_add(c, c.L.uhead, c.L.utail, c.L.ucnt, sidx, j);
     c.L.where[j] = (rc == 0) ? 1 : 0;
+    if (rc == 0)
+    {
+      c.L.uvn[j] = c.L.uvhead[sidx]; // new nodes start unvisited
+      c.L.uvhead[sidx] = j;
+    }
     if (rc == 2) return 2;
   }
 
@@ -378,7 +454,7 @@ __global__ void chain_init_kernel(ChainLists L, uint32_t num_strings)
 {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= num_strings) return;
-  L.uhead[s] = L.utail[s] = L.mhead[s] = L.mtail[s] = -1;
+  L.uhead[s] = L.utail[s] = L.mhead[s] = L.mtail[s] = L.uvhead[s] = -1;
   L.ucnt[s] = L.mcnt[s] = 0;
 }
 
@@ -399,6 +475,7 @@ __global__ void chain_resolve_kernel(
   c.ix = ix;
   c.R = R;
   c.L = L;
+  c.steps[0] = c.steps[1] = c.steps[2] = 0;
 
   const uint32_t head_string = raw[ix[j0]].group;
   uint32_t j = j0;
@@ -471,6 +548,10 @@ __global__ void chain_resolve_kernel(
       finals[slot++] = m;
     }
   }
+
+  atomicAdd(&st->dbg[0], c.steps[0]);
+  atomicAdd(&st->dbg[1], c.steps[1]);
+  atomicAdd(&st->dbg[2], c.steps[2]);
 
   // what is left in unconfirmed_matches[] of the chain's strings
   for (uint32_t k = j0; k < j; k++)
@@ -611,6 +692,8 @@ void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches)
     L.uhead = w.s_lists; L.utail = w.s_lists + w.R.num_strings; L.ucnt = w.s_lists + 2 * (size_t) w.R.num_strings;
     L.mhead = w.s_lists + 3 * (size_t) w.R.num_strings; L.mtail = w.s_lists + 4 * (size_t) w.R.num_strings;
     L.mcnt = w.s_lists + 5 * (size_t) w.R.num_strings;
+    L.uvhead = w.s_lists + 6 * (size_t) w.R.num_strings;
+    L.uvn = w.c_uvn;
     chain_init_kernel<<<GRID(w.R.num_strings), 0, s>>>(L, w.R.num_strings);
     chain_resolve_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags);
     (*launches) += 2;

@@ -26,6 +26,7 @@ struct ResolveWork
   int32_t* c_prv;
   int32_t* c_clen;
   int32_t* c_mlen;
+  int32_t* c_uvn;
   uint8_t* c_where;
   uint8_t* flags;
 
@@ -33,7 +34,7 @@ struct ResolveWork
   unsigned long long* str_min_key; // num_strings
   unsigned long long* str_cut_key; // num_strings, ~0 = no cut
   uint32_t* str_count;             // num_strings
-  int32_t* s_lists;                // 6 * num_strings
+  int32_t* s_lists;                // 7 * num_strings
 
   // outputs
   yrb_match* finals;
