@@ -115,6 +115,7 @@ struct yrb_scanner
   DevBuf<uint8_t> cub_tmp;
   DevBuf<int32_t> c_nxt, c_prv, c_clen, c_mlen, c_uvn, s_lists;
   DevBuf<uint8_t> c_where, flags8;
+  DevBuf<Raw> sraw;
   DevBuf<yrb_match> finals, unconf;
   DevBuf<unsigned long long> str_min_key, str_cut_key, str_err;
   DevBuf<uint32_t> str_count, too_many;
@@ -250,7 +251,7 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   s->d_raw.release(); s->ws_fast1.release(); s->ws_fast2.release(); s->ws_re1.release(); s->ws_re2.release();
   s->retry_fast.release(); s->retry_re.release();
   s->k0.release(); s->k1.release(); s->kF.release(); s->ix0.release(); s->ix1.release(); s->scr32.release();
-  s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release(); s->c_uvn.release();
+  s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release(); s->c_uvn.release(); s->sraw.release();
   s->s_lists.release(); s->c_where.release(); s->flags8.release(); s->finals.release(); s->unconf.release();
   s->str_min_key.release(); s->str_cut_key.release(); s->str_err.release(); s->str_count.release(); s->too_many.release();
   s->g_offsets.release(); s->g_data.release();
@@ -320,7 +321,7 @@ static int ensure_resolve_scratch(yrb_scanner* s, uint32_t n)
   if (s->rules->h.num_chains > 0)
   {
     rc |= s->c_nxt.ensure(n); rc |= s->c_prv.ensure(n); rc |= s->c_clen.ensure(n); rc |= s->c_mlen.ensure(n);
-    rc |= s->c_where.ensure(n); rc |= s->c_uvn.ensure(n); rc |= s->s_lists.ensure((size_t) 7 * ns);
+    rc |= s->c_where.ensure(n); rc |= s->c_uvn.ensure(n); rc |= s->sraw.ensure(n); rc |= s->s_lists.ensure((size_t) 7 * ns);
   }
   rc |= s->str_min_key.ensure(ns); rc |= s->str_cut_key.ensure(ns); rc |= s->str_count.ensure(ns);
   rc |= s->too_many.ensure(1024);
@@ -337,7 +338,7 @@ static void fill_work(yrb_scanner* s, ResolveWork& w, const Raw* raw, uint32_t n
   w.use_cut = 0;
   w.k0 = s->k0.p; w.k1 = s->k1.p; w.kF = s->kF.p; w.ix0 = s->ix0.p; w.ix1 = s->ix1.p; w.c_scratch_u32 = s->scr32.p;
   w.cub_tmp = s->cub_tmp.p; w.cub_tmp_bytes = s->cub_tmp.cap;
-  w.c_nxt = s->c_nxt.p; w.c_prv = s->c_prv.p; w.c_clen = s->c_clen.p; w.c_mlen = s->c_mlen.p; w.c_uvn = s->c_uvn.p; w.c_where = s->c_where.p;
+  w.c_nxt = s->c_nxt.p; w.c_prv = s->c_prv.p; w.c_clen = s->c_clen.p; w.c_mlen = s->c_mlen.p; w.c_uvn = s->c_uvn.p; w.sraw = s->sraw.p; w.c_where = s->c_where.p;
   w.flags = s->flags8.p;
   w.str_min_key = s->str_min_key.p; w.str_cut_key = s->str_cut_key.p; w.str_count = s->str_count.p;
   w.s_lists = s->s_lists.p;

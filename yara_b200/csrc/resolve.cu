@@ -170,14 +170,13 @@ struct ChainLists
 
 struct ChainCtx
 {
-  const Raw* raw;
-  const uint32_t* ix;
+  Raw* sraw;      // the chain records gathered into sorted order (sraw[j] = raw[ix[j]])
   DevRules R;
   ChainLists L;
   unsigned int steps[3];
 };
 
-static __device__ __forceinline__ int64_t c_off(const ChainCtx& c, int32_t j) { return c.raw[c.ix[j]].offset; }
+static __device__ __forceinline__ int64_t c_off(const ChainCtx& c, int32_t j) { return c.sraw[j].offset; }
 
 // scan.c:290-368 over index-linked lists; returns 0 ok / 1 duplicate dropped / 2 too many
 static __device__ int clist_add(ChainCtx& c, int32_t* head, int32_t* tail, int32_t* cnt, uint32_t s, int32_t j)
@@ -333,7 +332,7 @@ static __device__ void update_chain_length(
 // scan.c:406-632.  Returns 0, or 2 when a list hit the 1M cap.
 static __device__ int verify_chained(ChainCtx& c, int32_t j)
 {
-  const Raw r = c.raw[c.ix[j]];
+  const Raw r = c.sraw[j];
   const uint32_t sidx = r.string_idx;
   const yrb_string ms = c.R.S[sidx];
   const int64_t match_offset = r.offset;
@@ -374,13 +373,7 @@ static __device__ int verify_chained(ChainCtx& c, int32_t j)
 
   if (ms.flags & YRB_SF_CHAIN_TAIL)
   {
-    int32_t full_chain_length = 0;
-    uint32_t hs = sidx;
-    while (c.R.S[hs].chained_to != YRB_NONE)
-    {
-      full_chain_length++;
-      hs = c.R.S[hs].chained_to;
-    }
+    const uint32_t hs = ms.chain_head; // the head string of this chain (flattened at rules upload)
 
     // scan.c:519-534: every predecessor in range gets chain_length 1 (and recursively
     // 2, 3 ... up the chain); only not-yet-visited nodes can change anything
@@ -418,7 +411,6 @@ static __device__ int verify_chained(ChainCtx& c, int32_t j)
     }
 
     // scan.c:546-583: head matches whose whole chain is confirmed move to matches[]
-    (void) full_chain_length;
     for (int32_t k = ready; k >= 0;)
     {
       const int32_t next = c.L.uvn[k];
@@ -458,8 +450,20 @@ __global__ void chain_init_kernel(ChainLists L, uint32_t num_strings)
   L.ucnt[s] = L.mcnt[s] = 0;
 }
 
+// One thread replays a whole chain, so the records it walks are first gathered into
+// sorted order by all threads: sequential reads instead of two dependent random
+// gathers per record and per list step.
+__global__ void chain_gather_kernel(const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, Raw* sraw)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const uint64_t a = kA[j];
+  if ((a & A_CHAIN_BIT) && a != A_DROPPED)
+    sraw[j] = raw[ix[j]];
+}
+
 __global__ void chain_resolve_kernel(
-    const Raw* raw, uint32_t* ix, const uint64_t* kA, uint32_t n, DevRules R, ChainLists L, yrb_match* finals,
+    Raw* sraw, const uint64_t* kA, uint32_t n, DevRules R, ChainLists L, yrb_match* finals,
     yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap, int scan_flags)
 {
   const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -471,13 +475,12 @@ __global__ void chain_resolve_kernel(
   if (j0 > 0 && (kA[j0 - 1] >> OFFSET_BITS) == chain) return; // not the first record of its chain
 
   ChainCtx c;
-  c.raw = raw;
-  c.ix = ix;
+  c.sraw = sraw;
   c.R = R;
   c.L = L;
   c.steps[0] = c.steps[1] = c.steps[2] = 0;
 
-  const uint32_t head_string = raw[ix[j0]].group;
+  const uint32_t head_string = sraw[j0].group;
   uint32_t j = j0;
   uint64_t prev_key = ~0ULL;
   uint32_t disabled_string = YRB_NONE; // strings_temp_disabled after a TOO_MANY (at most one tracked per chain)
@@ -491,11 +494,11 @@ __global__ void chain_resolve_kernel(
     while (r_end < n && kA[r_end] == kA[j]) r_end++;
     for (uint32_t x = j + 1; x < r_end; x++)
     {
-      const uint32_t vx = ix[x];
-      const uint64_t kx = raw[vx].key;
+      if (sraw[x - 1].key <= sraw[x].key) continue; // already in order: the common case
+      const Raw vx = sraw[x];
       uint32_t y = x;
-      while (y > j && raw[ix[y - 1]].key > kx) { ix[y] = ix[y - 1]; y--; }
-      ix[y] = vx;
+      while (y > j && sraw[y - 1].key > vx.key) { sraw[y] = sraw[y - 1]; y--; }
+      sraw[y] = vx;
     }
 
     for (; j < r_end; j++)
@@ -503,7 +506,7 @@ __global__ void chain_resolve_kernel(
       L.nxt[j] = L.prv[j] = -1;
       L.where[j] = 0;
 
-      const Raw r = raw[ix[j]];
+      const Raw r = sraw[j];
       if (r.key == prev_key) continue; // re-emission of the same callback by the tier-2 verifier
       prev_key = r.key;
 
@@ -536,7 +539,7 @@ __global__ void chain_resolve_kernel(
     unsigned long long slot = (unsigned long long) st->n_sel + atomicAdd(&st->n_chain_out, (unsigned long long) cnt);
     for (int32_t k = L.mhead[head_string]; k >= 0; k = L.nxt[k])
     {
-      const Raw r = raw[ix[k]];
+      const Raw r = sraw[k];
       yrb_match m;
       m.offset = r.offset;
       m.string_idx = head_string;
@@ -558,7 +561,7 @@ __global__ void chain_resolve_kernel(
   {
     if (L.where[k] == 1)
     {
-      const Raw r = raw[ix[k]];
+      const Raw r = sraw[k];
       const unsigned long long slot = atomicAdd(&st->n_unconf, 1ULL);
       yrb_match m;
       m.offset = r.offset;
@@ -695,8 +698,9 @@ void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches)
     L.uvhead = w.s_lists + 6 * (size_t) w.R.num_strings;
     L.uvn = w.c_uvn;
     chain_init_kernel<<<GRID(w.R.num_strings), 0, s>>>(L, w.R.num_strings);
-    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags);
-    (*launches) += 2;
+    chain_gather_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.sraw);
+    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.sraw, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags);
+    (*launches) += 3;
   }
 }
 

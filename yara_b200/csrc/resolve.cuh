@@ -27,6 +27,7 @@ struct ResolveWork
   int32_t* c_clen;
   int32_t* c_mlen;
   int32_t* c_uvn;
+  Raw* sraw;
   uint8_t* c_where;
   uint8_t* flags;
 
