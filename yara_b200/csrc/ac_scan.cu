@@ -141,7 +141,7 @@ struct FtVariant { int threads, u, b4_bits; };
 static const FtVariant kVariants[] = {{1024, 4, 18}, {512, 4, 19}, {1024, 2, 19}};
 #define FT_NUM_VARIANTS 3
 static inline size_t ft_smem_bytes(const FtVariant& v)
-{ return (size_t) B3_WORDS * 4 + ((size_t) 1 << (v.b4_bits - 3)) + (size_t) (v.threads / 32) * v.u * FT_ROW; }
+{ return (size_t) B3_WORDS * 4 + ((size_t) 1 << (v.b4_bits - 3)) + (size_t) (v.threads / 32) * (v.u * FT_ROW + 32); }
 
 struct FilterDev
 {
@@ -232,6 +232,7 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5;
   uint8_t* wstage = stage + warp * (FT_U * FT_ROW);   // this warp's private rows
+  uint8_t* wqueue = stage + (FT_THREADS / 32) * (FT_U * FT_ROW) + warp * 32;   // and its survivor queue
 
   const uint8_t* __restrict__ d = V.d - V.g0; // d[p] = block byte p; (d + lo) is 16-byte aligned
   const int64_t ntiles = (hi - lo) / FT_TILE;
@@ -310,35 +311,85 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
 
     __syncwarp();
 
-    // ---- levels 2 and 3 for the pairs that passed
-    while (mask != 0)
-    {
-      const int s = __clz(mask) - (32 - 8 * FT_U);
-      mask &= ~(0x80000000u >> (s + 32 - 8 * FT_U));
-
-      const int u = s >> 3;
-      const int k = (s & 7) * 2;
-
-      // bytes p-3 .. p+1 of the pair's first position p, from this warp's staged row
-      const uint32_t off = 16 + lane * 16 + k - 3;
-      const uint8_t* row = wstage + u * FT_ROW;
-      const uint32_t x0 = *reinterpret_cast<const uint32_t*>(row + (off & ~3u));
-      const uint32_t x1 = *reinterpret_cast<const uint32_t*>(row + (off & ~3u) + 4);
-      const uint64_t x = ((uint64_t) x1 << 32) | x0;
-      const uint32_t sh = (off & 3u) * 8;
-
+    // ---- levels 2 and 3 for the pairs that passed.
+    // A lane finds 0.6 survivors per tile on average but the slowest lane of a warp
+    // 2.6, and a SIMT loop runs as long as its slowest lane: the warp's survivors are
+    // therefore dealt out evenly.  Each lane publishes (lane, n-th survivor) bytes at
+    // its prefix-sum position in a 32-entry warp queue; lane e then takes entry e,
+    // fetches the owner's mask by shuffle and the window bytes from the owner's
+    // staged row.
+    const uint32_t cnt = __popc(mask);
+    uint32_t incl = cnt;
 #pragma unroll
-      for (int e = 0; e < 2; e++)
+    for (int dd = 1; dd < 32; dd <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, dd);
+      if (lane >= (uint32_t) dd) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    const uint32_t excl = incl - cnt;
+    const bool dense = __any_sync(0xFFFFFFFFu, cnt > 8);   // (lane, n) must fit a byte: n < 8
+    const int64_t wpos = (int64_t) (tp - d) - (int64_t) lane * 16;   // block position of the warp's first byte
+
+#define LEVEL23(OL_, S_)                                                                            \
+  {                                                                                                 \
+    const int u_ = (S_) >> 3;                                                                       \
+    const int k_ = ((S_) & 7) * 2;                                                                  \
+    /* bytes p-3 .. p+1 of the pair's first position p, from the owner's staged row */              \
+    const uint32_t off_ = 16 + (OL_) * 16 + k_ - 3;                                                 \
+    const uint8_t* row_ = wstage + u_ * FT_ROW;                                                     \
+    const uint32_t x0_ = *reinterpret_cast<const uint32_t*>(row_ + (off_ & ~3u));                   \
+    const uint32_t x1_ = *reinterpret_cast<const uint32_t*>(row_ + (off_ & ~3u) + 4);               \
+    const uint64_t x_ = ((uint64_t) x1_ << 32) | x0_;                                               \
+    const uint32_t sh_ = (off_ & 3u) * 8;                                                           \
+    _Pragma("unroll") for (int e_ = 0; e_ < 2; e_++)                                                \
+    {                                                                                               \
+      const uint32_t w_ = (uint32_t) (x_ >> (sh_ + 8 * e_)); /* W(p + e) */                         \
+      if (bloom4_test<B4BITS>(sB4, w_))                                                             \
+      {                                                                                             \
+        const uint32_t mv_ = ht_lookup(F, w_);                                                      \
+        if (mv_ != 0)                                                                               \
+          emit_events(R, V, out, wpos + (int64_t) u_ * (FT_THREADS * 16) + (OL_) * 16 + k_ + e_ + 1, mv_); \
+      }                                                                                             \
+    }                                                                                               \
+  }
+
+    if (!dense)
+    {
+      for (uint32_t base_e = 0; base_e < total; base_e += 32)   // almost always a single round
       {
-        const uint32_t w = (uint32_t) (x >> (sh + 8 * e));   // W(p + e)
-        if (bloom4_test<B4BITS>(sB4, w))
+        for (uint32_t r = 0; r < cnt; r++)
         {
-          const uint32_t mv = ht_lookup(F, w);
-          if (mv != 0)
-            emit_events(R, V, out, (int64_t) (tp - d) + (int64_t) u * (FT_THREADS * 16) + k + e + 1, mv);
+          const uint32_t e = excl + r - base_e;
+          if (e < 32) wqueue[e] = (uint8_t) ((lane << 3) | r);
         }
+        __syncwarp();
+
+        const bool active = base_e + lane < total;
+        const uint32_t dsc = active ? wqueue[lane] : 0;
+        const uint32_t ol = dsc >> 3;
+        uint32_t om = __shfl_sync(0xFFFFFFFFu, mask, ol);
+        for (uint32_t r = dsc & 7; r > 0; r--)
+          om &= ~(0x80000000u >> __clz(om));
+        if (active)
+        {
+          const int sl = __clz(om) - (32 - 8 * FT_U);
+          LEVEL23(ol, sl);
+        }
+        __syncwarp();
       }
     }
+    else
+    {
+      // pathologically dense data: every lane works through its own survivors
+      while (mask != 0)
+      {
+        const int sl = __clz(mask) - (32 - 8 * FT_U);
+        mask &= ~(0x80000000u >> (sl + 32 - 8 * FT_U));
+        LEVEL23(lane, sl);
+      }
+    }
+#undef LEVEL23
 
     __syncwarp();
   }
