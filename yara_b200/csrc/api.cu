@@ -11,7 +11,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <new>
 #include <vector>
 
@@ -119,7 +118,6 @@ struct yrb_scanner
   DevBuf<yrb_match> finals, unconf;
   DevBuf<unsigned long long> str_min_key, str_cut_key, str_err;
   DevBuf<uint32_t> str_count, too_many;
-  bool cut_dirty = true;
 
   PinBuf<yrb_match> h_finals, h_unconf;
   PinBuf<uint32_t> h_too_many, h_str_count;

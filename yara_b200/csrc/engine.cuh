@@ -85,7 +85,7 @@ struct Raw
   uint32_t group;     // chain head idx for CHAIN_PART strings, else YRB_NONE
 };
 
-// Device-side counters / status of one scan, one 256-byte struct.
+// Device-side counters / status of one scan (copied to the host with one small D2H).
 struct ScanStatus
 {
   unsigned long long n_cand[NUM_CLS];
@@ -123,7 +123,7 @@ struct RawOut
 // Atom prefilter tables of one ruleset (ac_scan.cu, filter kernel).
 struct FilterTables
 {
-  const uint32_t* b3;     // 2^20-bit bitmap over hashed 3-byte keys (pair probe)
+  const uint32_t* b3;     // 2^20-bit blocked Bloom filter over 3-byte keys (pair probe, 2 bits per key)
   const uint32_t* b4;     // 2^19-bit Bloom filter (BLOOM_K probes) over 4-byte windows
   const void* ht;         // open-addressed {window, match_table value} table
   uint32_t ht_bits;
