@@ -69,6 +69,8 @@ typedef struct yrb_scanner yrb_scanner;
 #define YRB_OPT_SCAN_KERNEL   1
 #define YRB_OPT_H2D_CHUNK     2 /* bytes per H2D slice in yrb_scan_host (default 64 MiB) */
 
+struct yrb_seed;
+
 typedef struct yrb_scan_params
 {
   uint64_t base;           /* block->base (only added to fixed_offset checks, scan.c:1025) */
@@ -89,8 +91,27 @@ typedef struct yrb_scan_params
   int32_t defer_resolve;   /* 1: stop after verification; fetch raw records with
                               yrb_shard_raw and resolve all shards together with
                               yrb_resolve_raw */
-  int32_t reserved;
+  uint32_t n_seeds;        /* multi-block scans: what earlier blocks of this scan left in
+                              unconfirmed_matches[] of chained strings (scanner.c keeps those
+                              lists across blocks, types.h:806-816) */
+  const struct yrb_seed* seeds;
 } yrb_scan_params;
+
+/* One YR_MATCH of unconfirmed_matches[string] carried over from an earlier block of
+   the same scan (kind 0), or the fact that matches[string] is already non-empty
+   (kind 1: the FAST_MODE guard of scan.c:1021-1023).  At most 65535 per block. */
+typedef struct yrb_seed
+{
+  int64_t base;          /* YR_MATCH.base: base of the block it was found in */
+  int64_t offset;        /* YR_MATCH.offset, relative to THAT block (the reference compares
+                            these raw offsets across blocks, scan.c:474-488: reproduced) */
+  uint32_t string_idx;
+  int32_t match_length;
+  int32_t chain_length;
+  uint8_t xor_key;
+  uint8_t kind;
+  uint16_t reserved;
+} yrb_seed;
 
 typedef struct yrb_scan_stats
 {
@@ -118,6 +139,9 @@ typedef struct yrb_scan_result
   const yrb_match* unconfirmed;
   uint32_t n_too_many;     /* strings that hit YR_MAX_STRING_MATCHES, in firing order */
   const uint32_t* too_many;
+  uint32_t seeds_consumed; /* 1: `unconfirmed` is the complete new state of the chained strings' lists
+                              (the seeds that survived are in it, flagged YRB_MATCH_FROM_SEED) */
+  uint32_t reserved;
   yrb_scan_stats stats;
 } yrb_scan_result;
 /* Pointers inside a result are owned by the scanner and stay valid until its

@@ -154,12 +154,13 @@ typedef struct yrb_match
   uint32_t string_idx;
   int32_t match_length;
   uint8_t xor_key;
-  uint8_t flags;        /* bit0: unconfirmed (chain part awaiting its tail) */
-  uint16_t reserved;
+  uint8_t flags;        /* YRB_MATCH_* */
+  uint16_t seed;        /* YRB_MATCH_FROM_SEED: index of the yrb_seed this node was */
   int32_t chain_length; /* only meaningful for unconfirmed chain matches */
 } yrb_match;
 
-#define YRB_MATCH_UNCONFIRMED 1
+#define YRB_MATCH_UNCONFIRMED 1 /* chain part awaiting its tail */
+#define YRB_MATCH_FROM_SEED   2 /* a node carried over from an earlier block (yrb_scan_params.seeds) */
 
 #ifdef __cplusplus
 }

@@ -69,4 +69,6 @@ CASES = [
     (R("$a = { 31 32 33 34 [0-180] 35 ?? [0-180] 36 37 38 39 }"), b"1234" + b"5" * 170 + b"x" * 20 + b"6789" + b"5z" * 40 + b"6789"),
     (R("$a = /abcd.{0,150}e.{0,150}fgh/s"), b"abcd" + b"e" * 140 + b"zz" + b"fgh" + b"e" * 30 + b"fgh"),
     (R("$a = /abcd(x|y|z)+.{0,90}q/"), b"abcd" + b"xyz" * 40 + b"q" + b"x" * 30 + b"q"),
+    # backward-mode position lists keep duplicates (re.c:2323-2333): 52k live positions, far beyond the 4096-byte window
+    (R("$a = { 61 [0-40] ?? [0-40] ?? [0-30] 62 63 64 65 }"), b"x" * 50 + b"a" * 200 + b"bcde" + b"y" * 20),
 ]

@@ -53,13 +53,12 @@ def test_gpu_vs_reference(seed):
 @pytest.mark.gpu
 @pytest.mark.parametrize("seed", range(100, 108))
 def test_gpu_vs_reference_blocks(seed):
-    """multi-block scans (rules without unbounded jumps: see DESIGN.md a11)"""
+    """multi-block scans; chained strings whose parts fall into different blocks included
+    (unconfirmed matches are carried across blocks like scanner.c does)"""
     R, B = yrh.ref(), yrh.b200()
     src, insts = fuzzgen.gen_rules(seed, 50)
     good = []
     for s in src:
-        if _chains(s):
-            continue
         try:
             R.compile(s)
             good.append(s)

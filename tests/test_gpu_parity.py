@@ -56,8 +56,6 @@ def test_known_answer_cases_fast_mode(idx):
 def test_known_answer_cases_blocks(idx):
     """tests/test-rules.c pass 3: 1024-byte blocks with 256 bytes of overlap."""
     rule, data = CASES[idx]
-    if "[-]" in rule or "[250-300]" in rule:
-        pytest.skip("chains across blocks: see DESIGN.md (unconfirmed matches are not carried between blocks yet)")
     rr, rb = both(rule)
     assert_same(rr.scan_blocks(data, 1024, 256), rb.scan_blocks(data, 1024, 256))
 

@@ -35,7 +35,7 @@ YRB_MATCH_DTYPE = np.dtype(
         ("match_length", "<i4"),
         ("xor_key", "u1"),
         ("flags", "u1"),
-        ("reserved", "<u2"),
+        ("seed", "<u2"),
         ("chain_length", "<i4"),
     ]
 )

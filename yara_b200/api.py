@@ -8,7 +8,7 @@ import numpy as np
 
 YRB_MATCH_DTYPE = np.dtype(
     [("offset", "<i8"), ("string_idx", "<u4"), ("match_length", "<i4"), ("xor_key", "u1"), ("flags", "u1"),
-     ("reserved", "<u2"), ("chain_length", "<i4")]
+     ("seed", "<u2"), ("chain_length", "<i4")]
 )
 RAW_DTYPE = np.dtype(
     [("key", "<u8"), ("offset", "<i8"), ("string_idx", "<u4"), ("length", "<i4"), ("misc", "<u4"), ("group", "<u4")]
@@ -32,7 +32,8 @@ class ScanParams(C.Structure):
         ("own_begin", C.c_uint64),
         ("own_end", C.c_uint64),
         ("defer_resolve", C.c_int32),
-        ("reserved", C.c_int32),
+        ("n_seeds", C.c_uint32),
+        ("seeds", C.c_void_p),
     ]
 
 
@@ -61,6 +62,8 @@ class ScanResultC(C.Structure):
         ("unconfirmed", C.c_void_p),
         ("n_too_many", C.c_uint32),
         ("too_many", C.POINTER(C.c_uint32)),
+        ("seeds_consumed", C.c_uint32),
+        ("reserved", C.c_uint32),
         ("stats", ScanStats),
     ]
 

@@ -102,8 +102,8 @@ struct yrb_scanner
   DevBuf<uint8_t> d_data;
   DevBuf<Cand> d_cand[NUM_CLS];
   DevBuf<Raw> d_raw;
-  DevBuf<uint8_t> ws_fast1, ws_fast2, ws_re1, ws_re2;
-  DevBuf<uint32_t> retry_fast, retry_re;
+  DevBuf<uint8_t> ws_fast1, ws_fast2, ws_fast3, ws_re1, ws_re2;
+  DevBuf<uint32_t> retry_fast, retry_fast3, retry_re;
   VerifyWs vws = {};
   ScanStatus* d_status = nullptr;
   ScanStatus* h_status = nullptr;
@@ -115,6 +115,8 @@ struct yrb_scanner
   DevBuf<int32_t> c_nxt, c_prv, c_clen, c_mlen, c_uvn, s_lists;
   DevBuf<uint8_t> c_where, flags8;
   DevBuf<Raw> sraw;
+  DevBuf<yrb_seed> d_seeds;
+  DevBuf<int64_t> seed_base;
   DevBuf<yrb_match> finals, unconf;
   DevBuf<unsigned long long> str_min_key, str_cut_key, str_err;
   DevBuf<uint32_t> str_count, too_many;
@@ -247,9 +249,9 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   s->d_data.release();
   for (int c = 0; c < NUM_CLS; c++) s->d_cand[c].release();
   s->d_raw.release(); s->ws_fast1.release(); s->ws_fast2.release(); s->ws_re1.release(); s->ws_re2.release();
-  s->retry_fast.release(); s->retry_re.release();
+  s->retry_fast.release(); s->retry_fast3.release(); s->retry_re.release(); s->ws_fast3.release();
   s->k0.release(); s->k1.release(); s->kF.release(); s->ix0.release(); s->ix1.release(); s->scr32.release();
-  s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release(); s->c_uvn.release(); s->sraw.release();
+  s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release(); s->c_uvn.release(); s->sraw.release(); s->d_seeds.release(); s->seed_base.release();
   s->s_lists.release(); s->c_where.release(); s->flags8.release(); s->finals.release(); s->unconf.release();
   s->str_min_key.release(); s->str_cut_key.release(); s->str_err.release(); s->str_count.release(); s->too_many.release();
   s->g_offsets.release(); s->g_data.release();
@@ -279,6 +281,24 @@ extern "C" int yrb_scanner_set_option(yrb_scanner* s, int option, uint64_t value
     return YRB_SUCCESS;
   }
   return YRB_ERROR_BAD_ARGUMENT;
+}
+
+// Multi-block scans: the unconfirmed chain-part matches earlier blocks left behind
+// re-enter the resolve stage as records that sort before anything found in this block.
+__global__ void seeds_to_raw_kernel(const yrb_seed* seeds, uint32_t n, DevRules R, Raw* out, int64_t* seed_base)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const yrb_seed sd = seeds[k];
+  Raw r;
+  r.key = (uint64_t) (uint32_t) sd.chain_length;
+  r.offset = sd.offset;
+  r.string_idx = sd.string_idx;
+  r.length = sd.match_length;
+  r.misc = (uint32_t) sd.xor_key | (k << 8) | RAW_SEED | (sd.kind ? RAW_SEED_MARK : 0u);
+  r.group = sd.string_idx < R.num_strings ? R.S[sd.string_idx].chain_head : YRB_NONE;
+  out[k] = r;
+  seed_base[k] = sd.base;
 }
 
 // ------------------------------------------------------------- scan pipeline
@@ -319,7 +339,7 @@ static int ensure_resolve_scratch(yrb_scanner* s, uint32_t n)
   if (s->rules->h.num_chains > 0)
   {
     rc |= s->c_nxt.ensure(n); rc |= s->c_prv.ensure(n); rc |= s->c_clen.ensure(n); rc |= s->c_mlen.ensure(n);
-    rc |= s->c_where.ensure(n); rc |= s->c_uvn.ensure(n); rc |= s->sraw.ensure(n); rc |= s->s_lists.ensure((size_t) 7 * ns);
+    rc |= s->c_where.ensure(n); rc |= s->c_uvn.ensure(n); rc |= s->sraw.ensure(n); rc |= s->s_lists.ensure((size_t) 8 * ns);
   }
   rc |= s->str_min_key.ensure(ns); rc |= s->str_cut_key.ensure(ns); rc |= s->str_count.ensure(ns);
   rc |= s->too_many.ensure(1024);
@@ -334,6 +354,8 @@ static void fill_work(yrb_scanner* s, ResolveWork& w, const Raw* raw, uint32_t n
   w.scan_flags = scan_flags;
   w.has_chains = s->rules->h.num_chains > 0;
   w.use_cut = 0;
+  w.seed_base = s->seed_base.p;
+  w.cur_base = 0;
   w.k0 = s->k0.p; w.k1 = s->k1.p; w.kF = s->kF.p; w.ix0 = s->ix0.p; w.ix1 = s->ix1.p; w.c_scratch_u32 = s->scr32.p;
   w.cub_tmp = s->cub_tmp.p; w.cub_tmp_bytes = s->cub_tmp.cap;
   w.c_nxt = s->c_nxt.p; w.c_prv = s->c_prv.p; w.c_clen = s->c_clen.p; w.c_mlen = s->c_mlen.p; w.c_uvn = s->c_uvn.p; w.sraw = s->sraw.p; w.c_where = s->c_where.p;
@@ -362,6 +384,7 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
 
     ResolveWork w;
     fill_work(s, w, d_raw, n, params->scan_flags);
+    w.cur_base = (int64_t) params->base;
 
     for (int pass = 0;; pass++)
     {
@@ -610,13 +633,12 @@ static int scan_impl(
     size_t want = (size_t) ((n_cand[CLS_FAST] + 127) / 128) * 128;
     const size_t maxt = (size_t) s->rules->num_sms * 2048;
     if (want > maxt) want = maxt;
-    const size_t t2 = (size_t) s->rules->num_sms * 128;
     if (s->ws_fast1.ensure(want * fast_ws_bytes_per_thread(1)) != YRB_SUCCESS ||
-        s->ws_fast2.ensure(t2 * fast_ws_bytes_per_thread(2)) != YRB_SUCCESS ||
-        s->retry_fast.ensure((size_t) n_cand[CLS_FAST]) != YRB_SUCCESS)
+        s->retry_fast.ensure((size_t) n_cand[CLS_FAST]) != YRB_SUCCESS ||
+        s->retry_fast3.ensure((size_t) n_cand[CLS_FAST]) != YRB_SUCCESS)
       return YRB_ERROR_INSUFFICIENT_MEMORY;
+    s->vws.retry_fast3 = s->retry_fast3.p;
     s->vws.fast1 = s->ws_fast1.p; s->vws.fast1_threads = s->ws_fast1.cap / fast_ws_bytes_per_thread(1) / 128 * 128;
-    s->vws.fast2 = s->ws_fast2.p; s->vws.fast2_threads = t2;
     s->vws.retry_fast = s->retry_fast.p;
   }
   if (n_cand[CLS_RE] > 0)
@@ -625,13 +647,10 @@ static int scan_impl(
     size_t want = (size_t) ((n_cand[CLS_RE] + 127) / 128) * 128;
     const size_t maxt = (size_t) s->rules->num_sms * 2048;
     if (want > maxt) want = maxt;
-    const size_t t2 = (size_t) s->rules->num_sms * 128;
     if (s->ws_re1.ensure(want * re_ws_bytes_per_thread(sw, 1)) != YRB_SUCCESS ||
-        s->ws_re2.ensure(t2 * re_ws_bytes_per_thread(sw, 2)) != YRB_SUCCESS ||
         s->retry_re.ensure((size_t) n_cand[CLS_RE]) != YRB_SUCCESS)
       return YRB_ERROR_INSUFFICIENT_MEMORY;
     s->vws.re1 = s->ws_re1.p; s->vws.re1_threads = s->ws_re1.cap / re_ws_bytes_per_thread(sw, 1) / 128 * 128;
-    s->vws.re2 = s->ws_re2.p; s->vws.re2_threads = t2;
     s->vws.retry_re = s->retry_re.p;
   }
 
@@ -651,9 +670,45 @@ static int scan_impl(
       CK(cudaMemsetAsync(s->str_err.p, 0xFF, sizeof(unsigned long long) * s->rules->R.num_strings, s->stream));
 
     launch_verify(s->rules->R, V, co, n_cand, ro, s->vws, s->stream, &launches);
-    CK(cudaEventRecord(s->ev[2], s->stream));
     int rc = read_status(s);
     if (rc != YRB_SUCCESS) return rc;
+
+    if (hs->n_retry[0] > 0 || hs->n_retry[1] > 0)
+    {
+      // tier 2: the reference's full limits, only for what outgrew tier 1, only as many threads as needed
+      const size_t maxt2 = (size_t) s->rules->num_sms * 128;
+      if (hs->n_retry[0] > 0)
+      {
+        size_t t2 = ((size_t) hs->n_retry[0] + 127) / 128 * 128;
+        if (t2 > maxt2) t2 = maxt2;
+        if (s->ws_fast2.ensure(t2 * fast_ws_bytes_per_thread(2)) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+        s->vws.fast2 = s->ws_fast2.p; s->vws.fast2_threads = t2;
+      }
+      if (hs->n_retry[1] > 0)
+      {
+        size_t t2 = ((size_t) hs->n_retry[1] + 127) / 128 * 128;
+        if (t2 > maxt2) t2 = maxt2;
+        if (s->ws_re2.ensure(t2 * re_ws_bytes_per_thread(s->rules->R.stack_words, 2)) != YRB_SUCCESS)
+          return YRB_ERROR_INSUFFICIENT_MEMORY;
+        s->vws.re2 = s->ws_re2.p; s->vws.re2_threads = t2;
+      }
+      launch_verify_tier2(s->rules->R, V, co, ro, s->vws, hs->n_retry[0] > 0, hs->n_retry[1] > 0, s->stream, &launches);
+      rc = read_status(s);
+      if (rc != YRB_SUCCESS) return rc;
+    }
+
+    if (hs->n_retry3 > 0)
+    {
+      // rare: position lists that outgrew tier 2 (backward-mode duplicates); 16 MB per thread
+      const size_t t3 = hs->n_retry3 < 32 ? hs->n_retry3 : 32;
+      if (s->ws_fast3.ensure(t3 * fast_ws_bytes_per_thread(3)) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+      s->vws.fast3 = s->ws_fast3.p;
+      s->vws.fast3_threads = t3;
+      launch_verify_fast_tier3(s->rules->R, V, co, ro, s->vws, s->stream, &launches);
+      rc = read_status(s);
+      if (rc != YRB_SUCCESS) return rc;
+    }
+    CK(cudaEventRecord(s->ev[2], s->stream));
 
     if (hs->n_raw <= s->d_raw.cap) break;
     if (attempt > 2) return YRB_ERROR_INTERNAL_FATAL;
@@ -662,6 +717,7 @@ static int scan_impl(
     CK(cudaMemsetAsync(&s->d_status->err_key, 0xFF, sizeof(unsigned long long), s->stream));
     CK(cudaMemsetAsync(&s->d_status->n_retry[0], 0, 2 * sizeof(unsigned int), s->stream));
     CK(cudaMemsetAsync(&s->d_status->any_error, 0, sizeof(unsigned int), s->stream));
+    CK(cudaMemsetAsync(&s->d_status->n_retry3, 0, sizeof(unsigned int), s->stream));
   }
 
   if (hs->margin_fault)
@@ -671,6 +727,20 @@ static int scan_impl(
   if (n_raw >= (1ULL << 31)) return YRB_ERROR_INSUFFICIENT_MEMORY;
   res->stats.n_raw = n_raw;
   s->last_view = V;
+
+  uint32_t n_resolve = (uint32_t) n_raw;
+  if (params->n_seeds > 0 && !params->defer_resolve)
+  {
+    if (params->n_seeds > 65535 || params->seeds == nullptr || s->rules->h.num_chains == 0) return YRB_ERROR_BAD_ARGUMENT;
+    if (s->d_seeds.ensure(params->n_seeds) != YRB_SUCCESS || s->seed_base.ensure(params->n_seeds) != YRB_SUCCESS ||
+        s->d_raw.ensure((size_t) n_raw + params->n_seeds, true) != YRB_SUCCESS)
+      return YRB_ERROR_INSUFFICIENT_MEMORY;
+    CK(cudaMemcpyAsync(s->d_seeds.p, params->seeds, sizeof(yrb_seed) * params->n_seeds, cudaMemcpyHostToDevice, s->stream));
+    seeds_to_raw_kernel<<<(params->n_seeds + 255) / 256, 256, 0, s->stream>>>(
+        s->d_seeds.p, params->n_seeds, s->rules->R, s->d_raw.p + n_raw, s->seed_base.p);
+    launches++;
+    n_resolve += params->n_seeds;
+  }
 
   int rc = YRB_SUCCESS;
   if (params->defer_resolve)
@@ -693,7 +763,8 @@ static int scan_impl(
   }
   else
   {
-    rc = run_resolve(s, s->d_raw.p, (uint32_t) n_raw, params, res, &launches);
+    rc = run_resolve(s, s->d_raw.p, n_resolve, params, res, &launches);
+    res->seeds_consumed = (n_resolve > (uint32_t) n_raw) ? 1 : 0;
     CK(cudaEventRecord(s->ev[3], s->stream));
     CK(cudaStreamSynchronize(s->stream));
   }

@@ -81,9 +81,13 @@ struct Raw
   int64_t offset;     // block-relative match offset
   uint32_t string_idx;
   int32_t length;
-  uint32_t misc;      // bits 0-7 xor_key
+  uint32_t misc;      // bits 0-7 xor_key; RAW_SEED: carried over from an earlier block, bits 8-23 = seed index,
+                      // key = chain_length (the record was never "discovered" in this block)
   uint32_t group;     // chain head idx for CHAIN_PART strings, else YRB_NONE
 };
+
+#define RAW_SEED      0x80000000u
+#define RAW_SEED_MARK 0x40000000u   // kind 1: matches[string] is already non-empty
 
 // Device-side counters / status of one scan (copied to the host with one small D2H).
 struct ScanStatus
@@ -103,6 +107,8 @@ struct ScanStatus
   int n_sel;                    // surviving records of plain strings (ordered compaction)
   unsigned int any_error;       // some verifier reported an error (see report_error)
   unsigned int dbg[3];          // chain resolver step counters: list-insert walks, prune-loop steps, unvisited-scan steps
+  unsigned int n_retry3;        // fast-VM candidates that outgrew tier 2 as well (backward-mode lists hold duplicates)
+  unsigned int pad3[3];
 };
 
 struct CandOut
@@ -170,10 +176,18 @@ struct VerifyWs
   void* re2;   size_t re2_threads;
   uint32_t* retry_fast;
   uint32_t* retry_re;
+  uint32_t* retry_fast3;               // tier 2 -> tier 3 queue
+  void* fast3; size_t fast3_threads;   // tier 3: allocated only when something reaches it
 };
 
 void launch_verify(
     const DevRules& R, const ScanView& V, const CandOut& cands, const unsigned long long n_cand[NUM_CLS],
     const RawOut& out, const VerifyWs& W, cudaStream_t s, unsigned* launches);
 size_t fast_ws_bytes_per_thread(int tier);
+void launch_verify_tier2(
+    const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, bool fast, bool re,
+    cudaStream_t s, unsigned* launches);
+void launch_verify_fast_tier3(
+    const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, cudaStream_t s,
+    unsigned* launches);
 size_t re_ws_bytes_per_thread(uint32_t stack_words, int tier);

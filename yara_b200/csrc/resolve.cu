@@ -51,8 +51,9 @@ __global__ void build_key_a_kernel(
   const uint32_t sflags = R.S[r.string_idx].flags;
   uint64_t a;
 
-  if (r.group != YRB_NONE)
-    a = A_CHAIN_BIT | ((uint64_t) (r.group & 0x7FFFFF) << OFFSET_BITS) | (r.key >> KEY_I_SHIFT);
+  if (r.group != YRB_NONE) // seeds (earlier blocks) come before everything discovered in this block
+    a = A_CHAIN_BIT | ((uint64_t) (r.group & 0x7FFFFF) << OFFSET_BITS) |
+        ((r.misc & RAW_SEED) ? 0 : (r.key >> KEY_I_SHIFT) + 1);
   else
     a = ((uint64_t) r.string_idx << OFFSET_BITS) | (uint64_t) r.offset;
 
@@ -136,7 +137,7 @@ __global__ void write_plain_kernel(
   m.match_length = r.length;
   m.xor_key = (uint8_t) (r.misc & 0xFF);
   m.flags = 0;
-  m.reserved = 0;
+  m.seed = 0;
   m.chain_length = 0;
   out[k] = m;
 }
@@ -166,17 +167,26 @@ struct ChainLists
   int32_t* mcnt;
   int32_t* uvn;    // per record: next in its string's not-yet-visited list / in the ready list
   int32_t* uvhead; // per string
+  int32_t* prior;  // per string: matches[s] was already non-empty before this block
 };
 
 struct ChainCtx
 {
   Raw* sraw;      // the chain records gathered into sorted order (sraw[j] = raw[ix[j]])
+  const int64_t* seed_base;
+  int64_t cur_base;
   DevRules R;
   ChainLists L;
   unsigned int steps[3];
 };
 
 static __device__ __forceinline__ int64_t c_off(const ChainCtx& c, int32_t j) { return c.sraw[j].offset; }
+// base + offset, what _yr_scan_add_match_to_list orders and dedups by (scan.c:311-326)
+static __device__ __forceinline__ int64_t c_abs(const ChainCtx& c, int32_t j)
+{
+  const Raw& r = c.sraw[j];
+  return ((r.misc & RAW_SEED) ? c.seed_base[(r.misc >> 8) & 0xFFFF] : c.cur_base) + r.offset;
+}
 
 // scan.c:290-368 over index-linked lists; returns 0 ok / 1 duplicate dropped / 2 too many
 static __device__ int clist_add(ChainCtx& c, int32_t* head, int32_t* tail, int32_t* cnt, uint32_t s, int32_t j)
@@ -184,13 +194,13 @@ static __device__ int clist_add(ChainCtx& c, int32_t* head, int32_t* tail, int32
   if (cnt[s] == YRB_MAX_STRING_MATCHES)
     return 2;
 
-  const int64_t off = c_off(c, j);
+  const int64_t off = c_abs(c, j);
   int32_t ip = tail[s];
 
   while (ip >= 0)
   {
     c.steps[0]++;
-    const int64_t o = c_off(c, ip);
+    const int64_t o = c_abs(c, ip);
     if (off == o) return 1;
     if (off > o) break;
     ip = c.L.prv[ip];
@@ -447,6 +457,7 @@ __global__ void chain_init_kernel(ChainLists L, uint32_t num_strings)
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= num_strings) return;
   L.uhead[s] = L.utail[s] = L.mhead[s] = L.mtail[s] = L.uvhead[s] = -1;
+  L.prior[s] = 0;
   L.ucnt[s] = L.mcnt[s] = 0;
 }
 
@@ -464,7 +475,8 @@ __global__ void chain_gather_kernel(const Raw* raw, const uint32_t* ix, const ui
 
 __global__ void chain_resolve_kernel(
     Raw* sraw, const uint64_t* kA, uint32_t n, DevRules R, ChainLists L, yrb_match* finals,
-    yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap, int scan_flags)
+    yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap, int scan_flags,
+    const int64_t* seed_base, int64_t cur_base)
 {
   const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (j0 >= n) return;
@@ -476,6 +488,8 @@ __global__ void chain_resolve_kernel(
 
   ChainCtx c;
   c.sraw = sraw;
+  c.seed_base = seed_base;
+  c.cur_base = cur_base;
   c.R = R;
   c.L = L;
   c.steps[0] = c.steps[1] = c.steps[2] = 0;
@@ -507,6 +521,31 @@ __global__ void chain_resolve_kernel(
       L.where[j] = 0;
 
       const Raw r = sraw[j];
+
+      if (r.misc & RAW_SEED)
+      {
+        // state left by earlier blocks of this scan: goes straight back into its list
+        if (r.misc & RAW_SEED_MARK)
+        {
+          L.prior[r.string_idx] = 1;
+        }
+        else
+        {
+          L.clen[j] = (int32_t) r.key;
+          L.mlen[j] = r.length;
+          if (clist_add(c, L.uhead, L.utail, L.ucnt, r.string_idx, (int32_t) j) == 0)
+          {
+            L.where[j] = 1;
+            if (L.clen[j] == 0)
+            {
+              L.uvn[j] = L.uvhead[r.string_idx];
+              L.uvhead[r.string_idx] = (int32_t) j;
+            }
+          }
+        }
+        continue;
+      }
+
       if (r.key == prev_key) continue; // re-emission of the same callback by the tier-2 verifier
       prev_key = r.key;
 
@@ -519,7 +558,7 @@ __global__ void chain_resolve_kernel(
       {
         cur_cand = r.key >> KEY_SEQ_BITS;
         skip_cand = (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) &&
-                    L.mcnt[r.string_idx] > 0;
+                    (L.mcnt[r.string_idx] > 0 || L.prior[r.string_idx]);
       }
       if (skip_cand) continue;
 
@@ -545,8 +584,8 @@ __global__ void chain_resolve_kernel(
       m.string_idx = head_string;
       m.match_length = L.mlen[k];
       m.xor_key = (uint8_t) (r.misc & 0xFF);
-      m.flags = 0;
-      m.reserved = 0;
+      m.flags = (r.misc & RAW_SEED) ? YRB_MATCH_FROM_SEED : 0;
+      m.seed = (uint16_t) ((r.misc >> 8) & 0xFFFF);
       m.chain_length = L.clen[k];
       finals[slot++] = m;
     }
@@ -568,8 +607,8 @@ __global__ void chain_resolve_kernel(
       m.string_idx = r.string_idx;
       m.match_length = L.mlen[k];
       m.xor_key = (uint8_t) (r.misc & 0xFF);
-      m.flags = YRB_MATCH_UNCONFIRMED;
-      m.reserved = 0;
+      m.flags = YRB_MATCH_UNCONFIRMED | ((r.misc & RAW_SEED) ? YRB_MATCH_FROM_SEED : 0);
+      m.seed = (uint16_t) ((r.misc >> 8) & 0xFFFF);
       m.chain_length = L.clen[k];
       unconf[slot] = m;
     }
@@ -696,10 +735,11 @@ void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches)
     L.mhead = w.s_lists + 3 * (size_t) w.R.num_strings; L.mtail = w.s_lists + 4 * (size_t) w.R.num_strings;
     L.mcnt = w.s_lists + 5 * (size_t) w.R.num_strings;
     L.uvhead = w.s_lists + 6 * (size_t) w.R.num_strings;
+    L.prior = w.s_lists + 7 * (size_t) w.R.num_strings;
     L.uvn = w.c_uvn;
     chain_init_kernel<<<GRID(w.R.num_strings), 0, s>>>(L, w.R.num_strings);
     chain_gather_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.sraw);
-    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.sraw, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags);
+    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.sraw, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags, w.seed_base, w.cur_base);
     (*launches) += 3;
   }
 }

@@ -12,6 +12,8 @@ struct ResolveWork
   int scan_flags;
   int has_chains;
   int use_cut;
+  const int64_t* seed_base;   // per seed: YR_MATCH.base (device)
+  int64_t cur_base;           // base of the block being scanned
 
   // scratch, all sized for n_raw records unless noted
   uint64_t* k0;
@@ -35,7 +37,7 @@ struct ResolveWork
   unsigned long long* str_min_key; // num_strings
   unsigned long long* str_cut_key; // num_strings, ~0 = no cut
   uint32_t* str_count;             // num_strings
-  int32_t* s_lists;                // 7 * num_strings
+  int32_t* s_lists;                // 8 * num_strings
 
   // outputs
   yrb_match* finals;

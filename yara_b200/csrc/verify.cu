@@ -118,13 +118,15 @@ static __device__ __forceinline__ int32_t code_i32(const Ctx& c, uint32_t off)
 
 #define FAST_POS_CAP 4608       // tier 2: more than any forward-mode list can hold (<= 4097 distinct positions)
 #define FAST_POS_CAP_SMALL 96   // tier 1: what almost every candidate needs
+#define FAST_POS_CAP_HUGE (1 << 20) // tier 3: backward-mode lists are not kept duplicate-free by the reference
+                                    // (re.c:2323-2333) and can grow far beyond the window
 #define WS_RETRY (-2)           // internal: the small work area overflowed, verify again in tier 2
 
 struct FastPos
 {
   int32_t input;   // relative to the exec's input position
   int32_t round;
-  int16_t prev, next;
+  int32_t prev, next;
 };
 
 struct FastWs
@@ -133,7 +135,8 @@ struct FastWs
   int cap;
 };
 
-size_t fast_ws_bytes_per_thread(int tier) { return sizeof(FastPos) * (size_t) (tier == 1 ? FAST_POS_CAP_SMALL : FAST_POS_CAP); }
+size_t fast_ws_bytes_per_thread(int tier)
+{ return sizeof(FastPos) * (size_t) (tier == 1 ? FAST_POS_CAP_SMALL : tier == 2 ? FAST_POS_CAP : FAST_POS_CAP_HUGE); }
 
 // re.c:2150-2477.  Returns an ERROR_* code.  `pos` = block position of input_data.
 static __device__ int re_fast_exec(
@@ -264,10 +267,10 @@ static __device__ int re_fast_exec(
 
           P[ni].input = next_input;
           P[ni].round = round + 1;
-          P[ni].prev = (int16_t) insertion_point;
+          P[ni].prev = insertion_point;
           P[ni].next = P[insertion_point].next;
-          P[insertion_point].next = (int16_t) ni;
-          if (P[ni].next >= 0) P[P[ni].next].prev = (int16_t) ni;
+          P[insertion_point].next = ni;
+          if (P[ni].next >= 0) P[P[ni].next].prev = ni;
           if (insertion_point == last) last = ni;
         }
 
@@ -311,7 +314,7 @@ static __device__ int re_fast_exec(
         if (current == last) last = P[current].prev;
         if (P[current].prev >= 0) P[P[current].prev].next = P[current].next;
         if (P[current].next >= 0) P[P[current].next].prev = P[current].prev;
-        P[current].next = (int16_t) free_head;
+        P[current].next = free_head;
         free_head = current;
       }
 
@@ -1092,11 +1095,12 @@ verify_literal_kernel(DevRules R, ScanView V, const Cand* cands, unsigned long l
 // and verified again from scratch by tier 2 with the reference's full limits.
 // Records a candidate emitted before overflowing are emitted again with the same
 // discovery keys; resolve.cu treats equal keys as one record.
-template <bool TIER2>
+// TIER 1: every candidate; TIER 2: the retry queue of tier 1; TIER 3: the retry queue of tier 2
+template <int TIER>
 __global__ void __launch_bounds__(128)
 verify_fast_kernel(
     DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out, uint8_t* ws, size_t ws_per_thread,
-    int cap, uint32_t* retry)
+    int cap, const uint32_t* retry, uint32_t* retry_next)
 {
   const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
@@ -1104,11 +1108,12 @@ verify_fast_kernel(
   my.v = reinterpret_cast<FastPos*>(ws + tid * ws_per_thread);
   my.cap = cap;
 
-  if (TIER2) n = out.st->n_retry[0];
+  if (TIER == 2) n = out.st->n_retry[0];
+  if (TIER == 3) n = out.st->n_retry3;
 
   for (unsigned long long t = tid; t < n; t += stride)
   {
-    const unsigned long long ci = TIER2 ? retry[t] : t;
+    const unsigned long long ci = TIER > 1 ? retry[t] : t;
     const Cand cd = cands[ci];
     const yrb_acm m = R.acm[cd.acm_idx];
     const yrb_string s = R.S[m.string_idx];
@@ -1117,12 +1122,17 @@ verify_fast_kernel(
     int rc = verify_re<true>(c, &my, nullptr, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
     if (rc == WS_RETRY)
     {
-      if (!TIER2)
+      if (TIER == 1)
       {
-        retry[atomicAdd(&out.st->n_retry[0], 1u)] = (uint32_t) ci;
+        retry_next[atomicAdd(&out.st->n_retry[0], 1u)] = (uint32_t) ci;
         continue;
       }
-      atomicExch(&out.st->ws_overflow, 1u);
+      if (TIER == 2)
+      {
+        retry_next[atomicAdd(&out.st->n_retry3, 1u)] = (uint32_t) ci;
+        continue;
+      }
+      atomicExch(&out.st->ws_overflow, 1u); // the reference would still be calling malloc: give up honestly
       rc = YRB_ERROR_INSUFFICIENT_MEMORY;
     }
     if (rc != YRB_SUCCESS)
@@ -1197,12 +1207,10 @@ void launch_verify(
     unsigned blocks = (unsigned) ((threads + T - 1) / T);
     if ((unsigned long long) blocks * T > W.fast1_threads) blocks = (unsigned) (W.fast1_threads / T);
     if (blocks == 0) blocks = 1;
-    verify_fast_kernel<false><<<blocks, T, 0, s>>>(
+    verify_fast_kernel<1><<<blocks, T, 0, s>>>(
         R, V, cands.cand[CLS_FAST], n_cand[CLS_FAST], out, (uint8_t*) W.fast1, fast_ws_bytes_per_thread(1),
-        FAST_POS_CAP_SMALL, W.retry_fast);
-    verify_fast_kernel<true><<<(unsigned) (W.fast2_threads / T), T, 0, s>>>(
-        R, V, cands.cand[CLS_FAST], 0, out, (uint8_t*) W.fast2, fast_ws_bytes_per_thread(2), FAST_POS_CAP, W.retry_fast);
-    (*launches) += 2;
+        FAST_POS_CAP_SMALL, nullptr, W.retry_fast);
+    (*launches)++;
   }
 
   if (n_cand[CLS_RE] > 0)
@@ -1214,9 +1222,39 @@ void launch_verify(
     verify_re_kernel<false><<<blocks, T, 0, s>>>(
         R, V, cands.cand[CLS_RE], n_cand[CLS_RE], out, (uint8_t*) W.re1, re_ws_bytes_per_thread(R.stack_words, 1),
         RE_FIBERS_SMALL, W.retry_re);
-    verify_re_kernel<true><<<(unsigned) (W.re2_threads / T), T, 0, s>>>(
+    (*launches)++;
+  }
+}
+
+// Tier 2 (and 3) run only when tier 1 (2) queued something: their work areas are big
+// and most scans never need them.
+void launch_verify_tier2(
+    const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, bool fast, bool re,
+    cudaStream_t s, unsigned* launches)
+{
+  const int T = 128;
+  if (fast)
+  {
+    verify_fast_kernel<2><<<(unsigned) ((W.fast2_threads + T - 1) / T), T, 0, s>>>(
+        R, V, cands.cand[CLS_FAST], 0, out, (uint8_t*) W.fast2, fast_ws_bytes_per_thread(2), FAST_POS_CAP, W.retry_fast,
+        W.retry_fast3);
+    (*launches)++;
+  }
+  if (re)
+  {
+    verify_re_kernel<true><<<(unsigned) ((W.re2_threads + T - 1) / T), T, 0, s>>>(
         R, V, cands.cand[CLS_RE], 0, out, (uint8_t*) W.re2, re_ws_bytes_per_thread(R.stack_words, 2),
         YRB_RE_MAX_FIBERS, W.retry_re);
-    (*launches) += 2;
+    (*launches)++;
   }
+}
+
+void launch_verify_fast_tier3(
+    const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, cudaStream_t s,
+    unsigned* launches)
+{
+  verify_fast_kernel<3><<<(unsigned) ((W.fast3_threads + 31) / 32), 32, 0, s>>>(
+      R, V, cands.cand[CLS_FAST], 0, out, (uint8_t*) W.fast3, fast_ws_bytes_per_thread(3), FAST_POS_CAP_HUGE,
+      W.retry_fast3, nullptr);
+  (*launches)++;
 }

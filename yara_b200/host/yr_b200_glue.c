@@ -34,6 +34,8 @@ typedef struct rules_entry
   YR_RULES* rules;
   yrb_rules* dev;
   int device;
+  uint32_t* chain_strings; /* idx of every STRING_FLAGS_CHAIN_PART string */
+  uint32_t n_chain_strings;
   struct rules_entry* next;
 } rules_entry;
 
@@ -42,6 +44,7 @@ typedef struct scanner_entry
   YR_SCANNER* scanner;
   yrb_scanner* dev;
   yrb_rules* dev_rules;
+  rules_entry* re;
   struct scanner_entry* next;
 } scanner_entry;
 
@@ -80,7 +83,7 @@ static int fail_loudly(const char* what, int rc)
 }
 
 /* rules upload, lazily on first scan, shared by all scanners of this YR_RULES */
-static int get_rules(YR_RULES* rules, yrb_rules** out)
+static int get_rules(YR_RULES* rules, rules_entry** out)
 {
   int device = current_device();
   rules_entry* e;
@@ -89,7 +92,7 @@ static int get_rules(YR_RULES* rules, yrb_rules** out)
   {
     if (e->rules == rules && e->device == device)
     {
-      *out = e->dev;
+      *out = e;
       return ERROR_SUCCESS;
     }
   }
@@ -115,13 +118,27 @@ static int get_rules(YR_RULES* rules, yrb_rules** out)
   e->rules = rules;
   e->dev = dev;
   e->device = device;
+
+  for (uint32_t i = 0; i < rules->num_strings; i++)
+    if (STRING_IS_CHAIN_PART(&rules->strings_table[i]))
+      e->n_chain_strings++;
+
+  if (e->n_chain_strings > 0)
+  {
+    e->chain_strings = (uint32_t*) malloc(sizeof(uint32_t) * e->n_chain_strings);
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < rules->num_strings && e->chain_strings != NULL; i++)
+      if (STRING_IS_CHAIN_PART(&rules->strings_table[i]))
+        e->chain_strings[k++] = i;
+  }
+
   e->next = g_rules;
   g_rules = e;
-  *out = dev;
+  *out = e;
   return ERROR_SUCCESS;
 }
 
-static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out)
+static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out, rules_entry** re_out)
 {
   scanner_entry* e;
   int rc = ERROR_SUCCESS;
@@ -133,13 +150,17 @@ static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out)
     if (e->scanner == scanner)
     {
       *out = e->dev;
+      *re_out = e->re;
       pthread_mutex_unlock(&g_lock);
       return ERROR_SUCCESS;
     }
   }
 
+  rules_entry* re = NULL;
   yrb_rules* dev_rules = NULL;
-  rc = get_rules(scanner->rules, &dev_rules);
+  rc = get_rules(scanner->rules, &re);
+  if (rc == ERROR_SUCCESS)
+    dev_rules = re->dev;
 
   if (rc == ERROR_SUCCESS)
   {
@@ -169,9 +190,11 @@ static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out)
       e->scanner = scanner;
       e->dev = dev;
       e->dev_rules = dev_rules;
+      e->re = re;
       e->next = g_scanners;
       g_scanners = e;
       *out = dev;
+      *re_out = re;
     }
   }
 
@@ -230,6 +253,7 @@ void yr_b200_rules_release(YR_RULES* rules)
         }
       }
       yrb_rules_release(e->dev);
+      free(e->chain_strings);
       free(e);
       continue;
     }
@@ -303,7 +327,7 @@ static int too_many_protocol(YR_SCANNER* scanner, YR_STRING* string)
 
 static int materialise(
     YR_SCANNER* scanner, const uint8_t* block_data, YR_MEMORY_BLOCK* block, const yrb_match* recs, size_t n,
-    YR_MATCHES* lists, int confirmed, uint32_t max_match_data)
+    YR_MATCHES* lists, int confirmed, uint32_t max_match_data, YR_MATCH** seed_nodes)
 {
   YR_RULES* rules = scanner->rules;
 
@@ -314,6 +338,42 @@ static int materialise(
 
     if (yr_bitmask_is_set(scanner->strings_temp_disabled, string->idx))
       continue; /* disabled in an earlier block of this scan (scan.c:1018) */
+
+    if ((r->flags & YRB_MATCH_FROM_SEED) && seed_nodes != NULL)
+    {
+      /* a YR_MATCH node an earlier block created: it keeps its base and offset */
+      YR_MATCH* node = seed_nodes[r->seed];
+      node->prev = node->next = NULL;
+      node->chain_length = r->chain_length;
+
+      if (confirmed)
+      {
+        /* scan.c:561-576: total length up to the tail, data re-copied from the CURRENT block at
+           the node's own (block-relative) offset; the reference reads whatever lies there */
+        node->match_length = r->match_length;
+        node->data_length = r->match_length < (int32_t) max_match_data ? r->match_length : (int32_t) max_match_data;
+        if (node->data_length < 0) node->data_length = 0;
+        uint8_t* d = (uint8_t*) yr_notebook_alloc(scanner->matches_notebook, node->data_length > 0 ? node->data_length : 1);
+        if (d == NULL)
+          return ERROR_INSUFFICIENT_MEMORY;
+        memset(d, 0, node->data_length);
+        if (node->offset >= 0 && (size_t) node->offset < block->size)
+        {
+          size_t avail = block->size - (size_t) node->offset;
+          memcpy(d, block_data + node->offset, avail < (size_t) node->data_length ? avail : (size_t) node->data_length);
+        }
+        node->data = d;
+      }
+
+      int rcs = add_match_to_list(node, &lists[string->idx], 0);
+      if (rcs == ERROR_TOO_MANY_MATCHES)
+      {
+        rcs = too_many_protocol(scanner, string);
+        if (rcs != ERROR_SUCCESS)
+          return rcs;
+      }
+      continue;
+    }
 
     YR_MATCH* m = (YR_MATCH*) yr_notebook_alloc(scanner->matches_notebook, sizeof(YR_MATCH));
     if (m == NULL)
@@ -357,16 +417,78 @@ static int materialise(
   return ERROR_SUCCESS;
 }
 
+/* What earlier blocks of this scan left in unconfirmed_matches[] of the chained
+   strings (and which chain heads already have confirmed matches): handed to the
+   engine so that chains whose parts lie in different blocks resolve exactly as in
+   the reference, which keeps these lists across blocks (types.h:806-816). */
+static int collect_seeds(YR_SCANNER* scanner, rules_entry* re, yrb_seed** seeds_out, YR_MATCH*** nodes_out, uint32_t* n_out)
+{
+  uint32_t n = 0;
+  *seeds_out = NULL;
+  *nodes_out = NULL;
+  *n_out = 0;
+
+  for (uint32_t k = 0; k < re->n_chain_strings; k++)
+  {
+    uint32_t idx = re->chain_strings[k];
+    n += (uint32_t) scanner->unconfirmed_matches[idx].count;
+    if (scanner->matches[idx].head != NULL)
+      n++;
+  }
+
+  if (n == 0 || n > 65535)
+    return ERROR_SUCCESS; /* beyond 65535 carried nodes the continuation is dropped (documented) */
+
+  yrb_seed* seeds = (yrb_seed*) calloc(n, sizeof(yrb_seed));
+  YR_MATCH** nodes = (YR_MATCH**) calloc(n, sizeof(YR_MATCH*));
+  if (seeds == NULL || nodes == NULL)
+  {
+    free(seeds);
+    free(nodes);
+    return ERROR_INSUFFICIENT_MEMORY;
+  }
+
+  uint32_t i = 0;
+  for (uint32_t k = 0; k < re->n_chain_strings; k++)
+  {
+    uint32_t idx = re->chain_strings[k];
+    for (YR_MATCH* m = scanner->unconfirmed_matches[idx].head; m != NULL && i < n; m = m->next)
+    {
+      seeds[i].base = m->base;
+      seeds[i].offset = m->offset;
+      seeds[i].string_idx = idx;
+      seeds[i].match_length = m->match_length;
+      seeds[i].chain_length = m->chain_length;
+      seeds[i].xor_key = m->xor_key;
+      seeds[i].kind = 0;
+      nodes[i] = m;
+      i++;
+    }
+    if (scanner->matches[idx].head != NULL && i < n)
+    {
+      seeds[i].string_idx = idx;
+      seeds[i].kind = 1;
+      i++;
+    }
+  }
+
+  *seeds_out = seeds;
+  *nodes_out = nodes;
+  *n_out = i;
+  return ERROR_SUCCESS;
+}
+
 int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_MEMORY_BLOCK* block)
 {
   yrb_scanner* dev = NULL;
+  rules_entry* re = NULL;
   uint32_t max_match_data;
   int rc;
 
   if (scanner->timeout > 0 && yr_stopwatch_elapsed_ns(&scanner->stopwatch) > scanner->timeout)
     return ERROR_SCAN_TIMEOUT;
 
-  rc = get_scanner(scanner, &dev);
+  rc = get_scanner(scanner, &dev, &re);
   if (rc != ERROR_SUCCESS)
     return rc;
 
@@ -378,6 +500,18 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
   params.scan_flags = scanner->flags;
   params.too_many_action = 0; /* the user's answer is only known after asking: see below */
 
+  yrb_seed* seeds = NULL;
+  YR_MATCH** seed_nodes = NULL;
+  uint32_t n_seeds = 0;
+  if (re->n_chain_strings > 0 && re->chain_strings != NULL)
+  {
+    rc = collect_seeds(scanner, re, &seeds, &seed_nodes, &n_seeds);
+    if (rc != ERROR_SUCCESS)
+      return rc;
+    params.seeds = seeds;
+    params.n_seeds = n_seeds;
+  }
+
   static int timing = -1;
   if (timing < 0) timing = getenv("YRB_TIMING") != NULL;
   struct timespec t0, t1, t2;
@@ -386,14 +520,30 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
   yrb_scan_result res;
   rc = yrb_scan_host(dev, block_data, block->size, &params, &res);
   if (timing) clock_gettime(CLOCK_MONOTONIC, &t1);
+  free(seeds);
   if (rc != YRB_SUCCESS)
+  {
+    free(seed_nodes);
     return rc < 1000 ? rc : fail_loudly("yrb_scan_host", rc);
+  }
 
   if (res.error != 0)
   {
+    free(seed_nodes);
     if (res.error_string != YRB_NONE)
       scanner->last_error_string = &scanner->rules->strings_table[res.error_string];
     return res.error;
+  }
+
+  if (res.seeds_consumed)
+  {
+    /* `unconfirmed` is the complete new state of the chained strings' lists: rebuild them */
+    for (uint32_t k = 0; k < re->n_chain_strings; k++)
+    {
+      YR_MATCHES* l = &scanner->unconfirmed_matches[re->chain_strings[k]];
+      l->head = l->tail = NULL;
+      l->count = 0;
+    }
   }
 
   /* In fast mode a SINGLE_MATCH string that already matched in an earlier block is
@@ -412,12 +562,15 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
     res.n_matches = k;
   }
 
-  rc = materialise(scanner, block_data, block, res.matches, res.n_matches, scanner->matches, 1, max_match_data);
-  if (rc != ERROR_SUCCESS)
-    return rc;
-
   rc = materialise(
-      scanner, block_data, block, res.unconfirmed, res.n_unconfirmed, scanner->unconfirmed_matches, 0, max_match_data);
+      scanner, block_data, block, res.matches, res.n_matches, scanner->matches, 1, max_match_data, seed_nodes);
+
+  if (rc == ERROR_SUCCESS)
+    rc = materialise(
+        scanner, block_data, block, res.unconfirmed, res.n_unconfirmed, scanner->unconfirmed_matches, 0,
+        max_match_data, seed_nodes);
+
+  free(seed_nodes);
   if (rc != ERROR_SUCCESS)
     return rc;
 
