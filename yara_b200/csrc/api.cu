@@ -474,7 +474,7 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
   if (hs->err_key != ~0ULL && (hs->err_key | KEY_SEQ_MAX) < (first_abort | KEY_SEQ_MAX))
   {
     res->error = (int32_t) (hs->err_key & KEY_SEQ_MAX);
-    res->error_string = YRB_NONE;
+    res->error_string = hs->err_string < s->rules->R.num_strings ? hs->err_string : YRB_NONE;
   }
   return YRB_SUCCESS;
 }
@@ -552,6 +552,7 @@ static int scan_impl(
   {
     CK(cudaMemsetAsync(s->d_status, 0, sizeof(ScanStatus), s->stream));
     CK(cudaMemsetAsync(&s->d_status->err_key, 0xFF, sizeof(unsigned long long), s->stream));
+    CK(cudaMemsetAsync(&s->d_status->err_string, 0xFF, sizeof(unsigned int), s->stream));
 
     CandOut co;
     for (int c = 0; c < NUM_CLS; c++) { co.cand[c] = s->d_cand[c].p; co.cap[c] = s->d_cand[c].cap; }
@@ -756,7 +757,11 @@ static int scan_impl(
       launch_error_select(w, s->str_err.p, false, s->stream);
       int rc2 = read_status(s);
       if (rc2 != YRB_SUCCESS) return rc2;
-      if (hs->err_key != ~0ULL) res->error = (int32_t) (hs->err_key & KEY_SEQ_MAX);
+      if (hs->err_key != ~0ULL)
+      {
+        res->error = (int32_t) (hs->err_key & KEY_SEQ_MAX);
+        res->error_string = hs->err_string < s->rules->R.num_strings ? hs->err_string : YRB_NONE;
+      }
     }
     CK(cudaEventRecord(s->ev[3], s->stream));
     CK(cudaStreamSynchronize(s->stream));

@@ -108,7 +108,8 @@ struct ScanStatus
   unsigned int any_error;       // some verifier reported an error (see report_error)
   unsigned int dbg[3];          // chain resolver step counters: list-insert walks, prune-loop steps, unvisited-scan steps
   unsigned int n_retry3;        // fast-VM candidates that outgrew tier 2 as well (backward-mode lists hold duplicates)
-  unsigned int pad3[3];
+  unsigned int err_string;      // string of the candidate behind err_key (scanner->last_error_string)
+  unsigned int pad3[2];
 };
 
 struct CandOut

@@ -646,10 +646,20 @@ __global__ void error_select_kernel(
   atomicMin(&st->err_key, e);
 }
 
+// scan.c:1085-1086: last_error_string = the string of the failing candidate
+__global__ void error_string_kernel(const unsigned long long* str_err, uint32_t num_strings, ScanStatus* st)
+{
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= num_strings) return;
+  if (st->err_key != ~0ULL && str_err[s] == st->err_key)
+    st->err_string = s;
+}
+
 void launch_error_select(ResolveWork& w, unsigned long long* str_err, bool have_min_key, cudaStream_t s)
 {
   error_select_kernel<<<(w.R.num_strings + 255) / 256, 256, 0, s>>>(
       str_err, have_min_key ? w.str_min_key : nullptr, w.use_cut ? w.str_cut_key : nullptr, w.R, w.scan_flags, w.st);
+  error_string_kernel<<<(w.R.num_strings + 255) / 256, 256, 0, s>>>(str_err, w.R.num_strings, w.st);
 }
 
 // ---------------------------------------------------------------- 1M cap (a10)
