@@ -157,6 +157,10 @@ void yrb_rules_release(yrb_rules* rules);
 int yrb_scanner_create(yrb_rules* rules, yrb_scanner** out);
 void yrb_scanner_destroy(yrb_scanner* scanner);
 int yrb_scanner_set_option(yrb_scanner* scanner, int option, uint64_t value);
+/* Device bytes held by the scanner's block buffer; yrb_scanner_trim frees it (it is
+   re-allocated by the next scan).  Lets a pool of idle scanners bound its HBM use. */
+size_t yrb_scanner_footprint(yrb_scanner* scanner);
+void yrb_scanner_trim(yrb_scanner* scanner);
 
 /* Scan one block held in host memory: H2D (sliced, overlapped with the scan
    kernel), AC scan, verification, resolve, D2H of the match records. */

@@ -266,6 +266,20 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   delete s;
 }
 
+extern "C" size_t yrb_scanner_footprint(yrb_scanner* s)
+{
+  return s ? s->d_data.cap : 0;
+}
+
+extern "C" void yrb_scanner_trim(yrb_scanner* s)
+{
+  if (!s) return;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  cudaStreamSynchronize(s->copy_stream);
+  s->d_data.release();
+}
+
 extern "C" int yrb_scanner_set_option(yrb_scanner* s, int option, uint64_t value)
 {
   if (!s) return YRB_ERROR_BAD_ARGUMENT;

@@ -60,6 +60,8 @@ typedef struct pool_entry
 } pool_entry;
 static pool_entry g_pool[YR_B200_POOL_MAX];
 static int g_pool_n = 0;
+/* idle scanners may keep at most this many bytes of block buffers between them */
+#define YR_B200_POOL_BYTES ((size_t) 48 << 30)
 
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static rules_entry* g_rules = NULL;
@@ -214,6 +216,10 @@ void yr_b200_scanner_release(YR_SCANNER* scanner)
       *pp = e->next;
       if (g_pool_n < YR_B200_POOL_MAX)
       {
+        size_t held = yrb_scanner_footprint(e->dev);
+        for (int i = 0; i < g_pool_n; i++) held += yrb_scanner_footprint(g_pool[i].dev);
+        if (held > YR_B200_POOL_BYTES)
+          yrb_scanner_trim(e->dev);
         g_pool[g_pool_n].dev = e->dev;
         g_pool[g_pool_n].dev_rules = e->dev_rules;
         g_pool_n++;
