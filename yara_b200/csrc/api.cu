@@ -196,6 +196,10 @@ extern "C" int yrb_rules_create(const void* image, size_t image_size, int device
   int rc = build_filter_tables(image, device, &r->F, &r->d_filter);
   if (rc != YRB_SUCCESS) { cudaFree(r->d_image); delete r; return rc; }
 
+  // cudaMemcpy from pageable memory may return before the DMA has landed, and the
+  // scanners run on non-blocking streams that do not order after the legacy stream
+  CK(cudaDeviceSynchronize());
+
   *out = r;
   return YRB_SUCCESS;
 }
@@ -366,7 +370,7 @@ static void fill_work(yrb_scanner* s, ResolveWork& w, const Raw* raw, uint32_t n
   w.n_raw = n;
   w.R = s->rules->R;
   w.scan_flags = scan_flags;
-  w.has_chains = s->rules->h.num_chains > 0;
+  w.has_chains = s->rules->h.num_chains > 0;   // refined by the callers: chain records or seeds present
   w.use_cut = 0;
   w.seed_base = s->seed_base.p;
   w.cur_base = 0;
@@ -383,7 +387,7 @@ static void fill_work(yrb_scanner* s, ResolveWork& w, const Raw* raw, uint32_t n
 
 // Resolve `n` raw records resident at d_raw; fills result (matches, unconfirmed, too_many, error).
 static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_scan_params* params, yrb_scan_result* res,
-                       unsigned* launches)
+                       unsigned* launches, bool chain_records)
 {
   ScanStatus* hs = s->h_status;
   res->n_matches = res->n_unconfirmed = 0;
@@ -399,6 +403,7 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
     ResolveWork w;
     fill_work(s, w, d_raw, n, params->scan_flags);
     w.cur_base = (int64_t) params->base;
+    if (!chain_records) w.has_chains = 0;   // nothing for the chain kernels to do: three launches less
 
     for (int pass = 0;; pass++)
     {
@@ -485,10 +490,11 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
     res->error = YRB_ERROR_TOO_MANY_MATCHES;
     res->error_string = res->too_many[0];
   }
-  if (hs->err_key != ~0ULL && (hs->err_key | KEY_SEQ_MAX) < (first_abort | KEY_SEQ_MAX))
+  const unsigned long long err_key = ~hs->err_key_inv;
+  if (hs->err_key_inv != 0ULL && (err_key | KEY_SEQ_MAX) < (first_abort | KEY_SEQ_MAX))
   {
-    res->error = (int32_t) (hs->err_key & KEY_SEQ_MAX);
-    res->error_string = hs->err_string < s->rules->R.num_strings ? hs->err_string : YRB_NONE;
+    res->error = (int32_t) (err_key & KEY_SEQ_MAX);
+    res->error_string = hs->err_string1 ? hs->err_string1 - 1 : YRB_NONE;
   }
   return YRB_SUCCESS;
 }
@@ -565,8 +571,6 @@ static int scan_impl(
   for (int attempt = 0;; attempt++)
   {
     CK(cudaMemsetAsync(s->d_status, 0, sizeof(ScanStatus), s->stream));
-    CK(cudaMemsetAsync(&s->d_status->err_key, 0xFF, sizeof(unsigned long long), s->stream));
-    CK(cudaMemsetAsync(&s->d_status->err_string, 0xFF, sizeof(unsigned int), s->stream));
 
     CandOut co;
     for (int c = 0; c < NUM_CLS; c++) { co.cand[c] = s->d_cand[c].p; co.cap[c] = s->d_cand[c].cap; }
@@ -729,10 +733,9 @@ static int scan_impl(
     if (attempt > 2) return YRB_ERROR_INTERNAL_FATAL;
     if (s->d_raw.ensure((size_t) hs->n_raw + 1024) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
     CK(cudaMemsetAsync(&s->d_status->n_raw, 0, sizeof(unsigned long long), s->stream));
-    CK(cudaMemsetAsync(&s->d_status->err_key, 0xFF, sizeof(unsigned long long), s->stream));
     CK(cudaMemsetAsync(&s->d_status->n_retry[0], 0, 2 * sizeof(unsigned int), s->stream));
     CK(cudaMemsetAsync(&s->d_status->any_error, 0, sizeof(unsigned int), s->stream));
-    CK(cudaMemsetAsync(&s->d_status->n_retry3, 0, sizeof(unsigned int), s->stream));
+    CK(cudaMemsetAsync(&s->d_status->n_retry3, 0, 2 * sizeof(unsigned int), s->stream));   // n_retry3, n_chain_raw
   }
 
   if (hs->margin_fault)
@@ -771,10 +774,10 @@ static int scan_impl(
       launch_error_select(w, s->str_err.p, false, s->stream);
       int rc2 = read_status(s);
       if (rc2 != YRB_SUCCESS) return rc2;
-      if (hs->err_key != ~0ULL)
+      if (hs->err_key_inv != 0ULL)
       {
-        res->error = (int32_t) (hs->err_key & KEY_SEQ_MAX);
-        res->error_string = hs->err_string < s->rules->R.num_strings ? hs->err_string : YRB_NONE;
+        res->error = (int32_t) (~hs->err_key_inv & KEY_SEQ_MAX);
+        res->error_string = hs->err_string1 ? hs->err_string1 - 1 : YRB_NONE;
       }
     }
     CK(cudaEventRecord(s->ev[3], s->stream));
@@ -782,7 +785,7 @@ static int scan_impl(
   }
   else
   {
-    rc = run_resolve(s, s->d_raw.p, n_resolve, params, res, &launches);
+    rc = run_resolve(s, s->d_raw.p, n_resolve, params, res, &launches, hs->n_chain_raw > 0 || n_resolve > (uint32_t) n_raw);
     res->seeds_consumed = (n_resolve > (uint32_t) n_raw) ? 1 : 0;
     CK(cudaEventRecord(s->ev[3], s->stream));
     CK(cudaStreamSynchronize(s->stream));
@@ -831,12 +834,11 @@ extern "C" int yrb_resolve_raw(
   if (s->d_raw.ensure(n_records ? n_records : 1) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
   CK(cudaEventRecord(s->ev[2], s->stream));
   CK(cudaMemsetAsync(s->d_status, 0, sizeof(ScanStatus), s->stream));
-  CK(cudaMemsetAsync(&s->d_status->err_key, 0xFF, sizeof(unsigned long long), s->stream));
   if (n_records)
     CK(cudaMemcpyAsync(s->d_raw.p, records, n_records * sizeof(Raw), cudaMemcpyHostToDevice, s->stream));
   int rc = read_status(s);
   if (rc != YRB_SUCCESS) return rc;
-  rc = run_resolve(s, s->d_raw.p, (uint32_t) n_records, params, res, &launches);
+  rc = run_resolve(s, s->d_raw.p, (uint32_t) n_records, params, res, &launches, true);
   CK(cudaEventRecord(s->ev[3], s->stream));
   CK(cudaStreamSynchronize(s->stream));
   res->stats.n_raw = n_records;
@@ -1015,6 +1017,7 @@ extern "C" int yrb_dev_write(int device, void* d_ptr, size_t d_offset, const voi
   if (device < 0 || device >= yrb_device_count()) return YRB_ERROR_NO_DEVICE;
   CK(cudaSetDevice(device));
   CK(cudaMemcpy((uint8_t*) d_ptr + d_offset, src, bytes, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize()); // pageable source: the DMA may still be in flight when cudaMemcpy returns
   return YRB_SUCCESS;
 }
 

@@ -94,7 +94,8 @@ struct ScanStatus
 {
   unsigned long long n_cand[NUM_CLS];
   unsigned long long n_raw;
-  unsigned long long err_key;   // min over failing candidates of (key & ~seq) | error code
+  unsigned long long err_key_inv; // ~(min over failing candidates of (key & ~seq) | error code); 0 = no error
+                                  // (stored inverted so that a zero-filled status needs no second memset)
   unsigned long long n_final;
   unsigned long long n_unconf;
   unsigned long long n_chain_out;
@@ -108,8 +109,9 @@ struct ScanStatus
   unsigned int any_error;       // some verifier reported an error (see report_error)
   unsigned int dbg[3];          // chain resolver step counters: list-insert walks, prune-loop steps, unvisited-scan steps
   unsigned int n_retry3;        // fast-VM candidates that outgrew tier 2 as well (backward-mode lists hold duplicates)
-  unsigned int err_string;      // string of the candidate behind err_key (scanner->last_error_string)
-  unsigned int pad3[2];
+  unsigned int n_chain_raw;     // Raw records of chained strings (0: the chain kernels are skipped)
+  unsigned int err_string1;     // 1 + string of the candidate behind the error (scanner->last_error_string); 0 = none
+  unsigned int pad3[1];
 };
 
 struct CandOut

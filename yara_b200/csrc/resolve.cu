@@ -643,7 +643,7 @@ __global__ void error_select_kernel(
   if (str_cut_key != nullptr && str_cut_key[s] != ~0ULL && (str_cut_key[s] >> KEY_SEQ_BITS) < cand)
     return;
 
-  atomicMin(&st->err_key, e);
+  atomicMax(&st->err_key_inv, ~e);
 }
 
 // scan.c:1085-1086: last_error_string = the string of the failing candidate
@@ -651,8 +651,8 @@ __global__ void error_string_kernel(const unsigned long long* str_err, uint32_t 
 {
   const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= num_strings) return;
-  if (st->err_key != ~0ULL && str_err[s] == st->err_key)
-    st->err_string = s;
+  if (st->err_key_inv != 0ULL && str_err[s] == ~st->err_key_inv)
+    st->err_string1 = s + 1;
 }
 
 void launch_error_select(ResolveWork& w, unsigned long long* str_err, bool have_min_key, cudaStream_t s)
@@ -737,7 +737,7 @@ void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches)
   write_plain_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.ix0, w.st, n, w.finals);
   (*launches) += 4 + 10 + 3;
 
-  if (w.has_chains)
+  if (w.has_chains)   // the ruleset has chained strings AND this block produced records for them (or carries seeds)
   {
     ChainLists L;
     L.nxt = w.c_nxt; L.prv = w.c_prv; L.clen = w.c_clen; L.mlen = w.c_mlen; L.where = w.c_where;

@@ -90,6 +90,9 @@ static __device__ void match_callback(Ctx& c, int64_t match_pos, int32_t match_l
     c.out.raw[slot] = r;
   }
 
+  if (a.group != YRB_NONE)
+    atomicAdd(&c.out.st->n_chain_raw, 1u);
+
   c.seq++;
 }
 
