@@ -342,6 +342,11 @@ static int materialise(
     const yrb_match* r = &recs[i];
     YR_STRING* string = &rules->strings_table[r->string_idx];
 
+    /* the data copies below touch the block at random offsets (a cache and TLB miss each
+       in a multi-GiB block): get the next ones moving */
+    if (i + 12 < n && recs[i + 12].offset >= 0 && (size_t) recs[i + 12].offset < block->size)
+      __builtin_prefetch(block_data + recs[i + 12].offset);
+
     if (yr_bitmask_is_set(scanner->strings_temp_disabled, string->idx))
       continue; /* disabled in an earlier block of this scan (scan.c:1018) */
 
