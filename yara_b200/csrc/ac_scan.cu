@@ -20,18 +20,19 @@
 
 // ------------------------------------------------------------------ walk kernel
 
-#define WALK_CHUNK   256
+#define WALK_CHUNK       256   // bytes per thread for large ranges (3 bytes of look-back re-walk each)
+#define WALK_CHUNK_SMALL 32    // small ranges are latency bound: shorter dependent chains, more threads
 #define WALK_THREADS 128
 
 __global__ void __launch_bounds__(WALK_THREADS)
-ac_walk_kernel(DevRules R, ScanView V, CandOut out, int64_t lo, int64_t hi)
+ac_walk_kernel(DevRules R, ScanView V, CandOut out, int64_t lo, int64_t hi, int chunk)
 {
-  const int64_t a = lo + ((int64_t) blockIdx.x * WALK_THREADS + threadIdx.x) * WALK_CHUNK;
+  const int64_t a = lo + ((int64_t) blockIdx.x * WALK_THREADS + threadIdx.x) * chunk;
 
   if (a >= hi)
     return;
 
-  const int64_t b = (a + WALK_CHUNK < hi) ? a + WALK_CHUNK : hi;
+  const int64_t b = (a + chunk < hi) ? a + chunk : hi;
 
   int64_t p = a - 3;
   if (p < 0) p = 0;
@@ -100,9 +101,10 @@ void launch_ac_scan_walk(
   if (hi <= lo)
     return;
 
-  const int64_t nthreads = (hi - lo + WALK_CHUNK - 1) / WALK_CHUNK;
+  const int chunk = (hi - lo) < (8 << 20) ? WALK_CHUNK_SMALL : WALK_CHUNK;
+  const int64_t nthreads = (hi - lo + chunk - 1) / chunk;
   const unsigned blocks = (unsigned) ((nthreads + WALK_THREADS - 1) / WALK_THREADS);
-  ac_walk_kernel<<<blocks, WALK_THREADS, 0, s>>>(R, V, out, lo, hi);
+  ac_walk_kernel<<<blocks, WALK_THREADS, 0, s>>>(R, V, out, lo, hi, chunk);
 }
 
 // ---------------------------------------------------------------- filter kernel
