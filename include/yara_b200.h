@@ -173,6 +173,53 @@ int yrb_scan_device(
     yrb_scanner* scanner, const uint8_t* d_data, size_t size, const yrb_scan_params* params,
     yrb_scan_result* result);
 
+/*
+ * File batches (BASELINE config 4): many independent buffers --
+ * what cli/yara.c:365-457 feeds yr_rules_scan_file one at a time -- scanned with ONE
+ * launch sequence instead of ~20 launches and a few synchronisations each.  The items are
+ * concatenated in HBM; the Aho-Corasick guard `backtrack <= i` (scanner.c:104) is applied
+ * with i counted from the start of the item, which makes the candidates of every item
+ * exactly those of a scan that started at the root state there, and the verifiers see
+ * each item's own bounds.
+ *
+ * The batch runs the common, order-independent part of the resolve only.  An item whose
+ * result could depend on the rest (a chained string matched in it, a verifier raised an
+ * error in it, a string went over YR_MAX_STRING_MATCHES, SCAN_FLAGS_FAST_MODE is set,
+ * or the ruleset has zero-length atoms) is flagged YRB_ITEM_RESCAN and carries no
+ * matches: the caller scans it with yrb_scan_host, the general path.  For every other
+ * item the records equal those yrb_scan_host would return for it with base 0.
+ *
+ * With YRB_BATCH_ONE_ALLOCATION, items lying in ascending order inside one host
+ * allocation (at most 25 % of the span unused) keep their layout on the device and travel
+ * in large copies; anything else is packed at 16-byte boundaries with one copy per item.
+ * Pinned memory (yrb_host_alloc) is what makes either fast.
+ */
+typedef struct yrb_batch_item
+{
+  const uint8_t* data;
+  uint64_t size;
+} yrb_batch_item;
+
+#define YRB_ITEM_DONE   0
+#define YRB_ITEM_RESCAN 1
+
+typedef struct yrb_batch_result
+{
+  uint32_t n_items;
+  uint32_t n_rescan;          /* items flagged YRB_ITEM_RESCAN */
+  const uint8_t* item_state;  /* n_items entries */
+  const uint64_t* item_first; /* n_items + 1: item k owns matches[item_first[k] .. item_first[k+1]) */
+  const yrb_match* matches;   /* per item: string-major, ascending offsets relative to the item */
+  yrb_scan_stats stats;
+} yrb_batch_result;
+
+#define YRB_BATCH_ONE_ALLOCATION 1 /* all items lie inside ONE host allocation: the bytes between
+                                     them are readable and may be copied along */
+
+int yrb_scan_batch(
+    yrb_scanner* scanner, const yrb_batch_item* items, uint32_t n_items, int scan_flags, int batch_flags,
+    yrb_batch_result* result);
+
 /* Sharded scans: raw (pre-resolve) records of the last defer_resolve scan, as
    opaque 32-byte records in host memory ... */
 int yrb_shard_raw(yrb_scanner* scanner, const void** records, size_t* n_records);

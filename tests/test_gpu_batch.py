@@ -1,0 +1,180 @@
+"""GPU tests of yrb_scan_batch (include/yara_b200.h): a file batch scanned with one
+launch sequence must give, per item, exactly what a scan of that item alone gives --
+the reference scans every file from the root state with its own bounds
+(cli/yara.c:365-457 -> yr_rules_scan_file -> scanner.c:45-176)."""
+import random
+
+import numpy as np
+import pytest
+
+import yrh
+from yara_b200 import Engine, PinnedBuffer, synth
+from yara_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+def tuples(m):
+    return [(int(x["string_idx"]), int(x["offset"]), int(x["match_length"]), int(x["xor_key"])) for x in m]
+
+
+def canon(m):
+    return sorted(tuples(m))
+
+
+@pytest.fixture(scope="module", params=[4, 5])
+def setup(request):
+    # config 4: literals, hex with jumps (chains), nocase/wide/fullword, regexes; config 5: regexes, xor/base64
+    rs = synth.ruleset(request.param, 1500)
+    rules = yrh.b200().compile(rs.source)
+    image = rules.flatten()
+    return rs, image
+
+
+def make_items(rs, seed=3):
+    rng = random.Random(seed)
+    sizes = [0, 1, 3, 4, 5, 17, 100, 4096, 65536, 65537, 1 << 20, (1 << 20) + 3, 300000, 0, 70000, 2 * (1 << 20) + 11, 9, 33000]
+    sizes += [rng.randrange(8000, 70000) for _ in range(40)]   # small enough that many hold no chained-string plant
+    items = []
+    for k, n in enumerate(sizes):
+        if n >= 4096:
+            it = synth.corpus(rs, n, 4096 if n < 200000 else 2048, seed=100 + k, plant_seed=200 + k)
+        else:
+            it = synth.rand_bytes(100 + k, 0, n).copy()
+        items.append(it)
+    # instances cut in two by an item boundary must match in neither half; full instances at the very
+    # start / end of an item must match
+    plain = [sp for sp in rs.specs if sp.kind in ("text", "hexlit", "special", "textmod")][:6]
+    for j, sp in enumerate(plain):
+        inst = np.frombuffer(sp.instance(rng), dtype=np.uint8)
+        a, b = items[8 + j % 4], items[9 + j % 4]
+        cut = max(1, len(inst) // 2)
+        if len(a) > len(inst) and len(b) > len(inst):
+            a[len(a) - cut:] = inst[:cut]
+            b[: len(inst) - cut] = inst[cut:]
+    inst = np.frombuffer(plain[0].instance(rng), dtype=np.uint8)
+    items[4] = inst[:5].copy()           # a truncated instance as a whole tiny item
+    items[6] = np.concatenate([inst, synth.rand_bytes(5, 0, 100 - len(inst))]) if len(inst) < 100 else items[6]
+    return items
+
+
+def check_batch(eng, items, res, flags=0):
+    assert res.rc == 0
+    assert res.n_items == len(items)
+    n_rescan = 0
+    n_total = 0
+    for k, it in enumerate(items):
+        single = eng.scan_host(it, flags=flags)
+        assert single.rc == 0
+        if res.state[k] == api.ITEM_RESCAN:
+            n_rescan += 1
+            assert len(res.matches(k)) == 0
+            continue
+        assert single.error == 0
+        assert len(single.unconfirmed) == 0
+        got = tuples(res.matches(k))
+        # string-major, ascending offsets inside a string: the order yrb_scan_host uses for plain strings
+        assert got == tuples(single.matches), "item %d" % k
+        n_total += len(got)
+    assert n_rescan == res.n_rescan
+    return n_total, n_rescan
+
+
+@pytest.mark.parametrize("kernel", [api.KERNEL_FILTER, api.KERNEL_WALK])
+def test_packed_batch_equals_single_scans(setup, kernel):
+    rs, image = setup
+    eng = Engine(image, 0)
+    eng.set_option(api.OPT_SCAN_KERNEL, kernel)
+    items = make_items(rs)
+    res = eng.scan_batch(items)
+    n_total, n_rescan = check_batch(eng, items, res)
+    assert n_total > 50
+    # config 4 plants chained strings: some items must have been handed to the per-item path, not all
+    if any(sp.kind == "hexwild" for sp in rs.specs):
+        assert 0 < n_rescan < len(items)
+    assert res.stats["scan_kernel"] == kernel
+    eng.close()
+
+
+def test_batch_against_oracle(setup):
+    rs, image = setup
+    eng = Engine(image, 0)
+    items = make_items(rs, seed=9)[:12]
+    res = eng.scan_batch(items)
+    assert res.rc == 0
+    for k, it in enumerate(items):
+        if res.state[k] == api.ITEM_RESCAN:
+            continue
+        want = yrh.oracle_scan(image, it)
+        assert want.error == 0
+        assert canon(res.matches(k)) == canon(want.matches)
+    eng.close()
+
+
+def test_one_allocation_batch(setup):
+    """items laid out inside one pinned allocation keep their layout and are copied in slices"""
+    rs, image = setup
+    eng = Engine(image, 0)
+    eng.set_option(api.OPT_H2D_CHUNK, 1 << 20)   # several slices
+    items = make_items(rs, seed=4)
+    total = sum((len(i) + 63) & ~63 for i in items) + 64
+    pin = PinnedBuffer(total)
+    arena = pin.array
+    arena[:] = 0x41
+    views, o = [], 5     # deliberately unaligned starts
+    for it in items:
+        arena[o : o + len(it)] = it
+        views.append(arena[o : o + len(it)])
+        o += len(it) + (len(it) * 7) % 13
+    res = eng.scan_batch(views, one_allocation=True)
+    n_total, _ = check_batch(eng, views, res)
+    assert n_total > 50
+    # same items, not declared as one allocation
+    res2 = eng.scan_batch(views)
+    assert res2.rc == 0 and (res2.state == res.state).all()
+    assert tuples(res2.all) == tuples(res.all)
+    eng.close()
+
+
+def test_batch_without_chains_needs_no_rescan():
+    rs = synth.ruleset(2, 1000)
+    image = yrh.b200().compile(rs.source).flatten()
+    eng = Engine(image, 0)
+    items = [synth.corpus(rs, 65536 + 1000 * k, 4096, seed=k, plant_seed=50 + k) for k in range(40)]
+    res = eng.scan_batch(items)
+    n_total, n_rescan = check_batch(eng, items, res)
+    assert n_rescan == 0 and n_total > 400
+    # one launch sequence for the whole batch
+    assert res.stats["kernel_launches"] < 40
+    eng.close()
+
+
+def test_fast_mode_and_empty_batches(setup):
+    rs, image = setup
+    eng = Engine(image, 0)
+    items = make_items(rs)[:6]
+    res = eng.scan_batch(items, flags=1)       # SCAN_FLAGS_FAST_MODE: order dependent, per-item path only
+    assert res.rc == 0 and res.n_rescan == len(items) and (res.state == api.ITEM_RESCAN).all()
+    res = eng.scan_batch([])
+    assert res.rc == 0 and res.n_items == 0 and len(res.all) == 0
+    res = eng.scan_batch([np.zeros(0, np.uint8), np.zeros(0, np.uint8)])
+    assert res.rc == 0 and res.n_rescan == 0 and len(res.all) == 0
+    eng.close()
+
+
+def test_verifier_error_marks_only_its_item():
+    """ERROR_TOO_MANY_RE_FIBERS raised inside one item must not leak into the others"""
+    src = 'rule a { strings: $a = /ab(c|d|e|f|g|h|i|j|k|l|m){1,300}(c|d|e|f|g|h|i|j|k|l|m){1,300}x/ $b = "needle_in_item" condition: any of them }'
+    image = yrh.b200().compile(src).flatten()
+    eng = Engine(image, 0)
+    bad = np.frombuffer(b"ab" + b"cdefghijklm" * 200, dtype=np.uint8).copy()
+    single = eng.scan_host(bad)
+    good = np.frombuffer(b"....needle_in_item....", dtype=np.uint8).copy()
+    items = [good, bad, good.copy(), synth.rand_bytes(1, 0, 5000).copy()]
+    res = eng.scan_batch(items)
+    assert res.rc == 0
+    if single.error != 0:
+        assert res.state[1] == api.ITEM_RESCAN
+    assert res.state[0] == api.ITEM_DONE and res.state[2] == api.ITEM_DONE and res.state[3] == api.ITEM_DONE
+    assert len(res.matches(0)) == 1 and len(res.matches(2)) == 1 and len(res.matches(3)) == 0
+    eng.close()

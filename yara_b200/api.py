@@ -68,6 +68,46 @@ class ScanResultC(C.Structure):
     ]
 
 
+class BatchItem(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size", C.c_uint64)]
+
+
+class BatchResultC(C.Structure):
+    _fields_ = [
+        ("n_items", C.c_uint32),
+        ("n_rescan", C.c_uint32),
+        ("item_state", C.POINTER(C.c_uint8)),
+        ("item_first", C.POINTER(C.c_uint64)),
+        ("matches", C.c_void_p),
+        ("stats", ScanStats),
+    ]
+
+
+ITEM_DONE, ITEM_RESCAN = 0, 1
+BATCH_ONE_ALLOCATION = 1
+
+
+class BatchResult:
+    """yrb_batch_result copied out: state[k], and matches(k) = the item's yrb_match records."""
+
+    def __init__(self, rc, r: BatchResultC):
+        self.rc = rc
+        self.n_items = r.n_items
+        self.n_rescan = r.n_rescan
+        self.stats = {f[0]: getattr(r.stats, f[0]) for f in ScanStats._fields_}
+        n = r.n_items
+        self.state = np.ctypeslib.as_array(r.item_state, shape=(n,)).copy() if n else np.zeros(0, np.uint8)
+        self.first = np.ctypeslib.as_array(r.item_first, shape=(n + 1,)).copy() if n else np.zeros(1, np.uint64)
+        total = int(self.first[-1])
+        if total and r.matches:
+            self.all = np.frombuffer(C.string_at(r.matches, total * YRB_MATCH_DTYPE.itemsize), dtype=YRB_MATCH_DTYPE).copy()
+        else:
+            self.all = np.zeros(0, dtype=YRB_MATCH_DTYPE)
+
+    def matches(self, k):
+        return self.all[int(self.first[k]): int(self.first[k + 1])]
+
+
 class ScanResult:
     def __init__(self, rc, r: ScanResultC, copy=True):
         self.rc = rc
@@ -109,6 +149,7 @@ class _Lib:
             L.yrb_scanner_set_option.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
             L.yrb_scan_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ScanParams), C.POINTER(ScanResultC)]
             L.yrb_scan_device.argtypes = L.yrb_scan_host.argtypes
+            L.yrb_scan_batch.argtypes = [C.c_void_p, C.POINTER(BatchItem), C.c_uint32, C.c_int, C.c_int, C.POINTER(BatchResultC)]
             L.yrb_shard_raw.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
             L.yrb_resolve_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ScanParams), C.POINTER(ScanResultC)]
             L.yrb_gather_match_data.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -239,6 +280,18 @@ class Engine:
         p, r = self._params(**kw), ScanResultC()
         rc = self.L.yrb_scan_host(self.scanner, C.c_void_p(ptr), size, C.byref(p), C.byref(r))
         return ScanResult(rc, r, copy)
+
+    def scan_batch(self, items, flags=0, one_allocation=False):
+        """items: numpy uint8 arrays (kept alive by the caller) or (ptr, size) pairs."""
+        arr = (BatchItem * max(1, len(items)))()
+        for k, it in enumerate(items):
+            if isinstance(it, tuple):
+                arr[k].data, arr[k].size = it[0] or None, it[1]
+            else:
+                arr[k].data, arr[k].size = (it.ctypes.data if it.size else None), it.size
+        r = BatchResultC()
+        rc = self.L.yrb_scan_batch(self.scanner, arr, len(items), flags, BATCH_ONE_ALLOCATION if one_allocation else 0, C.byref(r))
+        return BatchResult(rc, r)
 
     def scan_device(self, dbuf, size=None, copy=True, **kw):
         p, r = self._params(**kw), ScanResultC()

@@ -126,6 +126,15 @@ struct yrb_scanner
   PinBuf<Raw> h_raw;
   size_t h_raw_n = 0;
 
+  // batch scans (yrb_scan_batch)
+  DevBuf<int64_t> seg_tab;
+  DevBuf<uint8_t> item_dirty;
+  PinBuf<int64_t> h_seg_tab;
+  PinBuf<uint8_t> h_item_dirty;
+  std::vector<uint8_t> b_state;
+  std::vector<uint64_t> b_first;
+  std::vector<yrb_match> b_matches;
+
   // last device-resident result (for yrb_gather_match_data)
   size_t last_n_final = 0;
   ScanView last_view;
@@ -499,9 +508,21 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
   return YRB_SUCCESS;
 }
 
+// Layout of one yrb_scan_batch call: where each item sits in the concatenation.
+struct BatchPlan
+{
+  const yrb_batch_item* items;
+  uint32_t n;
+  const int64_t* start;     // host copy of the segment starts (pinned, n entries)
+  bool one_allocation;      // the concatenation IS the host layout: copy it in large slices
+  const int64_t* d_start;
+  const int64_t* d_len;
+  uint8_t* d_dirty;
+};
+
 static int scan_impl(
     yrb_scanner* s, const uint8_t* h_data, const uint8_t* d_data_in, size_t size, const yrb_scan_params* params,
-    yrb_scan_result* res)
+    yrb_scan_result* res, const BatchPlan* bp = nullptr)
 {
   if (!s || !params || !res || (size > 0 && !h_data && !d_data_in)) return YRB_ERROR_BAD_ARGUMENT;
   CK(cudaSetDevice(s->device));
@@ -519,6 +540,12 @@ static int scan_impl(
   V.own_hi = params->block_size ? (int64_t) params->own_end : (int64_t) size;
   V.base = params->base;
   V.scan_flags = params->scan_flags;
+  if (bp)
+  {
+    V.n_seg = (int32_t) bp->n;
+    V.seg_start = bp->d_start;
+    V.seg_len = bp->d_len;
+  }
 
   if (V.gsize >= (1LL << 40) || V.g1 > V.gsize || V.own_hi > V.gsize || V.own_lo > V.own_hi)
     return YRB_ERROR_BAD_ARGUMENT;
@@ -551,7 +578,7 @@ static int scan_impl(
 
   // ---- H2D slices, each followed by its AC scan slice
   const size_t chunk = s->opt_h2d_chunk;
-  size_t n_slices = h_data ? (size + chunk - 1) / chunk : 0;
+  size_t n_slices = (h_data && !(bp && !bp->one_allocation)) ? (size + chunk - 1) / chunk : 0;
   while (s->slice_ev.size() < n_slices)
   {
     cudaEvent_t e;
@@ -576,13 +603,42 @@ static int scan_impl(
     for (int c = 0; c < NUM_CLS; c++) { co.cand[c] = s->d_cand[c].p; co.cap[c] = s->d_cand[c].cap; }
     co.st = s->d_status;
 
-    if (V.own_lo == 0)
+    if (V.own_lo == 0 && !bp)   // batches are refused for rulesets with root-state matches
     {
       launch_ac_event0(s->rules->R, V, co, s->stream);
       launches++;
     }
 
-    if (h_data && attempt == 0)
+    if (bp && !bp->one_allocation && attempt == 0)
+    {
+      // one copy per item into its packed place; a scan slice per ~chunk bytes of items
+      CK(cudaEventRecord(s->ev[5], s->stream));
+      CK(cudaStreamWaitEvent(s->copy_stream, s->ev[5], 0));
+      size_t n_groups = 0;
+      int64_t glo = 0;
+      for (uint32_t k = 0; k < bp->n; k++)
+      {
+        const uint64_t nb = bp->items[k].size;
+        if (nb) CK(cudaMemcpyAsync(s->d_data.p + bp->start[k], bp->items[k].data, nb, cudaMemcpyHostToDevice, s->copy_stream));
+        const int64_t end = bp->start[k] + (int64_t) nb;
+        if (k + 1 == bp->n || (size_t) (end - glo) >= chunk)
+        {
+          const int64_t ghi = (k + 1 == bp->n) ? (int64_t) size : end;
+          if (s->slice_ev.size() <= n_groups)
+          {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            s->slice_ev.push_back(e);
+          }
+          CK(cudaEventRecord(s->slice_ev[n_groups], s->copy_stream));
+          CK(cudaStreamWaitEvent(s->stream, s->slice_ev[n_groups], 0));
+          n_groups++;
+          if (ghi > glo) { launch_scan_slice(s, kernel, V, co, glo, ghi); launches++; }
+          glo = ghi;
+        }
+      }
+    }
+    else if (h_data && attempt == 0)
     {
       CK(cudaEventRecord(s->ev[5], s->stream));
       CK(cudaStreamWaitEvent(s->copy_stream, s->ev[5], 0)); // d_data may still be read by the previous scan
@@ -685,6 +741,7 @@ static int scan_impl(
     ro.cap = s->d_raw.cap;
     ro.st = s->d_status;
     ro.str_err = s->str_err.p;
+    ro.item_dirty = bp ? bp->d_dirty : nullptr;
     if (s->rules->h.code_size > 0) // only RE / hex strings can raise verifier errors
       CK(cudaMemsetAsync(s->str_err.p, 0xFF, sizeof(unsigned long long) * s->rules->R.num_strings, s->stream));
 
@@ -761,7 +818,29 @@ static int scan_impl(
   }
 
   int rc = YRB_SUCCESS;
-  if (params->defer_resolve)
+  if (bp)
+  {
+    // the order-independent part of the resolve only; items that need more are flagged dirty
+    if (n_raw > 0)
+    {
+      rc = ensure_resolve_scratch(s, (uint32_t) n_raw);
+      if (rc != YRB_SUCCESS) return rc;
+      if (s->h_finals.ensure((size_t) n_raw)) return YRB_ERROR_INSUFFICIENT_MEMORY;
+      ResolveWork w;
+      fill_work(s, w, s->d_raw.p, (uint32_t) n_raw, 0);
+      w.has_chains = 0;
+      launch_resolve(w, s->stream, &launches);
+      CK(cudaMemcpyAsync(s->h_finals.p, s->finals.p, (size_t) n_raw * sizeof(yrb_match), cudaMemcpyDeviceToHost, s->stream));
+      rc = read_status(s);
+      if (rc != YRB_SUCCESS) return rc;
+      res->n_matches = (size_t) hs->n_sel;
+      res->matches = s->h_finals.p;
+    }
+    CK(cudaMemcpyAsync(s->h_item_dirty.p, bp->d_dirty, bp->n, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaEventRecord(s->ev[3], s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  else if (params->defer_resolve)
   {
     if (s->h_raw.ensure(n_raw ? (size_t) n_raw : 1) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
     if (n_raw) CK(cudaMemcpyAsync(s->h_raw.p, s->d_raw.p, (size_t) n_raw * sizeof(Raw), cudaMemcpyDeviceToHost, s->stream));
@@ -812,6 +891,127 @@ extern "C" int yrb_scan_device(
 {
   static const uint8_t dummy = 0;
   return scan_impl(s, nullptr, d_data ? d_data : &dummy, size, params, result);
+}
+
+extern "C" int yrb_scan_batch(
+    yrb_scanner* s, const yrb_batch_item* items, uint32_t n_items, int scan_flags, int batch_flags,
+    yrb_batch_result* out)
+{
+  if (!s || !out || (n_items > 0 && !items) || n_items >= (1u << 30)) return YRB_ERROR_BAD_ARGUMENT;
+  CK(cudaSetDevice(s->device));
+  memset(out, 0, sizeof(*out));
+  out->n_items = n_items;
+
+  s->b_state.assign(n_items ? n_items : 1, YRB_ITEM_DONE);
+  s->b_first.assign((size_t) n_items + 1, 0);
+  s->b_matches.clear();
+  out->item_state = s->b_state.data();
+  out->item_first = s->b_first.data();
+  out->matches = s->b_matches.data();
+  if (n_items == 0) return YRB_SUCCESS;
+
+  // results that depend on order or on per-string scan state are the per-item path's business
+  if ((scan_flags & YRB_SCAN_FAST_MODE) || s->rules->F.root_match)
+  {
+    std::fill(s->b_state.begin(), s->b_state.end(), (uint8_t) YRB_ITEM_RESCAN);
+    out->n_rescan = n_items;
+    return YRB_SUCCESS;
+  }
+
+  if (s->h_seg_tab.ensure((size_t) 2 * n_items) || s->h_item_dirty.ensure(n_items) ||
+      s->seg_tab.ensure((size_t) 2 * n_items) || s->item_dirty.ensure(n_items))
+    return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  int64_t* start = s->h_seg_tab.p;
+  int64_t* len = s->h_seg_tab.p + n_items;
+  bool one_alloc = (batch_flags & YRB_BATCH_ONE_ALLOCATION) != 0;
+  const uint8_t* base = nullptr;
+  int64_t total = 0;
+
+  if (one_alloc)
+  {
+    // keep the host layout: start[k] = data[k] - data of the first non-empty item
+    int64_t used = 0;
+    for (uint32_t k = 0; k < n_items; k++)
+    {
+      len[k] = (int64_t) items[k].size;
+      if (len[k] == 0) { start[k] = total; continue; }
+      if (!items[k].data) return YRB_ERROR_BAD_ARGUMENT;
+      if (!base) base = items[k].data;
+      const int64_t o = (int64_t) (items[k].data - base);
+      if (o < total) { one_alloc = false; break; }   // not ascending / overlapping: pack instead
+      start[k] = o;
+      total = o + len[k];
+      used += len[k];
+    }
+    if (one_alloc && total > used + used / 4 + 4096) one_alloc = false;
+  }
+  if (!one_alloc)
+  {
+    total = 0;
+    for (uint32_t k = 0; k < n_items; k++)
+    {
+      if (items[k].size && !items[k].data) return YRB_ERROR_BAD_ARGUMENT;
+      start[k] = total;
+      len[k] = (int64_t) items[k].size;
+      total += (len[k] + 15) & ~(int64_t) 15;
+    }
+  }
+  if (total >= (1LL << 40)) return YRB_ERROR_BAD_ARGUMENT;
+
+  CK(cudaMemcpyAsync(s->seg_tab.p, s->h_seg_tab.p, sizeof(int64_t) * 2 * n_items, cudaMemcpyHostToDevice, s->stream));
+  CK(cudaMemsetAsync(s->item_dirty.p, 0, n_items, s->stream));
+  memset(s->h_item_dirty.p, 0, n_items);
+
+  BatchPlan bp;
+  bp.items = items;
+  bp.n = n_items;
+  bp.start = start;
+  bp.one_allocation = one_alloc;
+  bp.d_start = s->seg_tab.p;
+  bp.d_len = s->seg_tab.p + n_items;
+  bp.d_dirty = s->item_dirty.p;
+
+  yrb_scan_params params;
+  memset(&params, 0, sizeof(params));
+  params.scan_flags = scan_flags;
+  yrb_scan_result res;
+  static const uint8_t dummy = 0;
+  int rc = scan_impl(s, one_alloc && base ? base : &dummy, nullptr, (size_t) total, &params, &res, &bp);
+  if (rc != YRB_SUCCESS) return rc;
+  out->stats = res.stats;
+
+  const ScanStatus* hs = s->h_status;
+  if (res.n_matches > 0 && hs->over_cap)
+    memset(s->h_item_dirty.p, 1, n_items);   // some string's list would be truncated somewhere: sort it out per item
+
+  // distribute the string-major records over their items (stable, so each item stays string-major)
+  std::vector<uint32_t> item_of(res.n_matches);
+  for (size_t t = 0; t < res.n_matches; t++)
+  {
+    const int64_t o = res.matches[t].offset;
+    uint32_t k = (uint32_t) (std::upper_bound(start, start + n_items, o) - start) - 1;
+    item_of[t] = k;
+    if (!s->h_item_dirty.p[k]) s->b_first[(size_t) k + 1]++;
+  }
+  for (uint32_t k = 0; k < n_items; k++)
+  {
+    if (s->h_item_dirty.p[k]) { s->b_state[k] = YRB_ITEM_RESCAN; out->n_rescan++; }
+    s->b_first[(size_t) k + 1] += s->b_first[k];
+  }
+  s->b_matches.resize((size_t) s->b_first[n_items]);
+  std::vector<uint64_t> cur(s->b_first.begin(), s->b_first.end() - 1);
+  for (size_t t = 0; t < res.n_matches; t++)
+  {
+    const uint32_t k = item_of[t];
+    if (s->h_item_dirty.p[k]) continue;
+    yrb_match m = res.matches[t];
+    m.offset -= start[k];
+    s->b_matches[(size_t) cur[k]++] = m;
+  }
+  out->matches = s->b_matches.data();
+  s->last_n_final = 0;
+  return YRB_SUCCESS;
 }
 
 extern "C" int yrb_shard_raw(yrb_scanner* s, const void** records, size_t* n_records)

@@ -13,17 +13,31 @@ static __device__ __forceinline__ void emit_events(
 {
   uint32_t k = first;
   uint32_t chain_pos = 0;
+  int64_t rel = i;          // bytes consumed since the start of the scanned unit
+  int64_t size = V.gsize;
+
+  if (V.n_seg > 0)
+  {
+    // Batch mode: the state was reached over the concatenation, so it may be deeper than
+    // the item-local one; every entry it adds in front of the item-local chain has
+    // backtrack >= its depth > rel and is rejected by the guard below.
+    const int sg = seg_find(V, i - 1);
+    if (sg < 0) return;
+    rel = i - __ldg(&V.seg_start[sg]);
+    size = __ldg(&V.seg_len[sg]);
+    if (rel > size) return;   // byte i-1 lies in the gap behind item sg
+  }
 
   while (k != 0)
   {
     const yrb_acm m = R.acm[k - 1];
 
-    if ((int64_t) m.backtrack <= i)
+    if ((int64_t) m.backtrack <= rel)
     {
-      int64_t offset = i - (int64_t) m.backtrack;
+      int64_t offset = rel - (int64_t) m.backtrack;
 
       // scan.c:1015  `data_size - offset <= 0` (size_t arithmetic: only == 0)
-      if (offset != V.gsize)
+      if (offset != size)
       {
         const uint32_t sflags = R.S[m.string_idx].flags;
         bool ok = true;

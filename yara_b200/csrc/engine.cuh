@@ -65,8 +65,25 @@ struct ScanView
   int64_t own_hi;
   uint64_t base;
   int32_t scan_flags;
-  int32_t pad;
+  // Batch mode (yrb_scan_batch): the "block" is the concatenation of n_seg independent
+  // items; item k occupies [seg_start[k], seg_start[k] + seg_len[k]), ascending and disjoint,
+  // possibly with a few unowned bytes in between.  0 = ordinary single-block scan.
+  int32_t n_seg;
+  const int64_t* seg_start;
+  const int64_t* seg_len;
 };
+
+// the item holding concatenated byte p, or the one before the gap p lies in (-1: before item 0)
+static __device__ __forceinline__ int seg_find(const ScanView& V, int64_t p)
+{
+  int lo = 0, hi = V.n_seg;   // first k in [lo, hi) with seg_start[k] > p
+  while (lo < hi)
+  {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(&V.seg_start[mid]) > p) hi = mid; else lo = mid + 1;
+  }
+  return lo - 1;
+}
 
 struct Cand
 {
@@ -127,6 +144,7 @@ struct RawOut
   unsigned long long cap;
   ScanStatus* st;
   unsigned long long* str_err;  // per string: min over its failing candidates of (candidate key | error code)
+  uint8_t* item_dirty;          // batch mode: items whose result needs the general per-item path (else nullptr)
 };
 
 // Atom prefilter tables of one ruleset (ac_scan.cu, filter kernel).

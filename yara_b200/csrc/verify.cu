@@ -26,6 +26,8 @@ struct Ctx
   RawOut out;
   uint64_t cand_key;
   uint32_t seq;
+  int32_t seg;        // batch mode: the item being verified (d, g0, g1, gsize describe that item alone)
+  int64_t bias;       // batch mode: start of the item in the concatenation (added to reported offsets)
 };
 
 static __device__ __forceinline__ uint8_t byte_at(Ctx& c, int64_t p)
@@ -82,7 +84,7 @@ static __device__ void match_callback(Ctx& c, int64_t match_pos, int32_t match_l
   {
     Raw r;
     r.key = c.cand_key | (uint64_t) (c.seq < KEY_SEQ_MAX ? c.seq : KEY_SEQ_MAX);
-    r.offset = match_pos;
+    r.offset = match_pos + c.bias;
     r.string_idx = a.sidx;
     r.length = match_length;
     r.misc = a.xor_key & 0xFF;
@@ -91,7 +93,10 @@ static __device__ void match_callback(Ctx& c, int64_t match_pos, int32_t match_l
   }
 
   if (a.group != YRB_NONE)
+  {
     atomicAdd(&c.out.st->n_chain_raw, 1u);
+    if (c.out.item_dirty) c.out.item_dirty[c.seg] = 1;   // chains are resolved by the per-item path
+  }
 
   c.seq++;
 }
@@ -1064,16 +1069,39 @@ static __device__ int verify_re(Ctx& c, FastWs* fws, FiberPool* fp, const yrb_ac
 
 // -------------------------------------------------------------------- kernels
 
-static __device__ __forceinline__ void ctx_init(Ctx& c, const DevRules& R, const ScanView& V, const RawOut& out, const Cand& cd)
+// Returns the position (in the coordinates of c) the candidate's string would start at.
+static __device__ __forceinline__ int64_t ctx_init(
+    Ctx& c, const DevRules& R, const ScanView& V, const RawOut& out, const Cand& cd, const yrb_acm& m)
 {
+  const int64_t i = (int64_t) (cd.key >> KEY_I_SHIFT);
   c.R = &R;
+  c.out = out;
+  c.cand_key = cd.key;
+  c.seq = 0;
+
+  if (V.n_seg > 0)
+  {
+    c.seg = seg_find(V, i - 1);
+    c.bias = __ldg(&V.seg_start[c.seg]);
+    c.d = V.d + (c.bias - V.g0);
+    c.g0 = 0;
+    c.g1 = c.gsize = __ldg(&V.seg_len[c.seg]);
+    return i - c.bias - (int64_t) m.backtrack;
+  }
+
+  c.seg = 0;
+  c.bias = 0;
   c.d = V.d - V.g0;
   c.g0 = V.g0;
   c.g1 = V.g1;
   c.gsize = V.gsize;
-  c.out = out;
-  c.cand_key = cd.key;
-  c.seq = 0;
+  return i - (int64_t) m.backtrack;
+}
+
+static __device__ __forceinline__ void report_error_ctx(const Ctx& c, uint32_t sidx, int code)
+{
+  report_error(c.out, sidx, c.cand_key, code);
+  if (c.out.item_dirty) c.out.item_dirty[c.seg] = 1;
 }
 
 __global__ void __launch_bounds__(128)
@@ -1087,8 +1115,8 @@ verify_literal_kernel(DevRules R, ScanView V, const Cand* cands, unsigned long l
     const yrb_acm m = R.acm[cd.acm_idx];
     const yrb_string s = R.S[m.string_idx];
     Ctx c;
-    ctx_init(c, R, V, out, cd);
-    verify_literal(c, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
+    const int64_t at = ctx_init(c, R, V, out, cd, m);
+    verify_literal(c, m, s, at);
   }
 }
 
@@ -1121,8 +1149,8 @@ verify_fast_kernel(
     const yrb_acm m = R.acm[cd.acm_idx];
     const yrb_string s = R.S[m.string_idx];
     Ctx c;
-    ctx_init(c, R, V, out, cd);
-    int rc = verify_re<true>(c, &my, nullptr, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
+    const int64_t at = ctx_init(c, R, V, out, cd, m);
+    int rc = verify_re<true>(c, &my, nullptr, m, s, at);
     if (rc == WS_RETRY)
     {
       if (TIER == 1)
@@ -1139,7 +1167,7 @@ verify_fast_kernel(
       rc = YRB_ERROR_INSUFFICIENT_MEMORY;
     }
     if (rc != YRB_SUCCESS)
-      report_error(out, m.string_idx, cd.key, rc);
+      report_error_ctx(c, m.string_idx, rc);
   }
 }
 
@@ -1174,8 +1202,8 @@ verify_re_kernel(
     const yrb_acm m = R.acm[cd.acm_idx];
     const yrb_string s = R.S[m.string_idx];
     Ctx c;
-    ctx_init(c, R, V, out, cd);
-    int rc = verify_re<false>(c, nullptr, &p, m, s, (int64_t) (cd.key >> KEY_I_SHIFT) - (int64_t) m.backtrack);
+    const int64_t at = ctx_init(c, R, V, out, cd, m);
+    int rc = verify_re<false>(c, nullptr, &p, m, s, at);
     if (rc == WS_RETRY)
     {
       if (!TIER2)
@@ -1186,7 +1214,7 @@ verify_re_kernel(
       rc = YRB_ERROR_INTERNAL_FATAL;
     }
     if (rc != YRB_SUCCESS)
-      report_error(out, m.string_idx, cd.key, rc);
+      report_error_ctx(c, m.string_idx, rc);
   }
 }
 
