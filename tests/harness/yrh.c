@@ -328,3 +328,26 @@ double yrh_scan_mt(void* rules_, const uint8_t* buf, size_t size, int nthreads, 
   if (rc_out) *rc_out = rc;
   return (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
 }
+
+#ifdef YRH_B200
+/* file batches through the drop-in's glue (yara_b200/host/yr_b200.h) */
+typedef struct YR_B200_BATCH YR_B200_BATCH;
+int yr_b200_batch_scan(
+    YR_RULES* rules, const uint8_t* const* buffers, const size_t* sizes, uint32_t n, int flags, int one_allocation,
+    YR_B200_BATCH** batch);
+void yr_b200_batch_destroy(YR_B200_BATCH* batch);
+uint32_t yr_b200_batch_rescans(const YR_B200_BATCH* batch);
+
+int yrh_batch_begin(
+    void* rules, const uint8_t* const* buffers, const size_t* sizes, uint32_t n, int flags, int one_allocation,
+    void** batch, uint32_t* n_rescans)
+{
+  YR_B200_BATCH* b = NULL;
+  int rc = yr_b200_batch_scan((YR_RULES*) rules, buffers, sizes, n, flags, one_allocation, &b);
+  *batch = b;
+  if (rc == 0 && n_rescans != NULL) *n_rescans = yr_b200_batch_rescans(b);
+  return rc;
+}
+
+void yrh_batch_end(void* batch) { yr_b200_batch_destroy((YR_B200_BATCH*) batch); }
+#endif

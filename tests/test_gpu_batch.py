@@ -178,3 +178,39 @@ def test_verifier_error_marks_only_its_item():
     assert res.state[0] == api.ITEM_DONE and res.state[2] == api.ITEM_DONE and res.state[3] == api.ITEM_DONE
     assert len(res.matches(0)) == 1 and len(res.matches(2)) == 1 and len(res.matches(3)) == 0
     eng.close()
+
+
+def test_dropin_batch_is_transparent(setup):
+    """yr_b200_batch_scan + ordinary yr_rules_scan_mem per buffer == reference libyara per buffer:
+    same rule verdicts, same YR_MATCH lists (base, offset, length, data hash, xor key)."""
+    rs, image = setup
+    rb = yrh.b200().compile(rs.source)
+    rr = yrh.ref().compile(rs.source)
+    items = make_items(rs, seed=6)
+    want = [rr.scan(it).key() for it in items]
+    with rb.batch(items) as b:
+        assert b.rc == 0
+        assert b.n_rescans < len(items)
+        got = [rb.scan(it).key() for it in items]
+        # a buffer that was not part of the batch, and a prefix of one that was, are scanned normally
+        other = synth.corpus(rs, 50000, 4096, seed=77, plant_seed=78)
+        assert rb.scan(other).key() == rr.scan(other).key()
+        assert rb.scan(items[10][:5000]).key() == rr.scan(items[10][:5000]).key()
+        # fast mode never uses parked results
+        assert rb.scan(items[9], flags=1).key() == rr.scan(items[9], flags=1).key()
+    assert got == want
+    # after the batch is gone everything is scanned on demand again
+    assert [rb.scan(it).key() for it in items[:12]] == want[:12]
+
+
+def test_dropin_batch_multithreaded(setup):
+    from concurrent.futures import ThreadPoolExecutor
+    rs, image = setup
+    rb = yrh.b200().compile(rs.source)
+    items = make_items(rs, seed=8)
+    want = [rb.scan(it).key() for it in items]
+    with rb.batch(items) as b:
+        assert b.rc == 0
+        with ThreadPoolExecutor(4) as ex:
+            got = list(ex.map(lambda it: rb.scan(it).key(), items))
+    assert got == want

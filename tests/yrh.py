@@ -115,12 +115,43 @@ class Rules:
             return self.scan_blocks(data, block_size, overlap, flags, too_many_action, cap=n.value)
         return self._finish(rc, out, n, bits, tm)
 
+    def batch(self, arrays, flags=0, one_allocation=False):
+        """GPU drop-in only: scan `arrays` as one batch; scans of the same arrays while the returned
+        object is open take their matches from it (yara_b200/host/yr_b200.h)."""
+        return Batch(self, arrays, flags, one_allocation)
+
     def scan_mt(self, data, nthreads, flags=0):
         buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
         rc = C.c_int()
         secs = self.h.lib.yrh_scan_mt(
             self.ptr, buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size), nthreads, flags, C.byref(rc))
         return secs, rc.value
+
+
+class Batch:
+    def __init__(self, rules, arrays, flags, one_allocation):
+        L = rules.h.lib
+        L.yrh_batch_begin.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_uint32, C.c_int, C.c_int,
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+        L.yrh_batch_end.argtypes = [C.c_void_p]
+        n = len(arrays)
+        self.arrays = arrays          # keep the buffers alive
+        ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrays])
+        sizes = (C.c_size_t * max(n, 1))(*[a.size for a in arrays])
+        h, nres = C.c_void_p(), C.c_uint32()
+        self.rc = L.yrh_batch_begin(rules.ptr, ptrs, sizes, n, flags, 1 if one_allocation else 0, C.byref(h), C.byref(nres))
+        self.lib, self.handle, self.n_rescans = L, h, nres.value
+
+    def close(self):
+        if self.handle:
+            self.lib.yrh_batch_end(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 class Harness:

@@ -34,6 +34,28 @@ int yr_b200_scan_mem_block(
 void yr_b200_scanner_release(YR_SCANNER* scanner);
 void yr_b200_rules_release(YR_RULES* rules);
 
+/*
+ * File batches (optional accelerator; the libyara API itself is unchanged).  A caller
+ * with many buffers to scan -- the file queue of cli/yara.c:365-457 -- hands them over
+ * first; the GPU scans them with one launch sequence and the per-buffer results are
+ * parked in the batch.  While the batch is alive, yr_rules_scan_mem / yr_scanner_scan_mem
+ * of the same rules over one of those buffers (same pointer and size, block base 0,
+ * no SCAN_FLAGS_FAST_MODE) takes its string matches from the batch instead of scanning;
+ * condition evaluation and callbacks run as always.  Buffers whose result depends on
+ * scan state (chained strings, verifier errors, the 1M cap) are not parked and are
+ * scanned on demand as before, so results never differ from unbatched scans.
+ * The buffers must stay unchanged while the batch is alive; destroy the batch only
+ * when no scan is using it.
+ */
+typedef struct YR_B200_BATCH YR_B200_BATCH;
+
+int yr_b200_batch_scan(
+    YR_RULES* rules, const uint8_t* const* buffers, const size_t* sizes, uint32_t n, int flags,
+    int one_allocation, /* non-zero: all buffers lie in ascending order inside one allocation */
+    YR_B200_BATCH** batch);
+void yr_b200_batch_destroy(YR_B200_BATCH* batch);
+uint32_t yr_b200_batch_rescans(const YR_B200_BATCH* batch); /* buffers that were not parked */
+
 /* Which CUDA device the glue uses for new scanners (default: $YR_B200_DEVICE or 0). */
 void yr_b200_set_device(int device);
 

@@ -140,6 +140,214 @@ static int get_rules(YR_RULES* rules, rules_entry** out)
   return ERROR_SUCCESS;
 }
 
+/* ---- pool of idle device scanners; call with g_lock held */
+static yrb_scanner* pool_take(yrb_rules* dev_rules)
+{
+  for (int i = 0; i < g_pool_n; i++)
+  {
+    if (g_pool[i].dev_rules == dev_rules)
+    {
+      yrb_scanner* dev = g_pool[i].dev;
+      g_pool[i] = g_pool[--g_pool_n];
+      return dev;
+    }
+  }
+  return NULL;
+}
+
+static void pool_put(yrb_scanner* dev, yrb_rules* dev_rules)
+{
+  if (g_pool_n < YR_B200_POOL_MAX)
+  {
+    size_t held = yrb_scanner_footprint(dev);
+    for (int i = 0; i < g_pool_n; i++) held += yrb_scanner_footprint(g_pool[i].dev);
+    if (held > YR_B200_POOL_BYTES)
+      yrb_scanner_trim(dev);
+    g_pool[g_pool_n].dev = dev;
+    g_pool[g_pool_n].dev_rules = dev_rules;
+    g_pool_n++;
+  }
+  else
+  {
+    yrb_scanner_destroy(dev);
+  }
+}
+
+/* ---- file batches (yr_b200_batch_scan): results parked until the per-file scans ask for them */
+struct YR_B200_BATCH
+{
+  YR_RULES* rules;
+  uint32_t n;
+  const uint8_t** data;
+  size_t* sizes;
+  uint32_t* order;   /* item indices sorted by data pointer */
+  uint8_t* state;
+  uint64_t* first;
+  yrb_match* matches;
+  struct YR_B200_BATCH* next;
+};
+
+static YR_B200_BATCH* volatile g_batches = NULL;
+
+static const uint8_t** g_sort_keys;
+static int cmp_by_ptr(const void* a, const void* b)
+{
+  const uint8_t* pa = g_sort_keys[*(const uint32_t*) a];
+  const uint8_t* pb = g_sort_keys[*(const uint32_t*) b];
+  return pa < pb ? -1 : (pa > pb ? 1 : 0);
+}
+
+static void batch_free(YR_B200_BATCH* b)
+{
+  if (b == NULL) return;
+  free((void*) b->data); free(b->sizes); free(b->order); free(b->state); free(b->first); free(b->matches);
+  free(b);
+}
+
+int yr_b200_batch_scan(
+    YR_RULES* rules, const uint8_t* const* buffers, const size_t* sizes, uint32_t n, int flags, int one_allocation,
+    YR_B200_BATCH** batch)
+{
+  *batch = NULL;
+  YR_B200_BATCH* b = (YR_B200_BATCH*) calloc(1, sizeof(*b));
+  yrb_batch_item* items = (yrb_batch_item*) malloc(sizeof(yrb_batch_item) * (n ? n : 1));
+  if (b != NULL)
+  {
+    b->rules = rules;
+    b->n = n;
+    b->data = (const uint8_t**) malloc(sizeof(uint8_t*) * (n ? n : 1));
+    b->sizes = (size_t*) malloc(sizeof(size_t) * (n ? n : 1));
+    b->order = (uint32_t*) malloc(sizeof(uint32_t) * (n ? n : 1));
+    b->state = (uint8_t*) malloc(n ? n : 1);
+    b->first = (uint64_t*) calloc((size_t) n + 1, sizeof(uint64_t));
+  }
+  if (b == NULL || items == NULL || !b->data || !b->sizes || !b->order || !b->state || !b->first)
+  {
+    free(items);
+    batch_free(b);
+    return ERROR_INSUFFICIENT_MEMORY;
+  }
+  for (uint32_t k = 0; k < n; k++)
+  {
+    b->data[k] = items[k].data = buffers[k];
+    b->sizes[k] = sizes[k];
+    items[k].size = sizes[k];
+    b->order[k] = k;
+  }
+
+  /* a device scanner for the duration of the call */
+  rules_entry* re = NULL;
+  yrb_scanner* dev = NULL;
+  pthread_mutex_lock(&g_lock);
+  int rc = get_rules(rules, &re);
+  if (rc == ERROR_SUCCESS)
+    dev = pool_take(re->dev);
+  pthread_mutex_unlock(&g_lock);
+  if (rc == ERROR_SUCCESS && dev == NULL)
+  {
+    int r2 = yrb_scanner_create(re->dev, &dev);
+    if (r2 != YRB_SUCCESS)
+      rc = fail_loudly("yrb_scanner_create", r2);
+  }
+  if (rc != ERROR_SUCCESS)
+  {
+    free(items);
+    batch_free(b);
+    return rc;
+  }
+
+  yrb_batch_result res;
+  int r2 = yrb_scan_batch(dev, items, n, flags, one_allocation ? YRB_BATCH_ONE_ALLOCATION : 0, &res);
+  free(items);
+  if (r2 == YRB_SUCCESS)
+  {
+    memcpy(b->state, res.item_state, n);
+    memcpy(b->first, res.item_first, sizeof(uint64_t) * ((size_t) n + 1));
+    const size_t total = (size_t) res.item_first[n];
+    b->matches = (yrb_match*) malloc(sizeof(yrb_match) * (total ? total : 1));
+    if (b->matches == NULL)
+      rc = ERROR_INSUFFICIENT_MEMORY;
+    else if (total)
+      memcpy(b->matches, res.matches, sizeof(yrb_match) * total);
+  }
+  else
+  {
+    rc = r2 < 1000 ? r2 : fail_loudly("yrb_scan_batch", r2);
+  }
+
+  pthread_mutex_lock(&g_lock);
+  pool_put(dev, re->dev);
+  if (rc == ERROR_SUCCESS)
+  {
+    g_sort_keys = b->data;   /* under g_lock: qsort has no context argument */
+    qsort(b->order, n, sizeof(uint32_t), cmp_by_ptr);
+    b->next = g_batches;
+    g_batches = b;
+  }
+  pthread_mutex_unlock(&g_lock);
+
+  if (rc != ERROR_SUCCESS)
+  {
+    batch_free(b);
+    return rc;
+  }
+  *batch = b;
+  return ERROR_SUCCESS;
+}
+
+void yr_b200_batch_destroy(YR_B200_BATCH* batch)
+{
+  if (batch == NULL) return;
+  pthread_mutex_lock(&g_lock);
+  for (YR_B200_BATCH* volatile* pp = &g_batches; *pp != NULL; pp = &(*pp)->next)
+  {
+    if (*pp == batch)
+    {
+      *pp = batch->next;
+      break;
+    }
+  }
+  pthread_mutex_unlock(&g_lock);
+  batch_free(batch);
+}
+
+uint32_t yr_b200_batch_rescans(const YR_B200_BATCH* batch)
+{
+  uint32_t c = 0;
+  for (uint32_t k = 0; k < batch->n; k++) c += batch->state[k] != YRB_ITEM_DONE;
+  return c;
+}
+
+/* The parked records of (rules, data, size), if a live batch scanned exactly that buffer. */
+static int batch_lookup(YR_RULES* rules, const uint8_t* data, size_t size, const yrb_match** recs, size_t* n_recs)
+{
+  int found = 0;
+  pthread_mutex_lock(&g_lock);
+  for (YR_B200_BATCH* b = g_batches; b != NULL && !found; b = b->next)
+  {
+    if (b->rules != rules) continue;
+    uint32_t lo = 0, hi = b->n;
+    while (lo < hi)
+    {
+      uint32_t mid = (lo + hi) / 2;
+      if (b->data[b->order[mid]] < data) lo = mid + 1; else hi = mid;
+    }
+    for (; lo < b->n && b->data[b->order[lo]] == data; lo++)
+    {
+      const uint32_t k = b->order[lo];
+      if (b->sizes[k] == size && b->state[k] == YRB_ITEM_DONE)
+      {
+        *recs = b->matches + b->first[k];
+        *n_recs = (size_t) (b->first[k + 1] - b->first[k]);
+        found = 1;
+        break;
+      }
+    }
+  }
+  pthread_mutex_unlock(&g_lock);
+  return found;
+}
+
 static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out, rules_entry** re_out)
 {
   scanner_entry* e;
@@ -166,18 +374,8 @@ static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out, rules_entry** re_
 
   if (rc == ERROR_SUCCESS)
   {
-    yrb_scanner* dev = NULL;
+    yrb_scanner* dev = pool_take(dev_rules);
     int r2 = YRB_SUCCESS;
-
-    for (int i = 0; i < g_pool_n; i++)
-    {
-      if (g_pool[i].dev_rules == dev_rules)
-      {
-        dev = g_pool[i].dev;
-        g_pool[i] = g_pool[--g_pool_n];
-        break;
-      }
-    }
 
     if (dev == NULL)
       r2 = yrb_scanner_create(dev_rules, &dev);
@@ -214,20 +412,7 @@ void yr_b200_scanner_release(YR_SCANNER* scanner)
     {
       scanner_entry* e = *pp;
       *pp = e->next;
-      if (g_pool_n < YR_B200_POOL_MAX)
-      {
-        size_t held = yrb_scanner_footprint(e->dev);
-        for (int i = 0; i < g_pool_n; i++) held += yrb_scanner_footprint(g_pool[i].dev);
-        if (held > YR_B200_POOL_BYTES)
-          yrb_scanner_trim(e->dev);
-        g_pool[g_pool_n].dev = e->dev;
-        g_pool[g_pool_n].dev_rules = e->dev_rules;
-        g_pool_n++;
-      }
-      else
-      {
-        yrb_scanner_destroy(e->dev);
-      }
+      pool_put(e->dev, e->dev_rules);
       free(e);
       break;
     }
@@ -499,11 +684,21 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
   if (scanner->timeout > 0 && yr_stopwatch_elapsed_ns(&scanner->stopwatch) > scanner->timeout)
     return ERROR_SCAN_TIMEOUT;
 
+  FAIL_ON_ERROR(yr_get_configuration_uint32(YR_CONFIG_MAX_MATCH_DATA, &max_match_data));
+
+  /* already scanned as part of a live file batch?  (only items whose result is complete and
+     independent of scan state are parked there; the rest fall through to the scan below) */
+  if (g_batches != NULL && block->base == 0 && !(scanner->flags & SCAN_FLAGS_FAST_MODE))
+  {
+    const yrb_match* recs = NULL;
+    size_t n_recs = 0;
+    if (batch_lookup(scanner->rules, block_data, block->size, &recs, &n_recs))
+      return materialise(scanner, block_data, block, recs, n_recs, scanner->matches, 1, max_match_data, NULL);
+  }
+
   rc = get_scanner(scanner, &dev, &re);
   if (rc != ERROR_SUCCESS)
     return rc;
-
-  FAIL_ON_ERROR(yr_get_configuration_uint32(YR_CONFIG_MAX_MATCH_DATA, &max_match_data));
 
   yrb_scan_params params;
   memset(&params, 0, sizeof(params));
