@@ -34,6 +34,43 @@ def run(rules, n):
 rb = yrh.b200().compile(rs.source)
 rr = yrh.ref().compile(rs.source)
 run(rb, 4)  # warm-up: device buffers, pooled scanners
+
+# ---- the same blobs as file batches (yrb_scan_batch / yr_b200_batch_scan)
+from yara_b200 import Engine, PinnedBuffer
+image = rb.flatten()
+eng = Engine(image, 0)
+pin = PinnedBuffer(sum((s + 15) & ~15 for s in sizes))
+views, o = [], 0
+for b in blobs:
+    pin.array[o : o + len(b)] = b
+    views.append(pin.array[o : o + len(b)])
+    o += (len(b) + 15) & ~15
+for label, its, one in (("pageable, packed", blobs, False), ("pinned, packed", views, False), ("pinned, one allocation", views, True)):
+    for per in (len(its), 64):
+        eng.scan_batch(its[:per], one_allocation=one)
+        t = time.time(); nm = nr = nl = 0
+        for k in range(0, len(its), per):
+            r = eng.scan_batch(its[k : k + per], one_allocation=one)
+            assert r.rc == 0
+            nm += len(r.all); nr += r.n_rescan; nl += r.stats["kernel_launches"]
+        t = time.time() - t
+        print("engine batch (%s, %d items/batch): %.3f s  %.2f GB/s  %.0f files/s  (%d matches, %d rescans, %d launches)"
+              % (label, per, t, total / t / 1e9, nfiles / t, nm, nr, nl))
+eng.close()
+for n in nthreads:
+    t = time.time()
+    with rb.batch(views, one_allocation=True) as bt:
+        assert bt.rc == 0
+        tb0 = time.time() - t
+        def one(b):
+            r = rb.scan(b, cap=4096)
+            assert r.rc == 0
+            return len(r.matches)
+        with ThreadPoolExecutor(n) as ex:
+            m = sum(ex.map(one, views))
+    t = time.time() - t
+    print("drop-in batch + %2d scan threads: %.2f s (batch %.2f s)  %.2f GB/s  %.0f files/s  (%d matches, %d rescans)"
+          % (n, t, tb0, total / t / 1e9, nfiles / t, m, bt.n_rescans))
 for n in nthreads:
     tb, mb = run(rb, n)
     print("drop-in   %2d threads: %.2f s  %.2f GB/s  %.0f files/s  (%d matches)" % (n, tb, total / tb / 1e9, nfiles / tb, mb))

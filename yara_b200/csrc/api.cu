@@ -383,6 +383,9 @@ static void fill_work(yrb_scanner* s, ResolveWork& w, const Raw* raw, uint32_t n
   w.use_cut = 0;
   w.seed_base = s->seed_base.p;
   w.cur_base = 0;
+  w.n_seg = 0;
+  w.seg_start = w.seg_len = nullptr;
+  w.item_dirty = nullptr;
   w.k0 = s->k0.p; w.k1 = s->k1.p; w.kF = s->kF.p; w.ix0 = s->ix0.p; w.ix1 = s->ix1.p; w.c_scratch_u32 = s->scr32.p;
   w.cub_tmp = s->cub_tmp.p; w.cub_tmp_bytes = s->cub_tmp.cap;
   w.c_nxt = s->c_nxt.p; w.c_prv = s->c_prv.p; w.c_clen = s->c_clen.p; w.c_mlen = s->c_mlen.p; w.c_uvn = s->c_uvn.p; w.sraw = s->sraw.p; w.c_where = s->c_where.p;
@@ -828,12 +831,16 @@ static int scan_impl(
       if (s->h_finals.ensure((size_t) n_raw)) return YRB_ERROR_INSUFFICIENT_MEMORY;
       ResolveWork w;
       fill_work(s, w, s->d_raw.p, (uint32_t) n_raw, 0);
-      w.has_chains = 0;
+      w.has_chains = hs->n_chain_raw > 0;
+      w.n_seg = (int) bp->n;
+      w.seg_start = bp->d_start;
+      w.seg_len = bp->d_len;
+      w.item_dirty = bp->d_dirty;
       launch_resolve(w, s->stream, &launches);
       CK(cudaMemcpyAsync(s->h_finals.p, s->finals.p, (size_t) n_raw * sizeof(yrb_match), cudaMemcpyDeviceToHost, s->stream));
       rc = read_status(s);
       if (rc != YRB_SUCCESS) return rc;
-      res->n_matches = (size_t) hs->n_sel;
+      res->n_matches = (size_t) hs->n_sel + (size_t) hs->n_chain_out;
       res->matches = s->h_finals.p;
     }
     CK(cudaMemcpyAsync(s->h_item_dirty.p, bp->d_dirty, bp->n, cudaMemcpyDeviceToHost, s->stream));

@@ -74,15 +74,20 @@ struct ScanView
 };
 
 // the item holding concatenated byte p, or the one before the gap p lies in (-1: before item 0)
-static __device__ __forceinline__ int seg_find(const ScanView& V, int64_t p)
+static __device__ __forceinline__ int seg_find_in(const int64_t* __restrict__ seg_start, int n_seg, int64_t p)
 {
-  int lo = 0, hi = V.n_seg;   // first k in [lo, hi) with seg_start[k] > p
+  int lo = 0, hi = n_seg;   // first k in [lo, hi) with seg_start[k] > p
   while (lo < hi)
   {
     const int mid = (lo + hi) >> 1;
-    if (__ldg(&V.seg_start[mid]) > p) hi = mid; else lo = mid + 1;
+    if (__ldg(&seg_start[mid]) > p) hi = mid; else lo = mid + 1;
   }
   return lo - 1;
+}
+
+static __device__ __forceinline__ int seg_find(const ScanView& V, int64_t p)
+{
+  return seg_find_in(V.seg_start, V.n_seg, p);
 }
 
 struct Cand

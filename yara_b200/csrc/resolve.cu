@@ -476,7 +476,8 @@ __global__ void chain_gather_kernel(const Raw* raw, const uint32_t* ix, const ui
 __global__ void chain_resolve_kernel(
     Raw* sraw, const uint64_t* kA, uint32_t n, DevRules R, ChainLists L, yrb_match* finals,
     yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap, int scan_flags,
-    const int64_t* seed_base, int64_t cur_base)
+    const int64_t* seed_base, int64_t cur_base, int n_seg, const int64_t* seg_start, const int64_t* seg_len,
+    uint8_t* item_dirty)
 {
   const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (j0 >= n) return;
@@ -501,8 +502,59 @@ __global__ void chain_resolve_kernel(
   uint64_t cur_cand = ~0ULL;
   bool skip_cand = false;
 
+  // Batch mode: every item is a scan of its own (unconfirmed_matches[] and matches[] start
+  // empty, scanner.c:178-204), so at the first record past the current item the head's
+  // confirmed list is written out and the lists of the strings seen so far are emptied.
+  int cur_item = -1;
+  int64_t item_last = -1;   // largest input position i that still belongs to cur_item
+  uint32_t item_j0 = j0;
+
+  auto write_confirmed = [&]() {
+    const int32_t cnt = L.mcnt[head_string];
+    if (cnt <= 0) return;
+    unsigned long long slot = (unsigned long long) st->n_sel + atomicAdd(&st->n_chain_out, (unsigned long long) cnt);
+    for (int32_t k = L.mhead[head_string]; k >= 0; k = L.nxt[k])
+    {
+      const Raw r = sraw[k];
+      yrb_match m;
+      m.offset = r.offset;
+      m.string_idx = head_string;
+      m.match_length = L.mlen[k];
+      m.xor_key = (uint8_t) (r.misc & 0xFF);
+      m.flags = (r.misc & RAW_SEED) ? YRB_MATCH_FROM_SEED : 0;
+      m.seed = (uint16_t) ((r.misc >> 8) & 0xFFFF);
+      m.chain_length = L.clen[k];
+      finals[slot++] = m;
+    }
+  };
+
   while (j < n && (kA[j] >> OFFSET_BITS) == chain)
   {
+    if (n_seg > 0)
+    {
+      const int64_t i = (int64_t) (kA[j] & ((1ULL << OFFSET_BITS) - 1)) - 1;
+      if (i > item_last)
+      {
+        if (cur_item >= 0)
+        {
+          write_confirmed();
+          for (uint32_t k = item_j0; k < j; k++)
+          {
+            const uint32_t sx = sraw[k].string_idx;
+            L.uhead[sx] = L.utail[sx] = L.mhead[sx] = L.mtail[sx] = L.uvhead[sx] = -1;
+            L.ucnt[sx] = L.mcnt[sx] = 0;
+          }
+        }
+        cur_item = seg_find_in(seg_start, n_seg, i - 1);
+        item_last = seg_start[cur_item] + seg_len[cur_item];
+        item_j0 = j;
+        prev_key = ~0ULL;
+        disabled_string = YRB_NONE;
+        cur_cand = ~0ULL;
+        skip_cand = false;
+      }
+    }
+
     // records of this chain that share the input position: put them in discovery-key order
     uint32_t r_end = j + 1;
     while (r_end < n && kA[r_end] == kA[j]) r_end++;
@@ -567,36 +619,21 @@ __global__ void chain_resolve_kernel(
         const uint32_t slot = atomicAdd(&st->n_too_many, 1u);
         if (slot < too_many_cap) too_many[slot] = r.string_idx;
         disabled_string = r.string_idx;
+        if (n_seg > 0) item_dirty[cur_item] = 1;   // the callback protocol needs the per-item path
       }
     }
   }
 
   // confirmed matches of the chain's head string, in list order, after the plain strings' records
-  const int32_t cnt = L.mcnt[head_string];
-  if (cnt > 0)
-  {
-    unsigned long long slot = (unsigned long long) st->n_sel + atomicAdd(&st->n_chain_out, (unsigned long long) cnt);
-    for (int32_t k = L.mhead[head_string]; k >= 0; k = L.nxt[k])
-    {
-      const Raw r = sraw[k];
-      yrb_match m;
-      m.offset = r.offset;
-      m.string_idx = head_string;
-      m.match_length = L.mlen[k];
-      m.xor_key = (uint8_t) (r.misc & 0xFF);
-      m.flags = (r.misc & RAW_SEED) ? YRB_MATCH_FROM_SEED : 0;
-      m.seed = (uint16_t) ((r.misc >> 8) & 0xFFFF);
-      m.chain_length = L.clen[k];
-      finals[slot++] = m;
-    }
-  }
+  write_confirmed();
 
   atomicAdd(&st->dbg[0], c.steps[0]);
   atomicAdd(&st->dbg[1], c.steps[1]);
   atomicAdd(&st->dbg[2], c.steps[2]);
 
-  // what is left in unconfirmed_matches[] of the chain's strings
-  for (uint32_t k = j0; k < j; k++)
+  // what is left in unconfirmed_matches[] of the chain's strings (a batch item is a whole
+  // scan: its leftovers are dropped like yr_scanner_scan_mem_blocks does at the end, scanner.c:565)
+  for (uint32_t k = j0; k < j && n_seg == 0; k++)
   {
     if (L.where[k] == 1)
     {
@@ -749,7 +786,8 @@ void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches)
     L.uvn = w.c_uvn;
     chain_init_kernel<<<GRID(w.R.num_strings), 0, s>>>(L, w.R.num_strings);
     chain_gather_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.sraw);
-    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.sraw, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags, w.seed_base, w.cur_base);
+    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.sraw, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags, w.seed_base, w.cur_base,
+        w.n_seg, w.seg_start, w.seg_len, w.item_dirty);
     (*launches) += 3;
   }
 }

@@ -14,6 +14,10 @@ struct ResolveWork
   int use_cut;
   const int64_t* seed_base;   // per seed: YR_MATCH.base (device)
   int64_t cur_base;           // base of the block being scanned
+  int n_seg;                  // batch mode (ScanView): the chain replay starts afresh at every item
+  const int64_t* seg_start;
+  const int64_t* seg_len;
+  uint8_t* item_dirty;
 
   // scratch, all sized for n_raw records unless noted
   uint64_t* k0;

@@ -93,10 +93,7 @@ static __device__ void match_callback(Ctx& c, int64_t match_pos, int32_t match_l
   }
 
   if (a.group != YRB_NONE)
-  {
     atomicAdd(&c.out.st->n_chain_raw, 1u);
-    if (c.out.item_dirty) c.out.item_dirty[c.seg] = 1;   // chains are resolved by the per-item path
-  }
 
   c.seq++;
 }

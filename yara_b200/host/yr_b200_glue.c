@@ -256,9 +256,19 @@ int yr_b200_batch_scan(
     return rc;
   }
 
+  struct timespec t0, t1;
+  const int timing = getenv("YRB_TIMING") != NULL;
+  if (timing) clock_gettime(CLOCK_MONOTONIC, &t0);
   yrb_batch_result res;
   int r2 = yrb_scan_batch(dev, items, n, flags, one_allocation ? YRB_BATCH_ONE_ALLOCATION : 0, &res);
   free(items);
+  if (timing)
+  {
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    fprintf(stderr, "yara_b200: batch of %u buffers: engine %.3f ms (device %.3f ms: scan+h2d %.3f verify %.3f resolve %.3f), %u launches\n",
+            n, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6, res.stats.ms_total, res.stats.ms_scan,
+            res.stats.ms_verify, res.stats.ms_resolve, res.stats.kernel_launches);
+  }
   if (r2 == YRB_SUCCESS)
   {
     memcpy(b->state, res.item_state, n);
