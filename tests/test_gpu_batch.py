@@ -244,3 +244,23 @@ def test_chain_parts_in_neighbouring_items_do_not_connect():
         single = eng.scan_host(items[k])
         assert canon(single.matches) == canon(res.matches(k))
     eng.close()
+
+
+def test_file_sharding_over_ranks_equals_single_scans(setup):
+    """shard.plan_files + shard.scan_files for 3 (simulated) ranks: every file scanned exactly once,
+    records equal to a scan of the file alone"""
+    from yara_b200 import shard
+    rs, image = setup
+    eng = Engine(image, 0)
+    items = make_items(rs, seed=12)
+    got = {}
+    for ix in shard.plan_files([len(i) for i in items], 3):
+        part = shard.scan_files(eng, items, ix)
+        assert not (set(part) & set(got))
+        got.update(part)
+    assert sorted(got) == list(range(len(items)))
+    for k, it in enumerate(items):
+        single = eng.scan_host(it)
+        assert got[k][0] == single.error
+        assert canon(got[k][1]) == canon(single.matches)
+    eng.close()

@@ -10,6 +10,10 @@ over the concatenated raw records of all ranks (Engine.resolve_raw) on one GPU.
 
 No collective is on the data path: raw records (32 bytes per match callback) are
 gathered to rank 0, by plain D2H + host gather.
+
+File batches (BASELINE configs[3]) shard per file instead: plan_files() deals the
+files out by size, every rank scans its share with Engine.scan_batch, and the
+per-file records are gathered on the host the same way.
 """
 import numpy as np
 
@@ -65,3 +69,52 @@ def gather_raw(raw: np.ndarray, dist, dst=0):
     if dist.get_rank() != dst:
         return None
     return np.concatenate([np.frombuffer(p, dtype=RAW_DTYPE) for p in parts])
+
+
+# ------------------------------------------------------------------ file batches
+def plan_files(sizes, n: int):
+    """Deals files out to n ranks, largest first onto the least loaded rank (ties: lowest rank).
+    Returns n ascending index lists; every file appears exactly once."""
+    load = [0] * n
+    out = [[] for _ in range(n)]
+    for k in sorted(range(len(sizes)), key=lambda k: (-int(sizes[k]), k)):
+        g = min(range(n), key=lambda g: (load[g], g))
+        out[g].append(k)
+        load[g] += int(sizes[k])
+    return [sorted(ix) for ix in out]
+
+
+def scan_files(engine, files, indices, flags=0, one_allocation=False):
+    """One rank's share: scans files[k] for k in indices as one batch; whatever the batch hands
+    back as ITEM_RESCAN goes through the general single-buffer path.  Returns {k: yrb_match records}."""
+    from .api import ITEM_RESCAN
+    items = [files[k] for k in indices]
+    res = engine.scan_batch(items, flags=flags, one_allocation=one_allocation)
+    if res.rc != 0:
+        raise RuntimeError("yrb_scan_batch failed: %d" % res.rc)
+    out = {}
+    for j, k in enumerate(indices):
+        if res.state[j] == ITEM_RESCAN:
+            r = engine.scan_host(items[j], flags=flags)
+            if r.rc != 0:
+                raise RuntimeError("yrb_scan_host failed: %d" % r.rc)
+            out[k] = (r.error, r.matches)
+        else:
+            out[k] = (0, res.matches(j))
+    return out
+
+
+def gather_files(mine: dict, n_files: int, dist, dst=0):
+    """Per-file records of every rank -> list indexed by file on `dst` (plain host gather)."""
+    world = dist.get_world_size()
+    parts = [None] * world if dist.get_rank() == dst else None
+    dist.gather_object({k: (e, m.tobytes()) for k, (e, m) in mine.items()}, parts, dst=dst)
+    if dist.get_rank() != dst:
+        return None
+    from .api import YRB_MATCH_DTYPE
+    out = [None] * n_files
+    for p in parts:
+        for k, (e, b) in p.items():
+            assert out[k] is None, "file %d scanned twice" % k
+            out[k] = (e, np.frombuffer(b, dtype=YRB_MATCH_DTYPE))
+    return out
