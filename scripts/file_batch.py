@@ -13,6 +13,7 @@ from yara_b200 import synth
 nstrings = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 nfiles = int(sys.argv[2]) if len(sys.argv) > 2 else 600
 nthreads = [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else ["1", "8", "16"])]
+no_batch = "--no-batch" in sys.argv
 
 rs = synth.ruleset(4, nstrings)
 rng = random.Random(3)
@@ -33,7 +34,7 @@ def run(rules, n):
 
 rb = yrh.b200().compile(rs.source)
 rr = yrh.ref().compile(rs.source)
-run(rb, 4)  # warm-up: device buffers, pooled scanners
+run(rb, max(nthreads))  # warm-up: one pooled device scanner per thread (creating one costs ~50 ms)
 
 # ---- the same blobs as file batches (yrb_scan_batch / yr_b200_batch_scan)
 from yara_b200 import Engine, PinnedBuffer
@@ -45,7 +46,7 @@ for b in blobs:
     pin.array[o : o + len(b)] = b
     views.append(pin.array[o : o + len(b)])
     o += (len(b) + 15) & ~15
-for label, its, one in (("pageable, packed", blobs, False), ("pinned, packed", views, False), ("pinned, one allocation", views, True)):
+for label, its, one in (() if no_batch else (("pageable, packed", blobs, False), ("pinned, packed", views, False), ("pinned, one allocation", views, True))):
     for per in (len(its), 64):
         eng.scan_batch(its[:per], one_allocation=one)
         t = time.time(); nm = nr = nl = 0
@@ -57,7 +58,7 @@ for label, its, one in (("pageable, packed", blobs, False), ("pinned, packed", v
         print("engine batch (%s, %d items/batch): %.3f s  %.2f GB/s  %.0f files/s  (%d matches, %d rescans, %d launches)"
               % (label, per, t, total / t / 1e9, nfiles / t, nm, nr, nl))
 eng.close()
-for n in nthreads:
+for n in ([] if no_batch else nthreads):
     t = time.time()
     with rb.batch(views, one_allocation=True) as bt:
         assert bt.rc == 0
