@@ -179,11 +179,30 @@ static __device__ __forceinline__ uint32_t mulhi_u32(uint32_t a, uint32_t b)
   return r;
 }
 
+// mask * 2 + bit on the FMA pipe (the ALU pipe is the busy one in the filter kernel)
+static __device__ __forceinline__ uint32_t push_bit_fma(uint32_t mask, uint32_t bit)
+{
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(mask), "r"(bit));
+  return r;
+}
+
 static __device__ __forceinline__ uint32_t fshr16_fma(uint32_t lo, uint32_t hi)
 {
   uint32_t r;
   asm("{ .reg .u32 t; mul.hi.u32 t, %1, 65536; mad.lo.u32 %0, %2, 65536, t; }" : "=r"(r) : "r"(lo), "r"(hi));
   return r;
+}
+
+// Level 2 reuses B3: every hit window has BOTH of its 3-byte keys in it (its last three bytes,
+// probed by level 1 when the window is the first of its pair, and its first three, probed when
+// it is the second), so for a surviving pair the other key of each window is a second,
+// nearly independent test at the level-1 false-positive rate -- one LDS instead of the
+// BLOOM_K dependent probes of B4, which only has to vet what passes both.
+static __device__ __forceinline__ bool b3_test(const uint32_t* sB3, uint32_t key3)
+{
+  const uint32_t w = sB3[((key3 << 8) * HASH3_MUL) >> 17];
+  return ((w >> (key3 & 31)) & (w >> ((key3 >> 16) & 31)) & 1u) != 0;
 }
 
 template <int B4BITS>
@@ -202,14 +221,14 @@ static __device__ __forceinline__ bool bloom4_test(const uint32_t* sB4, uint32_t
   return true;
 }
 
-// Bit layout: bits are numbered MSB-first, so that `word << n` brings bit n to bit
-// 31 and one funnel shift appends it to a per-thread mask.  B3 is a blocked Bloom
-// filter with two bits per key inside ONE 32-bit word (one LDS per probe): word =
-// top 15 bits of hash3(key), n1 = low 5 bits of the key's first byte, n2 = low 5
-// bits of its third byte -- both are the low bits of registers the probe already
-// holds, and the shift instruction masks its count to 5 bits for free.  The two
-// tests are accumulated in two masks that are ANDed once per tile.
-// B4: word = idx >> 5, n = idx & 31.
+// B3 is a blocked Bloom filter with two bits per key inside ONE 32-bit word (one LDS
+// per probe): word = top 15 bits of hash3(key), bit n1 = low 5 bits of the key's first
+// byte, bit n2 = low 5 bits of its third byte -- both are the low bits of registers the
+// probe already holds, and the shift instruction masks its count to 5 bits for free.
+// `(w >> n1) & (w >> n2) & 1` is two shifts and one LOP3; the result is appended to the
+// per-thread survivor mask with an integer multiply-add, which runs on the FMA pipe
+// (the ALU pipe is the one this kernel saturates).
+// B4 (MSB-first bit numbering): word = idx >> 5, n = idx & 31.
 template <int FT_THREADS, int FT_U, int B4BITS>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, int64_t hi)
@@ -263,15 +282,15 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
   {
 
     // ---- level 1: one B3 probe per pair of positions, branch-free
-    uint32_t maskA = 0, maskB = 0;
+    uint32_t mask = 0;
     const bool has_next = tile + gridDim.x < ntiles;
 
 #define PROBE3(x, y)                                                                \
   {                                                                                 \
     const uint32_t h_ = (x) * H3;                                                   \
     const uint32_t w_ = sB3[h_ >> 17];                                              \
-    maskA = __funnelshift_l(__funnelshift_l(0u, w_, (x)), maskA, 1);                \
-    maskB = __funnelshift_l(__funnelshift_l(0u, w_, (y)), maskB, 1);                \
+    const uint32_t t_ = __funnelshift_r(w_, 0u, (x)) & __funnelshift_r(w_, 0u, (y)) & 1u; \
+    mask = push_bit_fma(mask, t_);                                                  \
   }
 
 #pragma unroll
@@ -309,7 +328,6 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
     }
 #undef PROBE3
     // mask bit (8*FT_U - 1 - slot) belongs to slot = u*8 + pair
-    uint32_t mask = maskA & maskB;
 
     __syncwarp();
 
@@ -347,7 +365,7 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
     _Pragma("unroll") for (int e_ = 0; e_ < 2; e_++)                                                \
     {                                                                                               \
       const uint32_t w_ = (uint32_t) (x_ >> (sh_ + 8 * e_)); /* W(p + e) */                         \
-      if (bloom4_test<B4BITS>(sB4, w_))                                                             \
+      if (b3_test(sB3, e_ == 0 ? (w_ & 0xFFFFFFu) : (w_ >> 8)) && bloom4_test<B4BITS>(sB4, w_))     \
       {                                                                                             \
         const uint32_t mv_ = ht_lookup(F, w_);                                                      \
         if (mv_ != 0)                                                                               \
@@ -511,9 +529,9 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
 
     const uint32_t k_suffix = w >> 8, k_prefix = w & 0xFFFFFF;
     // B3 entry of a 3-byte key: word = top 15 bits of the hash; TWO bits per key, numbered
-    // MSB-first: low 5 bits of the key's first byte and low 5 bits of its third byte
-    fs->b3[hash3(k_suffix) >> 5] |= (0x80000000u >> (k_suffix & 31)) | (0x80000000u >> ((k_suffix >> 16) & 31));
-    fs->b3[hash3(k_prefix) >> 5] |= (0x80000000u >> (k_prefix & 31)) | (0x80000000u >> ((k_prefix >> 16) & 31));
+    // (bit n = 1u << n): low 5 bits of the key's first byte and low 5 bits of its third byte
+    fs->b3[hash3(k_suffix) >> 5] |= (1u << (k_suffix & 31)) | (1u << ((k_suffix >> 16) & 31));
+    fs->b3[hash3(k_prefix) >> 5] |= (1u << (k_prefix & 31)) | (1u << ((k_prefix >> 16) & 31));
     {
       const uint32_t g1 = w * HASH4_MUL, g2 = (w * HASH4_MUL2) | 1u;
       uint32_t g = g1;
