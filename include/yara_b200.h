@@ -99,7 +99,7 @@ typedef struct yrb_scan_params
 
 /* One YR_MATCH of unconfirmed_matches[string] carried over from an earlier block of
    the same scan (kind 0), or the fact that matches[string] is already non-empty
-   (kind 1: the FAST_MODE guard of scan.c:1021-1023).  At most 65535 per block. */
+   (kind 1: the FAST_MODE guard of scan.c:1021-1023).  At most YRB_MAX_SEEDS (4M) per block. */
 typedef struct yrb_seed
 {
   int64_t base;          /* YR_MATCH.base: base of the block it was found in */

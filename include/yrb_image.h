@@ -153,14 +153,16 @@ typedef struct yrb_match
   int64_t offset;       /* block-relative, like YR_MATCH.offset */
   uint32_t string_idx;
   int32_t match_length;
-  uint8_t xor_key;
+  uint8_t xor_key;      /* YRB_MATCH_FROM_SEED: bits 16-21 of the seed index instead (the node keeps its own key) */
   uint8_t flags;        /* YRB_MATCH_* */
-  uint16_t seed;        /* YRB_MATCH_FROM_SEED: index of the yrb_seed this node was */
+  uint16_t seed;        /* YRB_MATCH_FROM_SEED: bits 0-15 of the index of the yrb_seed this node was */
   int32_t chain_length; /* only meaningful for unconfirmed chain matches */
 } yrb_match;
 
 #define YRB_MATCH_UNCONFIRMED 1 /* chain part awaiting its tail */
 #define YRB_MATCH_FROM_SEED   2 /* a node carried over from an earlier block (yrb_scan_params.seeds) */
+#define YRB_MAX_SEEDS         0x3FFFFFu
+#define YRB_MATCH_SEED_INDEX(m) ((uint32_t) (m)->seed | ((uint32_t) ((m)->xor_key & 0x3F) << 16))
 
 #ifdef __cplusplus
 }

@@ -139,3 +139,20 @@ def test_small_block_latency_smoke():
     for k in range(20):
         data = synth.corpus(rs, 65536 + 4096 * k, 4096, seed=100 + k, plant_seed=k)
         assert_same(rr.scan(data), rb.scan(data))
+
+
+def test_more_than_64k_chain_parts_carried_between_blocks():
+    """70,000 unconfirmed heads of a chained string at the end of block 1; the tails in block 2 must still
+    find them (yrb_scan_params.seeds carries up to 4M nodes; the seed index no longer fits 16 bits)"""
+    rule = "rule t { strings: $a = { 11 22 33 44 [300-400] 55 66 77 88 } condition: $a }"
+    rr, rb = both(rule)
+    head, tail = bytes.fromhex("11223344"), bytes.fromhex("55667788")
+    block = 70000 * 4
+    b2 = bytearray(b"." * block)
+    for off in (350, 100000, 100002, 279000):
+        b2[off : off + 4] = tail
+    data = np.frombuffer(head * 70000 + bytes(b2), dtype=np.uint8)
+    a = rr.scan_blocks(data, block, 0, cap=1 << 20)
+    b = rb.scan_blocks(data, block, 0, cap=1 << 20)
+    assert a.rc == 0 and len(a.matches) > 20
+    assert_same(a, b)

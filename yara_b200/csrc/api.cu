@@ -322,7 +322,7 @@ __global__ void seeds_to_raw_kernel(const yrb_seed* seeds, uint32_t n, DevRules 
   r.offset = sd.offset;
   r.string_idx = sd.string_idx;
   r.length = sd.match_length;
-  r.misc = (uint32_t) sd.xor_key | (k << 8) | RAW_SEED | (sd.kind ? RAW_SEED_MARK : 0u);
+  r.misc = (uint32_t) sd.xor_key | (k << 8) | RAW_SEED | (sd.kind ? RAW_SEED_MARK : 0u);   // k < 2^22
   r.group = sd.string_idx < R.num_strings ? R.S[sd.string_idx].chain_head : YRB_NONE;
   out[k] = r;
   seed_base[k] = sd.base;
@@ -809,7 +809,7 @@ static int scan_impl(
   uint32_t n_resolve = (uint32_t) n_raw;
   if (params->n_seeds > 0 && !params->defer_resolve)
   {
-    if (params->n_seeds > 65535 || params->seeds == nullptr || s->rules->h.num_chains == 0) return YRB_ERROR_BAD_ARGUMENT;
+    if (params->n_seeds > YRB_MAX_SEEDS || params->seeds == nullptr || s->rules->h.num_chains == 0) return YRB_ERROR_BAD_ARGUMENT;
     if (s->d_seeds.ensure(params->n_seeds) != YRB_SUCCESS || s->seed_base.ensure(params->n_seeds) != YRB_SUCCESS ||
         s->d_raw.ensure((size_t) n_raw + params->n_seeds, true) != YRB_SUCCESS)
       return YRB_ERROR_INSUFFICIENT_MEMORY;

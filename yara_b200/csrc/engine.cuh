@@ -103,11 +103,12 @@ struct Raw
   int64_t offset;     // block-relative match offset
   uint32_t string_idx;
   int32_t length;
-  uint32_t misc;      // bits 0-7 xor_key; RAW_SEED: carried over from an earlier block, bits 8-23 = seed index,
+  uint32_t misc;      // bits 0-7 xor_key; RAW_SEED: carried over from an earlier block, bits 8-29 = seed index,
                       // key = chain_length (the record was never "discovered" in this block)
   uint32_t group;     // chain head idx for CHAIN_PART strings, else YRB_NONE
 };
 
+#define RAW_SEED_IDX_MASK 0x3FFFFFu
 #define RAW_SEED      0x80000000u
 #define RAW_SEED_MARK 0x40000000u   // kind 1: matches[string] is already non-empty
 

@@ -185,7 +185,7 @@ static __device__ __forceinline__ int64_t c_off(const ChainCtx& c, int32_t j) { 
 static __device__ __forceinline__ int64_t c_abs(const ChainCtx& c, int32_t j)
 {
   const Raw& r = c.sraw[j];
-  return ((r.misc & RAW_SEED) ? c.seed_base[(r.misc >> 8) & 0xFFFF] : c.cur_base) + r.offset;
+  return ((r.misc & RAW_SEED) ? c.seed_base[(r.misc >> 8) & RAW_SEED_IDX_MASK] : c.cur_base) + r.offset;
 }
 
 // scan.c:290-368 over index-linked lists; returns 0 ok / 1 duplicate dropped / 2 too many
@@ -523,6 +523,7 @@ __global__ void chain_resolve_kernel(
       m.xor_key = (uint8_t) (r.misc & 0xFF);
       m.flags = (r.misc & RAW_SEED) ? YRB_MATCH_FROM_SEED : 0;
       m.seed = (uint16_t) ((r.misc >> 8) & 0xFFFF);
+      if (r.misc & RAW_SEED) m.xor_key = (uint8_t) ((r.misc >> 24) & 0x3F);   // seed index bits 16-21
       m.chain_length = L.clen[k];
       finals[slot++] = m;
     }
@@ -646,6 +647,7 @@ __global__ void chain_resolve_kernel(
       m.xor_key = (uint8_t) (r.misc & 0xFF);
       m.flags = YRB_MATCH_UNCONFIRMED | ((r.misc & RAW_SEED) ? YRB_MATCH_FROM_SEED : 0);
       m.seed = (uint16_t) ((r.misc >> 8) & 0xFFFF);
+      if (r.misc & RAW_SEED) m.xor_key = (uint8_t) ((r.misc >> 24) & 0x3F);   // seed index bits 16-21
       m.chain_length = L.clen[k];
       unconf[slot] = m;
     }

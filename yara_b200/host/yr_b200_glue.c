@@ -548,7 +548,7 @@ static int materialise(
     if ((r->flags & YRB_MATCH_FROM_SEED) && seed_nodes != NULL)
     {
       /* a YR_MATCH node an earlier block created: it keeps its base and offset */
-      YR_MATCH* node = seed_nodes[r->seed];
+      YR_MATCH* node = seed_nodes[YRB_MATCH_SEED_INDEX(r)];
       node->prev = node->next = NULL;
       node->chain_length = r->chain_length;
 
@@ -642,8 +642,10 @@ static int collect_seeds(YR_SCANNER* scanner, rules_entry* re, yrb_seed** seeds_
       n++;
   }
 
-  if (n == 0 || n > 65535)
-    return ERROR_SUCCESS; /* beyond 65535 carried nodes the continuation is dropped (documented) */
+  if (n == 0)
+    return ERROR_SUCCESS;
+  if (n > YRB_MAX_SEEDS)
+    return fail_loudly("more than 4M chain-part matches carried between blocks", ERROR_INTERNAL_FATAL_ERROR);
 
   yrb_seed* seeds = (yrb_seed*) calloc(n, sizeof(yrb_seed));
   YR_MATCH** nodes = (YR_MATCH**) calloc(n, sizeof(YR_MATCH*));
