@@ -156,3 +156,20 @@ def test_more_than_64k_chain_parts_carried_between_blocks():
     b = rb.scan_blocks(data, block, 0, cap=1 << 20)
     assert a.rc == 0 and len(a.matches) > 20
     assert_same(a, b)
+
+
+def test_zero_width_loop_that_never_ends_in_the_reference():
+    """/^zzyc.((\\b)*?)zbz/ over "zzyc\\0a...": yr_re_exec cycles forever at one input position (the exit
+    branch dies on a literal mismatch, the loop branch re-splits into the fiber just freed).  The
+    reference only survives such data when an EARLIER candidate fails with ERROR_TOO_MANY_RE_FIBERS;
+    the GPU verifies every candidate, cuts the cycle and reports it as the same error (found by
+    scripts/fuzz_sweep.py, seed 1002)."""
+    rule = r"rule r { strings: $s2 = /^zzyc.((\b)*?)zbz/ condition: $s2 }"
+    rr, rb = both(rule)
+    # an earlier exploding candidate decides the scan in both implementations
+    data = b"xx zzyc zbz ....... zzyc\x00accd0az_zzb1x"
+    a, b = rr.scan(data), rb.scan(data)
+    assert a.rc == 46 and b.rc == 46
+    # the cycling candidate alone: the reference would never return; the GPU path answers
+    b = rb.scan(b"zzyc\x00accd0az_zzb1x")
+    assert b.rc == 46

@@ -28,6 +28,9 @@
     }                                                                                             \
   } while (0)
 
+static bool trace_on() { static int t = -1; if (t < 0) t = getenv("YRB_TRACE") != nullptr; return t != 0; }
+#define TRACE(...) do { if (trace_on()) { fprintf(stderr, "yrb200 trace: " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
+
 // ------------------------------------------------------------------- structs
 
 struct yrb_rules
@@ -748,9 +751,11 @@ static int scan_impl(
     if (s->rules->h.code_size > 0) // only RE / hex strings can raise verifier errors
       CK(cudaMemsetAsync(s->str_err.p, 0xFF, sizeof(unsigned long long) * s->rules->R.num_strings, s->stream));
 
+    TRACE("verify tier 1: %llu literal, %llu fast, %llu re candidates", n_cand[0], n_cand[1], n_cand[2]);
     launch_verify(s->rules->R, V, co, n_cand, ro, s->vws, s->stream, &launches);
     int rc = read_status(s);
     if (rc != YRB_SUCCESS) return rc;
+    TRACE("tier 1 done: retry fast %u re %u, raw %llu, any_error %u", hs->n_retry[0], hs->n_retry[1], hs->n_raw, hs->any_error);
 
     if (hs->n_retry[0] > 0 || hs->n_retry[1] > 0)
     {
@@ -774,18 +779,34 @@ static int scan_impl(
       launch_verify_tier2(s->rules->R, V, co, ro, s->vws, hs->n_retry[0] > 0, hs->n_retry[1] > 0, s->stream, &launches);
       rc = read_status(s);
       if (rc != YRB_SUCCESS) return rc;
+      TRACE("tier 2 done: retry3 %u, raw %llu, any_error %u", hs->n_retry3, hs->n_raw, hs->any_error);
     }
 
     if (hs->n_retry3 > 0)
     {
-      // rare: position lists that outgrew tier 2 (backward-mode duplicates); 16 MB per thread
-      const size_t t3 = hs->n_retry3 < 32 ? hs->n_retry3 : 32;
+      // rare: position lists that outgrew tier 2 (backward-mode duplicates).  Tier 3: 64k positions
+      // (768 KB) per thread, as many threads as there are candidates up to 2048; tier 4: 1M
+      // positions (12 MB) per thread for what is left, 32 threads.
+      size_t t3 = hs->n_retry3 < 2048 ? hs->n_retry3 : 2048;
+      t3 = (t3 + 31) / 32 * 32;
       if (s->ws_fast3.ensure(t3 * fast_ws_bytes_per_thread(3)) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
       s->vws.fast3 = s->ws_fast3.p;
       s->vws.fast3_threads = t3;
-      launch_verify_fast_tier3(s->rules->R, V, co, ro, s->vws, s->stream, &launches);
+      CK(cudaMemsetAsync(&s->d_status->n_retry[0], 0, sizeof(unsigned int), s->stream));
+      launch_verify_fast_tier3(s->rules->R, V, co, ro, s->vws, 3, s->stream, &launches);
       rc = read_status(s);
       if (rc != YRB_SUCCESS) return rc;
+      TRACE("tier 3 done: %u candidates left for tier 4", hs->n_retry[0]);
+      if (hs->n_retry[0] > 0)
+      {
+        const size_t t4 = 32;
+        if (s->ws_fast3.ensure(t4 * fast_ws_bytes_per_thread(4)) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+        s->vws.fast3 = s->ws_fast3.p;
+        s->vws.fast3_threads = t4;
+        launch_verify_fast_tier3(s->rules->R, V, co, ro, s->vws, 4, s->stream, &launches);
+        rc = read_status(s);
+        if (rc != YRB_SUCCESS) return rc;
+      }
     }
     CK(cudaEventRecord(s->ev[2], s->stream));
 
@@ -871,7 +892,9 @@ static int scan_impl(
   }
   else
   {
+    TRACE("resolve: %u records, chain records %u", n_resolve, hs->n_chain_raw);
     rc = run_resolve(s, s->d_raw.p, n_resolve, params, res, &launches, hs->n_chain_raw > 0 || n_resolve > (uint32_t) n_raw);
+    TRACE("resolve done: rc %d error %d", rc, res->error);
     res->seeds_consumed = (n_resolve > (uint32_t) n_raw) ? 1 : 0;
     CK(cudaEventRecord(s->ev[3], s->stream));
     CK(cudaStreamSynchronize(s->stream));

@@ -215,6 +215,6 @@ void launch_verify_tier2(
     const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, bool fast, bool re,
     cudaStream_t s, unsigned* launches);
 void launch_verify_fast_tier3(
-    const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, cudaStream_t s,
-    unsigned* launches);
+    const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, int tier,
+    cudaStream_t s, unsigned* launches);
 size_t re_ws_bytes_per_thread(uint32_t stack_words, int tier);

@@ -559,7 +559,10 @@ __global__ void chain_resolve_kernel(
     // records of this chain that share the input position: put them in discovery-key order
     uint32_t r_end = j + 1;
     while (r_end < n && kA[r_end] == kA[j]) r_end++;
-    for (uint32_t x = j + 1; x < r_end; x++)
+    // (the seeds -- position 0 -- keep the order the caller gave them in, ascending base + offset per
+    // string: each then goes to the tail of its list in O(1); their `key` is a chain length, not a key)
+    const bool seed_group = (kA[j] & ((1ULL << OFFSET_BITS) - 1)) == 0;
+    for (uint32_t x = j + 1; x < r_end && !seed_group; x++)
     {
       if (sraw[x - 1].key <= sraw[x].key) continue; // already in order: the common case
       const Raw vx = sraw[x];

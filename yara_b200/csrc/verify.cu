@@ -123,7 +123,8 @@ static __device__ __forceinline__ int32_t code_i32(const Ctx& c, uint32_t off)
 
 #define FAST_POS_CAP 4608       // tier 2: more than any forward-mode list can hold (<= 4097 distinct positions)
 #define FAST_POS_CAP_SMALL 96   // tier 1: what almost every candidate needs
-#define FAST_POS_CAP_HUGE (1 << 20) // tier 3: backward-mode lists are not kept duplicate-free by the reference
+#define FAST_POS_CAP_MID (1 << 16)  // tier 3: backward-mode lists are not kept duplicate-free by the reference
+#define FAST_POS_CAP_HUGE (1 << 20) // tier 4: the few candidates that outgrow even that
                                     // (re.c:2323-2333) and can grow far beyond the window
 #define WS_RETRY (-2)           // internal: the small work area overflowed, verify again in tier 2
 
@@ -141,7 +142,7 @@ struct FastWs
 };
 
 size_t fast_ws_bytes_per_thread(int tier)
-{ return sizeof(FastPos) * (size_t) (tier == 1 ? FAST_POS_CAP_SMALL : tier == 2 ? FAST_POS_CAP : FAST_POS_CAP_HUGE); }
+{ return sizeof(FastPos) * (size_t) (tier == 1 ? FAST_POS_CAP_SMALL : tier == 2 ? FAST_POS_CAP : tier == 3 ? FAST_POS_CAP_MID : FAST_POS_CAP_HUGE); }
 
 // re.c:2150-2477.  Returns an ERROR_* code.  `pos` = block position of input_data.
 static __device__ int re_fast_exec(
@@ -352,6 +353,7 @@ struct Fiber
   int16_t pad;
 };
 
+#define RE_STEPS_PER_POSITION_MAX (1u << 20)
 #define RE_FIBERS_SMALL 64      // tier 1 pool; tier 2 has the reference's RE_MAX_FIBERS = 1024
 
 struct FiberPool
@@ -722,12 +724,27 @@ static __device__ int re_exec(
     }
 
     fiber = p.head;
+    uint32_t steps = 0;
 
     while (fiber >= 0)
     {
       const uint32_t ip = p.f[fiber].ip;
       const uint32_t op = code_u8(c, ip);
       int action = 0; // 0 none, 1 continue, 2 kill, 3 kill tail
+
+      // A zero-width loop such as /a(\b)*?b/ can cycle at ONE input position without growing the
+      // fiber list: the exit branch dies on a literal mismatch, the loop branch re-splits into the
+      // fiber just freed, forever.  yr_re_exec (re.c:1693) has no way out of that either -- the
+      // reference spins until killed -- and a scan only ends there because an EARLIER candidate
+      // fails with ERROR_TOO_MANY_RE_FIBERS first.  Every candidate is verified here, in
+      // parallel, so the cycle is cut after far more steps than a terminating execution can
+      // take (each of the <= 1024 fibers runs a handful of zero-width ops per position) and
+      // reported as the same explosion; the earliest failing candidate still decides the scan.
+      if (++steps > RE_STEPS_PER_POSITION_MAX)
+      {
+        fiber_kill_all(p);
+        return YRB_ERROR_TOO_MANY_RE_FIBERS;
+      }
       bool match, kill;
 
 #define PROLOG                                                                                        \
@@ -1124,6 +1141,9 @@ verify_literal_kernel(DevRules R, ScanView V, const Cand* cands, unsigned long l
 // Records a candidate emitted before overflowing are emitted again with the same
 // discovery keys; resolve.cu treats equal keys as one record.
 // TIER 1: every candidate; TIER 2: the retry queue of tier 1; TIER 3: the retry queue of tier 2
+// (64k positions, up to 2048 threads); TIER 4: the retry queue of tier 3 (1M positions, 32 threads).
+// Tiers 3 and 4 alternate between the two queues: tier 3 reads retry_fast3 / n_retry3 and refills
+// retry_fast / n_retry[0] (reset by the host in between), which tier 4 reads.
 template <int TIER>
 __global__ void __launch_bounds__(128)
 verify_fast_kernel(
@@ -1136,7 +1156,7 @@ verify_fast_kernel(
   my.v = reinterpret_cast<FastPos*>(ws + tid * ws_per_thread);
   my.cap = cap;
 
-  if (TIER == 2) n = out.st->n_retry[0];
+  if (TIER == 2 || TIER == 4) n = out.st->n_retry[0];
   if (TIER == 3) n = out.st->n_retry3;
 
   for (unsigned long long t = tid; t < n; t += stride)
@@ -1158,6 +1178,11 @@ verify_fast_kernel(
       if (TIER == 2)
       {
         retry_next[atomicAdd(&out.st->n_retry3, 1u)] = (uint32_t) ci;
+        continue;
+      }
+      if (TIER == 3)
+      {
+        retry_next[atomicAdd(&out.st->n_retry[0], 1u)] = (uint32_t) ci;
         continue;
       }
       atomicExch(&out.st->ws_overflow, 1u); // the reference would still be calling malloc: give up honestly
@@ -1278,11 +1303,17 @@ void launch_verify_tier2(
 }
 
 void launch_verify_fast_tier3(
-    const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, cudaStream_t s,
-    unsigned* launches)
+    const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, int tier,
+    cudaStream_t s, unsigned* launches)
 {
-  verify_fast_kernel<3><<<(unsigned) ((W.fast3_threads + 31) / 32), 32, 0, s>>>(
-      R, V, cands.cand[CLS_FAST], 0, out, (uint8_t*) W.fast3, fast_ws_bytes_per_thread(3), FAST_POS_CAP_HUGE,
-      W.retry_fast3, nullptr);
+  const unsigned blocks = (unsigned) ((W.fast3_threads + 31) / 32);
+  if (tier == 3)
+    verify_fast_kernel<3><<<blocks, 32, 0, s>>>(
+        R, V, cands.cand[CLS_FAST], 0, out, (uint8_t*) W.fast3, fast_ws_bytes_per_thread(3), FAST_POS_CAP_MID,
+        W.retry_fast3, W.retry_fast);
+  else
+    verify_fast_kernel<4><<<blocks, 32, 0, s>>>(
+        R, V, cands.cand[CLS_FAST], 0, out, (uint8_t*) W.fast3, fast_ws_bytes_per_thread(4), FAST_POS_CAP_HUGE,
+        W.retry_fast, nullptr);
   (*launches)++;
 }
