@@ -173,3 +173,13 @@ def test_zero_width_loop_that_never_ends_in_the_reference():
     # the cycling candidate alone: the reference would never return; the GPU path answers
     b = rb.scan(b"zzyc\x00accd0az_zzb1x")
     assert b.rc == 46
+
+
+def test_repeat_any_recursion_as_deep_as_the_fiber_pool():
+    """/a1dx((.?)+yy0)/: _yr_re_fiber_sync recurses once per REPEAT_ANY split (re.c:1626) until the
+    1024 fibers are used up -> ERROR_TOO_MANY_RE_FIBERS, not an internal error of the frame stack
+    (found by scripts/fuzz_sweep.py, seed 1123)."""
+    rr, rb = both("rule r { strings: $s0 = /a1dx((.?)+yy0)/i condition: $s0 }")
+    for data in (b"a1dx", b"zza1dxabcyy0 tail", b"nothing here"):
+        assert_same(rr.scan(data), rb.scan(data))
+    assert rb.scan(b"a1dx").rc == 46

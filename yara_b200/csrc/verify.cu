@@ -353,6 +353,15 @@ struct Fiber
   int16_t pad;
 };
 
+#define SYNC_MAX_DEPTH 24
+
+struct SyncFrame
+{
+  int last;
+  int resume;
+  uint32_t mask[4];
+};
+
 #define RE_STEPS_PER_POSITION_MAX (1u << 20)
 #define RE_FIBERS_SMALL 64      // tier 1 pool; tier 2 has the reference's RE_MAX_FIBERS = 1024
 
@@ -364,11 +373,15 @@ struct FiberPool
   int stack_words;
   int free_head;
   int head, tail;
+  SyncFrame* frames; // tier 2: cap frames in the work area (a frame is only pushed after a split, so depth <= fibers);
+                     // tier 1: nullptr, fiber_sync uses SYNC_MAX_DEPTH frames of local memory and asks for tier 2 beyond
 };
 
 size_t re_ws_bytes_per_thread(uint32_t stack_words, int tier)
 {
   size_t b = (size_t) (tier == 1 ? RE_FIBERS_SMALL : YRB_RE_MAX_FIBERS) * (sizeof(Fiber) + sizeof(uint16_t) * stack_words);
+  b = (b + 15) & ~(size_t) 15;
+  if (tier != 1) b += (size_t) YRB_RE_MAX_FIBERS * sizeof(SyncFrame);
   return (b + 15) & ~(size_t) 15;
 }
 
@@ -490,18 +503,12 @@ static __device__ __forceinline__ void fiber_kill_all(FiberPool& p)
 // re.c:1441-1654 _yr_re_fiber_sync.  The reference recurses for REPEAT_ANY
 // (re.c:1626); here the recursion is an explicit frame stack.  The set of
 // already-executed split ids (ids < RE_MAX_SPLIT_ID = 128) is a 128-bit mask.
-#define SYNC_MAX_DEPTH 24
-
-struct SyncFrame
-{
-  int last;
-  int resume;
-  uint32_t mask[4];
-};
 
 static __device__ int fiber_sync(Ctx& c, FiberPool& p, int fiber_to_sync)
 {
-  SyncFrame frames[SYNC_MAX_DEPTH];
+  SyncFrame local_frames[SYNC_MAX_DEPTH];
+  SyncFrame* frames = p.frames ? p.frames : local_frames;
+  const int max_depth = p.frames ? p.cap : SYNC_MAX_DEPTH;
   int depth = 0;
 
   uint32_t mask[4] = {0, 0, 0, 0};
@@ -636,8 +643,8 @@ static __device__ int fiber_sync(Ctx& c, FiberPool& p, int fiber_to_sync)
         p.f[branch_b].rc = -1;
 
         // recursive _yr_re_fiber_sync(branch_b), then continue at `next`
-        if (depth == SYNC_MAX_DEPTH)
-          return YRB_ERROR_INTERNAL_FATAL;
+        if (depth == max_depth)   // the reference recurses (re.c:1626) as deep as it has fibers
+          return p.frames ? YRB_ERROR_INTERNAL_FATAL : WS_RETRY;
         frames[depth].last = last;
         frames[depth].resume = next;
         frames[depth].mask[0] = mask[0]; frames[depth].mask[1] = mask[1];
@@ -1210,6 +1217,13 @@ verify_re_kernel(
   p.stacks = reinterpret_cast<uint16_t*>(p.f + cap);
   p.cap = cap;
   p.stack_words = (int) R.stack_words;
+  p.frames = nullptr;
+  if (TIER2)
+  {
+    size_t fb = (size_t) cap * (sizeof(Fiber) + sizeof(uint16_t) * R.stack_words);
+    fb = (fb + 15) & ~(size_t) 15;
+    p.frames = reinterpret_cast<SyncFrame*>(ws + tid * ws_per_thread + fb);
+  }
 
   // free list over the pool (kept consistent across candidates: every exec returns all of its fibers)
   for (int f = 0; f < cap; f++)
