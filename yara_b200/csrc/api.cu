@@ -807,6 +807,8 @@ static int scan_impl(
         rc = read_status(s);
         if (rc != YRB_SUCCESS) return rc;
       }
+      // up to 1.5 GB that almost no scan needs: do not keep it in a (possibly pooled) scanner
+      if (s->ws_fast3.cap > ((size_t) 256 << 20)) { s->ws_fast3.release(); s->vws.fast3 = nullptr; s->vws.fast3_threads = 0; }
     }
     CK(cudaEventRecord(s->ev[2], s->stream));
 
