@@ -134,7 +134,7 @@ struct ScanStatus
   unsigned int n_retry3;        // fast-VM candidates that outgrew tier 2 as well (backward-mode lists hold duplicates)
   unsigned int n_chain_raw;     // Raw records of chained strings (0: the chain kernels are skipped)
   unsigned int err_string1;     // 1 + string of the candidate behind the error (scanner->last_error_string); 0 = none
-  unsigned int pad3[1];
+  unsigned int n_chain_starts;  // chains present among the Raw records (resolve.cu: one warp each)
 };
 
 struct CandOut

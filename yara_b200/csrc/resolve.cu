@@ -464,28 +464,47 @@ __global__ void chain_init_kernel(ChainLists L, uint32_t num_strings)
 // One thread replays a whole chain, so the records it walks are first gathered into
 // sorted order by all threads: sequential reads instead of two dependent random
 // gathers per record and per list step.
-__global__ void chain_gather_kernel(const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, Raw* sraw)
+__global__ void chain_gather_kernel(
+    const Raw* raw, const uint32_t* ix, const uint64_t* kA, uint32_t n, Raw* sraw, uint32_t* starts, ScanStatus* st)
 {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const uint64_t a = kA[j];
   if ((a & A_CHAIN_BIT) && a != A_DROPPED)
+  {
     sraw[j] = raw[ix[j]];
+    // first record of its chain: one warp of chain_resolve_kernel will replay it
+    if (j == 0 || (kA[j - 1] >> OFFSET_BITS) != (a >> OFFSET_BITS))
+      starts[atomicAdd(&st->n_chain_starts, 1u)] = j;
+  }
 }
 
-__global__ void chain_resolve_kernel(
+// One WARP per chain.  Lane 0 replays the chain exactly like the reference would (the
+// list logic is order dependent); the other lanes look ahead.  A callback of a non-head
+// part whose predecessor's unconfirmed list is empty does nothing at all in
+// _yr_scan_verify_chained_string_match (scan.c:452-500: the loop over that list has no
+// iterations, add_match stays false) -- and on unlucky data such callbacks come by the
+// tens of millions (a short tail part after an unbounded jump matches everywhere, the
+// head almost never).  So before every step the warp classifies the next 32 records
+// against the CURRENT list state and skips the longest run of such no-ops that ends on
+// a group boundary (records sharing an input position are ordered by lane 0 first, so a
+// group is skipped only as a whole); everything else goes through lane 0 one group at a
+// time.  The state only changes in lane 0's steps, so the classification is exact.
+__global__ void __launch_bounds__(128)
+chain_resolve_kernel(
     Raw* sraw, const uint64_t* kA, uint32_t n, DevRules R, ChainLists L, yrb_match* finals,
     yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap, int scan_flags,
     const int64_t* seed_base, int64_t cur_base, int n_seg, const int64_t* seg_start, const int64_t* seg_len,
-    uint8_t* item_dirty)
+    uint8_t* item_dirty, const uint32_t* starts)
 {
-  const uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j0 >= n) return;
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (warp >= st->n_chain_starts) return;
 
-  const uint64_t a0 = kA[j0];
-  if (!(a0 & A_CHAIN_BIT) || a0 == A_DROPPED) return;
-  const uint64_t chain = a0 >> OFFSET_BITS;
-  if (j0 > 0 && (kA[j0 - 1] >> OFFSET_BITS) == chain) return; // not the first record of its chain
+  const uint32_t j0 = starts[warp];
+  const uint64_t chain = kA[j0] >> OFFSET_BITS;
+  const uint64_t POS_MASK = (1ULL << OFFSET_BITS) - 1;
 
   ChainCtx c;
   c.sraw = sraw;
@@ -496,18 +515,21 @@ __global__ void chain_resolve_kernel(
   c.steps[0] = c.steps[1] = c.steps[2] = 0;
 
   const uint32_t head_string = sraw[j0].group;
-  uint32_t j = j0;
-  uint64_t prev_key = ~0ULL;
-  uint32_t disabled_string = YRB_NONE; // strings_temp_disabled after a TOO_MANY (at most one tracked per chain)
+  uint32_t j = j0;                      // uniform across the warp
+  uint64_t prev_key = ~0ULL;            // lane 0's replay state from here on
+  uint32_t disabled_string = YRB_NONE;  // strings_temp_disabled after a TOO_MANY (at most one tracked per chain)
   uint64_t cur_cand = ~0ULL;
   bool skip_cand = false;
 
   // Batch mode: every item is a scan of its own (unconfirmed_matches[] and matches[] start
   // empty, scanner.c:178-204), so at the first record past the current item the head's
-  // confirmed list is written out and the lists of the strings seen so far are emptied.
+  // confirmed list is written out and the lists of the strings replayed so far are emptied.
   int cur_item = -1;
-  int64_t item_last = -1;   // largest input position i that still belongs to cur_item
+  int64_t item_last = -1;   // largest input position i that still belongs to cur_item (uniform copy)
   uint32_t item_j0 = j0;
+  uint32_t touched[16];     // strings lane 0 replayed a record of in the current item
+  int n_touched = 0;
+  bool touched_overflow = false;
 
   auto write_confirmed = [&]() {
     const int32_t cnt = L.mcnt[head_string];
@@ -529,130 +551,316 @@ __global__ void chain_resolve_kernel(
     }
   };
 
-  while (j < n && (kA[j] >> OFFSET_BITS) == chain)
+  auto reset_string = [&](uint32_t sx) {
+    L.uhead[sx] = L.utail[sx] = L.mhead[sx] = L.mtail[sx] = L.uvhead[sx] = -1;
+    L.ucnt[sx] = L.mcnt[sx] = 0;
+  };
+
+  uint32_t sorted_until = j0;   // records in [j, sorted_until) are in replay order (uniform)
+
+  for (;;)
   {
-    if (n_seg > 0)
+    // ---- look-ahead (all lanes): first record at or after j that needs lane 0.  Inside the part
+    // that is already in replay order every record stands for itself; beyond it, records that share
+    // an input position are not ordered yet, so such a group is skipped only as a whole.
+    // O(records / 32) warp steps in total.
+    uint32_t scan = j, last_gs = j, stop = j;
+    bool found = false, chain_done = false, finished = false;
+    uint64_t a_carry = 0;
+    while (!finished)
     {
-      const int64_t i = (int64_t) (kA[j] & ((1ULL << OFFSET_BITS) - 1)) - 1;
-      if (i > item_last)
+      // eight windows of 32 records per round: their dependent loads (record -> string -> list
+      // count) are in flight together, the round costs one latency chain instead of eight
+      constexpr int LA = 8;
+      uint64_t av[LA];
+      bool inv[LA], skv[LA];
+      uint32_t sidx[LA], misc[LA];
+#pragma unroll
+      for (int u = 0; u < LA; u++)
       {
-        if (cur_item >= 0)
+        const uint32_t jj = scan + (uint32_t) u * 32u + lane;
+        av[u] = ~0ULL;
+        sidx[u] = 0;
+        misc[u] = 0;
+        if (jj < n)
         {
-          write_confirmed();
-          for (uint32_t k = item_j0; k < j; k++)
-          {
-            const uint32_t sx = sraw[k].string_idx;
-            L.uhead[sx] = L.utail[sx] = L.mhead[sx] = L.mtail[sx] = L.uvhead[sx] = -1;
-            L.ucnt[sx] = L.mcnt[sx] = 0;
-          }
+          av[u] = kA[jj];
+          sidx[u] = sraw[jj].string_idx;   // meaningful only for chain records (checked below)
+          misc[u] = sraw[jj].misc;
         }
-        cur_item = seg_find_in(seg_start, n_seg, i - 1);
-        item_last = seg_start[cur_item] + seg_len[cur_item];
-        item_j0 = j;
-        prev_key = ~0ULL;
-        disabled_string = YRB_NONE;
-        cur_cand = ~0ULL;
-        skip_cand = false;
+      }
+#pragma unroll
+      for (int u = 0; u < LA; u++)
+      {
+        inv[u] = (av[u] >> OFFSET_BITS) == chain;
+        skv[u] = false;
+        if (inv[u])
+        {
+          const uint32_t pred = R.S[sidx[u]].chained_to;
+          skv[u] = !(misc[u] & RAW_SEED) && pred != YRB_NONE && __ldcg(&L.ucnt[pred]) == 0;
+          if (n_seg > 0 && (int64_t) (av[u] & POS_MASK) - 1 > item_last)
+            skv[u] = false;   // first record of the next item: lane 0 has to close the current one
+        }
+      }
+
+#pragma unroll
+      for (int u = 0; u < LA; u++)
+      {
+        if (finished) break;
+        const uint32_t jj = scan + lane;
+        const uint64_t a = av[u];
+        const bool in_chain = inv[u];
+        const unsigned vm = __ballot_sync(FULL, in_chain);   // a prefix of the lanes: a chain's records are contiguous
+        const uint32_t nvalid = (uint32_t) __popc(vm);
+        if (nvalid == 0)
+        {
+          chain_done = (scan == j);
+          stop = scan;
+          finished = true;
+          break;
+        }
+        const unsigned ns = vm & ~__ballot_sync(FULL, skv[u]);
+
+        uint64_t a_prev = __shfl_up_sync(FULL, a, 1);
+        if (lane == 0) a_prev = (scan == j) ? ~a : a_carry;   // j itself always starts a group
+        const unsigned gm = __ballot_sync(FULL, in_chain && (jj < sorted_until || a != a_prev));
+
+        if (ns)
+        {
+          const uint32_t fl = (uint32_t) (__ffs(ns) - 1);
+          const unsigned upto = gm & (fl >= 31 ? FULL : ((2u << fl) - 1u));
+          if (upto) last_gs = scan + 31u - (uint32_t) __clz(upto);
+          found = true;
+          finished = true;
+          break;
+        }
+        if (gm) last_gs = scan + 31u - (uint32_t) __clz(gm);
+        a_carry = __shfl_sync(FULL, a, nvalid - 1);
+        stop = scan + nvalid;
+        if (nvalid < 32)
+        {
+          finished = true;   // the chain ends inside this window, nothing left for lane 0
+          break;
+        }
+        scan += 32;
       }
     }
+    if (chain_done)
+      break;
 
-    // records of this chain that share the input position: put them in discovery-key order
-    uint32_t r_end = j + 1;
-    while (r_end < n && kA[r_end] == kA[j]) r_end++;
-    // (the seeds -- position 0 -- keep the order the caller gave them in, ascending base + offset per
-    // string: each then goes to the tail of its list in O(1); their `key` is a chain length, not a key)
-    const bool seed_group = (kA[j] & ((1ULL << OFFSET_BITS) - 1)) == 0;
-    for (uint32_t x = j + 1; x < r_end && !seed_group; x++)
+    const uint32_t skip_to = found ? last_gs : stop;
+    if (skip_to > j)
     {
-      if (sraw[x - 1].key <= sraw[x].key) continue; // already in order: the common case
-      const Raw vx = sraw[x];
-      uint32_t y = x;
-      while (y > j && sraw[y - 1].key > vx.key) { sraw[y] = sraw[y - 1]; y--; }
-      sraw[y] = vx;
+      for (uint32_t k = j + lane; k < skip_to; k += 32)
+        L.where[k] = 0;   // in no list
+      j = skip_to;
+      prev_key = ~0ULL;
+      cur_cand = ~0ULL;
+      skip_cand = false;
+      continue;
     }
 
-    for (; j < r_end; j++)
+    if (j >= sorted_until)
     {
-      L.nxt[j] = L.prv[j] = -1;
-      L.where[j] = 0;
-
-      const Raw r = sraw[j];
-
-      if (r.misc & RAW_SEED)
+      // ---- a new group of records that share the input position of record j: find its end and put
+      // it in discovery-key order (all lanes check; lane 0 sorts in the rare unordered case).
+      // The seeds -- position 0 -- keep the order the caller gave them in, ascending base + offset per
+      // string: each then goes to the tail of its list in O(1); their `key` is a chain length, not a key.
+      const uint64_t a_j = kA[j];
+      const bool seed_group = (a_j & POS_MASK) == 0;
+      uint32_t r_end = j;
+      bool ordered = true;
+      for (;;)
       {
-        // state left by earlier blocks of this scan: goes straight back into its list
-        if (r.misc & RAW_SEED_MARK)
+        const uint32_t k = r_end + lane;
+        const bool same = k < n && kA[k] == a_j;
+        const unsigned sm2 = __ballot_sync(FULL, same);
+        const bool bad = same && k > j && !seed_group && sraw[k - 1].key > sraw[k].key;
+        const unsigned cnt = (sm2 == FULL) ? 32u : (uint32_t) (__ffs(~sm2) - 1);
+        const unsigned bm = __ballot_sync(FULL, bad) & (cnt >= 32 ? FULL : ((1u << cnt) - 1u));
+        if (bm) ordered = false;
+        r_end += cnt;
+        if (cnt < 32) break;
+      }
+      if (!ordered && lane == 0)
+      {
+        for (uint32_t x = j + 1; x < r_end; x++)
         {
-          L.prior[r.string_idx] = 1;
+          if (sraw[x - 1].key <= sraw[x].key) continue;
+          const Raw vx = sraw[x];
+          uint32_t y = x;
+          while (y > j && sraw[y - 1].key > vx.key) { sraw[y] = sraw[y - 1]; y--; }
+          sraw[y] = vx;
         }
-        else
+        __threadfence_block();
+      }
+      __syncwarp();
+      sorted_until = r_end;
+      continue;   // look again: inside the ordered group single records can be skipped
+    }
+
+    // ---- lane 0 replays record j and what follows it in the ordered part, up to the next no-op
+    uint32_t j_next = j;
+    if (lane == 0)
+    {
+      uint32_t jq = j;
+      for (; jq < sorted_until; jq++)
+      {
+        const Raw r = sraw[jq];
+
+        if (jq > j && !(r.misc & RAW_SEED))
         {
-          L.clen[j] = (int32_t) r.key;
-          L.mlen[j] = r.length;
-          if (clist_add(c, L.uhead, L.utail, L.ucnt, r.string_idx, (int32_t) j) == 0)
+          const uint32_t pred = R.S[r.string_idx].chained_to;
+          if (pred != YRB_NONE && L.ucnt[pred] == 0)
+            break;   // a no-op: let the warp skip ahead from here
+        }
+
+        if (n_seg > 0)
+        {
+          const int64_t i = (int64_t) (kA[jq] & POS_MASK) - 1;
+          if (i > item_last)
           {
-            L.where[j] = 1;
-            if (L.clen[j] == 0)
+            if (cur_item >= 0)
             {
-              L.uvn[j] = L.uvhead[r.string_idx];
-              L.uvhead[r.string_idx] = (int32_t) j;
+              write_confirmed();
+              if (touched_overflow)
+                for (uint32_t k = item_j0; k < jq; k++) reset_string(sraw[k].string_idx);
+              else
+                for (int t = 0; t < n_touched; t++) reset_string(touched[t]);
+            }
+            n_touched = 0;
+            touched_overflow = false;
+            cur_item = seg_find_in(seg_start, n_seg, i - 1);
+            item_last = seg_start[cur_item] + seg_len[cur_item];
+            item_j0 = jq;
+            prev_key = ~0ULL;
+            disabled_string = YRB_NONE;
+            cur_cand = ~0ULL;
+            skip_cand = false;
+          }
+          if (!touched_overflow)
+          {
+            int t = 0;
+            while (t < n_touched && touched[t] != r.string_idx) t++;
+            if (t == n_touched)
+            {
+              if (n_touched < 16) touched[n_touched++] = r.string_idx; else touched_overflow = true;
             }
           }
         }
-        continue;
+
+        L.nxt[jq] = L.prv[jq] = -1;
+        L.where[jq] = 0;
+
+        if (r.misc & RAW_SEED)
+        {
+          // state left by earlier blocks of this scan: goes straight back into its list
+          if (r.misc & RAW_SEED_MARK)
+          {
+            L.prior[r.string_idx] = 1;
+          }
+          else
+          {
+            L.clen[jq] = (int32_t) r.key;
+            L.mlen[jq] = r.length;
+            if (clist_add(c, L.uhead, L.utail, L.ucnt, r.string_idx, (int32_t) jq) == 0)
+            {
+              L.where[jq] = 1;
+              if (L.clen[jq] == 0)
+              {
+                L.uvn[jq] = L.uvhead[r.string_idx];
+                L.uvhead[r.string_idx] = (int32_t) jq;
+              }
+            }
+          }
+          continue;
+        }
+
+        if (r.key == prev_key) continue; // re-emission of the same callback by the tier-2 verifier
+        prev_key = r.key;
+
+        if (r.string_idx == disabled_string) continue;
+
+        // scan.c:1021-1023: the FAST_MODE / SINGLE_MATCH guard is evaluated once per
+        // candidate, before verification, against matches[string->idx] (only ever
+        // non-empty for the chain's head string)
+        if ((r.key >> KEY_SEQ_BITS) != cur_cand)
+        {
+          cur_cand = r.key >> KEY_SEQ_BITS;
+          skip_cand = (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) &&
+                      (L.mcnt[r.string_idx] > 0 || L.prior[r.string_idx]);
+        }
+        if (skip_cand) continue;
+
+        if (verify_chained(c, (int32_t) jq) == 2)
+        {
+          const uint32_t slot = atomicAdd(&st->n_too_many, 1u);
+          if (slot < too_many_cap) too_many[slot] = r.string_idx;
+          disabled_string = r.string_idx;
+          if (n_seg > 0) item_dirty[cur_item] = 1;   // the callback protocol needs the per-item path
+        }
       }
-
-      if (r.key == prev_key) continue; // re-emission of the same callback by the tier-2 verifier
-      prev_key = r.key;
-
-      if (r.string_idx == disabled_string) continue;
-
-      // scan.c:1021-1023: the FAST_MODE / SINGLE_MATCH guard is evaluated once per
-      // candidate, before verification, against matches[string->idx] (only ever
-      // non-empty for the chain's head string)
-      if ((r.key >> KEY_SEQ_BITS) != cur_cand)
-      {
-        cur_cand = r.key >> KEY_SEQ_BITS;
-        skip_cand = (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) &&
-                    (L.mcnt[r.string_idx] > 0 || L.prior[r.string_idx]);
-      }
-      if (skip_cand) continue;
-
-      if (verify_chained(c, (int32_t) j) == 2)
-      {
-        const uint32_t slot = atomicAdd(&st->n_too_many, 1u);
-        if (slot < too_many_cap) too_many[slot] = r.string_idx;
-        disabled_string = r.string_idx;
-        if (n_seg > 0) item_dirty[cur_item] = 1;   // the callback protocol needs the per-item path
-      }
+      j_next = jq;
+      __threadfence_block();
     }
+    __syncwarp();
+    j = __shfl_sync(FULL, j_next, 0);
+    item_last = __shfl_sync(FULL, item_last, 0);
   }
 
-  // confirmed matches of the chain's head string, in list order, after the plain strings' records
-  write_confirmed();
-
-  atomicAdd(&st->dbg[0], c.steps[0]);
-  atomicAdd(&st->dbg[1], c.steps[1]);
-  atomicAdd(&st->dbg[2], c.steps[2]);
-
-  // what is left in unconfirmed_matches[] of the chain's strings (a batch item is a whole
-  // scan: its leftovers are dropped like yr_scanner_scan_mem_blocks does at the end, scanner.c:565)
-  for (uint32_t k = j0; k < j && n_seg == 0; k++)
+  if (lane == 0)
   {
-    if (L.where[k] == 1)
+    // confirmed matches of the chain's head string, in list order, after the plain strings' records
+    write_confirmed();
+    atomicAdd(&st->dbg[0], c.steps[0]);
+    atomicAdd(&st->dbg[1], c.steps[1]);
+    atomicAdd(&st->dbg[2], c.steps[2]);
+    __threadfence_block();
+  }
+  __syncwarp();
+
+  // what is left in unconfirmed_matches[] of the chain's strings, in record order (a batch item is a
+  // whole scan: its leftovers are dropped like yr_scanner_scan_mem_blocks does at the end, scanner.c:565)
+  if (n_seg == 0)
+  {
+    for (uint32_t base0 = j0; base0 < j; base0 += 256)
     {
-      const Raw r = sraw[k];
-      const unsigned long long slot = atomicAdd(&st->n_unconf, 1ULL);
-      yrb_match m;
-      m.offset = r.offset;
-      m.string_idx = r.string_idx;
-      m.match_length = L.mlen[k];
-      m.xor_key = (uint8_t) (r.misc & 0xFF);
-      m.flags = YRB_MATCH_UNCONFIRMED | ((r.misc & RAW_SEED) ? YRB_MATCH_FROM_SEED : 0);
-      m.seed = (uint16_t) ((r.misc >> 8) & 0xFFFF);
-      if (r.misc & RAW_SEED) m.xor_key = (uint8_t) ((r.misc >> 24) & 0x3F);   // seed index bits 16-21
-      m.chain_length = L.clen[k];
-      unconf[slot] = m;
+      // eight windows per round; almost all of them hold nothing (one latency chain per round)
+      uint8_t wv[8];
+      bool any = false;
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+      {
+        const uint32_t k = base0 + (uint32_t) u * 32u + lane;
+        wv[u] = k < j ? L.where[k] : (uint8_t) 0;
+        any = any || wv[u] == 1;
+      }
+      if (!__any_sync(FULL, any)) continue;
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+      {
+        const uint32_t k = base0 + (uint32_t) u * 32u + lane;
+        const bool keep = wv[u] == 1;
+        const unsigned km = __ballot_sync(FULL, keep);
+        if (km == 0) continue;
+        unsigned long long slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(&st->n_unconf, (unsigned long long) __popc(km));
+        slot0 = __shfl_sync(FULL, slot0, 0);
+        if (keep)
+        {
+          const Raw r = sraw[k];
+          yrb_match m;
+          m.offset = r.offset;
+          m.string_idx = r.string_idx;
+          m.match_length = L.mlen[k];
+          m.xor_key = (uint8_t) (r.misc & 0xFF);
+          m.flags = YRB_MATCH_UNCONFIRMED | ((r.misc & RAW_SEED) ? YRB_MATCH_FROM_SEED : 0);
+          m.seed = (uint16_t) ((r.misc >> 8) & 0xFFFF);
+          if (r.misc & RAW_SEED) m.xor_key = (uint8_t) ((r.misc >> 24) & 0x3F);   // seed index bits 16-21
+          m.chain_length = L.clen[k];
+          unconf[slot0 + __popc(km & ((1u << lane) - 1u))] = m;
+        }
+      }
     }
   }
 }
@@ -790,9 +998,13 @@ void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches)
     L.prior = w.s_lists + 7 * (size_t) w.R.num_strings;
     L.uvn = w.c_uvn;
     chain_init_kernel<<<GRID(w.R.num_strings), 0, s>>>(L, w.R.num_strings);
-    chain_gather_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.sraw);
-    chain_resolve_kernel<<<GRID(n), 0, s>>>(w.sraw, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags, w.seed_base, w.cur_base,
-        w.n_seg, w.seg_start, w.seg_len, w.item_dirty);
+    cudaMemsetAsync(&w.st->n_chain_starts, 0, sizeof(unsigned int), s);
+    chain_gather_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.sraw, w.c_scratch_u32, w.st);
+    // one warp per chain present in the records (at most one chain per string)
+    const uint32_t max_chains = w.R.num_strings < n ? w.R.num_strings : n;
+    chain_resolve_kernel<<<(max_chains * 32 + 127) / 128, 128, 0, s>>>(
+        w.sraw, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags, w.seed_base, w.cur_base,
+        w.n_seg, w.seg_start, w.seg_len, w.item_dirty, w.c_scratch_u32);
     (*launches) += 3;
   }
 }
