@@ -22,6 +22,7 @@
 #include "resolve.cuh"
 
 #define OFFSET_BITS 40
+#define FLOOD_RUN 16   // chain replay: consecutive no-op callbacks after which the warp looks ahead
 #define A_CHAIN_BIT (1ULL << 63)
 #define A_DROPPED   (~0ULL)
 
@@ -557,188 +558,230 @@ chain_resolve_kernel(
   };
 
   uint32_t sorted_until = j0;   // records in [j, sorted_until) are in replay order (uniform)
+  bool flood = false;           // lane 0 ran into a run of no-op callbacks: look ahead with the whole warp (uniform)
 
   for (;;)
   {
-    // ---- look-ahead (all lanes): first record at or after j that needs lane 0.  Inside the part
-    // that is already in replay order every record stands for itself; beyond it, records that share
-    // an input position are not ordered yet, so such a group is skipped only as a whole.
-    // O(records / 32) warp steps in total.
-    uint32_t scan = j, last_gs = j, stop = j;
-    bool found = false, chain_done = false, finished = false;
-    uint64_t a_carry = 0;
-    while (!finished)
+    if (flood)
     {
-      // eight windows of 32 records per round: their dependent loads (record -> string -> list
-      // count) are in flight together, the round costs one latency chain instead of eight
-      constexpr int LA = 8;
-      uint64_t av[LA];
-      bool inv[LA], skv[LA];
-      uint32_t sidx[LA], misc[LA];
-#pragma unroll
-      for (int u = 0; u < LA; u++)
+      // ---- look-ahead (all lanes): first record at or after j that needs lane 0.  Inside the part
+      // that is already in replay order every record stands for itself; beyond it, records that share
+      // an input position are not ordered yet, so such a group is skipped only as a whole.
+      // O(records / 32) warp steps in total.
+      uint32_t scan = j, last_gs = j, stop = j;
+      bool found = false, chain_done = false, finished = false;
+      uint64_t a_carry = 0;
+      while (!finished)
       {
-        const uint32_t jj = scan + (uint32_t) u * 32u + lane;
-        av[u] = ~0ULL;
-        sidx[u] = 0;
-        misc[u] = 0;
-        if (jj < n)
+        // eight windows of 32 records per round: their dependent loads (record -> string -> list
+        // count) are in flight together, the round costs one latency chain instead of eight
+        constexpr int LA = 8;
+        uint64_t av[LA];
+        bool inv[LA], skv[LA];
+        uint32_t sidx[LA], misc[LA];
+  #pragma unroll
+        for (int u = 0; u < LA; u++)
         {
-          av[u] = kA[jj];
-          sidx[u] = sraw[jj].string_idx;   // meaningful only for chain records (checked below)
-          misc[u] = sraw[jj].misc;
+          const uint32_t jj = scan + (uint32_t) u * 32u + lane;
+          av[u] = ~0ULL;
+          sidx[u] = 0;
+          misc[u] = 0;
+          if (jj < n)
+          {
+            av[u] = kA[jj];
+            sidx[u] = sraw[jj].string_idx;   // meaningful only for chain records (checked below)
+            misc[u] = sraw[jj].misc;
+          }
+        }
+  #pragma unroll
+        for (int u = 0; u < LA; u++)
+        {
+          inv[u] = (av[u] >> OFFSET_BITS) == chain;
+          skv[u] = false;
+          if (inv[u])
+          {
+            const uint32_t pred = R.S[sidx[u]].chained_to;
+            skv[u] = !(misc[u] & RAW_SEED) && pred != YRB_NONE && __ldcg(&L.ucnt[pred]) == 0;
+            if (n_seg > 0 && (int64_t) (av[u] & POS_MASK) - 1 > item_last)
+              skv[u] = false;   // first record of the next item: lane 0 has to close the current one
+          }
+        }
+
+  #pragma unroll
+        for (int u = 0; u < LA; u++)
+        {
+          if (finished) break;
+          const uint32_t jj = scan + lane;
+          const uint64_t a = av[u];
+          const bool in_chain = inv[u];
+          const unsigned vm = __ballot_sync(FULL, in_chain);   // a prefix of the lanes: a chain's records are contiguous
+          const uint32_t nvalid = (uint32_t) __popc(vm);
+          if (nvalid == 0)
+          {
+            chain_done = (scan == j);
+            stop = scan;
+            finished = true;
+            break;
+          }
+          const unsigned ns = vm & ~__ballot_sync(FULL, skv[u]);
+
+          uint64_t a_prev = __shfl_up_sync(FULL, a, 1);
+          if (lane == 0) a_prev = (scan == j) ? ~a : a_carry;   // j itself always starts a group
+          const unsigned gm = __ballot_sync(FULL, in_chain && (jj < sorted_until || a != a_prev));
+
+          if (ns)
+          {
+            const uint32_t fl = (uint32_t) (__ffs(ns) - 1);
+            const unsigned upto = gm & (fl >= 31 ? FULL : ((2u << fl) - 1u));
+            if (upto) last_gs = scan + 31u - (uint32_t) __clz(upto);
+            found = true;
+            finished = true;
+            break;
+          }
+          if (gm) last_gs = scan + 31u - (uint32_t) __clz(gm);
+          a_carry = __shfl_sync(FULL, a, nvalid - 1);
+          stop = scan + nvalid;
+          if (nvalid < 32)
+          {
+            finished = true;   // the chain ends inside this window, nothing left for lane 0
+            break;
+          }
+          scan += 32;
         }
       }
-#pragma unroll
-      for (int u = 0; u < LA; u++)
+      if (chain_done)
+        break;
+
+      const uint32_t skip_to = found ? last_gs : stop;
+      if (skip_to > j)
       {
-        inv[u] = (av[u] >> OFFSET_BITS) == chain;
-        skv[u] = false;
-        if (inv[u])
-        {
-          const uint32_t pred = R.S[sidx[u]].chained_to;
-          skv[u] = !(misc[u] & RAW_SEED) && pred != YRB_NONE && __ldcg(&L.ucnt[pred]) == 0;
-          if (n_seg > 0 && (int64_t) (av[u] & POS_MASK) - 1 > item_last)
-            skv[u] = false;   // first record of the next item: lane 0 has to close the current one
-        }
+        for (uint32_t k = j + lane; k < skip_to; k += 32)
+          L.where[k] = 0;   // in no list
+        j = skip_to;
+        prev_key = ~0ULL;
+        cur_cand = ~0ULL;
+        skip_cand = false;
+        continue;
       }
 
-#pragma unroll
-      for (int u = 0; u < LA; u++)
+      if (j >= sorted_until)
       {
-        if (finished) break;
-        const uint32_t jj = scan + lane;
-        const uint64_t a = av[u];
-        const bool in_chain = inv[u];
-        const unsigned vm = __ballot_sync(FULL, in_chain);   // a prefix of the lanes: a chain's records are contiguous
-        const uint32_t nvalid = (uint32_t) __popc(vm);
-        if (nvalid == 0)
+        // a new, possibly huge group of records that share the input position of record j: find its
+        // end and check its order with all lanes; lane 0 sorts in the rare unordered case
+        const uint64_t a_j = kA[j];
+        const bool seed_group = (a_j & POS_MASK) == 0;
+        uint32_t r_end = j;
+        bool ordered = true;
+        for (;;)
         {
-          chain_done = (scan == j);
-          stop = scan;
-          finished = true;
-          break;
+          const uint32_t k = r_end + lane;
+          const bool same = k < n && kA[k] == a_j;
+          const unsigned sm2 = __ballot_sync(FULL, same);
+          const bool bad = same && k > j && !seed_group && sraw[k - 1].key > sraw[k].key;
+          const unsigned cnt = (sm2 == FULL) ? 32u : (uint32_t) (__ffs(~sm2) - 1);
+          const unsigned bm = __ballot_sync(FULL, bad) & (cnt >= 32 ? FULL : ((1u << cnt) - 1u));
+          if (bm) ordered = false;
+          r_end += cnt;
+          if (cnt < 32) break;
         }
-        const unsigned ns = vm & ~__ballot_sync(FULL, skv[u]);
-
-        uint64_t a_prev = __shfl_up_sync(FULL, a, 1);
-        if (lane == 0) a_prev = (scan == j) ? ~a : a_carry;   // j itself always starts a group
-        const unsigned gm = __ballot_sync(FULL, in_chain && (jj < sorted_until || a != a_prev));
-
-        if (ns)
+        if (!ordered && lane == 0)
         {
-          const uint32_t fl = (uint32_t) (__ffs(ns) - 1);
-          const unsigned upto = gm & (fl >= 31 ? FULL : ((2u << fl) - 1u));
-          if (upto) last_gs = scan + 31u - (uint32_t) __clz(upto);
-          found = true;
-          finished = true;
-          break;
+          for (uint32_t x = j + 1; x < r_end; x++)
+          {
+            if (sraw[x - 1].key <= sraw[x].key) continue;
+            const Raw vx = sraw[x];
+            uint32_t y = x;
+            while (y > j && sraw[y - 1].key > vx.key) { sraw[y] = sraw[y - 1]; y--; }
+            sraw[y] = vx;
+          }
+          __threadfence_block();
         }
-        if (gm) last_gs = scan + 31u - (uint32_t) __clz(gm);
-        a_carry = __shfl_sync(FULL, a, nvalid - 1);
-        stop = scan + nvalid;
-        if (nvalid < 32)
-        {
-          finished = true;   // the chain ends inside this window, nothing left for lane 0
-          break;
-        }
-        scan += 32;
+        __syncwarp();
+        sorted_until = r_end;
+        continue;   // look again: inside the ordered group single records can be skipped
       }
     }
-    if (chain_done)
-      break;
 
-    const uint32_t skip_to = found ? last_gs : stop;
-    if (skip_to > j)
-    {
-      for (uint32_t k = j + lane; k < skip_to; k += 32)
-        L.where[k] = 0;   // in no list
-      j = skip_to;
-      prev_key = ~0ULL;
-      cur_cand = ~0ULL;
-      skip_cand = false;
-      continue;
-    }
-
-    if (j >= sorted_until)
-    {
-      // ---- a new group of records that share the input position of record j: find its end and put
-      // it in discovery-key order (all lanes check; lane 0 sorts in the rare unordered case).
-      // The seeds -- position 0 -- keep the order the caller gave them in, ascending base + offset per
-      // string: each then goes to the tail of its list in O(1); their `key` is a chain length, not a key.
-      const uint64_t a_j = kA[j];
-      const bool seed_group = (a_j & POS_MASK) == 0;
-      uint32_t r_end = j;
-      bool ordered = true;
-      for (;;)
-      {
-        const uint32_t k = r_end + lane;
-        const bool same = k < n && kA[k] == a_j;
-        const unsigned sm2 = __ballot_sync(FULL, same);
-        const bool bad = same && k > j && !seed_group && sraw[k - 1].key > sraw[k].key;
-        const unsigned cnt = (sm2 == FULL) ? 32u : (uint32_t) (__ffs(~sm2) - 1);
-        const unsigned bm = __ballot_sync(FULL, bad) & (cnt >= 32 ? FULL : ((1u << cnt) - 1u));
-        if (bm) ordered = false;
-        r_end += cnt;
-        if (cnt < 32) break;
-      }
-      if (!ordered && lane == 0)
-      {
-        for (uint32_t x = j + 1; x < r_end; x++)
-        {
-          if (sraw[x - 1].key <= sraw[x].key) continue;
-          const Raw vx = sraw[x];
-          uint32_t y = x;
-          while (y > j && sraw[y - 1].key > vx.key) { sraw[y] = sraw[y - 1]; y--; }
-          sraw[y] = vx;
-        }
-        __threadfence_block();
-      }
-      __syncwarp();
-      sorted_until = r_end;
-      continue;   // look again: inside the ordered group single records can be skipped
-    }
-
-    // ---- lane 0 replays record j and what follows it in the ordered part, up to the next no-op
-    uint32_t j_next = j;
+    // ---- lane 0 replays records from j on, group by group, until the chain ends or it has seen
+    // FLOOD_RUN no-op callbacks in a row (then the warp looks ahead instead)
+    uint32_t j_next = j, sorted_next = sorted_until;
+    int flags_next = 0;   // 1: flood, 2: chain finished
     if (lane == 0)
     {
       uint32_t jq = j;
-      for (; jq < sorted_until; jq++)
+      uint32_t su = sorted_until;
+      int noop_run = 0;
+      for (;;)
       {
-        const Raw r = sraw[jq];
+        if (jq >= n || (kA[jq] >> OFFSET_BITS) != chain) { flags_next = 2; break; }
 
-        if (jq > j && !(r.misc & RAW_SEED))
+        if (jq >= su)
         {
-          const uint32_t pred = R.S[r.string_idx].chained_to;
-          if (pred != YRB_NONE && L.ucnt[pred] == 0)
-            break;   // a no-op: let the warp skip ahead from here
+          // records of this chain that share the input position: put them in discovery-key order.
+          // The seeds -- position 0 -- keep the order the caller gave them in, ascending base + offset
+          // per string: each then goes to the tail of its list in O(1); their `key` is a chain length.
+          uint32_t r_end = jq + 1;
+          while (r_end < n && r_end < jq + 64 && kA[r_end] == kA[jq]) r_end++;
+          if (r_end == jq + 64 && r_end < n && kA[r_end] == kA[jq])
+          {
+            flags_next = 1;   // a long group (one candidate can fire thousands of callbacks): the warp
+            break;            // finds its end, checks its order and skips inside it
+          }
+          const bool seed_group = (kA[jq] & POS_MASK) == 0;
+          for (uint32_t x = jq + 1; x < r_end && !seed_group; x++)
+          {
+            if (sraw[x - 1].key <= sraw[x].key) continue; // already in order: the common case
+            const Raw vx = sraw[x];
+            uint32_t y = x;
+            while (y > jq && sraw[y - 1].key > vx.key) { sraw[y] = sraw[y - 1]; y--; }
+            sraw[y] = vx;
+          }
+          su = r_end;
         }
 
-        if (n_seg > 0)
+        for (; jq < su; jq++)
         {
-          const int64_t i = (int64_t) (kA[jq] & POS_MASK) - 1;
-          if (i > item_last)
+          const Raw r = sraw[jq];
+
+          if (n_seg > 0)
           {
-            if (cur_item >= 0)
+            const int64_t i = (int64_t) (kA[jq] & POS_MASK) - 1;
+            if (i > item_last)
             {
-              write_confirmed();
-              if (touched_overflow)
-                for (uint32_t k = item_j0; k < jq; k++) reset_string(sraw[k].string_idx);
-              else
-                for (int t = 0; t < n_touched; t++) reset_string(touched[t]);
+              if (cur_item >= 0)
+              {
+                write_confirmed();
+                if (touched_overflow)
+                  for (uint32_t k = item_j0; k < jq; k++) reset_string(sraw[k].string_idx);
+                else
+                  for (int t = 0; t < n_touched; t++) reset_string(touched[t]);
+              }
+              n_touched = 0;
+              touched_overflow = false;
+              cur_item = seg_find_in(seg_start, n_seg, i - 1);
+              item_last = seg_start[cur_item] + seg_len[cur_item];
+              item_j0 = jq;
+              prev_key = ~0ULL;
+              disabled_string = YRB_NONE;
+              cur_cand = ~0ULL;
+              skip_cand = false;
             }
-            n_touched = 0;
-            touched_overflow = false;
-            cur_item = seg_find_in(seg_start, n_seg, i - 1);
-            item_last = seg_start[cur_item] + seg_len[cur_item];
-            item_j0 = jq;
-            prev_key = ~0ULL;
-            disabled_string = YRB_NONE;
-            cur_cand = ~0ULL;
-            skip_cand = false;
           }
-          if (!touched_overflow)
+
+          if (!(r.misc & RAW_SEED))
+          {
+            // scan.c:452-500: nothing to look at in the predecessor's list, nothing happens
+            const uint32_t pred = R.S[r.string_idx].chained_to;
+            if (pred != YRB_NONE && L.ucnt[pred] == 0)
+            {
+              L.where[jq] = 0;
+              if (++noop_run >= FLOOD_RUN) { flags_next = 1; jq++; break; }
+              continue;
+            }
+          }
+          noop_run = 0;
+
+          if (n_seg > 0 && !touched_overflow)
           {
             int t = 0;
             while (t < n_touched && touched[t] != r.string_idx) t++;
@@ -747,65 +790,72 @@ chain_resolve_kernel(
               if (n_touched < 16) touched[n_touched++] = r.string_idx; else touched_overflow = true;
             }
           }
-        }
 
-        L.nxt[jq] = L.prv[jq] = -1;
-        L.where[jq] = 0;
+          L.nxt[jq] = L.prv[jq] = -1;
+          L.where[jq] = 0;
 
-        if (r.misc & RAW_SEED)
-        {
-          // state left by earlier blocks of this scan: goes straight back into its list
-          if (r.misc & RAW_SEED_MARK)
+          if (r.misc & RAW_SEED)
           {
-            L.prior[r.string_idx] = 1;
-          }
-          else
-          {
-            L.clen[jq] = (int32_t) r.key;
-            L.mlen[jq] = r.length;
-            if (clist_add(c, L.uhead, L.utail, L.ucnt, r.string_idx, (int32_t) jq) == 0)
+            // state left by earlier blocks of this scan: goes straight back into its list
+            if (r.misc & RAW_SEED_MARK)
             {
-              L.where[jq] = 1;
-              if (L.clen[jq] == 0)
+              L.prior[r.string_idx] = 1;
+            }
+            else
+            {
+              L.clen[jq] = (int32_t) r.key;
+              L.mlen[jq] = r.length;
+              if (clist_add(c, L.uhead, L.utail, L.ucnt, r.string_idx, (int32_t) jq) == 0)
               {
-                L.uvn[jq] = L.uvhead[r.string_idx];
-                L.uvhead[r.string_idx] = (int32_t) jq;
+                L.where[jq] = 1;
+                if (L.clen[jq] == 0)
+                {
+                  L.uvn[jq] = L.uvhead[r.string_idx];
+                  L.uvhead[r.string_idx] = (int32_t) jq;
+                }
               }
             }
+            continue;
           }
-          continue;
+
+          if (r.key == prev_key) continue; // re-emission of the same callback by the tier-2 verifier
+          prev_key = r.key;
+
+          if (r.string_idx == disabled_string) continue;
+
+          // scan.c:1021-1023: the FAST_MODE / SINGLE_MATCH guard is evaluated once per
+          // candidate, before verification, against matches[string->idx] (only ever
+          // non-empty for the chain's head string)
+          if ((r.key >> KEY_SEQ_BITS) != cur_cand)
+          {
+            cur_cand = r.key >> KEY_SEQ_BITS;
+            skip_cand = (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) &&
+                        (L.mcnt[r.string_idx] > 0 || L.prior[r.string_idx]);
+          }
+          if (skip_cand) continue;
+
+          if (verify_chained(c, (int32_t) jq) == 2)
+          {
+            const uint32_t slot = atomicAdd(&st->n_too_many, 1u);
+            if (slot < too_many_cap) too_many[slot] = r.string_idx;
+            disabled_string = r.string_idx;
+            if (n_seg > 0) item_dirty[cur_item] = 1;   // the callback protocol needs the per-item path
+          }
         }
-
-        if (r.key == prev_key) continue; // re-emission of the same callback by the tier-2 verifier
-        prev_key = r.key;
-
-        if (r.string_idx == disabled_string) continue;
-
-        // scan.c:1021-1023: the FAST_MODE / SINGLE_MATCH guard is evaluated once per
-        // candidate, before verification, against matches[string->idx] (only ever
-        // non-empty for the chain's head string)
-        if ((r.key >> KEY_SEQ_BITS) != cur_cand)
-        {
-          cur_cand = r.key >> KEY_SEQ_BITS;
-          skip_cand = (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) &&
-                      (L.mcnt[r.string_idx] > 0 || L.prior[r.string_idx]);
-        }
-        if (skip_cand) continue;
-
-        if (verify_chained(c, (int32_t) jq) == 2)
-        {
-          const uint32_t slot = atomicAdd(&st->n_too_many, 1u);
-          if (slot < too_many_cap) too_many[slot] = r.string_idx;
-          disabled_string = r.string_idx;
-          if (n_seg > 0) item_dirty[cur_item] = 1;   // the callback protocol needs the per-item path
-        }
+        if (flags_next) break;
       }
       j_next = jq;
+      sorted_next = su;
       __threadfence_block();
     }
     __syncwarp();
     j = __shfl_sync(FULL, j_next, 0);
+    sorted_until = __shfl_sync(FULL, sorted_next, 0);
     item_last = __shfl_sync(FULL, item_last, 0);
+    flags_next = __shfl_sync(FULL, flags_next, 0);
+    if (flags_next == 2)
+      break;
+    flood = flags_next == 1;
   }
 
   if (lane == 0)
