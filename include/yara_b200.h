@@ -30,6 +30,10 @@
  *                                 (no reference equivalent; used for the
  *                                 HBM-resident throughput figure and by callers
  *                                 that produce data on the device).
+ *   yrb_scan_batch                N independent buffers -- N x yr_rules_scan_mem over a file
+ *                                 queue (cli/yara.c:365-457), each of which would run
+ *                                 _yr_scanner_scan_mem_block from the root state -- with one
+ *                                 launch sequence; results per buffer equal yrb_scan_host's.
  *   yrb_shard_*                   byte-range sharding of ONE block over several
  *                                 GPUs/processes; no reference
  *                                 equivalent (a buffer is always scanned by one
