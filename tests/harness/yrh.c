@@ -351,3 +351,14 @@ int yrh_batch_begin(
 
 void yrh_batch_end(void* batch) { yr_b200_batch_destroy((YR_B200_BATCH*) batch); }
 #endif
+
+#if defined(YRH_B200) || defined(YRH_PREFILTER)
+/* condition-VM pre-filter counters (yara_b200/host/yr_b200_prefilter.c) */
+void yr_b200_prefilter_stats(uint64_t* evaluated, uint64_t* skipped);
+void yr_b200_prefilter_classes(YR_RULES* rules, uint32_t counts[4]);
+int yr_b200_prefilter_enabled(void);
+
+int yrh_prefilter_enabled(void) { return yr_b200_prefilter_enabled(); }
+void yrh_prefilter_stats(uint64_t* evaluated, uint64_t* skipped) { yr_b200_prefilter_stats(evaluated, skipped); }
+void yrh_prefilter_classes(void* rules, uint32_t* counts) { yr_b200_prefilter_classes((YR_RULES*) rules, counts); }
+#endif

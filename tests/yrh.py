@@ -200,6 +200,33 @@ def ref() -> Harness:
     return _cache["ref"]
 
 
+def refpf_path():
+    return os.path.join(ROOT, "oracle", "_ref", "libyrh_refpf.so")
+
+
+def refpf() -> Harness:
+    """reference + the condition-VM pre-filter hooks only (CPU); the filter obeys $YR_B200_RULE_PREFILTER,
+    read once at the first scan"""
+    if "refpf" not in _cache:
+        h = Harness(refpf_path())
+        h.lib.yrh_prefilter_stats.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        h.lib.yrh_prefilter_classes.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        _cache["refpf"] = h
+    return _cache["refpf"]
+
+
+def prefilter_stats(h):
+    e, s = C.c_uint64(), C.c_uint64()
+    h.lib.yrh_prefilter_stats(C.byref(e), C.byref(s))
+    return e.value, s.value
+
+
+def prefilter_classes(h, rules):
+    c = (C.c_uint32 * 4)()
+    h.lib.yrh_prefilter_classes(rules.ptr, c)
+    return {"impure": c[0], "unknown": c[1], "skippable": c[2], "true_without_matches": c[3]}
+
+
 def b200() -> Harness:
     if "b200" not in _cache:
         _cache["b200"] = Harness(b200_path())

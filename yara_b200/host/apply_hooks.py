@@ -11,10 +11,56 @@ anything else means the reference drifted and the build stops.
              scanner.c:287   yr_scanner_destroy: yr_b200_scanner_release(scanner)
   rules.c    #include "yr_b200.h"
              rules.c:515     yr_rules_destroy: yr_b200_rules_release(rules)
+  condition-VM pre-filter (yr_b200_prefilter.c, off unless $YR_B200_RULE_PREFILTER is set):
+  scanner.c  scanner.c:518   yr_b200_prefilter_begin/end around yr_execute_code
+  exec.c     exec.c:1168     OP_INIT_RULE: `|| yr_b200_prefilter_skip(...)` next to RULE_IS_DISABLED
+             exec.c:1191     OP_MATCH_RULE: yr_b200_prefilter_learn(...)
+
+The "*_pf" variants build oracle/_ref/libyara_refpf.so, the CPU validation library of the
+pre-filter: the reference with ONLY the pre-filter hooks (no GPU path), matches noted in
+scan.c:642 (_yr_scan_match_callback).
 """
 import sys
 
+EXEC_CALL = (
+    "      { result = yr_execute_code(scanner); },\n",
+    "      { yr_b200_prefilter_begin(scanner); result = yr_execute_code(scanner); yr_b200_prefilter_end(scanner); },\n",
+)
+DESTROY_ANCHOR = "  RE_FIBER* fiber = scanner->re_fiber_pool.fibers.head;\n"
+RULES_ANCHOR = "  YR_EXTERNAL_VARIABLE* external = rules->ext_vars_table;\n\n  while (!EXTERNAL_VARIABLE_IS_NULL(external))\n  {\n    if (external->type == EXTERNAL_VARIABLE_TYPE_MALLOC_STRING)\n      yr_free(external->value.s);"
+
 EDITS = {
+    "scanner_pf": [
+        ('#include "exception.h"\n', '#include "exception.h"\n#include "yr_b200.h"\n'),
+        EXEC_CALL,
+        (DESTROY_ANCHOR, "  yr_b200_prefilter_scanner_release(scanner);\n\n" + DESTROY_ANCHOR),
+    ],
+    "rules_pf": [
+        ("#include <yara/utils.h>\n", '#include <yara/utils.h>\n#include "yr_b200.h"\n'),
+        (RULES_ANCHOR, RULES_ANCHOR.replace("\n\n  while", "\n\n  yr_b200_prefilter_rules_release(rules);\n\n  while", 1)),
+    ],
+    "scan_pf": [
+        ("#include <yara/utils.h>\n", '#include <yara/utils.h>\n#include "yr_b200.h"\n'),
+        (
+            "  YR_STRING* string = callback_args->string;\n  YR_MATCH* new_match;\n",
+            "  YR_STRING* string = callback_args->string;\n  YR_MATCH* new_match;\n\n  yr_b200_prefilter_note(callback_args->context, string);\n",
+        ),
+    ],
+    "exec": [
+        ("#include <yara/utils.h>\n", '#include <yara/utils.h>\n#include "yr_b200.h"\n'),
+        (
+            "      ip = jmp_if(RULE_IS_DISABLED(current_rule), ip);\n",
+            "      ip = jmp_if(\n          RULE_IS_DISABLED(current_rule) || yr_b200_prefilter_skip(context, current_rule_idx), ip);\n",
+        ),
+        (
+            "      if (!RULE_IS_DISABLED(current_rule))\n        ip += sizeof(uint32_t);\n",
+            "      if (!(RULE_IS_DISABLED(current_rule) || yr_b200_prefilter_skip(context, current_rule_idx)))\n        ip += sizeof(uint32_t);\n",
+        ),
+        (
+            "      if (!is_undef(r1) && r1.i)\n        yr_bitmask_set(context->rule_matches_flags, r2.i);\n",
+            "      yr_b200_prefilter_learn(context, (uint32_t) r2.i, !is_undef(r1) && r1.i);\n\n      if (!is_undef(r1) && r1.i)\n        yr_bitmask_set(context->rule_matches_flags, r2.i);\n",
+        ),
+    ],
     "scanner": [
         ('#include "exception.h"\n', '#include "exception.h"\n#include "yr_b200.h"\n'),
         (
@@ -25,6 +71,7 @@ EDITS = {
             "  RE_FIBER* fiber = scanner->re_fiber_pool.fibers.head;\n",
             "  yr_b200_scanner_release(scanner);\n\n  RE_FIBER* fiber = scanner->re_fiber_pool.fibers.head;\n",
         ),
+        EXEC_CALL,
     ],
     "rules": [
         ("#include <yara/utils.h>\n", '#include <yara/utils.h>\n#include "yr_b200.h"\n'),

@@ -56,6 +56,23 @@ int yr_b200_batch_scan(
 void yr_b200_batch_destroy(YR_B200_BATCH* batch);
 uint32_t yr_b200_batch_rescans(const YR_B200_BATCH* batch); /* buffers that were not parked */
 
+/*
+ * Condition-VM pre-filter (yr_b200_prefilter.c; off unless $YR_B200_RULE_PREFILTER is set).
+ * Hook sites: scanner.c:518 (begin/end around yr_execute_code), exec.c:1168-1173 (skip test next
+ * to RULE_IS_DISABLED in OP_INIT_RULE), exec.c:1185 (learn in OP_MATCH_RULE); matches are noted
+ * where they are created (materialise() in the glue).
+ */
+int yr_b200_prefilter_enabled(void);
+void yr_b200_prefilter_note(YR_SCAN_CONTEXT* context, YR_STRING* string);
+void yr_b200_prefilter_begin(YR_SCAN_CONTEXT* context);
+int yr_b200_prefilter_skip(YR_SCAN_CONTEXT* context, uint32_t rule_idx);
+void yr_b200_prefilter_learn(YR_SCAN_CONTEXT* context, uint32_t rule_idx, int result);
+void yr_b200_prefilter_end(YR_SCAN_CONTEXT* context);
+void yr_b200_prefilter_stats(uint64_t* evaluated, uint64_t* skipped);
+void yr_b200_prefilter_classes(YR_RULES* rules, uint32_t counts[4]);
+void yr_b200_prefilter_scanner_release(YR_SCAN_CONTEXT* context);
+void yr_b200_prefilter_rules_release(YR_RULES* rules);
+
 /* Which CUDA device the glue uses for new scanners (default: $YR_B200_DEVICE or 0). */
 void yr_b200_set_device(int device);
 

@@ -414,6 +414,7 @@ static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out, rules_entry** re_
 
 void yr_b200_scanner_release(YR_SCANNER* scanner)
 {
+  yr_b200_prefilter_scanner_release(scanner);
   pthread_mutex_lock(&g_lock);
   scanner_entry** pp = &g_scanners;
   while (*pp != NULL)
@@ -433,6 +434,7 @@ void yr_b200_scanner_release(YR_SCANNER* scanner)
 
 void yr_b200_rules_release(YR_RULES* rules)
 {
+  yr_b200_prefilter_rules_release(rules);
   pthread_mutex_lock(&g_lock);
   rules_entry** pp = &g_rules;
   while (*pp != NULL)
@@ -536,6 +538,8 @@ static int materialise(
   {
     const yrb_match* r = &recs[i];
     YR_STRING* string = &rules->strings_table[r->string_idx];
+
+    yr_b200_prefilter_note(scanner, string); /* condition-VM pre-filter: this rule has something to look at */
 
     /* the data copies below touch the block at random offsets (a cache and TLB miss each
        in a multi-GiB block): get the next ones moving */
