@@ -355,7 +355,7 @@ void yrh_batch_end(void* batch) { yr_b200_batch_destroy((YR_B200_BATCH*) batch);
 #if defined(YRH_B200) || defined(YRH_PREFILTER)
 /* condition-VM pre-filter counters (yara_b200/host/yr_b200_prefilter.c) */
 void yr_b200_prefilter_stats(uint64_t* evaluated, uint64_t* skipped);
-void yr_b200_prefilter_classes(YR_RULES* rules, uint32_t counts[4]);
+void yr_b200_prefilter_classes(YR_RULES* rules, uint32_t counts[5]);
 int yr_b200_prefilter_enabled(void);
 
 int yrh_prefilter_enabled(void) { return yr_b200_prefilter_enabled(); }

@@ -72,6 +72,7 @@ def test_every_condition_shape_stays_identical_over_repeated_scans():
     e1, s1 = yrh.prefilter_stats(P)
     cls = yrh.prefilter_classes(P, rp)
     assert s1 > s0, "nothing was ever skipped"
+    assert cls["walked"] == rp.num_rules          # the classifier decoded the whole condition code
     assert cls["skippable"] >= 15 and cls["true_without_matches"] >= 5
     # data / filesize / rule references / the global rule must never be classified pure
     assert cls["impure"] >= 5 + 1 + 2
@@ -86,6 +87,7 @@ def test_known_answer_cases(idx):
     for buf in (noise, data, noise, data, b"", data):
         same(rr.scan(buf), rp.scan(buf))
     same(rr.scan_blocks(data, 1024, 256), rp.scan_blocks(data, 1024, 256))
+    assert yrh.prefilter_classes(P, rp)["walked"] == rp.num_rules
 
 
 @pytest.mark.parametrize("seed", range(10))
@@ -115,7 +117,8 @@ def test_file_batch_shape_skips_almost_every_rule():
     nrules, nfiles = rp.num_rules, len(files) - 1
     assert (e1 - e0) + (s1 - s0) == nrules * nfiles
     assert (s1 - s0) > 0.5 * nrules * nfiles
-    assert yrh.prefilter_classes(P, rp)["impure"] == 0
+    cls = yrh.prefilter_classes(P, rp)
+    assert cls["impure"] == 0 and cls["walked"] == nrules
 
 
 @pytest.mark.parametrize("name", ["test-rules_refpf", "test-api_refpf", "test-async_refpf"])

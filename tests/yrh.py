@@ -222,9 +222,9 @@ def prefilter_stats(h):
 
 
 def prefilter_classes(h, rules):
-    c = (C.c_uint32 * 4)()
+    c = (C.c_uint32 * 5)()
     h.lib.yrh_prefilter_classes(rules.ptr, c)
-    return {"impure": c[0], "unknown": c[1], "skippable": c[2], "true_without_matches": c[3]}
+    return {"impure": c[0], "unknown": c[1], "skippable": c[2], "true_without_matches": c[3], "walked": c[4]}
 
 
 def b200() -> Harness:

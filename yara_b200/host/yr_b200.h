@@ -69,7 +69,7 @@ int yr_b200_prefilter_skip(YR_SCAN_CONTEXT* context, uint32_t rule_idx);
 void yr_b200_prefilter_learn(YR_SCAN_CONTEXT* context, uint32_t rule_idx, int result);
 void yr_b200_prefilter_end(YR_SCAN_CONTEXT* context);
 void yr_b200_prefilter_stats(uint64_t* evaluated, uint64_t* skipped);
-void yr_b200_prefilter_classes(YR_RULES* rules, uint32_t counts[4]);
+void yr_b200_prefilter_classes(YR_RULES* rules, uint32_t counts[5]);
 void yr_b200_prefilter_scanner_release(YR_SCAN_CONTEXT* context);
 void yr_b200_prefilter_rules_release(YR_RULES* rules);
 

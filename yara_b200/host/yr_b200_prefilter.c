@@ -50,6 +50,7 @@ typedef struct pf_rules
 {
   YR_RULES* rules;
   uint32_t n;
+  uint32_t walked; /* rules whose code the classifier reached (== n unless the code layout surprised it) */
   uint8_t* state;
   struct pf_rules* next;
 } pf_rules;
@@ -124,13 +125,14 @@ static int pure_operand_size(uint8_t op)
 
 /* Walks the condition code: OP_IMPORT* then per rule OP_INIT_RULE <jump:i32> <rule:u32> ... OP_MATCH_RULE
    <rule:u64>, finally OP_HALT (parser.c / grammar.y emit it in this shape). */
-static void classify(YR_RULES* rules, uint8_t* state)
+static uint32_t classify(YR_RULES* rules, uint8_t* state)
 {
   const uint8_t* ip = rules->code_start;
+  uint32_t walked = 0;
   memset(state, PF_IMPURE, rules->num_rules);
 
   if (ip == NULL)
-    return;
+    return 0;
 
   for (;;)
   {
@@ -142,14 +144,14 @@ static void classify(YR_RULES* rules, uint8_t* state)
       continue;
     }
     if (op != OP_INIT_RULE)
-      return; /* OP_HALT, or a layout this code does not know: everything left stays impure */
+      return walked; /* OP_HALT, or a layout this code does not know: everything left stays impure */
 
     int32_t off;
     uint32_t idx;
     memcpy(&off, ip + 1, sizeof(off));
     memcpy(&idx, ip + 1 + sizeof(int32_t), sizeof(idx));
     if (off <= 0 || idx >= rules->num_rules)
-      return;
+      return walked;
 
     const uint8_t* end = ip + off; /* the jump is relative to the opcode (exec.c:159-186) */
     const uint8_t* p = ip + 1 + sizeof(int32_t) + sizeof(uint32_t);
@@ -175,6 +177,7 @@ static void classify(YR_RULES* rules, uint8_t* state)
       pure = 0;
 
     state[idx] = pure ? PF_UNKNOWN : PF_IMPURE;
+    walked++;
     ip = end;
   }
 }
@@ -197,7 +200,7 @@ static pf_rules* rules_entry_for(YR_RULES* rules)
     free(e);
     return NULL;
   }
-  classify(rules, e->state);
+  e->walked = classify(rules, e->state);
   e->next = g_pf_rules;
   g_pf_rules = e;
   return e;
@@ -332,14 +335,18 @@ void yr_b200_prefilter_stats(uint64_t* evaluated, uint64_t* skipped)
   *skipped = __atomic_load_n(&g_pf_skipped, __ATOMIC_RELAXED);
 }
 
-/* how the rules of a YR_RULES were classified: counts of impure / not yet known / skippable / true */
-void yr_b200_prefilter_classes(YR_RULES* rules, uint32_t counts[4])
+/* how the rules of a YR_RULES were classified: counts of impure / not yet known / skippable / true,
+   and (counts[4]) how many rules the classifier reached */
+void yr_b200_prefilter_classes(YR_RULES* rules, uint32_t counts[5])
 {
-  memset(counts, 0, 4 * sizeof(uint32_t));
+  memset(counts, 0, 5 * sizeof(uint32_t));
   pthread_mutex_lock(&g_pf_lock);
   pf_rules* e = rules_entry_for(rules);
   if (e != NULL)
+  {
     for (uint32_t i = 0; i < e->n; i++) counts[e->state[i] & 3]++;
+    counts[4] = e->walked;
+  }
   pthread_mutex_unlock(&g_pf_lock);
 }
 
