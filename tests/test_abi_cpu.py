@@ -36,6 +36,26 @@ def test_dropin_exports_libyara_api_and_hooks():
     assert not hasattr(lib, "yr_scan_verify_match")
 
 
+def test_dropin_exports_the_whole_public_api_of_the_reference_build():
+    """drop-in means drop-in: every yr_* symbol the reference library (built from the same sources by
+    oracle/Makefile) exports is exported by libyara_b200.so too, except the CPU verification path"""
+    import subprocess
+    ref = os.path.join(ROOT, "oracle", "_ref", "libyara_ref.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+
+    def exported(path):
+        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+        return set(l.split()[-1] for l in out.splitlines() if l.split() and l.split()[-1].startswith("yr_"))
+
+    a, b = exported(ref), exported(DROPIN)
+    missing = sorted(a - b)
+    # scan.c is not linked (no CPU fallback): its three entry points are the only ones allowed to be absent
+    assert set(missing) <= {"yr_scan_verify_match", "yr_scan_base64_callback_dummy"}, missing
+    assert "yr_scan_verify_match" in missing
+    assert len(a) > 150
+
+
 def test_no_cpu_fallback():
     lib = ctypes.CDLL(LIB)
     if lib.yrb_device_count() > 0:
