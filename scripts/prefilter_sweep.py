@@ -3,7 +3,7 @@
 oracle/_ref/libyara_refpf.so (reference + pre-filter hooks, filter ON) over tests/fuzzgen.py seeds;
 every ruleset is scanned repeatedly so that learnt skips are exercised.
 
-  python scripts/prefilter_sweep.py FIRST LAST"""
+  python scripts/prefilter_sweep.py FIRST LAST [skip,seeds]   (skip: seeds on which the reference hangs)"""
 import os, sys, time
 os.environ["YR_B200_RULE_PREFILTER"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,9 +13,12 @@ import fuzzgen, yrh
 from yara_b200 import synth
 
 first, last = int(sys.argv[1]), int(sys.argv[2])
+skip = set(int(x) for x in sys.argv[3].split(",") if x) if len(sys.argv) > 3 else set()
 R, P = yrh.ref(), yrh.refpf()
 bad, done, t0 = [], 0, time.time()
 for seed in range(first, last):
+    if seed in skip:
+        continue
     src, insts = fuzzgen.gen_rules(seed, 50)
     good = []
     for s in src:
