@@ -130,3 +130,18 @@ def test_reference_programs_with_the_filter_on(name):
     env = dict(os.environ, TOP_SRCDIR=os.path.join(REFDIR, "top"), YR_B200_RULE_PREFILTER="1")
     p = subprocess.run([exe], cwd=REFDIR, env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+
+
+def test_threads_sharing_one_rules_object():
+    """yr_rules_scan_mem from several threads over one YR_RULES (limits.h YR_MAX_THREADS): the learnt
+    classification is shared, the per-scan match marks are not"""
+    from concurrent.futures import ThreadPoolExecutor
+    rs = synth.ruleset(4, 2000)
+    R, P = yrh.ref(), yrh.refpf()
+    rr, rp = R.compile(rs.source), P.compile(rs.source)
+    files = [synth.corpus(rs, 30000 + 777 * k, 2048, seed=k, plant_seed=90 + k) for k in range(48)]
+    want = [rr.scan(f).key() for f in files]
+    for _ in range(2):
+        with ThreadPoolExecutor(8) as ex:
+            got = list(ex.map(lambda f: rp.scan(f).key(), files))
+        assert got == want
