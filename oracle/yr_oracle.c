@@ -274,6 +274,25 @@ static int verify_chained(
 
 /* ------------------------------------------------- match callback (a9) */
 
+/* Optional trace of the _yr_scan_match_callback calls that survive the fullword test, in call order
+   (single-threaded test aid: tests/test_vm_host_cpu.py compares it with the records the product's
+   verifier code produces). */
+static yro_callback* g_trace = NULL;
+static size_t g_trace_cap = 0, g_trace_n = 0;
+
+void yro_trace_begin(yro_callback* buf, size_t cap)
+{
+  g_trace = buf;
+  g_trace_cap = cap;
+  g_trace_n = 0;
+}
+
+size_t yro_trace_end(void)
+{
+  g_trace = NULL;
+  return g_trace_n; /* may exceed cap: the caller retries with a larger buffer */
+}
+
 /* scan.c:634-765 _yr_scan_match_callback.  match_pos = match_data - data. */
 static int match_callback(octx_t* c, int64_t match_pos, int32_t match_length, int re_flags, const cbargs_t* a)
 {
@@ -300,6 +319,20 @@ static int match_callback(octx_t* c, int64_t match_pos, int32_t match_length, in
       if (match_pos + match_length < size && is_alnum(d[match_pos + match_length]))
         return YRB_SUCCESS;
     }
+  }
+
+  if (g_trace != NULL)
+  {
+    if (g_trace_n < g_trace_cap)
+    {
+      yro_callback* t = &g_trace[g_trace_n];
+      t->offset = match_pos;
+      t->string_idx = a->sidx;
+      t->length = match_length;
+      t->xor_key = a->xor_key;
+      t->pad = 0;
+    }
+    g_trace_n++;
   }
 
   if (s->flags & YRB_SF_CHAIN_PART)

@@ -55,6 +55,19 @@ yro_result* yro_scan_block(
 
 void yro_result_free(yro_result* r);
 
+/* Trace of the match callbacks of the next yro_scan_block calls (see yr_oracle.c). */
+typedef struct yro_callback
+{
+  int64_t offset;
+  uint32_t string_idx;
+  int32_t length;
+  uint32_t xor_key;
+  uint32_t pad;
+} yro_callback;
+
+void yro_trace_begin(yro_callback* buf, size_t cap);
+size_t yro_trace_end(void);
+
 /* Only the AC walk: emits (i, acm_index) for every yr_scan_verify_match call,
    in discovery order.  Returns the count; writes at most cap pairs. */
 size_t yro_ac_events(

@@ -1,0 +1,130 @@
+"""CPU replay of the PRODUCT's verifier code against the oracle.
+
+tests/harness/vm_host.cpp compiles yara_b200/csrc/verify.cu and emit.cuh -- candidate emission, the
+literal compare family, the fast hex VM, the fiber VM and their work-area tiers, error reporting --
+for the CPU (tests/harness/cuda_host_shim.h) and runs the kernels as ordinary functions, one thread
+of a 1x1 grid.  What comes out (match-callback records in discovery-key order, the earliest verifier
+error) must equal the oracle's callback trace of the same block: the same device code the GPU runs,
+checked without a GPU.  (The scan kernels and the resolve stage use warp collectives / CUB and stay
+with the -m gpu tests.)"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import fuzzgen
+import yrh
+from cases import CASES
+from yara_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "tests", "harness", "libvmhost.so")
+HAVE = os.path.exists(LIB) and os.path.exists(yrh.ref_path())
+pytestmark = pytest.mark.skipif(not HAVE, reason="tests/harness/libvmhost.so or oracle/_ref not built")
+
+RAW = np.dtype([("key", "<u8"), ("offset", "<i8"), ("string_idx", "<u4"), ("length", "<i4"), ("xor_key", "<u4"), ("group", "<u4")])
+CB = np.dtype([("offset", "<i8"), ("string_idx", "<u4"), ("length", "<i4"), ("xor_key", "<u4"), ("pad", "<u4")])
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_cand", C.c_uint64 * 3), ("n_raw", C.c_uint64), ("retry_fast", C.c_uint32), ("retry_re", C.c_uint32),
+                ("retry_fast3", C.c_uint32), ("retry_fast4", C.c_uint32), ("error", C.c_int32), ("error_string", C.c_uint32),
+                ("error_key", C.c_uint64)]
+
+
+_lib = None
+
+
+def vmlib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(LIB)
+        _lib.vmh_run.restype = C.c_longlong
+        _lib.vmh_run.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(Stats)]
+    return _lib
+
+
+def vm_run(image, data, cap=1 << 16):
+    img = np.frombuffer(image, dtype=np.uint8)
+    buf = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+    out = np.zeros(cap, dtype=RAW)
+    st = Stats()
+    n = vmlib().vmh_run(img.ctypes.data_as(C.c_void_p), buf.ctypes.data_as(C.c_void_p), buf.size, 0, 0,
+                        out.ctypes.data_as(C.c_void_p), cap, C.byref(st))
+    assert n >= 0
+    if n > cap:
+        return vm_run(image, data, cap=int(n))
+    return out[:n], st
+
+
+def oracle_trace(image, data, cap=1 << 16):
+    lib = yrh._oracle_lib()
+    lib.yro_trace_begin.argtypes = [C.c_void_p, C.c_size_t]
+    lib.yro_trace_end.restype = C.c_size_t
+    buf = np.zeros(cap, dtype=CB)
+    lib.yro_trace_begin(buf.ctypes.data_as(C.c_void_p), cap)
+    o = yrh.oracle_scan(image, data)
+    n = lib.yro_trace_end()
+    if n > cap:
+        return oracle_trace(image, data, cap=int(n))
+    return buf[:n], o
+
+
+def check(image, data):
+    want, o = oracle_trace(image, data)
+    got, st = vm_run(image, data)
+    if o.error == 0:
+        assert st.error == 0
+    else:
+        # the reference stops at its first failing candidate; the product verifies every candidate and keeps
+        # the earliest failure: same code, and everything discovered before it is the same
+        assert st.error == o.error
+        got = got[got["key"] < st.error_key]
+    n = len(got)
+    if o.error != 0:
+        n = min(len(got), len(want))   # callbacks of the failing candidate itself may precede its error
+    else:
+        assert len(got) == len(want), (len(got), len(want))
+    for f in ("string_idx", "offset", "length", "xor_key"):
+        assert np.array_equal(got[f][:n].astype(np.int64), want[f][:n].astype(np.int64)), f
+    b = want[:n]
+    return len(b), st
+
+
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_known_answer_cases(idx):
+    rule, data = CASES[idx]
+    image = yrh.ref().compile(rule).flatten()
+    check(image, data)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_rulesets(seed):
+    R = yrh.ref()
+    text, insts, n = fuzzgen.compile_filtered(R, seed, 60)
+    image = R.compile(text).flatten()
+    data = fuzzgen.gen_data(seed, insts, (1 << 15) + 13 * seed)
+    n, st = check(image, data)
+    assert n > 0
+
+
+@pytest.mark.parametrize("cfg,n", [(2, 500), (3, 2000), (4, 2000), (5, 800)])
+def test_synthetic_rulesets(cfg, n):
+    rs = synth.ruleset(cfg, n)
+    image = yrh.ref().compile(rs.source).flatten()
+    data = synth.corpus(rs, 1 << 19, 512)
+    nrec, st = check(image, data)
+    assert nrec > 500
+
+
+def test_tiers_are_exercised():
+    """the known-answer cases include position lists / fiber counts that outgrow tier 1, tier 2 and tier 3:
+    the replay takes the same escalation path as the GPU"""
+    R = yrh.ref()
+    seen = {"retry_fast": 0, "retry_re": 0, "retry_fast3": 0}
+    for rule, data in CASES:
+        _, st = vm_run(R.compile(rule).flatten(), data)
+        for k in seen:
+            seen[k] += getattr(st, k)
+    assert seen["retry_fast"] > 0 and seen["retry_re"] > 0 and seen["retry_fast3"] > 0, seen

@@ -1254,6 +1254,7 @@ verify_re_kernel(
   }
 }
 
+#ifndef YRB_HOST_EMULATION   // tests/harness/vm_host.cpp compiles the device code above for the CPU and drives it itself
 void launch_verify(
     const DevRules& R, const ScanView& V, const CandOut& cands, const unsigned long long n_cand[NUM_CLS],
     const RawOut& out, const VerifyWs& W, cudaStream_t s, unsigned* launches)
@@ -1331,3 +1332,4 @@ void launch_verify_fast_tier3(
         W.retry_fast, nullptr);
   (*launches)++;
 }
+#endif
