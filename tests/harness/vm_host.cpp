@@ -8,8 +8,15 @@
  *   Aho-Corasick walk (ac_step / emit_events) -> Cand[] per class
  *   tier 1 kernels -> tier 2 for what overflowed -> tiers 3 and 4 of the fast VM
  * and hands back the Raw records in discovery-key order plus the earliest verifier error, which
- * tests/test_vm_host_cpu.py compares with the oracle's match-callback trace.  The resolve stage and
- * the scan kernels use warp collectives and CUB and are covered by the GPU tests only.
+ * tests/test_vm_host_cpu.py compares with the oracle's match-callback trace.
+ *
+ * vmh_scan() goes on through the resolve stage (yara_b200/csrc/resolve_kernels.cuh: sort keys, the
+ * (string, offset) selection, FAST_MODE guard, the chain replay with its look-ahead, verifier error
+ * selection) in the order of resolve.cu's launch_resolve, with std::stable_sort standing in for the
+ * CUB radix sort and a loop for DeviceSelect::Flagged, and returns what yrb_scan_host would: confirmed
+ * and unconfirmed matches and the scan's error.  Every kernel is called once per "thread" of the grid
+ * it is launched with on the device; chain_resolve_kernel runs with a single lane per chain.
+ * Not covered here: the scan kernels (prefilter, walk), the 1M-cap second pass, seeds, batches.
  *
  * Built by oracle/Makefile into oracle/_ref-independent tests/harness output (libvmhost.so).
  */
@@ -22,6 +29,29 @@
 
 #include "../../yara_b200/csrc/verify.cu"
 #include "../../yara_b200/csrc/emit.cuh"
+
+#define YRB_WARP 1   /* chain_resolve_kernel: one lane per chain here, the collectives of the shim are identities */
+#include "../../yara_b200/csrc/resolve_kernels.cuh"
+
+static void set_grid_1x1()
+{
+  threadIdx.x = blockIdx.x = 0;
+  blockDim.x = gridDim.x = 1;
+}
+
+/* calls `f` once per thread of a launch of ceil(n / block) blocks of `block` threads */
+template <typename F> static void launch_per_thread(uint64_t n, unsigned block, F f)
+{
+  blockDim.x = block;
+  gridDim.x = (unsigned) ((n + block - 1) / block);
+  for (uint64_t t = 0; t < (uint64_t) gridDim.x * block; t++)
+  {
+    blockIdx.x = (unsigned) (t / block);
+    threadIdx.x = (unsigned) (t % block);
+    f();
+  }
+  set_grid_1x1();
+}
 
 extern "C" {
 
@@ -48,11 +78,164 @@ typedef struct vmh_stats
   uint64_t error_key;     /* discovery key (seq bits cleared) of the failing candidate */
 } vmh_stats;
 
+static long long run_verify(
+    const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, std::vector<Raw>& kept,
+    std::vector<unsigned long long>& str_err_out, vmh_stats* stats);
+
 /* Returns the number of distinct records (may exceed cap: call again with a larger buffer), or -1 on a bad image. */
 long long vmh_run(
     const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, vmh_raw* out, size_t cap,
     vmh_stats* stats)
 {
+  std::vector<Raw> kept;
+  std::vector<unsigned long long> str_err;
+  const long long rc = run_verify(image, data, size, base, scan_flags, kept, str_err, stats);
+  if (rc < 0)
+    return rc;
+  std::stable_sort(kept.begin(), kept.end(), [](const Raw& a, const Raw& b) { return a.key < b.key; });
+  size_t n = 0;
+  for (size_t k = 0; k < kept.size(); k++)
+  {
+    if (n < cap)
+    {
+      out[n].key = kept[k].key;
+      out[n].offset = kept[k].offset;
+      out[n].string_idx = kept[k].string_idx;
+      out[n].length = kept[k].length;
+      out[n].xor_key = kept[k].misc & 0xFF;
+      out[n].group = kept[k].group;
+    }
+    n++;
+  }
+  return (long long) n;
+}
+
+typedef struct vmh_result
+{
+  int32_t error;
+  uint32_t error_string;
+  uint64_t n_matches;       /* may exceed the capacity given: call again with more room */
+  uint64_t n_unconfirmed;
+  uint32_t n_too_many;
+  uint32_t over_cap;        /* some string went over YR_MAX_STRING_MATCHES: the second pass is not replayed here */
+} vmh_result;
+
+/* verification + resolve: what yrb_scan_host returns for one block (no seeds, no cap second pass) */
+int vmh_scan(
+    const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, yrb_match* matches, size_t cap_m,
+    yrb_match* unconfirmed, size_t cap_u, vmh_result* res, vmh_stats* stats)
+{
+  std::vector<Raw> raw;
+  std::vector<unsigned long long> str_err;
+  memset(res, 0, sizeof(*res));
+  res->error_string = YRB_NONE;
+  if (run_verify(image, data, size, base, scan_flags, raw, str_err, stats) < 0)
+    return -1;
+
+  const yrb_image_header* h = (const yrb_image_header*) image;
+  DevRules R;
+  memset(&R, 0, sizeof(R));
+  R.T = yrb_img_trans(image);
+  R.M = yrb_img_match(image);
+  R.acm = yrb_img_acm(image);
+  R.S = yrb_img_strings(image);
+  R.lit = yrb_img_lit(image);
+  R.code = yrb_img_code(image);
+  R.lower = yrb_img_lower(image);
+  R.alter = yrb_img_alter(image);
+  R.tables_size = h->tables_size;
+  R.num_acm = h->num_acm;
+  R.num_strings = h->num_strings;
+  R.stack_words = h->max_re_stack + 1;
+
+  const uint32_t n = (uint32_t) raw.size();
+  const uint32_t ns = R.num_strings ? R.num_strings : 1;
+  ScanStatus st;
+  memset(&st, 0, sizeof(st));
+  std::vector<unsigned long long> str_min_key(ns, ~0ULL);
+  std::vector<uint32_t> str_count(ns, 0);
+  std::vector<yrb_match> finals(n + 1), unconf(n + 1);
+  std::vector<uint32_t> too_many(1024);
+
+  if (n > 0)
+  {
+    /* ---- launch_resolve (resolve.cu), kernel by kernel */
+    std::vector<uint64_t> k0(n), k1(n);
+    std::vector<uint32_t> ix0(n), ix1(n), sel(n), starts(n);
+    std::vector<uint8_t> flags(n, 0);
+
+    if (scan_flags & YRB_SCAN_FAST_MODE)
+      launch_per_thread(n, 256, [&] { fastmode_min_kernel(raw.data(), n, R, str_min_key.data()); });
+    launch_per_thread(n, 256, [&] {
+      build_key_a_kernel(raw.data(), n, R, scan_flags, str_min_key.data(), nullptr, k0.data(), ix0.data());
+    });
+
+    /* cub::DeviceRadixSort::SortPairs (stable) */
+    std::vector<uint32_t> order(n);
+    for (uint32_t j = 0; j < n; j++) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return k0[a] < k0[b]; });
+    for (uint32_t j = 0; j < n; j++) { k1[j] = k0[order[j]]; ix1[j] = ix0[order[j]]; }
+
+    launch_per_thread(n, 256, [&] { select_plain_kernel(raw.data(), ix1.data(), k1.data(), n, R, str_count.data(), flags.data()); });
+    launch_per_thread(R.num_strings, 256, [&] { check_cap_kernel(str_count.data(), R.num_strings, &st); });
+
+    /* cub::DeviceSelect::Flagged over a counting iterator */
+    int n_sel = 0;
+    for (uint32_t j = 0; j < n; j++) if (flags[j]) sel[n_sel++] = j;
+    st.n_sel = n_sel;
+    launch_per_thread(n, 256, [&] { write_plain_kernel(raw.data(), ix1.data(), sel.data(), &st, n, finals.data()); });
+
+    if (h->num_chains > 0 && st.n_chain_raw + 0 >= 0)
+    {
+      std::vector<int32_t> nxt(n), prv(n), clen(n), mlen(n), uvn(n), lists((size_t) 8 * ns);
+      std::vector<uint8_t> where(n);
+      std::vector<Raw> sraw(n);
+      ChainLists L;
+      L.nxt = nxt.data(); L.prv = prv.data(); L.clen = clen.data(); L.mlen = mlen.data(); L.where = where.data();
+      L.uhead = lists.data(); L.utail = lists.data() + ns; L.ucnt = lists.data() + 2 * (size_t) ns;
+      L.mhead = lists.data() + 3 * (size_t) ns; L.mtail = lists.data() + 4 * (size_t) ns; L.mcnt = lists.data() + 5 * (size_t) ns;
+      L.uvhead = lists.data() + 6 * (size_t) ns; L.prior = lists.data() + 7 * (size_t) ns;
+      L.uvn = uvn.data();
+      launch_per_thread(R.num_strings, 256, [&] { chain_init_kernel(L, R.num_strings); });
+      st.n_chain_starts = 0;
+      launch_per_thread(n, 256, [&] { chain_gather_kernel(raw.data(), ix1.data(), k1.data(), n, sraw.data(), starts.data(), &st); });
+      launch_per_thread(st.n_chain_starts, 128, [&] {
+        chain_resolve_kernel(sraw.data(), k1.data(), n, R, L, finals.data(), unconf.data(), &st, too_many.data(), 1024, scan_flags,
+                             nullptr, (int64_t) base, 0, nullptr, nullptr, nullptr, starts.data());
+      });
+    }
+  }
+
+  /* ---- verifier errors (launch_error_select) */
+  bool any_err = false;
+  for (uint32_t s = 0; s < R.num_strings; s++) any_err = any_err || str_err[s] != ~0ULL;
+  if (any_err)
+  {
+    launch_per_thread(R.num_strings, 256, [&] {
+      error_select_kernel(str_err.data(), n > 0 ? str_min_key.data() : nullptr, nullptr, R, scan_flags, &st);
+    });
+    launch_per_thread(R.num_strings, 256, [&] { error_string_kernel(str_err.data(), R.num_strings, &st); });
+    if (st.err_key_inv != 0ULL)
+    {
+      res->error = (int32_t) (~st.err_key_inv & KEY_SEQ_MAX);
+      res->error_string = st.err_string1 ? st.err_string1 - 1 : YRB_NONE;
+    }
+  }
+
+  res->n_matches = (uint64_t) st.n_sel + st.n_chain_out;
+  res->n_unconfirmed = st.n_unconf;
+  res->n_too_many = st.n_too_many;
+  res->over_cap = st.over_cap;
+  for (uint64_t k = 0; k < res->n_matches && k < cap_m; k++) matches[k] = finals[k];
+  for (uint64_t k = 0; k < res->n_unconfirmed && k < cap_u; k++) unconfirmed[k] = unconf[k];
+  return 0;
+}
+
+static long long run_verify(
+    const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, std::vector<Raw>& kept_out,
+    std::vector<unsigned long long>& str_err_out, vmh_stats* stats)
+{
+  set_grid_1x1();
   const yrb_image_header* h = (const yrb_image_header*) image;
   if (h->magic != YRB_IMAGE_MAGIC || h->version != YRB_IMAGE_VERSION)
     return -1;
@@ -229,34 +412,20 @@ long long vmh_run(
     stats->error_string = err_string;
   }
 
-  /* drop what a tier emitted for candidates it handed on, then discovery order */
+  /* drop what a tier emitted for candidates it handed on */
   raw.resize((size_t) st.n_raw);
-  std::vector<Raw> kept;
-  kept.reserve(raw.size());
+  kept_out.clear();
+  kept_out.reserve(raw.size());
   size_t stage = 0;
   for (size_t k = 0; k < raw.size(); k++)
   {
     while (stage < stage_end.size() && k >= stage_end[stage]) stage++;
     if (stage < handed_on.size() && handed_on[stage].count(raw[k].key >> KEY_SEQ_BITS))
       continue;
-    kept.push_back(raw[k]);
+    kept_out.push_back(raw[k]);
   }
-  std::stable_sort(kept.begin(), kept.end(), [](const Raw& a, const Raw& b) { return a.key < b.key; });
-  size_t n = 0;
-  for (size_t k = 0; k < kept.size(); k++)
-  {
-    if (n < cap)
-    {
-      out[n].key = kept[k].key;
-      out[n].offset = kept[k].offset;
-      out[n].string_idx = kept[k].string_idx;
-      out[n].length = kept[k].length;
-      out[n].xor_key = kept[k].misc & 0xFF;
-      out[n].group = kept[k].group;
-    }
-    n++;
-  }
-  return (long long) n;
+  str_err_out = str_err;
+  return (long long) kept_out.size();
 }
 
 } /* extern "C" */
