@@ -16,7 +16,8 @@
  * CUB radix sort and a loop for DeviceSelect::Flagged, and returns what yrb_scan_host would: confirmed
  * and unconfirmed matches and the scan's error.  Every kernel is called once per "thread" of the grid
  * it is launched with on the device; chain_resolve_kernel runs with a single lane per chain.
- * Not covered here: the scan kernels (prefilter, walk), the 1M-cap second pass, seeds, batches.
+ * vmh_scan_batch() does the same in batch mode (ScanView.n_seg > 0, the device side of yrb_scan_batch).
+ * Not covered here: the scan kernels (prefilter, walk), the 1M-cap second pass, seeds.
  *
  * Built by oracle/Makefile into oracle/_ref-independent tests/harness output (libvmhost.so).
  */
@@ -80,7 +81,8 @@ typedef struct vmh_stats
 
 static long long run_verify(
     const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, std::vector<Raw>& kept,
-    std::vector<unsigned long long>& str_err_out, vmh_stats* stats);
+    std::vector<unsigned long long>& str_err_out, vmh_stats* stats, int n_seg = 0, const int64_t* seg_start = nullptr,
+    const int64_t* seg_len = nullptr, uint8_t* item_dirty = nullptr);
 
 /* Returns the number of distinct records (may exceed cap: call again with a larger buffer), or -1 on a bad image. */
 long long vmh_run(
@@ -121,15 +123,38 @@ typedef struct vmh_result
 } vmh_result;
 
 /* verification + resolve: what yrb_scan_host returns for one block (no seeds, no cap second pass) */
+static int scan_common(
+    const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, yrb_match* matches, size_t cap_m,
+    yrb_match* unconfirmed, size_t cap_u, vmh_result* res, vmh_stats* stats, int n_seg, const int64_t* seg_start,
+    const int64_t* seg_len, uint8_t* item_dirty);
+
 int vmh_scan(
     const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, yrb_match* matches, size_t cap_m,
     yrb_match* unconfirmed, size_t cap_u, vmh_result* res, vmh_stats* stats)
+{
+  return scan_common(image, data, size, base, scan_flags, matches, cap_m, unconfirmed, cap_u, res, stats, 0, nullptr, nullptr, nullptr);
+}
+
+/* Batch mode (yrb_scan_batch): `data` is the concatenation, item k = [seg_start[k], seg_start[k] + seg_len[k]).
+   matches come back string-major with CONCATENATION offsets (the host side of yrb_scan_batch splits them by item);
+   item_dirty[k] != 0: the item needs the per-item path. */
+int vmh_scan_batch(
+    const void* image, const uint8_t* data, size_t size, int n_seg, const int64_t* seg_start, const int64_t* seg_len,
+    yrb_match* matches, size_t cap_m, uint8_t* item_dirty, vmh_result* res, vmh_stats* stats)
+{
+  return scan_common(image, data, size, 0, 0, matches, cap_m, nullptr, 0, res, stats, n_seg, seg_start, seg_len, item_dirty);
+}
+
+static int scan_common(
+    const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, yrb_match* matches, size_t cap_m,
+    yrb_match* unconfirmed, size_t cap_u, vmh_result* res, vmh_stats* stats, int n_seg, const int64_t* seg_start,
+    const int64_t* seg_len, uint8_t* item_dirty)
 {
   std::vector<Raw> raw;
   std::vector<unsigned long long> str_err;
   memset(res, 0, sizeof(*res));
   res->error_string = YRB_NONE;
-  if (run_verify(image, data, size, base, scan_flags, raw, str_err, stats) < 0)
+  if (run_verify(image, data, size, base, scan_flags, raw, str_err, stats, n_seg, seg_start, seg_len, item_dirty) < 0)
     return -1;
 
   const yrb_image_header* h = (const yrb_image_header*) image;
@@ -201,13 +226,14 @@ int vmh_scan(
       launch_per_thread(n, 256, [&] { chain_gather_kernel(raw.data(), ix1.data(), k1.data(), n, sraw.data(), starts.data(), &st); });
       launch_per_thread(st.n_chain_starts, 128, [&] {
         chain_resolve_kernel(sraw.data(), k1.data(), n, R, L, finals.data(), unconf.data(), &st, too_many.data(), 1024, scan_flags,
-                             nullptr, (int64_t) base, 0, nullptr, nullptr, nullptr, starts.data());
+                             nullptr, (int64_t) base, n_seg, seg_start, seg_len, item_dirty, starts.data());
       });
     }
   }
 
-  /* ---- verifier errors (launch_error_select) */
+  /* ---- verifier errors (launch_error_select); in batch mode they only mark their item */
   bool any_err = false;
+  if (n_seg > 0) std::fill(str_err.begin(), str_err.end(), ~0ULL);
   for (uint32_t s = 0; s < R.num_strings; s++) any_err = any_err || str_err[s] != ~0ULL;
   if (any_err)
   {
@@ -233,7 +259,8 @@ int vmh_scan(
 
 static long long run_verify(
     const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, std::vector<Raw>& kept_out,
-    std::vector<unsigned long long>& str_err_out, vmh_stats* stats)
+    std::vector<unsigned long long>& str_err_out, vmh_stats* stats, int n_seg, const int64_t* seg_start,
+    const int64_t* seg_len, uint8_t* item_dirty)
 {
   set_grid_1x1();
   const yrb_image_header* h = (const yrb_image_header*) image;
@@ -265,6 +292,9 @@ static long long run_verify(
   V.own_hi = (int64_t) size;
   V.base = base;
   V.scan_flags = scan_flags;
+  V.n_seg = n_seg;          /* batch mode (yrb_scan_batch): the block is a concatenation of items */
+  V.seg_start = seg_start;
+  V.seg_len = seg_len;
 
   ScanStatus st;
   memset(&st, 0, sizeof(st));
@@ -320,7 +350,7 @@ static long long run_verify(
     ro.cap = raw.size();
     ro.st = &st;
     ro.str_err = str_err.data();
-    ro.item_dirty = nullptr;
+    ro.item_dirty = item_dirty;
 
     /* A candidate that outgrows a tier is verified again from scratch by the next one, which emits
        its records again (resolve.cu treats equal keys as one record); here the records a tier emitted

@@ -202,3 +202,110 @@ def test_scan_synthetic_rulesets(cfg, n):
     data = synth.corpus(rs, 1 << 19, 512)
     assert check_scan(image, data, 0) > 500
     check_scan(image, data, 1)
+
+
+# ------------------------------------------------------------------ batch mode (yrb_scan_batch) on the CPU
+def vm_scan_batch(image, items, rng):
+    """the device side of yrb_scan_batch: one walk / verify / resolve over the concatenation; returns the
+    per-item records (item-relative offsets) and the items flagged for the per-item path"""
+    from yara_b200.api import YRB_MATCH_DTYPE
+    lib = vmlib()
+    lib.vmh_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                   C.c_void_p, C.POINTER(Result), C.POINTER(Stats)]
+    starts, parts, cur = [], [], 0
+    for it in items:
+        starts.append(cur)
+        parts.append(it)
+        cur += len(it)
+        pad = (-cur) % 16 if rng.random() < 0.7 else rng.choice([0, 1, 5])     # the engine packs at 16-byte boundaries
+        if pad:
+            src = items[rng.randrange(len(items))]
+            parts.append(np.resize(src, pad).astype(np.uint8) if len(src) else np.zeros(pad, np.uint8))
+            cur += pad
+    concat = np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(1, np.uint8)
+    st_a = np.array(starts, dtype=np.int64)
+    ln_a = np.array([len(i) for i in items], dtype=np.int64)
+    dirty = np.zeros(max(1, len(items)), dtype=np.uint8)
+    img = np.frombuffer(image, dtype=np.uint8)
+    cap = 1 << 16
+    while True:
+        m = np.zeros(cap, dtype=YRB_MATCH_DTYPE)
+        res, st = Result(), Stats()
+        rc = lib.vmh_scan_batch(img.ctypes.data_as(C.c_void_p), concat.ctypes.data_as(C.c_void_p), cur, len(items),
+                                st_a.ctypes.data_as(C.c_void_p), ln_a.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p), cap,
+                                dirty.ctypes.data_as(C.c_void_p), C.byref(res), C.byref(st))
+        assert rc == 0
+        if res.n_matches <= cap:
+            break
+        cap = int(res.n_matches)
+        dirty[:] = 0
+    m = m[: res.n_matches]
+    owner = np.searchsorted(st_a, m["offset"], side="right") - 1
+    per_item = []
+    for k in range(len(items)):
+        sel = m[owner == k].copy()
+        sel["offset"] -= st_a[k]
+        per_item.append(sel)
+    return per_item, dirty, res
+
+
+def check_batch(image, items, rng):
+    per_item, dirty, res = vm_scan_batch(image, items, rng)
+    if res.over_cap:
+        pytest.skip("1M cap")
+    n = 0
+    for k, it in enumerate(items):
+        o = yrh.oracle_scan(image, it)
+        if dirty[k]:
+            assert o.error != 0 or o.too_many, "item %d flagged without a reason" % k
+            continue
+        assert o.error == 0, "item %d: the oracle fails (%d) but the batch did not flag it" % (k, o.error)
+        f = ("string_idx", "offset", "match_length", "xor_key")
+        assert canon(per_item[k], f) == canon(o.matches, f), "item %d of %d" % (k, len(items))
+        n += len(o.matches)
+    return n
+
+
+def ragged(data, rng, n):
+    data = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    cuts = sorted(set([0, len(data)] + [rng.randrange(len(data) + 1) for _ in range(n)]))
+    items = [np.ascontiguousarray(data[a:b]) for a, b in zip(cuts, cuts[1:])]
+    items.insert(rng.randrange(len(items) + 1), np.zeros(0, np.uint8))
+    items.append(np.ascontiguousarray(data))          # and the whole buffer as one more item
+    return items
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_batch_fuzz_rulesets(seed):
+    import random
+    R = yrh.ref()
+    text, insts, n = fuzzgen.compile_filtered(R, seed, 50)
+    image = R.compile(text).flatten()
+    if np.frombuffer(image, dtype=np.uint32, count=1, offset=int(np.frombuffer(image[56:64], dtype=np.uint64)[0]))[0] != 0:
+        pytest.skip("root-state matches: batches are refused")
+    data = fuzzgen.gen_data(seed, insts, 1 << 14)
+    rng = random.Random(seed)
+    check_batch(image, ragged(data, rng, 12), rng)
+
+
+@pytest.mark.parametrize("cfg,n", [(3, 1500), (4, 2000), (5, 600)])
+def test_batch_synthetic_rulesets(cfg, n):
+    import random
+    rs = synth.ruleset(cfg, n)
+    image = yrh.ref().compile(rs.source).flatten()
+    data = synth.corpus(rs, 1 << 18, 512)
+    rng = random.Random(cfg)
+    assert check_batch(image, ragged(data, rng, 30), rng) > 300
+
+
+def test_batch_chain_parts_in_neighbouring_items():
+    import random
+    src = "rule a { strings: $a = { 11 22 33 44 [300-400] 55 66 77 88 [250-300] 99 AA BB CC } condition: $a }"
+    image = yrh.ref().compile(src).flatten()
+    head, mid, tail = bytes.fromhex("11223344"), bytes.fromhex("55667788"), bytes.fromhex("99aabbcc")
+    whole = np.frombuffer(b"." * 50 + head + b"." * 350 + mid + b"." * 260 + tail + b"." * 20, dtype=np.uint8).copy()
+    c1, c2 = 50 + 4 + 100, 50 + 4 + 350 + 4 + 100
+    items = [whole[:c1].copy(), whole[c1:].copy(), whole.copy(), whole[:c2].copy(), whole[c2:].copy(), whole.copy()]
+    per_item, dirty, res = vm_scan_batch(image, items, random.Random(1))
+    assert [len(x) for x in per_item] == [0, 0, 1, 0, 0, 1] and not dirty.any()
+    check_batch(image, items, random.Random(2))
