@@ -99,7 +99,10 @@ def test_known_answer_cases(idx):
     check(image, data)
 
 
-@pytest.mark.parametrize("seed", range(24))
+FUZZ_SEEDS = [s for s in range(24) if s != 19]   # 19: half a minute of fiber VM on the CPU; scripts/vm_host_sweep.py runs it
+
+
+@pytest.mark.parametrize("seed", FUZZ_SEEDS)
 def test_fuzz_rulesets(seed):
     R = yrh.ref()
     text, insts, n = fuzzgen.compile_filtered(R, seed, 60)
@@ -155,7 +158,12 @@ def vm_scan(image, data, flags=0, cap=1 << 16):
 
 
 def canon(a, fields):
-    return sorted(tuple(int(x[f]) for f in fields) for x in a)
+    """rows of the named fields as int64, sorted lexicographically (a list of tuples, cheaply)"""
+    if len(a) == 0:
+        return []
+    t = np.stack([np.asarray(a[f]).astype(np.int64) for f in fields], axis=1)
+    t = t[np.lexsort(t.T[::-1])]
+    return t.tolist()
 
 
 def check_scan(image, data, flags):
@@ -166,12 +174,13 @@ def check_scan(image, data, flags):
     assert res.error == o.error
     if o.error != 0:
         return 0
-    # inside one string the records must already be in YR_MATCHES list order
-    last = {}
-    for x in m:
-        s_, off = int(x["string_idx"]), int(x["offset"])
-        assert last.get(s_, -1) < off
-        last[s_] = off
+    # the records of one string are contiguous and already in YR_MATCHES list order (ascending offsets)
+    if len(m) > 1:
+        sid, off = m["string_idx"].astype(np.int64), m["offset"].astype(np.int64)
+        same = sid[1:] == sid[:-1]
+        assert (off[1:][same] > off[:-1][same]).all()
+        starts = np.concatenate([[True], ~same])
+        assert len(np.unique(sid[starts])) == int(starts.sum())
     assert canon(m, ("string_idx", "offset", "match_length", "xor_key")) == canon(o.matches, ("string_idx", "offset", "match_length", "xor_key"))
     assert canon(u, ("string_idx", "offset", "match_length", "chain_length")) == canon(o.unconfirmed, ("string_idx", "offset", "match_length", "chain_length"))
     return len(m)
@@ -185,7 +194,7 @@ def test_scan_known_answer_cases(idx):
         check_scan(image, data, flags)
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", FUZZ_SEEDS)
 def test_scan_fuzz_rulesets(seed):
     R = yrh.ref()
     text, insts, n = fuzzgen.compile_filtered(R, seed, 60)
