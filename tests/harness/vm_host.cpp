@@ -126,7 +126,19 @@ typedef struct vmh_result
 static int scan_common(
     const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, yrb_match* matches, size_t cap_m,
     yrb_match* unconfirmed, size_t cap_u, vmh_result* res, vmh_stats* stats, int n_seg, const int64_t* seg_start,
-    const int64_t* seg_len, uint8_t* item_dirty);
+    const int64_t* seg_len, uint8_t* item_dirty, const yrb_seed* seeds = nullptr, uint32_t n_seeds = 0,
+    uint32_t* too_many_out = nullptr);
+
+/* one block of a multi-block scan: `seeds` = what earlier blocks left behind (yrb_scan_params.seeds);
+   too_many_out: room for 1024 string indices */
+int vmh_scan_seeds(
+    const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, const yrb_seed* seeds, uint32_t n_seeds,
+    yrb_match* matches, size_t cap_m, yrb_match* unconfirmed, size_t cap_u, uint32_t* too_many_out, vmh_result* res,
+    vmh_stats* stats)
+{
+  return scan_common(image, data, size, base, scan_flags, matches, cap_m, unconfirmed, cap_u, res, stats, 0, nullptr, nullptr,
+                     nullptr, seeds, n_seeds, too_many_out);
+}
 
 int vmh_scan(
     const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, yrb_match* matches, size_t cap_m,
@@ -148,7 +160,7 @@ int vmh_scan_batch(
 static int scan_common(
     const void* image, const uint8_t* data, size_t size, uint64_t base, int scan_flags, yrb_match* matches, size_t cap_m,
     yrb_match* unconfirmed, size_t cap_u, vmh_result* res, vmh_stats* stats, int n_seg, const int64_t* seg_start,
-    const int64_t* seg_len, uint8_t* item_dirty)
+    const int64_t* seg_len, uint8_t* item_dirty, const yrb_seed* seeds, uint32_t n_seeds, uint32_t* too_many_out)
 {
   std::vector<Raw> raw;
   std::vector<unsigned long long> str_err;
@@ -172,6 +184,22 @@ static int scan_common(
   R.num_acm = h->num_acm;
   R.num_strings = h->num_strings;
   R.stack_words = h->max_re_stack + 1;
+
+  /* api.cu seeds_to_raw_kernel: the nodes earlier blocks left behind re-enter as records that sort first */
+  std::vector<int64_t> seed_base(n_seeds ? n_seeds : 1);
+  for (uint32_t k = 0; k < n_seeds; k++)
+  {
+    const yrb_seed sd = seeds[k];
+    Raw r;
+    r.key = (uint64_t) (uint32_t) sd.chain_length;
+    r.offset = sd.offset;
+    r.string_idx = sd.string_idx;
+    r.length = sd.match_length;
+    r.misc = (uint32_t) sd.xor_key | (k << 8) | RAW_SEED | (sd.kind ? RAW_SEED_MARK : 0u);
+    r.group = sd.string_idx < R.num_strings ? R.S[sd.string_idx].chain_head : YRB_NONE;
+    raw.push_back(r);
+    seed_base[k] = sd.base;
+  }
 
   const uint32_t n = (uint32_t) raw.size();
   const uint32_t ns = R.num_strings ? R.num_strings : 1;
@@ -226,7 +254,7 @@ static int scan_common(
       launch_per_thread(n, 256, [&] { chain_gather_kernel(raw.data(), ix1.data(), k1.data(), n, sraw.data(), starts.data(), &st); });
       launch_per_thread(st.n_chain_starts, 128, [&] {
         chain_resolve_kernel(sraw.data(), k1.data(), n, R, L, finals.data(), unconf.data(), &st, too_many.data(), 1024, scan_flags,
-                             nullptr, (int64_t) base, n_seg, seg_start, seg_len, item_dirty, starts.data());
+                             seed_base.data(), (int64_t) base, n_seg, seg_start, seg_len, item_dirty, starts.data());
       });
     }
   }
@@ -254,6 +282,7 @@ static int scan_common(
   res->over_cap = st.over_cap;
   for (uint64_t k = 0; k < res->n_matches && k < cap_m; k++) matches[k] = finals[k];
   for (uint64_t k = 0; k < res->n_unconfirmed && k < cap_u; k++) unconfirmed[k] = unconf[k];
+  for (uint32_t k = 0; too_many_out != nullptr && k < res->n_too_many && k < 1024; k++) too_many_out[k] = too_many[k];
   return 0;
 }
 

@@ -1,0 +1,136 @@
+"""CPU tests of the libyara glue (yara_b200/host/yr_b200_glue.c + the hook lines), end to end through the
+unchanged libyara API: tests/harness/libyara_b200cpu.so is the drop-in's own objects linked against a
+TEST stand-in for the CUDA engine (tests/harness/fake_engine.cpp) that replays the product's verify /
+resolve device code on the CPU.  What the GPU tests check on a B200 -- YR_MATCH materialisation, cross-block
+chains (seeds), parked file-batch results, the pre-filter's note site -- is checked here against the reference
+library without a GPU.  The product itself has no CPU path (tests/test_abi_cpu.py::test_no_cpu_fallback)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import fuzzgen
+import yrh
+from cases import CASES
+from yara_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE = os.path.exists(yrh.b200cpu_path()) and os.path.exists(yrh.ref_path())
+pytestmark = pytest.mark.skipif(not HAVE, reason="tests/harness/libyrh_b200cpu.so or oracle/_ref not built")
+
+
+def same(a, b, what=""):
+    assert a.rc == b.rc, (what, a.rc, b.rc)
+    if a.rc == 0:
+        assert a.matches.tobytes() == b.matches.tobytes(), what
+        assert a.rule_bits.tobytes() == b.rule_bits.tobytes(), what
+    assert a.too_many_calls == b.too_many_calls, what
+
+
+def capped(ref_result):
+    """the stand-in does not replay the second pass of the 1M cap"""
+    return ref_result.too_many_calls > 0 or ref_result.rc == 30
+
+
+def run_cases():
+    R, B = yrh.ref(), yrh.b200cpu()
+    n = 0
+    for idx, (rule, data) in enumerate(CASES):
+        rr, rb = R.compile(rule), B.compile(rule)
+        for flags in (0, 1):
+            a = rr.scan(data, flags=flags, cap=1 << 20)
+            if capped(a):
+                continue
+            same(a, rb.scan(data, flags=flags, cap=1 << 20), "case %d flags %d" % (idx, flags))
+            n += 1
+        a = rr.scan_blocks(data, 1024, 256, cap=1 << 20)
+        if not capped(a):
+            same(a, rb.scan_blocks(data, 1024, 256, cap=1 << 20), "case %d blocks" % idx)
+            n += 1
+    return n
+
+
+def run_fuzz(seeds):
+    R, B = yrh.ref(), yrh.b200cpu()
+    for seed in seeds:
+        text, insts, n = fuzzgen.compile_filtered(R, seed, 50)
+        rr, rb = R.compile(text), B.compile(text)
+        data = np.frombuffer(bytes(fuzzgen.gen_data(seed, insts, (1 << 14) + 13 * seed)), dtype=np.uint8)
+        for flags in (0, 1):
+            a = rr.scan(data, flags=flags, cap=1 << 20)
+            if not capped(a):
+                same(a, rb.scan(data, flags=flags, cap=1 << 20), "seed %d flags %d" % (seed, flags))
+        a = rr.scan_blocks(data, 1024, 256, cap=1 << 20)          # chains whose parts lie in different blocks: seeds
+        if not capped(a):
+            same(a, rb.scan_blocks(data, 1024, 256, cap=1 << 20), "seed %d blocks" % seed)
+        # the same data as a parked file batch
+        cuts = sorted(set([0, len(data)] + [(seed * 7919 + k * 10007) % len(data) for k in range(6)]))
+        items = [np.ascontiguousarray(data[a_:b_]) for a_, b_ in zip(cuts, cuts[1:])] + [data]
+        want = [rr.scan(it, cap=1 << 20) for it in items]
+        with rb.batch(items) as bt:
+            assert bt.rc == 0
+            for k, it in enumerate(items):
+                if not capped(want[k]):
+                    same(want[k], rb.scan(it, cap=1 << 20), "seed %d batch item %d" % (seed, k))
+
+
+def run_file_batch():
+    rs = synth.ruleset(4, 1500)
+    R, B = yrh.ref(), yrh.b200cpu()
+    rr, rb = R.compile(rs.source), B.compile(rs.source)
+    files = [synth.corpus(rs, 9000 + 700 * k, 2048, seed=k, plant_seed=30 + k) for k in range(24)]
+    want = [rr.scan(f) for f in files]
+    with rb.batch(files) as bt:
+        assert bt.rc == 0 and bt.n_rescans == 0
+        for rounds in range(2):
+            for k, f in enumerate(files):
+                same(want[k], rb.scan(f), "file %d" % k)
+    for k, f in enumerate(files[:6]):      # and without the batch
+        same(want[k], rb.scan(f), "file %d unbatched" % k)
+
+
+def test_known_answer_cases_through_the_glue():
+    assert run_cases() > 100
+
+
+def test_fuzz_rulesets_through_the_glue():
+    run_fuzz(range(8))
+
+
+def test_file_batch_through_the_glue():
+    run_file_batch()
+
+
+def test_the_same_with_the_other_prefilter_setting():
+    """$YR_B200_RULE_PREFILTER is read once per process: this process has it set (tests/test_prefilter_cpu.py sets
+    it when the suite is collected), so the checks above ran with the filter on; run them once more in a fresh
+    process with the opposite setting"""
+    env = dict(os.environ)
+    on_here = env.get("YR_B200_RULE_PREFILTER", "") not in ("", "0")
+    if on_here:
+        env.pop("YR_B200_RULE_PREFILTER")
+    else:
+        env["YR_B200_RULE_PREFILTER"] = "1"
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_glue_cpu as t; "
+            "t.run_cases(); t.run_fuzz(range(4)); t.run_file_batch(); print('GLUE_OK')" % (ROOT, os.path.join(ROOT, "tests")))
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "GLUE_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+@pytest.mark.parametrize("prefilter", ["", "1"])
+@pytest.mark.parametrize("name", ["test-rules_b200cpu", "test-async_b200cpu"])
+def test_reference_programs_through_the_glue(name, prefilter):
+    """the reference's own test programs (test-rules: ~1,500 assertions x 3 passes incl. 1024-byte blocks), compiled
+    unmodified and linked against the stand-in build of the drop-in.  (test-api is left out: its
+    test_too_many_matches needs the second pass of the 1M cap, which only the real engine has.)"""
+    exe = os.path.join(ROOT, "oracle", "_ref", name)
+    if not os.path.exists(exe):
+        pytest.skip("%s not built" % name)
+    env = dict(os.environ, TOP_SRCDIR=os.path.join(ROOT, "oracle", "_ref", "top"))
+    env.pop("YR_B200_RULE_PREFILTER", None)
+    if prefilter:
+        env["YR_B200_RULE_PREFILTER"] = prefilter
+    p = subprocess.run([exe], cwd=os.path.join(ROOT, "oracle", "_ref"), env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]

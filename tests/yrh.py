@@ -200,6 +200,18 @@ def ref() -> Harness:
     return _cache["ref"]
 
 
+def b200cpu_path():
+    return os.path.join(ROOT, "tests", "harness", "libyrh_b200cpu.so")
+
+
+def b200cpu() -> Harness:
+    """TEST stand-in: the drop-in's glue linked against tests/harness/fake_engine.cpp, which replays the
+    product's verify / resolve device code on the CPU -- drives yr_b200_glue.c without a GPU"""
+    if "b200cpu" not in _cache:
+        _cache["b200cpu"] = Harness(b200cpu_path())
+    return _cache["b200cpu"]
+
+
 def refpf_path():
     return os.path.join(ROOT, "oracle", "_ref", "libyrh_refpf.so")
 
