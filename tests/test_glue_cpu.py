@@ -104,22 +104,18 @@ def test_file_batch_through_the_glue():
 
 
 def test_the_same_with_the_other_prefilter_setting():
-    """$YR_B200_RULE_PREFILTER is read once per process: this process has it set (tests/test_prefilter_cpu.py sets
-    it when the suite is collected), so the checks above ran with the filter on; run them once more in a fresh
+    """$YR_B200_RULE_PREFILTER is read once per process (on unless "0"): run the checks above once more in a fresh
     process with the opposite setting"""
     env = dict(os.environ)
-    on_here = env.get("YR_B200_RULE_PREFILTER", "") not in ("", "0")
-    if on_here:
-        env.pop("YR_B200_RULE_PREFILTER")
-    else:
-        env["YR_B200_RULE_PREFILTER"] = "1"
+    on_here = not env.get("YR_B200_RULE_PREFILTER", "").startswith("0")
+    env["YR_B200_RULE_PREFILTER"] = "0" if on_here else "1"
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_glue_cpu as t; "
             "t.run_cases(); t.run_fuzz(range(4)); t.run_file_batch(); print('GLUE_OK')" % (ROOT, os.path.join(ROOT, "tests")))
     p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "GLUE_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
 
 
-@pytest.mark.parametrize("prefilter", ["", "1"])
+@pytest.mark.parametrize("prefilter", ["0", "1"])
 @pytest.mark.parametrize("name", ["test-rules_b200cpu", "test-async_b200cpu"])
 def test_reference_programs_through_the_glue(name, prefilter):
     """the reference's own test programs (test-rules: ~1,500 assertions x 3 passes incl. 1024-byte blocks), compiled

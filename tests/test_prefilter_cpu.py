@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 import pytest
 
-os.environ["YR_B200_RULE_PREFILTER"] = "1"   # read once, at the first scan of the refpf library
+os.environ["YR_B200_RULE_PREFILTER"] = "1"   # (the default) read once, at the first scan of the refpf library
 
 import fuzzgen
 import yrh

@@ -11,7 +11,7 @@ anything else means the reference drifted and the build stops.
              scanner.c:287   yr_scanner_destroy: yr_b200_scanner_release(scanner)
   rules.c    #include "yr_b200.h"
              rules.c:515     yr_rules_destroy: yr_b200_rules_release(rules)
-  condition-VM pre-filter (yr_b200_prefilter.c, off unless $YR_B200_RULE_PREFILTER is set):
+  condition-VM pre-filter (yr_b200_prefilter.c, on unless YR_B200_RULE_PREFILTER=0):
   scanner.c  scanner.c:518   yr_b200_prefilter_begin/end around yr_execute_code
   exec.c     exec.c:1168     OP_INIT_RULE: `|| yr_b200_prefilter_skip(...)` next to RULE_IS_DISABLED
              exec.c:1191     OP_MATCH_RULE: yr_b200_prefilter_learn(...)

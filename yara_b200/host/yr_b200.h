@@ -57,7 +57,7 @@ void yr_b200_batch_destroy(YR_B200_BATCH* batch);
 uint32_t yr_b200_batch_rescans(const YR_B200_BATCH* batch); /* buffers that were not parked */
 
 /*
- * Condition-VM pre-filter (yr_b200_prefilter.c; off unless $YR_B200_RULE_PREFILTER is set).
+ * Condition-VM pre-filter (yr_b200_prefilter.c; on unless YR_B200_RULE_PREFILTER=0).
  * Hook sites: scanner.c:518 (begin/end around yr_execute_code), exec.c:1168-1173 (skip test next
  * to RULE_IS_DISABLED in OP_INIT_RULE), exec.c:1185 (learn in OP_MATCH_RULE); matches are noted
  * where they are created (materialise() in the glue).

@@ -22,8 +22,8 @@
  *       the first time such a rule is evaluated with none of its strings matched, the value
  *       OP_MATCH_RULE pops is remembered (a pure rule has only one value there).
  *
- * Off unless $YR_B200_RULE_PREFILTER is set (this round): the hooks then cost one
- * thread-local compare per rule.  No GPU code here; the same file is compiled into
+ * On by default; YR_B200_RULE_PREFILTER=0 turns it off (the hooks then cost one
+ * thread-local compare per rule).  No GPU code here; the same file is compiled into
  * libyara_b200.so and into oracle/_ref/libyara_refpf.so (reference + these hooks only), which
  * runs the reference's own test programs with the filter on.
  */
@@ -80,8 +80,8 @@ int yr_b200_prefilter_enabled(void)
   static int on = -1;
   if (on < 0)
   {
-    const char* e = getenv("YR_B200_RULE_PREFILTER");
-    on = (e != NULL && e[0] != '\0' && e[0] != '0') ? 1 : 0;
+    const char* e = getenv("YR_B200_RULE_PREFILTER"); /* on unless set to 0 */
+    on = (e != NULL && e[0] == '0') ? 0 : 1;
   }
   return on;
 }
