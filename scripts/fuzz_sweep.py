@@ -7,8 +7,7 @@ differs; exit code 1 if any did.
   python scripts/fuzz_sweep.py FIRST LAST [time-limit-seconds] [skip,seeds] [cpu]
 
 With `cpu` as the 5th argument the drop-in is the TEST stand-in build (tests/harness/libyara_b200cpu.so: the
-same glue objects, the product's verify / resolve device code replayed on the CPU) -- no GPU needed; scans
-that hit the 1M cap are skipped there.
+same glue objects, the product's verify / resolve device code replayed on the CPU) -- no GPU needed.
 
 Seeds on which the REFERENCE does not terminate (yr_re_exec cycles on zero-width loops, DESIGN.md
 section 7) must be skipped: pre-screen with the reference alone and pass them as the 4th argument."""
@@ -32,8 +31,6 @@ def note(*a):
     print(*a, file=log, flush=True)
 
 def same(a, b):
-    if CPU and (a.too_many_calls > 0 or a.rc == 30):
-        return True      # the stand-in engine does not replay the second pass of the 1M cap
     if a.rc != b.rc:
         return False
     return a.rc != 0 or (a.matches.tobytes() == b.matches.tobytes() and a.rule_bits.tobytes() == b.rule_bits.tobytes())

@@ -6,12 +6,11 @@
  * protocol, seeds across blocks, parked batch results, the pre-filter's note site -- end to end
  * through the unchanged libyara API.
  *
- * It is built into tests/harness/cpu/libyrb200.so next to a copy of the drop-in that resolves
- * `-lyrb200` there (rpath $ORIGIN); nothing outside tests/ loads it.  The product library
+ * It is built into tests/harness/libyrb200cpu.so, and the drop-in's own objects are linked against
+ * it as tests/harness/libyara_b200cpu.so (yara_b200/Makefile); nothing outside tests/ loads either.  The product library
  * (yara_b200/libyrb200.so) has no CPU path and fails with YRB_ERROR_NO_DEVICE without a GPU.
  *
- * Not replayed: the scan kernels (the walk of vm_host.cpp stands in for them), the second pass of
- * the 1M cap (such a scan fails with ERROR_INTERNAL_FATAL_ERROR here), shards, device-resident data.
+ * Not replayed: the scan kernels (the walk of vm_host.cpp stands in for them), shards, device-resident data.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -33,6 +32,10 @@ typedef struct vmh_result
   uint64_t n_unconfirmed;
   uint32_t n_too_many;
   uint32_t over_cap;
+  uint64_t first_cut_key;
+  uint64_t error_key;
+  uint32_t n_cuts;
+  uint32_t pad;
 } vmh_result;
 
 typedef struct vmh_stats
@@ -133,23 +136,29 @@ int yrb_scan_host(yrb_scanner* s, const uint8_t* data, size_t size, const yrb_sc
       break;
     cap = (size_t) std::max(res.n_matches, res.n_unconfirmed);
   }
-  if (res.over_cap)
-    return 31; /* ERROR_INTERNAL_FATAL_ERROR: the cap's second pass is not replayed by the stand-in */
-
-  out->error = res.error;
-  out->error_string = res.error_string;
+  /* error precedence as in api.cu run_resolve: the earliest failing candidate in discovery order
+     (scanner.c:111) vs. the earliest TOO_MANY abort */
+  const unsigned long long SEQ = (1ULL << 13) - 1;   /* KEY_SEQ_MAX */
+  unsigned long long first_abort = ~0ULL;
+  const uint32_t ntm = res.n_too_many > 1024 ? 1024 : res.n_too_many;
+  if (p->too_many_action != 0 && ntm > 0)
+  {
+    first_abort = res.n_cuts ? res.first_cut_key : 0;
+    out->error = YRB_ERROR_TOO_MANY_MATCHES;
+    out->error_string = s->tm[0];
+  }
+  if (res.error != 0 && (res.error_key | SEQ) < (first_abort | SEQ))
+  {
+    out->error = res.error;
+    out->error_string = res.error_string;
+  }
   out->n_matches = (size_t) res.n_matches;
   out->matches = s->m.data();
   out->n_unconfirmed = (size_t) res.n_unconfirmed;
   out->unconfirmed = s->u.data();
-  out->n_too_many = res.n_too_many > 1024 ? 1024 : res.n_too_many;
+  out->n_too_many = ntm;
   out->too_many = s->tm.data();
   out->seeds_consumed = p->n_seeds > 0 ? 1 : 0;
-  if (p->too_many_action != 0 && out->n_too_many > 0 && out->error == 0)
-  {
-    out->error = YRB_ERROR_TOO_MANY_MATCHES;
-    out->error_string = out->too_many[0];
-  }
   out->stats.bytes = size;
   out->stats.n_candidates = st.n_cand[0] + st.n_cand[1] + st.n_cand[2];
   out->stats.n_raw = st.n_raw;

@@ -17,7 +17,7 @@
  * and unconfirmed matches and the scan's error.  Every kernel is called once per "thread" of the grid
  * it is launched with on the device; chain_resolve_kernel runs with a single lane per chain.
  * vmh_scan_batch() does the same in batch mode (ScanView.n_seg > 0, the device side of yrb_scan_batch).
- * Not covered here: the scan kernels (prefilter, walk), the 1M-cap second pass, seeds.
+ * Not covered here: the scan kernels (prefilter, walk).
  *
  * Built by oracle/Makefile into oracle/_ref-independent tests/harness output (libvmhost.so).
  */
@@ -119,7 +119,11 @@ typedef struct vmh_result
   uint64_t n_matches;       /* may exceed the capacity given: call again with more room */
   uint64_t n_unconfirmed;
   uint32_t n_too_many;
-  uint32_t over_cap;        /* some string went over YR_MAX_STRING_MATCHES: the second pass is not replayed here */
+  uint32_t over_cap;        /* a string is still over YR_MAX_STRING_MATCHES (batch mode: the whole batch is re-scanned per item) */
+  uint64_t first_cut_key;   /* 1M cap: discovery key at which the first string was cut (0 = none was) */
+  uint64_t error_key;       /* discovery key | code of the verifier error */
+  uint32_t n_cuts;
+  uint32_t pad;
 } vmh_result;
 
 /* verification + resolve: what yrb_scan_host returns for one block (no seeds, no cap second pass) */
@@ -210,17 +214,24 @@ static int scan_common(
   std::vector<yrb_match> finals(n + 1), unconf(n + 1);
   std::vector<uint32_t> too_many(1024);
 
-  if (n > 0)
-  {
-    /* ---- launch_resolve (resolve.cu), kernel by kernel */
-    std::vector<uint64_t> k0(n), k1(n);
-    std::vector<uint32_t> ix0(n), ix1(n), sel(n), starts(n);
-    std::vector<uint8_t> flags(n, 0);
+  std::vector<unsigned long long> str_cut_key(ns, ~0ULL);
+  std::vector<std::pair<unsigned long long, uint32_t>> cuts;   /* (cut key, string), api.cu run_resolve */
+  std::vector<uint64_t> k0(n), k1(n), kF(n);
+  std::vector<uint32_t> ix0(n), ix1(n), sel(n), starts(n);
+  std::vector<uint8_t> flags(n, 0);
 
+  /* ---- launch_resolve (resolve.cu), kernel by kernel */
+  auto resolve_pass = [&](bool use_cut) {
+    std::fill(flags.begin(), flags.end(), 0);
+    std::fill(str_count.begin(), str_count.end(), 0);
     if (scan_flags & YRB_SCAN_FAST_MODE)
+    {
+      std::fill(str_min_key.begin(), str_min_key.end(), ~0ULL);
       launch_per_thread(n, 256, [&] { fastmode_min_kernel(raw.data(), n, R, str_min_key.data()); });
+    }
     launch_per_thread(n, 256, [&] {
-      build_key_a_kernel(raw.data(), n, R, scan_flags, str_min_key.data(), nullptr, k0.data(), ix0.data());
+      build_key_a_kernel(raw.data(), n, R, scan_flags, str_min_key.data(), use_cut ? str_cut_key.data() : nullptr, k0.data(),
+                         ix0.data());
     });
 
     /* cub::DeviceRadixSort::SortPairs (stable) */
@@ -238,7 +249,7 @@ static int scan_common(
     st.n_sel = n_sel;
     launch_per_thread(n, 256, [&] { write_plain_kernel(raw.data(), ix1.data(), sel.data(), &st, n, finals.data()); });
 
-    if (h->num_chains > 0 && st.n_chain_raw + 0 >= 0)
+    if (h->num_chains > 0)
     {
       std::vector<int32_t> nxt(n), prv(n), clen(n), mlen(n), uvn(n), lists((size_t) 8 * ns);
       std::vector<uint8_t> where(n);
@@ -257,7 +268,44 @@ static int scan_common(
                              seed_base.data(), (int64_t) base, n_seg, seg_start, seg_len, item_dirty, starts.data());
       });
     }
+  };
+
+  if (n > 0)
+  {
+    resolve_pass(false);
+
+    if (st.over_cap && n_seg == 0)
+    {
+      /* api.cu run_resolve + resolve.cu resolve_cap_cut: the cut key of every over-cap string, then once more
+         without the cut records */
+      for (uint32_t t = 0; t < R.num_strings; t++)
+      {
+        if (str_count[t] <= YRB_MAX_STRING_MATCHES)
+          continue;
+        unsigned int n_first = 0;
+        launch_per_thread(n, 256, [&] { cap_mark_first_kernel(raw.data(), ix1.data(), k1.data(), n, kF.data(), t, &n_first); });
+        if (n_first <= YRB_MAX_STRING_MATCHES)
+          continue;
+        std::sort(kF.begin(), kF.begin() + n_first);
+        launch_per_thread(n, 256, [&] { cap_cut_kernel(raw.data(), n, t, kF.data(), &str_cut_key[t]); });
+        if (str_cut_key[t] != ~0ULL)
+          cuts.push_back(std::make_pair(str_cut_key[t], t));
+      }
+      st.n_chain_out = 0;
+      st.n_unconf = 0;
+      st.n_too_many = 0;
+      st.over_cap = 0;
+      resolve_pass(true);
+      st.over_cap = 0;   /* handled */
+    }
   }
+
+  /* cut strings fire their TOO_MANY callback in discovery order of the cut, after the chained strings' */
+  std::sort(cuts.begin(), cuts.end());
+  for (auto& c : cuts)
+    if (st.n_too_many < 1024) too_many[st.n_too_many++] = c.second;
+  res->first_cut_key = cuts.empty() ? 0 : cuts[0].first;
+  res->n_cuts = (uint32_t) cuts.size();
 
   /* ---- verifier errors (launch_error_select); in batch mode they only mark their item */
   bool any_err = false;
@@ -266,13 +314,15 @@ static int scan_common(
   if (any_err)
   {
     launch_per_thread(R.num_strings, 256, [&] {
-      error_select_kernel(str_err.data(), n > 0 ? str_min_key.data() : nullptr, nullptr, R, scan_flags, &st);
+      error_select_kernel(str_err.data(), n > 0 ? str_min_key.data() : nullptr, cuts.empty() ? nullptr : str_cut_key.data(), R,
+                          scan_flags, &st);
     });
     launch_per_thread(R.num_strings, 256, [&] { error_string_kernel(str_err.data(), R.num_strings, &st); });
     if (st.err_key_inv != 0ULL)
     {
       res->error = (int32_t) (~st.err_key_inv & KEY_SEQ_MAX);
       res->error_string = st.err_string1 ? st.err_string1 - 1 : YRB_NONE;
+      res->error_key = ~st.err_key_inv;
     }
   }
 

@@ -136,7 +136,8 @@ def test_tiers_are_exercised():
 # ------------------------------------------------------------------ verification + resolve
 class Result(C.Structure):
     _fields_ = [("error", C.c_int32), ("error_string", C.c_uint32), ("n_matches", C.c_uint64), ("n_unconfirmed", C.c_uint64),
-                ("n_too_many", C.c_uint32), ("over_cap", C.c_uint32)]
+                ("n_too_many", C.c_uint32), ("over_cap", C.c_uint32), ("first_cut_key", C.c_uint64), ("error_key", C.c_uint64),
+                ("n_cuts", C.c_uint32), ("pad", C.c_uint32)]
 
 
 def vm_scan(image, data, flags=0, cap=1 << 16):
@@ -169,8 +170,8 @@ def canon(a, fields):
 def check_scan(image, data, flags):
     o = yrh.oracle_scan(image, data, flags=flags)
     m, u, res = vm_scan(image, data, flags)
-    if res.over_cap or o.too_many:
-        pytest.skip("1M cap: its second pass is host orchestration, covered by the GPU tests")
+    assert not res.over_cap
+    assert res.n_too_many == len(o.too_many)
     assert res.error == o.error
     if o.error != 0:
         return 0
@@ -318,3 +319,16 @@ def test_batch_chain_parts_in_neighbouring_items():
     per_item, dirty, res = vm_scan_batch(image, items, random.Random(1))
     assert [len(x) for x in per_item] == [0, 0, 1, 0, 0, 1] and not dirty.any()
     check_batch(image, items, random.Random(2))
+
+
+def test_scan_one_million_match_cap():
+    """YR_MAX_STRING_MATCHES (scan.c:303-307): the cut key and the second resolve pass, replayed on the CPU"""
+    R = yrh.ref()
+    image = R.compile('rule t { strings: $a = "aa" $b = "ab" condition: any of them }').flatten()
+    data = np.frombuffer(b"a" * 1000100 + b"ab" * 10, dtype=np.uint8)
+    o = yrh.oracle_scan(image, data)
+    assert len(o.too_many) == 1
+    m, u, res = vm_scan(image, data, 0, cap=1 << 21)
+    assert res.n_too_many == 1 and res.n_cuts == 1 and not res.over_cap
+    f = ("string_idx", "offset", "match_length", "xor_key")
+    assert len(m) == len(o.matches) and canon(m, f) == canon(o.matches, f)
