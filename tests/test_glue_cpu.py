@@ -128,3 +128,23 @@ def test_reference_programs_through_the_glue(name, prefilter):
         env["YR_B200_RULE_PREFILTER"] = prefilter
     p = subprocess.run([exe], cwd=os.path.join(ROOT, "oracle", "_ref"), env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+
+
+def test_parked_result_is_not_used_for_the_first_block_of_a_multi_block_scan():
+    """a parked batch item carries the COMPLETE result of a one-block scan (leftover unconfirmed chain parts are
+    dropped, as at the end of a scan); if the same bytes come in as the first block of a multi-block scan, the
+    chain parts they leave behind must survive into the next block, so the parked result must not be used"""
+    rule = "rule t { strings: $a = { 11 22 33 44 [300-400] 55 66 77 88 } condition: $a }"
+    R, B = yrh.ref(), yrh.b200cpu()
+    rr, rb = R.compile(rule), B.compile(rule)
+    # the reference compares raw block-relative offsets across blocks (scan.c:474-488): head at offset 100 of block 0,
+    # tail at offset 450 of block 1
+    data = np.frombuffer(b"." * 100 + bytes.fromhex("11223344") + b"." * (1024 + 450 - 104) + bytes.fromhex("55667788") + b"." * 300,
+                         dtype=np.uint8).copy()
+    want = rr.scan_blocks(data, 1024, 0)
+    assert len(want.matches) == 1                      # head in block 0, tail in block 1
+    first_block = data[:1024]                          # same address and size as block 0 of the scan below
+    with rb.batch([first_block]) as bt:
+        assert bt.rc == 0
+        same(rr.scan(first_block), rb.scan(first_block), "the parked item itself")
+        same(want, rb.scan_blocks(data, 1024, 0), "multi-block scan over a parked first block")

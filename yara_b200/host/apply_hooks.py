@@ -9,6 +9,8 @@ anything else means the reference drifted and the build stops.
   scanner.c  #include "yr_b200.h"
              scanner.c:495   _yr_scanner_scan_mem_block -> yr_b200_scan_mem_block
              scanner.c:287   yr_scanner_destroy: yr_b200_scanner_release(scanner)
+             scanner.c:660   yr_scanner_scan_mem: yr_b200_single_block_scan(scanner, 1/0) around the scan
+                             (parked file-batch results are complete one-block results)
   rules.c    #include "yr_b200.h"
              rules.c:515     yr_rules_destroy: yr_b200_rules_release(rules)
   condition-VM pre-filter (yr_b200_prefilter.c, on unless YR_B200_RULE_PREFILTER=0):
@@ -72,6 +74,12 @@ EDITS = {
             "  yr_b200_scanner_release(scanner);\n\n  RE_FIBER* fiber = scanner->re_fiber_pool.fibers.head;\n",
         ),
         EXEC_CALL,
+        (
+            "  int result = yr_scanner_scan_mem_blocks(scanner, &iterator);\n",
+            "  yr_b200_single_block_scan(scanner, 1); /* yr_scanner_scan_mem: this block is the whole scan */\n"
+            "  int result = yr_scanner_scan_mem_blocks(scanner, &iterator);\n"
+            "  yr_b200_single_block_scan(scanner, 0);\n",
+        ),
     ],
     "rules": [
         ("#include <yara/utils.h>\n", '#include <yara/utils.h>\n#include "yr_b200.h"\n'),

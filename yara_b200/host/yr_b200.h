@@ -32,6 +32,10 @@ int yr_b200_scan_mem_block(
     YR_MEMORY_BLOCK* block);
 
 void yr_b200_scanner_release(YR_SCANNER* scanner);
+
+/* yr_scanner_scan_mem brackets its scan with (scanner, 1) / (scanner, 0): only then is a block known to
+   be the whole scan, which is what a parked file-batch result stands for. */
+void yr_b200_single_block_scan(YR_SCANNER* scanner, int on);
 void yr_b200_rules_release(YR_RULES* rules);
 
 /*

@@ -189,6 +189,11 @@ struct YR_B200_BATCH
 
 static YR_B200_BATCH* volatile g_batches = NULL;
 
+/* the scanner this thread is running a ONE-block scan for (yr_scanner_scan_mem), if any */
+static __thread YR_SCANNER* t_single_block_scanner = NULL;
+
+void yr_b200_single_block_scan(YR_SCANNER* scanner, int on) { t_single_block_scanner = on ? scanner : NULL; }
+
 static const uint8_t** g_sort_keys;
 static int cmp_by_ptr(const void* a, const void* b)
 {
@@ -703,8 +708,11 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
   FAIL_ON_ERROR(yr_get_configuration_uint32(YR_CONFIG_MAX_MATCH_DATA, &max_match_data));
 
   /* already scanned as part of a live file batch?  (only items whose result is complete and
-     independent of scan state are parked there; the rest fall through to the scan below) */
-  if (g_batches != NULL && block->base == 0 && !(scanner->flags & SCAN_FLAGS_FAST_MODE))
+     independent of scan state are parked there; the rest fall through to the scan below).  A parked
+     result is that of a whole one-block scan -- chain parts left unconfirmed at its end are dropped --
+     so it only stands in for yr_scanner_scan_mem, never for the first block of a longer scan. */
+  if (g_batches != NULL && t_single_block_scanner == scanner && block->base == 0 &&
+      !(scanner->flags & SCAN_FLAGS_FAST_MODE))
   {
     const yrb_match* recs = NULL;
     size_t n_recs = 0;
