@@ -350,6 +350,9 @@ int yrh_batch_begin(
 }
 
 void yrh_batch_end(void* batch) { yr_b200_batch_destroy((YR_B200_BATCH*) batch); }
+
+uint64_t yr_b200_batch_hits(void);
+uint64_t yrh_batch_hits(void) { return yr_b200_batch_hits(); }
 #endif
 
 #if defined(YRH_B200) || defined(YRH_PREFILTER)

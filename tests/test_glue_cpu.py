@@ -81,13 +81,16 @@ def run_file_batch():
     rr, rb = R.compile(rs.source), B.compile(rs.source)
     files = [synth.corpus(rs, 9000 + 700 * k, 2048, seed=k, plant_seed=30 + k) for k in range(24)]
     want = [rr.scan(f) for f in files]
+    h0 = yrh.batch_hits(B)
     with rb.batch(files) as bt:
         assert bt.rc == 0 and bt.n_rescans == 0
         for rounds in range(2):
             for k, f in enumerate(files):
                 same(want[k], rb.scan(f), "file %d" % k)
+        assert yrh.batch_hits(B) - h0 == 2 * len(files)     # every one of them came from the parked results
     for k, f in enumerate(files[:6]):      # and without the batch
         same(want[k], rb.scan(f), "file %d unbatched" % k)
+    assert yrh.batch_hits(B) - h0 == 2 * len(files)
 
 
 def test_known_answer_cases_through_the_glue():

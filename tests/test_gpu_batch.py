@@ -195,10 +195,13 @@ def test_dropin_batch_is_transparent(setup):
     rr = yrh.ref().compile(rs.source)
     items = make_items(rs, seed=6)
     want = [rr.scan(it).key() for it in items]
+    h0 = yrh.batch_hits(yrh.b200())
     with rb.batch(items) as b:
         assert b.rc == 0
         assert b.n_rescans == 0
         got = [rb.scan(it).key() for it in items]
+        # served from the parked results, not scanned again (empty items have no address to be found by)
+        assert yrh.batch_hits(yrh.b200()) - h0 >= sum(1 for it in items if len(it) > 0)
         # a buffer that was not part of the batch, and a prefix of one that was, are scanned normally
         other = synth.corpus(rs, 50000, 4096, seed=77, plant_seed=78)
         assert rb.scan(other).key() == rr.scan(other).key()

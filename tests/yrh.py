@@ -227,6 +227,12 @@ def refpf() -> Harness:
     return _cache["refpf"]
 
 
+def batch_hits(h):
+    """scans the drop-in served from parked file-batch results so far"""
+    h.lib.yrh_batch_hits.restype = C.c_uint64
+    return h.lib.yrh_batch_hits()
+
+
 def prefilter_stats(h):
     e, s = C.c_uint64(), C.c_uint64()
     h.lib.yrh_prefilter_stats(C.byref(e), C.byref(s))
@@ -240,6 +246,10 @@ def prefilter_classes(h, rules):
 
 
 def b200() -> Harness:
+    """the GPU drop-in.  With YRH_B200_IMPL=cpu in the environment (a development aid: lets the harness-level
+    GPU tests be dry-run without a GPU) the stand-in build of tests/harness/ is returned instead."""
+    if os.environ.get("YRH_B200_IMPL") == "cpu":
+        return b200cpu()
     if "b200" not in _cache:
         _cache["b200"] = Harness(b200_path())
     return _cache["b200"]

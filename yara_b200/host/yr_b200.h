@@ -59,6 +59,7 @@ int yr_b200_batch_scan(
     YR_B200_BATCH** batch);
 void yr_b200_batch_destroy(YR_B200_BATCH* batch);
 uint32_t yr_b200_batch_rescans(const YR_B200_BATCH* batch); /* buffers that were not parked */
+uint64_t yr_b200_batch_hits(void);                          /* scans served from parked results so far */
 
 /*
  * Condition-VM pre-filter (yr_b200_prefilter.c; on unless YR_B200_RULE_PREFILTER=0).

@@ -194,6 +194,9 @@ static __thread YR_SCANNER* t_single_block_scanner = NULL;
 
 void yr_b200_single_block_scan(YR_SCANNER* scanner, int on) { t_single_block_scanner = on ? scanner : NULL; }
 
+static uint64_t g_batch_hits = 0; /* scans served from parked results (tests, statistics) */
+uint64_t yr_b200_batch_hits(void) { return __atomic_load_n(&g_batch_hits, __ATOMIC_RELAXED); }
+
 static const uint8_t** g_sort_keys;
 static int cmp_by_ptr(const void* a, const void* b)
 {
@@ -717,7 +720,10 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
     const yrb_match* recs = NULL;
     size_t n_recs = 0;
     if (batch_lookup(scanner->rules, block_data, block->size, &recs, &n_recs))
+    {
+      __atomic_fetch_add(&g_batch_hits, 1, __ATOMIC_RELAXED);
       return materialise(scanner, block_data, block, recs, n_recs, scanner->matches, 1, max_match_data, NULL);
+    }
   }
 
   rc = get_scanner(scanner, &dev, &re);
