@@ -353,6 +353,9 @@ void yrh_batch_end(void* batch) { yr_b200_batch_destroy((YR_B200_BATCH*) batch);
 
 uint64_t yr_b200_batch_hits(void);
 uint64_t yrh_batch_hits(void) { return yr_b200_batch_hits(); }
+
+void yr_b200_coalesce_stats(uint64_t* batches, uint64_t* scans);
+void yrh_coalesce_stats(uint64_t* batches, uint64_t* scans) { yr_b200_coalesce_stats(batches, scans); }
 #endif
 
 #if defined(YRH_B200) || defined(YRH_PREFILTER)

@@ -151,3 +151,44 @@ def test_parked_result_is_not_used_for_the_first_block_of_a_multi_block_scan():
         assert bt.rc == 0
         same(rr.scan(first_block), rb.scan(first_block), "the parked item itself")
         same(want, rb.scan_blocks(data, 1024, 0), "multi-block scan over a parked first block")
+
+
+COALESCE_CODE = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import ctypes as C
+from concurrent.futures import ThreadPoolExecutor
+import numpy as np
+import yrh
+from yara_b200 import synth
+rs = synth.ruleset(4, 1500)
+R, B = yrh.ref(), yrh.b200cpu()
+rr, rb = R.compile(rs.source), B.compile(rs.source)
+files = [synth.corpus(rs, 9000 + 531 * k, 2048, seed=k, plant_seed=40 + k) for k in range(64)]
+files.append(np.zeros(0, np.uint8))
+want = [rr.scan(f).key() for f in files]
+for rounds in range(3):
+    with ThreadPoolExecutor(8) as ex:
+        got = list(ex.map(lambda f: rb.scan(f).key(), files))
+    assert got == want, "round %%d" %% rounds
+# fast mode and multi-block scans never go through a shared batch
+assert rb.scan(files[3], flags=1).key() == rr.scan(files[3], flags=1).key()
+assert rb.scan_blocks(files[5], 1024, 256).key() == rr.scan_blocks(files[5], 1024, 256).key()
+b, s = C.c_uint64(), C.c_uint64()
+B.lib.yrh_coalesce_stats(C.byref(b), C.byref(s))
+print("COALESCE_OK batches %%d scans %%d" %% (b.value, s.value))
+"""
+
+
+@pytest.mark.parametrize("n", ["8", "2"])
+def test_request_coalescing(n):
+    """$YR_B200_COALESCE=N: concurrent one-block scans of the same rules share one yrb_scan_batch call; results
+    stay those of the reference.  (Read once per process, hence the subprocess.)"""
+    env = dict(os.environ, YR_B200_COALESCE=n)
+    p = subprocess.run([sys.executable, "-c", COALESCE_CODE % (ROOT, os.path.join(ROOT, "tests"))], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert p.returncode == 0 and "COALESCE_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("COALESCE_OK")][0].split()
+    batches, scans = int(line[2]), int(line[4])
+    assert scans == 3 * 64                      # every non-empty one-block scan went through a shared batch
+    assert batches < scans                      # ... and some batches really held more than one scan

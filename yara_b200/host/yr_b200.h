@@ -78,6 +78,10 @@ void yr_b200_prefilter_classes(YR_RULES* rules, uint32_t counts[5]);
 void yr_b200_prefilter_scanner_release(YR_SCAN_CONTEXT* context);
 void yr_b200_prefilter_rules_release(YR_RULES* rules);
 
+/* Request coalescing ($YR_B200_COALESCE=N, off by default): concurrent one-block scans of the same
+   rules share one yrb_scan_batch call; how many batches served how many scans so far. */
+void yr_b200_coalesce_stats(uint64_t* batches, uint64_t* scans);
+
 /* Which CUDA device the glue uses for new scanners (default: $YR_B200_DEVICE or 0). */
 void yr_b200_set_device(int device);
 

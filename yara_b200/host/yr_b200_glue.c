@@ -366,6 +366,195 @@ static int batch_lookup(YR_RULES* rules, const uint8_t* data, size_t size, const
   return found;
 }
 
+/* ---- request coalescing ($YR_B200_COALESCE=N, off by default).  `yara -p N` has N threads that each
+   scan one file at a time (cli/yara.c:1246-1290); every such scan is ~20 launches and a few
+   synchronisations for microseconds of GPU work.  With coalescing, one-block scans of the same YR_RULES
+   that are in flight at the same time are handed to ONE yrb_scan_batch call: the first thread to arrive
+   leads -- it takes everything pending (its own request included, at most N), runs the batch and hands
+   every waiter its records -- and whoever arrives while it is busy forms the next batch.  Results are
+   those of yrb_scan_batch, i.e. of a scan of the buffer alone; items it flags YRB_ITEM_RESCAN fall
+   through to the ordinary path.  No change of the libyara API or of the CLI. */
+typedef struct co_req
+{
+  YR_RULES* rules;
+  const uint8_t* data;
+  size_t size;
+  int flags;
+  int state; /* 0 pending, 1 records ready, 2 scan it yourself, 3 failed (rc) */
+  int rc;
+  yrb_match* recs;
+  size_t n_recs;
+  struct co_req* next;
+} co_req;
+
+static pthread_mutex_t g_co_lock = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_co_cond = PTHREAD_COND_INITIALIZER;
+static co_req* g_co_head = NULL;
+static co_req* g_co_tail = NULL;
+static int g_co_leading = 0;
+static int g_co_max = -1;
+static uint64_t g_co_batches = 0, g_co_scans = 0;
+
+static int co_max(void)
+{
+  if (g_co_max < 0)
+  {
+    const char* e = getenv("YR_B200_COALESCE");
+    int v = e ? atoi(e) : 0;
+    g_co_max = v < 2 ? 0 : (v > 1024 ? 1024 : v);
+  }
+  return g_co_max;
+}
+
+void yr_b200_coalesce_stats(uint64_t* batches, uint64_t* scans)
+{
+  *batches = __atomic_load_n(&g_co_batches, __ATOMIC_RELAXED);
+  *scans = __atomic_load_n(&g_co_scans, __ATOMIC_RELAXED);
+}
+
+/* the leader's part: one engine batch over reqs[0..n), all of one YR_RULES and one flag set */
+static void co_run_batch(co_req** reqs, uint32_t n)
+{
+  int rc = ERROR_SUCCESS;
+  rules_entry* re = NULL;
+  yrb_scanner* dev = NULL;
+  yrb_batch_item* items = (yrb_batch_item*) malloc(sizeof(yrb_batch_item) * n);
+
+  if (items == NULL)
+    rc = ERROR_INSUFFICIENT_MEMORY;
+
+  if (rc == ERROR_SUCCESS)
+  {
+    pthread_mutex_lock(&g_lock);
+    rc = get_rules(reqs[0]->rules, &re);
+    if (rc == ERROR_SUCCESS)
+      dev = pool_take(re->dev);
+    pthread_mutex_unlock(&g_lock);
+    if (rc == ERROR_SUCCESS && dev == NULL)
+    {
+      int r2 = yrb_scanner_create(re->dev, &dev);
+      if (r2 != YRB_SUCCESS)
+        rc = fail_loudly("yrb_scanner_create", r2);
+    }
+  }
+
+  if (rc == ERROR_SUCCESS)
+  {
+    for (uint32_t k = 0; k < n; k++)
+    {
+      items[k].data = reqs[k]->data;
+      items[k].size = reqs[k]->size;
+    }
+    yrb_batch_result res;
+    int r2 = yrb_scan_batch(dev, items, n, reqs[0]->flags, 0, &res);
+    if (r2 != YRB_SUCCESS)
+    {
+      rc = r2 < 1000 ? r2 : fail_loudly("yrb_scan_batch", r2);
+    }
+    else
+    {
+      for (uint32_t k = 0; k < n; k++)
+      {
+        co_req* r = reqs[k];
+        if (res.item_state[k] != YRB_ITEM_DONE)
+        {
+          r->state = 2;
+          continue;
+        }
+        r->n_recs = (size_t) (res.item_first[k + 1] - res.item_first[k]);
+        r->recs = (yrb_match*) malloc(sizeof(yrb_match) * (r->n_recs ? r->n_recs : 1));
+        if (r->recs == NULL)
+        {
+          r->state = 3;
+          r->rc = ERROR_INSUFFICIENT_MEMORY;
+          continue;
+        }
+        memcpy(r->recs, res.matches + res.item_first[k], sizeof(yrb_match) * r->n_recs);
+        r->state = 1;
+      }
+    }
+    pthread_mutex_lock(&g_lock);
+    pool_put(dev, re->dev);
+    pthread_mutex_unlock(&g_lock);
+  }
+
+  free(items);
+  if (rc != ERROR_SUCCESS)
+  {
+    for (uint32_t k = 0; k < n; k++)
+    {
+      reqs[k]->state = 3;
+      reqs[k]->rc = rc;
+    }
+  }
+  __atomic_fetch_add(&g_co_batches, 1, __ATOMIC_RELAXED);
+  __atomic_fetch_add(&g_co_scans, n, __ATOMIC_RELAXED);
+}
+
+/* Blocks until r is resolved one way or the other; returns r->state. */
+static int co_submit(co_req* r)
+{
+  co_req* mine[1024];
+
+  pthread_mutex_lock(&g_co_lock);
+  r->next = NULL;
+  if (g_co_tail) g_co_tail->next = r; else g_co_head = r;
+  g_co_tail = r;
+
+  while (r->state == 0)
+  {
+    if (g_co_leading)
+    {
+      pthread_cond_wait(&g_co_cond, &g_co_lock);
+      continue;
+    }
+
+    /* lead: my own request plus whatever else is pending for the same rules and flags, up to the cap
+       (one slot stays reserved for my own request until the walk has met it) */
+    g_co_leading = 1;
+    uint32_t n = 0;
+    const uint32_t cap = (uint32_t) co_max();
+    int seen_me = 0;
+    co_req** pp = &g_co_head;
+    co_req* last = NULL;
+    while (*pp != NULL)
+    {
+      co_req* q = *pp;
+      int take;
+      if (q == r)
+      {
+        take = 1;
+        seen_me = 1;
+      }
+      else
+      {
+        take = q->rules == r->rules && q->flags == r->flags && n < cap - (seen_me ? 0u : 1u);
+      }
+      if (take)
+      {
+        *pp = q->next;
+        q->next = NULL;
+        mine[n++] = q;
+      }
+      else
+      {
+        last = q;
+        pp = &q->next;
+      }
+    }
+    g_co_tail = last;
+    pthread_mutex_unlock(&g_co_lock);
+
+    co_run_batch(mine, n);
+
+    pthread_mutex_lock(&g_co_lock);
+    g_co_leading = 0;
+    pthread_cond_broadcast(&g_co_cond);
+  }
+  pthread_mutex_unlock(&g_co_lock);
+  return r->state;
+}
+
 static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out, rules_entry** re_out)
 {
   scanner_entry* e;
@@ -724,6 +913,28 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
       __atomic_fetch_add(&g_batch_hits, 1, __ATOMIC_RELAXED);
       return materialise(scanner, block_data, block, recs, n_recs, scanner->matches, 1, max_match_data, NULL);
     }
+  }
+
+  /* one-block scans in flight on several threads share one engine batch (off unless $YR_B200_COALESCE) */
+  if (co_max() > 1 && t_single_block_scanner == scanner && block->base == 0 && block->size > 0 &&
+      !(scanner->flags & SCAN_FLAGS_FAST_MODE))
+  {
+    co_req r;
+    memset(&r, 0, sizeof(r));
+    r.rules = scanner->rules;
+    r.data = block_data;
+    r.size = block->size;
+    r.flags = scanner->flags;
+    const int st = co_submit(&r);
+    if (st == 1)
+    {
+      rc = materialise(scanner, block_data, block, r.recs, r.n_recs, scanner->matches, 1, max_match_data, NULL);
+      free(r.recs);
+      return rc;
+    }
+    if (st == 3)
+      return r.rc;
+    /* st == 2: the batch could not answer for this buffer: scan it on its own */
   }
 
   rc = get_scanner(scanner, &dev, &re);
