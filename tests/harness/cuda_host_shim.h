@@ -17,8 +17,9 @@
 #undef __launch_bounds__
 #define __launch_bounds__(...)
 struct yrb_shim_dim { unsigned x, y, z; };
-/* the driver sets these before it calls a kernel as a function */
-static yrb_shim_dim threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
+/* the driver sets these before it calls a kernel as a function; per host thread, so that several
+   threads can replay scans at the same time (yr_rules_scan_mem from N threads through the stand-in) */
+static thread_local yrb_shim_dim threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {1, 1, 1}, gridDim = {1, 1, 1};
 
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 

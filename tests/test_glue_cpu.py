@@ -192,3 +192,20 @@ def test_request_coalescing(n):
     batches, scans = int(line[2]), int(line[4])
     assert scans == 3 * 64                      # every non-empty one-block scan went through a shared batch
     assert batches < scans                      # ... and some batches really held more than one scan
+
+
+def test_concurrent_scans_through_the_glue():
+    """yr_rules_scan_mem from several threads at once over one YR_RULES (limits.h YR_MAX_THREADS), no batch parked:
+    every thread goes through the engine on its own pooled scanner"""
+    from concurrent.futures import ThreadPoolExecutor
+    rs = synth.ruleset(4, 1500)
+    R, B = yrh.ref(), yrh.b200cpu()
+    rr, rb = R.compile(rs.source), B.compile(rs.source)
+    files = [synth.corpus(rs, 20000 + 913 * k, 1024, seed=k, plant_seed=20 + k) for k in range(32)]
+    want = [rr.scan(f).key() for f in files]
+    for rounds in range(3):
+        with ThreadPoolExecutor(8) as ex:
+            got = list(ex.map(lambda f: rb.scan(f).key(), files))
+        assert got == want
+    secs, rc = rb.scan_mt(files[0], 8)
+    assert rc == 0
