@@ -38,6 +38,11 @@
  *                                 GPUs/processes; no reference
  *                                 equivalent (a buffer is always scanned by one
  *                                 thread there, cli/yara.c:1246).
+ *   yrb_multi_*                   the same sharding driven from ONE process: what
+ *                                 yr_rules_scan_mem (rules.c:172-207) of the drop-in
+ *                                 calls for a large block when several GPUs are
+ *                                 configured; the reference's way to use more
+ *                                 workers is per file only (cli/yara.c:1561-1610).
  *
  * Errors are the reference's ERROR_* values (error.h:40-109): 0 success,
  * 1 insufficient memory, 30 too many matches, 46 too many RE fibers, 31 internal.
@@ -232,6 +237,31 @@ int yrb_resolve_raw(
     yrb_scanner* scanner, const void* records, size_t n_records, const yrb_scan_params* params,
     yrb_scan_result* result);
 
+/*
+ * ONE block over several GPUs of this node, driven from one process.  Every
+ * device holds a replica of the rules image and one scanner; a block is cut into byte-range
+ * shards (boundaries at multiples of 4096) that additionally read yrb_multi_margin() bytes either
+ * side; each device copies, scans and verifies its shard concurrently (one persistent host thread
+ * per device); the raw records are brought to the first device with peer copies and resolved there
+ * once.  No collective, no NCCL.  The result equals yrb_scan_host's on one device, bit for bit.
+ * Multi-block scans (params->n_seeds > 0) are not sharded: YRB_ERROR_BAD_ARGUMENT.
+ */
+typedef struct yrb_multi yrb_multi;
+int yrb_multi_create(const void* image, size_t image_size, const int* devices, int n_devices, yrb_multi** out);
+void yrb_multi_destroy(yrb_multi* multi);
+int yrb_multi_device_count(const yrb_multi* multi);
+uint64_t yrb_multi_margin(const yrb_multi* multi);
+/* the shard plan for a block of block_size bytes: device g reads [g0[g], g1[g]) and owns the
+   Aho-Corasick events of [own0[g], own1[g]); arrays of yrb_multi_device_count() entries */
+int yrb_multi_plan(
+    const yrb_multi* multi, uint64_t block_size, uint64_t* g0, uint64_t* g1, uint64_t* own0, uint64_t* own1);
+int yrb_multi_scan_host(
+    yrb_multi* multi, const uint8_t* data, size_t size, const yrb_scan_params* params, yrb_scan_result* result);
+/* shards already resident: d_shards[g] (memory of device g) holds block bytes [g0[g], g1[g]) */
+int yrb_multi_scan_device(
+    yrb_multi* multi, const uint8_t* const* d_shards, const uint64_t* g0, const uint64_t* g1, const uint64_t* own0,
+    const uint64_t* own1, uint64_t block_size, const yrb_scan_params* params, yrb_scan_result* result);
+
 /* Copies min(match_length, max_match_data) bytes of every match of the last
    yrb_scan_device result into out (packed back to back, offsets[] = start of
    each, offsets[n] = total): the data copy of scan.c:723-737 for callers whose
@@ -239,6 +269,13 @@ int yrb_resolve_raw(
 int yrb_gather_match_data(
     yrb_scanner* scanner, const uint8_t* d_data, uint32_t max_match_data, uint8_t* out, size_t out_cap,
     uint64_t* offsets);
+
+/* The atom-prefilter tables are a pure function of the rules image; they are built once per image
+   and kept in a process-wide registry and in a disk cache keyed by a hash of the image
+   ($YR_B200_CACHE_DIR, default ~/.cache/yara_b200; YR_B200_CACHE=0: no files) -- the device-side
+   counterpart of loading compiled rules instead of compiling them (yr_rules_load, rules.c:372-431,
+   arena.c:543).  How often yrb_rules_create found them in the registry / on disk / had to build. */
+void yrb_filter_cache_stats(unsigned* from_registry, unsigned* from_disk, unsigned* built);
 
 /* Utilities for benchmarks/tests: device memory owned by the scanner's device,
    counter-based corpus bytes (identical to yara_b200.synth.rand_bytes) and

@@ -138,7 +138,7 @@ int yrb_scan_host(yrb_scanner* s, const uint8_t* data, size_t size, const yrb_sc
   }
   /* error precedence as in api.cu run_resolve: the earliest failing candidate in discovery order
      (scanner.c:111) vs. the earliest TOO_MANY abort */
-  const unsigned long long SEQ = (1ULL << 13) - 1;   /* KEY_SEQ_MAX */
+  const unsigned long long SEQ = (1ULL << 17) - 1;   /* KEY_SEQ_MAX (engine.cuh) */
   unsigned long long first_abort = ~0ULL;
   const uint32_t ntm = res.n_too_many > 1024 ? 1024 : res.n_too_many;
   if (p->too_many_action != 0 && ntm > 0)

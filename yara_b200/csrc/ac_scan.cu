@@ -22,6 +22,7 @@
 
 #define WALK_CHUNK       256   // bytes per thread for large ranges (3 bytes of look-back re-walk each)
 #define WALK_CHUNK_SMALL 32    // small ranges are latency bound: shorter dependent chains, more threads
+#define WALK_CHUNK_TINY  8     // heads/tails of filter slices (< 1 MiB): ~11 dependent steps instead of 35
 #define WALK_THREADS 128
 
 __global__ void __launch_bounds__(WALK_THREADS)
@@ -101,7 +102,7 @@ void launch_ac_scan_walk(
   if (hi <= lo)
     return;
 
-  const int chunk = (hi - lo) < (8 << 20) ? WALK_CHUNK_SMALL : WALK_CHUNK;
+  const int chunk = (hi - lo) < (1 << 20) ? WALK_CHUNK_TINY : ((hi - lo) < (8 << 20) ? WALK_CHUNK_SMALL : WALK_CHUNK);
   const int64_t nthreads = (hi - lo + chunk - 1) / chunk;
   const unsigned blocks = (unsigned) ((nthreads + WALK_THREADS - 1) / WALK_THREADS);
   ac_walk_kernel<<<blocks, WALK_THREADS, 0, s>>>(R, V, out, lo, hi, chunk);
@@ -122,8 +123,9 @@ void launch_ac_scan_walk(
 //            have in common; set for the suffix3 and the prefix3 of every hit
 //            window.  Branch-free: one IMAD hash, one LDS, the bit lands in a
 //            per-thread mask.
-//   level 2  B4: 2^19-bit Bloom filter (k = 4) in shared memory over the 4-byte window,
-//            only for positions of pairs that passed level 1.
+//   level 2  B3 again with the OTHER 3-byte key of each of the pair's two windows, then
+//            B4: 2^18- or 2^19-bit Bloom filter (k = 4, per kernel variant) in shared
+//            memory over the 4-byte window; only for pairs that passed level 1.
 //   level 3  exact: open-addressed hash table (window -> match_table value of
 //            the state the reference walk would be in), L2-resident; then
 //            emit_events() exactly as the walk kernel does.
@@ -139,11 +141,17 @@ void launch_ac_scan_walk(
 
 // Kernel variants (threads per CTA, 16-byte chunks per thread per tile, log2 of the
 // B4 Bloom filter size); all three fit the 227 KB of shared memory with B3.
-struct FtVariant { int threads, u, b4_bits; };
-static const FtVariant kVariants[] = {{1024, 4, 18}, {512, 4, 19}, {1024, 2, 19}};
-#define FT_NUM_VARIANTS 3
+struct FtVariant { int threads, u, b4_bits, tma_bufs; };   // tma_bufs: 0 = LDG + staging rows (round 1), else TMA buffers per warp
+static const FtVariant kVariants[] = {{1024, 4, 18, 0}, {512, 4, 19, 0}, {1024, 2, 19, 0},
+                                      {1024, 4, 18, 1}, {768, 4, 18, 1}};   // 3-4: variant T
+#define FT_NUM_VARIANTS 5
+#define FT_DEFAULT_VARIANT 3
 static inline size_t ft_smem_bytes(const FtVariant& v)
-{ return (size_t) B3_WORDS * 4 + ((size_t) 1 << (v.b4_bits - 3)) + (size_t) (v.threads / 32) * (v.u * FT_ROW + 32); }
+{
+  return (size_t) B3_WORDS * 4 + ((size_t) 1 << (v.b4_bits - 3)) +
+         (v.tma_bufs == 0 ? (size_t) (v.threads / 32) * (v.u * FT_ROW + 32)
+                          : (size_t) (v.threads / 32) * (16 + 2048 + 16 + 64));
+}
 
 struct FilterDev
 {
@@ -172,25 +180,11 @@ static __device__ __forceinline__ uint32_t ht_lookup(const FilterDev& F, uint32_
 // real hits: 2^19 bits for ~36k windows and k = 4 gives ~0.3 % false positives.
 // Integer multiplies run on the FMA pipe; shifts/logic on the (saturated) ALU pipe.
 // Inline PTX keeps ptxas from strength-reducing them back into shifts.
-static __device__ __forceinline__ uint32_t mulhi_u32(uint32_t a, uint32_t b)
-{
-  uint32_t r;
-  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-  return r;
-}
-
 // mask * 2 + bit on the FMA pipe (the ALU pipe is the busy one in the filter kernel)
 static __device__ __forceinline__ uint32_t push_bit_fma(uint32_t mask, uint32_t bit)
 {
   uint32_t r;
   asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(mask), "r"(bit));
-  return r;
-}
-
-static __device__ __forceinline__ uint32_t fshr16_fma(uint32_t lo, uint32_t hi)
-{
-  uint32_t r;
-  asm("{ .reg .u32 t; mul.hi.u32 t, %1, 65536; mad.lo.u32 %0, %2, 65536, t; }" : "=r"(r) : "r"(lo), "r"(hi));
   return r;
 }
 
@@ -258,7 +252,6 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
   const uint8_t* __restrict__ d = V.d - V.g0; // d[p] = block byte p; (d + lo) is 16-byte aligned
   const int64_t ntiles = (hi - lo) / FT_TILE;
   const uint32_t H3 = HASH3_MUL << 8;
-  const uint8_t* sB3b = reinterpret_cast<const uint8_t*>(sB3);
 
   // [lo, hi) is a whole number of tiles (the host gives the remainder to the walk kernel),
   // so no load needs a bounds check
@@ -417,19 +410,290 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
 }
 
 
-// ---- host: enumerate hit windows of the compiled automaton, build B3 / B4 / hash table
+// ---- variant T: the same three levels, fed by TMA.
+//
+// ac_filter_kernel moves every input byte LDG.128 -> registers -> STS.128 (staging for level 2):
+// per 2 KB warp-tile that is ~26 global + 20 shared wavefronts on the l1tex data pipe, which the
+// kernel saturates (96 %, profiles/r01_ncu_filter_final2_16gib_summary.txt), beside the ~120 of
+// the level-1 gathers.  Here each warp owns a buffer of 16 + 2048 bytes; one elected lane
+// fetches a whole warp-tile (plus the 16 bytes in front of it: the halo travels with the data,
+// no second read) with ONE cp.async.bulk that completes on the buffer's mbarrier.  Level 1 reads
+// its chunks back with conflict-free LDS.128; the LDGs, the halo LDGs and all staging stores are
+// gone.  The buffer is handed back to TMA as soon as the tile is in registers -- level 2 fetches
+// the five bytes of a surviving window from global memory (an L2 hit: the tile has just been
+// read) -- so the copy of the next tile has a whole tile's worth of work to land.
+// Measured steps (profiles/r02_kernel_sweep*.txt, 4 GiB, scan kernel GB/s; round-1 kernel 2755):
+//   level 2 straight from registers, no staging at all        2055 (-23 % shared wavefronts, +42 % instructions)
+//   4-slot ring of 512-byte TMA copies + that level 2          1776
+//   one TMA copy per warp-tile, refill after level 2           2799 (mbarrier wait = 14 % of stall samples)
+//   same with two buffers on 16 warps / 24 warps one buffer    2441 / 2560
+//   refill right after the LDS.128s, level 2 from L2           2829 (16 GiB: 2991 vs 2895; no pipe saturated any more:
+//                                                                    LSU 82 %, ALU 78 %, issue 74 %)
+//   + 16-bit queue descriptors, window-address arithmetic, word address on the FMA pipe: see DESIGN.md
+#define FT_T_TILE 2048            // bytes per warp and round
+#define FT_T_BUF  (16 + FT_T_TILE)
 
-struct FilterStorage
+static __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
+static __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory"); }
+static __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar)
 {
-  uint32_t b3[B3_WORDS];
-  uint32_t b4[1u << (19 - 5)];   // sized for the largest variant
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+static __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+
+// shared-memory accesses by 32-bit window address: one base register for the whole kernel (a
+// generic pointer makes the compiler rebuild the window base from %cluster_ctaid in every
+// divergent region), and non-volatile loads of the read-only tables that ptxas may schedule freely
+static __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{ uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+static __device__ __forceinline__ uint32_t lds_u16_v(uint32_t a)
+{ uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+static __device__ __forceinline__ void sts_u16_v(uint32_t a, uint32_t v)
+{ asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// idx * 4 + base on the FMA pipe (an LEA or SHF + LOP3 would sit on the ALU pipe, the busier one).
+// `four` is the constant 4 in a register the compiler cannot see through: with an immediate 4
+// ptxas strength-reduces the multiply-add back into an LEA (ALU pipe).
+static __device__ __forceinline__ uint32_t word_addr_fma(uint32_t idx, uint32_t four, uint32_t base)
+{ uint32_t r; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(idx), "r"(four), "r"(base)); return r; }
+
+static __device__ __forceinline__ bool b3_test_a(uint32_t sB3_a, uint32_t key3)
+{
+  const uint32_t w = lds_u32(sB3_a + ((((key3 << 8) * HASH3_MUL) >> 17) << 2));
+  return ((w >> (key3 & 31)) & (w >> ((key3 >> 16) & 31)) & 1u) != 0;
+}
+
+template <int B4BITS>
+static __device__ __forceinline__ bool bloom4_test_a(uint32_t sB4_a, uint32_t w)
+{
+  const uint32_t g1 = w * HASH4_MUL, g2 = (w * HASH4_MUL2) | 1u;
+  uint32_t g = g1;
+#pragma unroll
+  for (int k = 0; k < BLOOM_K; k++)
+  {
+    const uint32_t i4 = g >> (32 - B4BITS);
+    if (!((lds_u32(sB4_a + (i4 >> 5) * 4) << (i4 & 31)) & 0x80000000u))
+      return false;
+    g += g2;
+  }
+  return true;
+}
+
+template <int NWARPS, int B4BITS>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, int64_t hi)
+{
+  constexpr int FT_THREADS = NWARPS * 32, FT_U = FT_T_TILE / 512;
+  constexpr int FT_TILE = NWARPS * FT_T_TILE;         // bytes per CTA and round; warp w owns [w * 2048, (w + 1) * 2048) of it
+  constexpr uint32_t B4_WORDS = 1u << (B4BITS - 5);
+  constexpr int WARP_BYTES = FT_T_BUF + 16 + 64;      // buffer | mbarrier (8 B) + pad | survivor queue (32 x u16)
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint32_t* sB3 = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* sB4 = sB3 + B3_WORDS;
+  uint8_t* stage = smem_raw + (B3_WORDS + B4_WORDS) * 4;
+
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint8_t* wbuf = stage + warp * WARP_BYTES;    // 16 B halo | 4 x 512 B chunks, contiguous
+  const uint32_t sB3_a = smem_u32(sB3);
+  const uint32_t sB4_a = sB3_a + B3_WORDS * 4;
+  const uint32_t wbuf_a = smem_u32(wbuf);
+  const uint32_t wbar_a = wbuf_a + FT_T_BUF;
+  const uint32_t wq_a = wbuf_a + FT_T_BUF + 16;
+
+  if (lane == 0)
+  {
+    mbar_init(wbar_a, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  {
+    const uint4* g3 = reinterpret_cast<const uint4*>(F.b3);
+    const uint4* g4 = reinterpret_cast<const uint4*>(F.b4);
+    uint4* s3 = reinterpret_cast<uint4*>(sB3);
+    uint4* s4 = reinterpret_cast<uint4*>(sB4);
+    for (uint32_t i = threadIdx.x; i < B3_WORDS / 4; i += FT_THREADS) s3[i] = __ldg(&g3[i]);
+    for (uint32_t i = threadIdx.x; i < B4_WORDS / 4; i += FT_THREADS) s4[i] = __ldg(&g4[i]);
+  }
+  __syncthreads();
+
+  const uint8_t* __restrict__ d = V.d - V.g0; // d[p] = block byte p; (d + lo) is 16-byte aligned and lo >= 16
+  const int64_t ntiles = (hi - lo) / FT_TILE;
+  const uint32_t H3 = HASH3_MUL << 8;
+  const int64_t tstep = (int64_t) gridDim.x * FT_TILE;
+  const uint32_t four = 4u + (F.ht_bits >> 31);   // == 4 (ht_bits <= 28), opaque to the compiler: see word_addr_fma
+
+  // this warp's tile of the current round (block bytes [tp - d, tp - d + 2048))
+  const uint8_t* tp = d + lo + (int64_t) blockIdx.x * FT_TILE + (int64_t) warp * FT_T_TILE;
+
+  if (lane == 0 && (int64_t) blockIdx.x < ntiles)
+  {
+    mbar_expect_tx(wbar_a, FT_T_BUF);
+    bulk_g2s(wbuf_a, tp - 16, FT_T_BUF, wbar_a);
+  }
+
+  uint32_t parity = 0;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tp += tstep)
+  {
+    mbar_wait(wbar_a, parity);
+    parity ^= 1u;
+
+    uint4 vv[FT_U];
+    uint32_t mm[FT_U];
+#pragma unroll
+    for (int u = 0; u < FT_U; u++)
+    {
+      vv[u] = *reinterpret_cast<const uint4*>(wbuf + 16 + u * 512 + lane * 16);
+      mm[u] = __shfl_up_sync(0xFFFFFFFFu, vv[u].w, 1);
+      if (lane == 0) mm[u] = *reinterpret_cast<const uint32_t*>(wbuf + 12 + u * 512);
+    }
+
+    // The tile is in registers (the shuffles above made every lane wait for its loads) and level 2
+    // takes its window bytes from global memory (L2: the tile has just been read), so the buffer
+    // can be refilled NOW, a whole tile's worth of work ahead of its next use.
+    __syncwarp();
+    if (lane == 0 && tile + (int64_t) gridDim.x < ntiles)
+    {
+      mbar_expect_tx(wbar_a, FT_T_BUF);
+      bulk_g2s(wbuf_a, tp + tstep - 16, FT_T_BUF, wbar_a);
+    }
+
+    // ---- level 1: one B3 probe per pair of positions, branch-free.  Per probe: IMAD (hash), SHF,
+    // IMAD (word address), LDS, 2 SHF + LOP3 (the two bits), IMAD (append): 4 ALU-pipe instructions.
+    uint32_t mask = 0;
+
+#define PROBE3(x, y)                                                                \
+  {                                                                                 \
+    const uint32_t h_ = (x) * H3;                                                   \
+    const uint32_t w_ = lds_u32(word_addr_fma(h_ >> 17, four, sB3_a));              \
+    const uint32_t t_ = __funnelshift_r(w_, 0u, (x)) & __funnelshift_r(w_, 0u, (y)) & 1u; \
+    mask = push_bit_fma(mask, t_);                                                  \
+  }
+
+#pragma unroll
+    for (int u = 0; u < FT_U; u++)
+    {
+      const uint32_t m = mm[u];
+      const uint32_t w0 = vv[u].x, w1 = vv[u].y, w2 = vv[u].z, w3 = vv[u].w;
+      const uint32_t f0 = __funnelshift_r(m, w0, 16), f1 = __funnelshift_r(w0, w1, 16);
+      const uint32_t f2 = __funnelshift_r(w1, w2, 16), f3 = __funnelshift_r(w2, w3, 16);
+      PROBE3(f0, w0);
+      PROBE3(w0, f1);
+      PROBE3(f1, w1);
+      PROBE3(w1, f2);
+      PROBE3(f2, w2);
+      PROBE3(w2, f3);
+      PROBE3(f3, w3);
+      PROBE3(w3, w3 >> 16);
+    }
+#undef PROBE3
+    // mask bit (31 - sl) belongs to slot sl = u * 8 + pair: clz(mask) is the first slot that passed
+
+    // ---- levels 2 and 3.  A lane finds 0.6 survivors per tile on average but the slowest lane of
+    // a warp 2.6, so the warp's survivors are dealt out evenly: lane L's n-th survivor goes to
+    // queue position (survivors of lanes < L) + n as a 16-bit descriptor (L << 5 | slot); lane e
+    // then takes entry e and fetches the five window bytes itself.
+    const uint32_t cnt = __popc(mask);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1)
+    {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, dd);
+      if (lane >= (uint32_t) dd) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint32_t pos = incl - cnt;   // queue position of this lane's next survivor
+    uint32_t rem = mask;
+    const int64_t wpos = (int64_t) (tp - d);   // block position of the warp-tile's first byte
+
+    for (uint32_t base_e = 0; base_e < total; base_e += 32)   // almost always a single round
+    {
+      while (rem != 0 && pos < base_e + 32)
+      {
+        const uint32_t sl = (uint32_t) __clz(rem);
+        rem &= ~(0x80000000u >> sl);
+        sts_u16_v(wq_a + 2 * (pos - base_e), (lane << 5) | sl);
+        pos++;
+      }
+      __syncwarp();
+
+      if (base_e + lane < total)
+      {
+        const uint32_t dsc = lds_u16_v(wq_a + 2 * lane);
+        // first position p of the pair = tile byte u * 512 + owner * 16 + 2 * pair
+        const uint32_t pb = ((dsc & 0x18u) << 6) + ((dsc >> 5) << 4) + ((dsc & 7u) << 1);
+        const uint8_t* src = tp + pb - 3;   // bytes p-3 .. p+1
+        const uint32_t al = (uint32_t) ((uintptr_t) src & 3u);
+        const uint32_t x0 = *reinterpret_cast<const uint32_t*>(src - al);
+        const uint32_t x1 = *reinterpret_cast<const uint32_t*>(src - al + 4);
+        const uint32_t wa = __funnelshift_r(x0, x1, al * 8);          // W(p)
+        const uint32_t wb = __funnelshift_rc(x0, x1, al * 8 + 8);     // W(p + 1)
+        if (b3_test_a(sB3_a, wa & 0xFFFFFFu) && bloom4_test_a<B4BITS>(sB4_a, wa))
+        {
+          const uint32_t mv = ht_lookup(F, wa);
+          if (mv != 0) emit_events(R, V, out, wpos + pb + 1, mv);
+        }
+        if (b3_test_a(sB3_a, wb >> 8) && bloom4_test_a<B4BITS>(sB4_a, wb))
+        {
+          const uint32_t mv = ht_lookup(F, wb);
+          if (mv != 0) emit_events(R, V, out, wpos + pb + 2, mv);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+
+// ---- host: enumerate hit windows of the compiled automaton, build B3 / B4 / hash table
+//
+// The tables are a pure function of the rules image, and building them is the expensive part of
+// a rules upload (a breadth-first walk over the trie plus a few hundred thousand hash inserts).
+// They are therefore built once per image: kept in a process-wide registry keyed by a 64-bit
+// hash of the image (every device of a yrb_multi, every re-upload of the same YR_RULES gets
+// them for an upload), and stored in a disk cache (the device-side analogue of
+// the reference's compiled-rules file, arena.c:543/627 -- $YR_B200_CACHE_DIR, default
+// $XDG_CACHE_HOME or ~/.cache /yara_b200; YR_B200_CACHE=0 turns the disk part off) so that a new
+// process that loads the same rules (yr_rules_load of a .yarc) skips the build.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+struct FilterHost
+{
+  int usable = 0, has_d1 = 0, has_d2 = 0, root_match = 0, variant = 0;
+  uint32_t ht_bits = 0, n_windows = 0;
+  float fill3 = 0.f;
+  std::vector<uint32_t> b3, b4;
+  std::vector<uint2> ht;
 };
 
 static int ft_variant_index()
 {
   const char* e = getenv("YRB_FILTER_VARIANT");
-  int v = e ? atoi(e) : 0;
-  return (v < 0 || v >= FT_NUM_VARIANTS) ? 0 : v;
+  int v = e ? atoi(e) : FT_DEFAULT_VARIANT;
+  return (v < 0 || v >= FT_NUM_VARIANTS) ? FT_DEFAULT_VARIANT : v;
 }
 
 static uint32_t host_ac_step(const uint32_t* T, uint32_t state, uint32_t byte)
@@ -444,25 +708,20 @@ static uint32_t host_ac_step(const uint32_t* T, uint32_t state, uint32_t byte)
   return t >> 9;
 }
 
-#include <vector>
-
-int build_filter_tables(const void* image, int device, FilterTables* out, void** d_storage)
+static void filter_host_build(const void* image, FilterHost* out)
 {
-  (void) device;
-  memset(out, 0, sizeof(*out));
-  *d_storage = nullptr;
-
   const yrb_image_header* h = (const yrb_image_header*) image;
   const uint32_t* T = yrb_img_trans(image);
   const uint32_t* M = yrb_img_match(image);
+  out->variant = ft_variant_index();
 
   if (h->tables_size < 257)
-    return YRB_SUCCESS;
+    return;
 
   if (M[0] != 0)
   {
     out->root_match = 1; // every position is an event: nothing to filter
-    return YRB_SUCCESS;
+    return;
   }
 
   // breadth-first over the trie (depth <= YR_MAX_ATOM_LENGTH), remembering each state's path
@@ -507,16 +766,15 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
   }
 
   if (out->has_d1 || out->has_d2 || windows.empty() || n_d3 > 512)
-    return YRB_SUCCESS; // not usable: the engine falls back to the walk kernel
+    return; // not usable: the engine falls back to the walk kernel
 
-  FilterStorage* fs = new FilterStorage();
-  memset(fs, 0, sizeof(*fs));
-  const int variant = ft_variant_index();
-  const int b4_bits = kVariants[variant].b4_bits;
+  const int b4_bits = kVariants[out->variant].b4_bits;
+  out->b3.assign(B3_WORDS, 0);
+  out->b4.assign((size_t) 1 << (b4_bits - 5), 0);
 
   uint32_t ht_bits = 4;
   while ((1ull << ht_bits) < windows.size() * 2) ht_bits++;
-  std::vector<uint2> ht((size_t) 1 << ht_bits, make_uint2(0, 0));
+  out->ht.assign((size_t) 1 << ht_bits, make_uint2(0, 0));
   const uint32_t ht_mask = (1u << ht_bits) - 1;
 
   for (uint32_t w : windows)
@@ -530,50 +788,213 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
     const uint32_t k_suffix = w >> 8, k_prefix = w & 0xFFFFFF;
     // B3 entry of a 3-byte key: word = top 15 bits of the hash; TWO bits per key, numbered
     // (bit n = 1u << n): low 5 bits of the key's first byte and low 5 bits of its third byte
-    fs->b3[hash3(k_suffix) >> 5] |= (1u << (k_suffix & 31)) | (1u << ((k_suffix >> 16) & 31));
-    fs->b3[hash3(k_prefix) >> 5] |= (1u << (k_prefix & 31)) | (1u << ((k_prefix >> 16) & 31));
+    out->b3[hash3(k_suffix) >> 5] |= (1u << (k_suffix & 31)) | (1u << ((k_suffix >> 16) & 31));
+    out->b3[hash3(k_prefix) >> 5] |= (1u << (k_prefix & 31)) | (1u << ((k_prefix >> 16) & 31));
     {
       const uint32_t g1 = w * HASH4_MUL, g2 = (w * HASH4_MUL2) | 1u;
       uint32_t g = g1;
       for (int k = 0; k < BLOOM_K; k++)
       {
         const uint32_t i4 = g >> (32 - b4_bits);
-        fs->b4[i4 >> 5] |= 0x80000000u >> (i4 & 31);
+        out->b4[i4 >> 5] |= 0x80000000u >> (i4 & 31);
         g += g2;
       }
     }
 
     uint32_t slot = (w * HT_MUL) >> (32 - ht_bits);
-    while (ht[slot].y != 0 && ht[slot].x != w) slot = (slot + 1) & ht_mask;
-    ht[slot] = make_uint2(w, mv);
+    while (out->ht[slot].y != 0 && out->ht[slot].x != w) slot = (slot + 1) & ht_mask;
+    out->ht[slot] = make_uint2(w, mv);
   }
 
   size_t pop3 = 0;
-  for (uint32_t i = 0; i < B3_WORDS; i++) pop3 += (size_t) __builtin_popcount(fs->b3[i]);
-  const double fill3 = (double) pop3 / (double) (1u << B3_BITS);
-
-  if (fill3 > (getenv("YRB_FILTER_MAX_FILL") ? atof(getenv("YRB_FILTER_MAX_FILL")) : 0.45))
-  {
-    delete fs;
-    return YRB_SUCCESS; // too dense to filter anything
-  }
-
-  uint8_t* dptr = nullptr;
-  const size_t ht_bytes = ht.size() * sizeof(uint2);
-  const size_t total = sizeof(FilterStorage) + ht_bytes;
-  if (cudaMalloc((void**) &dptr, total) != cudaSuccess) { cudaGetLastError(); delete fs; return YRB_ERROR_INSUFFICIENT_MEMORY; }
-  cudaMemcpy(dptr, fs, sizeof(FilterStorage), cudaMemcpyHostToDevice);
-  cudaMemcpy(dptr + sizeof(FilterStorage), ht.data(), ht_bytes, cudaMemcpyHostToDevice);
-  delete fs;
-
-  out->b3 = reinterpret_cast<const uint32_t*>(dptr);
-  out->b4 = reinterpret_cast<const uint32_t*>(dptr + sizeof(uint32_t) * B3_WORDS);
-  out->ht = reinterpret_cast<const void*>(dptr + sizeof(FilterStorage));
+  for (uint32_t i = 0; i < B3_WORDS; i++) pop3 += (size_t) __builtin_popcount(out->b3[i]);
+  out->fill3 = (float) ((double) pop3 / (double) (1u << B3_BITS));
   out->ht_bits = ht_bits;
   out->n_windows = (uint32_t) windows.size();
-  out->fill3 = (float) fill3;
+
+  if (out->fill3 > (getenv("YRB_FILTER_MAX_FILL") ? atof(getenv("YRB_FILTER_MAX_FILL")) : 0.45))
+  {
+    out->b3.clear(); out->b4.clear(); out->ht.clear();
+    return; // too dense to filter anything
+  }
   out->usable = 1;
-  out->variant = variant;
+}
+
+// ---- the cache: process-wide registry + files
+
+#define FT_CACHE_MAGIC 0x42544659u /* "YFTB" */
+#define FT_CACHE_VERSION 3u
+
+struct FtCacheHeader
+{
+  uint32_t magic, version;
+  uint64_t image_hash, image_size;
+  int32_t usable, has_d1, has_d2, root_match, variant;
+  uint32_t ht_bits, n_windows;
+  float fill3;
+  uint64_t n_b3, n_b4, n_ht;
+  uint64_t payload_hash;
+};
+
+static uint64_t hash64(const void* p, size_t n, uint64_t seed)
+{
+  // word-wise multiply-xorshift (wyhash-like mixing); only has to tell rules images apart
+  const uint8_t* b = (const uint8_t*) p;
+  uint64_t h = seed ^ (n * 0x9E3779B97F4A7C15ULL);
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8)
+  {
+    uint64_t w;
+    memcpy(&w, b + i, 8);
+    h = (h ^ w) * 0xFF51AFD7ED558CCDULL;
+    h ^= h >> 32;
+  }
+  uint64_t tail = 0;
+  if (i < n) memcpy(&tail, b + i, n - i);
+  h = (h ^ tail) * 0xC4CEB9FE1A85EC53ULL;
+  return h ^ (h >> 29);
+}
+
+static std::string ft_cache_dir()
+{
+  const char* off = getenv("YR_B200_CACHE");
+  if (off && off[0] == '0') return "";
+  std::string dir;
+  if (const char* e = getenv("YR_B200_CACHE_DIR")) dir = e;
+  else if (const char* x = getenv("XDG_CACHE_HOME")) dir = std::string(x) + "/yara_b200";
+  else if (const char* hm = getenv("HOME")) dir = std::string(hm) + "/.cache/yara_b200";
+  else return "";
+  // mkdir -p of the last two components is all a default path needs
+  const size_t cut = dir.rfind('/');
+  if (cut != std::string::npos && cut > 0) mkdir(dir.substr(0, cut).c_str(), 0700);
+  mkdir(dir.c_str(), 0700);
+  return dir;
+}
+
+static std::string ft_cache_path(const std::string& dir, uint64_t key, int variant)
+{
+  char name[96];
+  snprintf(name, sizeof(name), "/%016llx-v%d.ftab", (unsigned long long) key, variant);
+  return dir + name;
+}
+
+static uint64_t ft_payload_hash(const FilterHost& f)
+{
+  uint64_t h = hash64(f.b3.data(), f.b3.size() * 4, 1);
+  h = hash64(f.b4.data(), f.b4.size() * 4, h);
+  return hash64(f.ht.data(), f.ht.size() * sizeof(uint2), h);
+}
+
+static bool ft_cache_load(const std::string& path, uint64_t key, uint64_t image_size, int variant, FilterHost* out)
+{
+  FILE* fp = fopen(path.c_str(), "rb");
+  if (!fp) return false;
+  FtCacheHeader hd;
+  bool ok = fread(&hd, sizeof(hd), 1, fp) == 1 && hd.magic == FT_CACHE_MAGIC && hd.version == FT_CACHE_VERSION &&
+            hd.image_hash == key && hd.image_size == image_size && hd.variant == variant && hd.n_b3 <= B3_WORDS &&
+            hd.n_b4 <= (1u << 20) && hd.n_ht <= (1ull << 28);
+  if (ok)
+  {
+    out->usable = hd.usable; out->has_d1 = hd.has_d1; out->has_d2 = hd.has_d2; out->root_match = hd.root_match;
+    out->variant = hd.variant; out->ht_bits = hd.ht_bits; out->n_windows = hd.n_windows; out->fill3 = hd.fill3;
+    out->b3.resize((size_t) hd.n_b3); out->b4.resize((size_t) hd.n_b4); out->ht.resize((size_t) hd.n_ht);
+    ok = (hd.n_b3 == 0 || fread(out->b3.data(), 4, out->b3.size(), fp) == out->b3.size()) &&
+         (hd.n_b4 == 0 || fread(out->b4.data(), 4, out->b4.size(), fp) == out->b4.size()) &&
+         (hd.n_ht == 0 || fread(out->ht.data(), sizeof(uint2), out->ht.size(), fp) == out->ht.size()) &&
+         ft_payload_hash(*out) == hd.payload_hash;
+  }
+  fclose(fp);
+  if (!ok) *out = FilterHost();
+  return ok;
+}
+
+static void ft_cache_store(const std::string& path, uint64_t key, uint64_t image_size, const FilterHost& f)
+{
+  // write to a private name, then rename: readers never see a partial file
+  char tmp[64];
+  snprintf(tmp, sizeof(tmp), ".tmp.%ld", (long) getpid());
+  const std::string tpath = path + tmp;
+  FILE* fp = fopen(tpath.c_str(), "wb");
+  if (!fp) return;
+  FtCacheHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  hd.magic = FT_CACHE_MAGIC; hd.version = FT_CACHE_VERSION; hd.image_hash = key; hd.image_size = image_size;
+  hd.usable = f.usable; hd.has_d1 = f.has_d1; hd.has_d2 = f.has_d2; hd.root_match = f.root_match; hd.variant = f.variant;
+  hd.ht_bits = f.ht_bits; hd.n_windows = f.n_windows; hd.fill3 = f.fill3;
+  hd.n_b3 = f.b3.size(); hd.n_b4 = f.b4.size(); hd.n_ht = f.ht.size();
+  hd.payload_hash = ft_payload_hash(f);
+  bool ok = fwrite(&hd, sizeof(hd), 1, fp) == 1 &&
+            (f.b3.empty() || fwrite(f.b3.data(), 4, f.b3.size(), fp) == f.b3.size()) &&
+            (f.b4.empty() || fwrite(f.b4.data(), 4, f.b4.size(), fp) == f.b4.size()) &&
+            (f.ht.empty() || fwrite(f.ht.data(), sizeof(uint2), f.ht.size(), fp) == f.ht.size());
+  ok = (fclose(fp) == 0) && ok;
+  if (!ok || rename(tpath.c_str(), path.c_str()) != 0) unlink(tpath.c_str());
+}
+
+static std::mutex g_ft_mu;
+static std::map<std::pair<uint64_t, int>, std::shared_ptr<const FilterHost>> g_ft_registry;
+static unsigned g_ft_stats[3] = {0, 0, 0};   // served from: registry, disk, built
+
+extern "C" void yrb_filter_cache_stats(unsigned* from_registry, unsigned* from_disk, unsigned* built)
+{
+  std::lock_guard<std::mutex> lk(g_ft_mu);
+  if (from_registry) *from_registry = g_ft_stats[0];
+  if (from_disk) *from_disk = g_ft_stats[1];
+  if (built) *built = g_ft_stats[2];
+}
+
+static std::shared_ptr<const FilterHost> filter_host_tables(const void* image, size_t image_size)
+{
+  const uint64_t key = hash64(image, image_size, 0x59415241ULL);
+  const int variant = ft_variant_index();
+  std::lock_guard<std::mutex> lk(g_ft_mu);   // building under the lock: concurrent uploads of one image wait instead of building twice
+  auto it = g_ft_registry.find(std::make_pair(key, variant));
+  if (it != g_ft_registry.end()) { g_ft_stats[0]++; return it->second; }
+
+  std::shared_ptr<FilterHost> f(new FilterHost());
+  const std::string dir = ft_cache_dir();
+  const std::string path = dir.empty() ? std::string() : ft_cache_path(dir, key, variant);
+  if (!path.empty() && ft_cache_load(path, key, image_size, variant, f.get()))
+  {
+    g_ft_stats[1]++;
+  }
+  else
+  {
+    filter_host_build(image, f.get());
+    g_ft_stats[2]++;
+    if (!path.empty()) ft_cache_store(path, key, image_size, *f);
+  }
+  if (g_ft_registry.size() >= 16) g_ft_registry.erase(g_ft_registry.begin());   // a handful of rulesets per process at most
+  g_ft_registry[std::make_pair(key, variant)] = f;
+  return f;
+}
+
+int build_filter_tables(const void* image, size_t image_size, int device, FilterTables* out, void** d_storage)
+{
+  (void) device;
+  memset(out, 0, sizeof(*out));
+  *d_storage = nullptr;
+
+  const std::shared_ptr<const FilterHost> f = filter_host_tables(image, image_size);
+  out->has_d1 = f->has_d1; out->has_d2 = f->has_d2; out->root_match = f->root_match; out->variant = f->variant;
+  if (!f->usable)
+    return YRB_SUCCESS;
+
+  uint8_t* dptr = nullptr;
+  const size_t b3_bytes = f->b3.size() * 4, b4_bytes = f->b4.size() * 4, ht_bytes = f->ht.size() * sizeof(uint2);
+  const size_t total = b3_bytes + b4_bytes + ht_bytes;
+  if (cudaMalloc((void**) &dptr, total) != cudaSuccess) { cudaGetLastError(); return YRB_ERROR_INSUFFICIENT_MEMORY; }
+  cudaMemcpy(dptr, f->b3.data(), b3_bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(dptr + b3_bytes, f->b4.data(), b4_bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(dptr + b3_bytes + b4_bytes, f->ht.data(), ht_bytes, cudaMemcpyHostToDevice);
+
+  out->b3 = reinterpret_cast<const uint32_t*>(dptr);
+  out->b4 = reinterpret_cast<const uint32_t*>(dptr + b3_bytes);
+  out->ht = reinterpret_cast<const void*>(dptr + b3_bytes + b4_bytes);
+  out->ht_bits = f->ht_bits;
+  out->n_windows = f->n_windows;
+  out->fill3 = f->fill3;
+  out->usable = 1;
   *d_storage = dptr;
 
   static bool attr_set[64] = {false};
@@ -584,6 +1005,8 @@ int build_filter_tables(const void* image, int device, FilterTables* out, void**
     cudaFuncSetAttribute(ac_filter_kernel<1024, 4, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[0]));
     cudaFuncSetAttribute(ac_filter_kernel<512, 4, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[1]));
     cudaFuncSetAttribute(ac_filter_kernel<1024, 2, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[2]));
+    cudaFuncSetAttribute(ac_filter_tma_kernel<32, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[3]));
+    cudaFuncSetAttribute(ac_filter_tma_kernel<24, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[4]));
     attr_set[dev] = true;
   }
   return YRB_SUCCESS;
@@ -629,7 +1052,10 @@ void launch_ac_scan_filter(
   {
   case 0: ac_filter_kernel<1024, 4, 18><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   case 1: ac_filter_kernel<512, 4, 19><<<grid, 512, smem, s>>>(R, fd, V, out, flo, fhi); break;
-  default: ac_filter_kernel<1024, 2, 19><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  case 2: ac_filter_kernel<1024, 2, 19><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  case 3: ac_filter_tma_kernel<32, 18><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  case 4: ac_filter_tma_kernel<24, 18><<<grid, 768, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  default: ac_filter_kernel<1024, 4, 18><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   }
 
   launch_ac_scan_walk(R, V, out, fhi, hi, s);

@@ -8,6 +8,7 @@
 // run concurrently against one read-only device image.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,11 +53,19 @@ struct DevBuf
   T* p = nullptr;
   size_t cap = 0; // elements
 
+  // Small, frequently regrown scratch doubles; anything beyond 64 MiB (the resident block above
+  // all: a 16 GiB block must not take 32 GiB of HBM, nor a 130 GB one fail) is sized exactly,
+  // rounded up to 2 MiB.
   int ensure(size_t n, bool keep = false)
   {
     if (n <= cap) return YRB_SUCCESS;
     size_t ncap = cap ? cap : 1;
     while (ncap < n) ncap *= 2;
+    if (ncap * sizeof(T) > ((size_t) 64 << 20))
+    {
+      const size_t gran = ((size_t) 2 << 20) / sizeof(T) ? ((size_t) 2 << 20) / sizeof(T) : 1;
+      ncap = (n + gran - 1) / gran * gran;
+    }
     T* np = nullptr;
     cudaError_t e = cudaMalloc((void**) &np, ncap * sizeof(T));
     if (e != cudaSuccess) { cudaGetLastError(); return YRB_ERROR_INSUFFICIENT_MEMORY; }
@@ -101,6 +110,8 @@ struct yrb_scanner
 
   int opt_kernel = YRB_KERNEL_AUTO;
   size_t opt_h2d_chunk = 64u << 20;
+  bool shard_of_multi = false;   // yrb_multi worker: a deferred scan leaves its Raw records (and error keys) on the device
+  uint32_t shard_n_chain_raw = 0, shard_any_error = 0;
 
   DevBuf<uint8_t> d_data;
   DevBuf<Cand> d_cand[NUM_CLS];
@@ -158,22 +169,35 @@ extern "C" const char* yrb_version(void) { return "yara_b200 0.1 (sm_100a; libya
 
 // ---------------------------------------------------------------------- rules
 
-extern "C" int yrb_rules_create(const void* image, size_t image_size, int device, yrb_rules** out)
+// The discovery key gives the position inside a state's YR_AC_MATCH chain KEY_CHAIN_BITS bits
+// (emit.cuh).  A longer chain would make later entries share one key and the "first wins / last
+// wins" rules of the resolve ambiguous: refuse such a ruleset loudly instead of saturating.
+extern "C" void yrb_rules_release(yrb_rules* r);
+
+static uint32_t longest_match_chain(const void* image)
 {
-  if (image == nullptr || out == nullptr || image_size < sizeof(yrb_image_header))
-    return YRB_ERROR_BAD_ARGUMENT;
-
   const yrb_image_header* h = (const yrb_image_header*) image;
-  if (h->magic != YRB_IMAGE_MAGIC || h->version != YRB_IMAGE_VERSION || h->total_size != image_size)
-    return YRB_ERROR_BAD_IMAGE;
+  const yrb_acm* acm = yrb_img_acm(image);
+  std::vector<uint32_t> len((size_t) h->num_acm + 1, 0);   // len[k]: entries from acm[k-1] to the end of its chain
+  std::vector<uint32_t> path;
+  uint32_t best = 0;
+  for (uint32_t k0 = 1; k0 <= h->num_acm; k0++)
+  {
+    if (len[k0]) continue;
+    path.clear();
+    uint32_t k = k0;
+    while (k != 0 && k <= h->num_acm && len[k] == 0 && path.size() <= h->num_acm) { path.push_back(k); k = acm[k - 1].next; }
+    uint32_t l = (k != 0 && k <= h->num_acm) ? len[k] : 0;
+    for (size_t j = path.size(); j-- > 0;) len[path[j]] = ++l;
+    if (len[k0] > best) best = len[k0];
+  }
+  return best;
+}
 
-  if (device < 0 || device >= yrb_device_count())
-    return YRB_ERROR_NO_DEVICE;
-
+static int rules_init(yrb_rules* r, const void* image, size_t image_size, int device)
+{
+  const yrb_image_header* h = (const yrb_image_header*) image;
   CK(cudaSetDevice(device));
-
-  yrb_rules* r = new (std::nothrow) yrb_rules();
-  if (!r) return YRB_ERROR_INSUFFICIENT_MEMORY;
 
   r->device = device;
   r->refs = 1;
@@ -182,9 +206,14 @@ extern "C" int yrb_rules_create(const void* image, size_t image_size, int device
   r->d_image = nullptr;
   r->d_filter = nullptr;
 
-  if (cudaMalloc(&r->d_image, image_size) != cudaSuccess) { cudaGetLastError(); delete r; return YRB_ERROR_INSUFFICIENT_MEMORY; }
-  if (cudaMemcpy(r->d_image, image, image_size, cudaMemcpyHostToDevice) != cudaSuccess)
-  { cudaFree(r->d_image); delete r; return YRB_ERROR_CUDA; }
+  if (longest_match_chain(image) > KEY_CHAIN_MAX)
+  {
+    fprintf(stderr, "yrb200: a state's YR_AC_MATCH chain has more than %u entries; the discovery key cannot order them\n", KEY_CHAIN_MAX);
+    return YRB_ERROR_BAD_IMAGE;
+  }
+
+  CK(cudaMalloc(&r->d_image, image_size));
+  CK(cudaMemcpy(r->d_image, image, image_size, cudaMemcpyHostToDevice));
 
   const uint8_t* b = (const uint8_t*) r->d_image;
   r->R.T = (const uint32_t*) (b + h->off_trans);
@@ -205,13 +234,38 @@ extern "C" int yrb_rules_create(const void* image, size_t image_size, int device
   r->num_sms = prop.multiProcessorCount;
 
   memset(&r->F, 0, sizeof(r->F));
-  int rc = build_filter_tables(image, device, &r->F, &r->d_filter);
-  if (rc != YRB_SUCCESS) { cudaFree(r->d_image); delete r; return rc; }
+  int rc = build_filter_tables(image, image_size, device, &r->F, &r->d_filter);
+  if (rc != YRB_SUCCESS) return rc;
 
   // cudaMemcpy from pageable memory may return before the DMA has landed, and the
   // scanners run on non-blocking streams that do not order after the legacy stream
   CK(cudaDeviceSynchronize());
+  return YRB_SUCCESS;
+}
 
+extern "C" int yrb_rules_create(const void* image, size_t image_size, int device, yrb_rules** out)
+{
+  if (image == nullptr || out == nullptr || image_size < sizeof(yrb_image_header))
+    return YRB_ERROR_BAD_ARGUMENT;
+
+  const yrb_image_header* h = (const yrb_image_header*) image;
+  if (h->magic != YRB_IMAGE_MAGIC || h->version != YRB_IMAGE_VERSION || h->total_size != image_size)
+    return YRB_ERROR_BAD_IMAGE;
+
+  if (device < 0 || device >= yrb_device_count())
+    return YRB_ERROR_NO_DEVICE;
+
+  yrb_rules* r = new (std::nothrow) yrb_rules();
+  if (!r) return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  r->refs = 1;
+  r->device = device;
+  const int rc = rules_init(r, image, image_size, device);
+  if (rc != YRB_SUCCESS)
+  {
+    yrb_rules_release(r);   // frees whatever was built
+    return rc;
+  }
   *out = r;
   return YRB_SUCCESS;
 }
@@ -232,12 +286,25 @@ extern "C" void yrb_rules_release(yrb_rules* r)
 
 // -------------------------------------------------------------------- scanner
 
+extern "C" void yrb_scanner_destroy(yrb_scanner* s);
+
+static int scanner_init(yrb_scanner* s)
+{
+  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 6; i++) CK(cudaEventCreate(&s->ev[i]));
+  CK(cudaMalloc((void**) &s->d_status, sizeof(ScanStatus)));
+  CK(cudaHostAlloc((void**) &s->h_status, sizeof(ScanStatus), cudaHostAllocDefault));
+  memset(s->h_status, 0, sizeof(ScanStatus));
+  return YRB_SUCCESS;
+}
+
 extern "C" int yrb_scanner_create(yrb_rules* rules, yrb_scanner** out)
 {
   if (!rules || !out) return YRB_ERROR_BAD_ARGUMENT;
   CK(cudaSetDevice(rules->device));
 
-  yrb_scanner* s = new (std::nothrow) yrb_scanner();
+  yrb_scanner* s = new (std::nothrow) yrb_scanner();   // value-initialised: every handle starts out null
   if (!s) return YRB_ERROR_INSUFFICIENT_MEMORY;
 
   s->rules = rules;
@@ -246,12 +313,12 @@ extern "C" int yrb_scanner_create(yrb_rules* rules, yrb_scanner** out)
   if (const char* e = getenv("YRB_SCAN_KERNEL")) // test hook: 1 = walk, 2 = filter
     s->opt_kernel = atoi(e);
 
-  CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 6; i++) CK(cudaEventCreate(&s->ev[i]));
-  CK(cudaMalloc((void**) &s->d_status, sizeof(ScanStatus)));
-  CK(cudaHostAlloc((void**) &s->h_status, sizeof(ScanStatus), cudaHostAllocDefault));
-
+  const int rc = scanner_init(s);
+  if (rc != YRB_SUCCESS)
+  {
+    yrb_scanner_destroy(s);   // tolerates a partially built scanner
+    return rc;
+  }
   *out = s;
   return YRB_SUCCESS;
 }
@@ -260,8 +327,8 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
 {
   if (!s) return;
   cudaSetDevice(s->device);
-  cudaStreamSynchronize(s->stream);
-  cudaStreamSynchronize(s->copy_stream);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
   s->d_data.release();
   for (int c = 0; c < NUM_CLS; c++) s->d_cand[c].release();
   s->d_raw.release(); s->ws_fast1.release(); s->ws_fast2.release(); s->ws_re1.release(); s->ws_re2.release();
@@ -271,13 +338,15 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   s->s_lists.release(); s->c_where.release(); s->flags8.release(); s->finals.release(); s->unconf.release();
   s->str_min_key.release(); s->str_cut_key.release(); s->str_err.release(); s->str_count.release(); s->too_many.release();
   s->g_offsets.release(); s->g_data.release();
+  s->seg_tab.release(); s->item_dirty.release(); s->h_seg_tab.release(); s->h_item_dirty.release();
   s->h_finals.release(); s->h_unconf.release(); s->h_too_many.release(); s->h_str_count.release(); s->h_raw.release();
   if (s->d_status) cudaFree(s->d_status);
   if (s->h_status) cudaFreeHost(s->h_status);
   for (auto e : s->slice_ev) cudaEventDestroy(e);
-  for (int i = 0; i < 6; i++) cudaEventDestroy(s->ev[i]);
-  cudaStreamDestroy(s->stream);
-  cudaStreamDestroy(s->copy_stream);
+  for (int i = 0; i < 6; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  cudaGetLastError();
   yrb_rules_release(s->rules);
   delete s;
 }
@@ -553,7 +622,7 @@ static int scan_impl(
     V.seg_len = bp->d_len;
   }
 
-  if (V.gsize >= (1LL << 40) || V.g1 > V.gsize || V.own_hi > V.gsize || V.own_lo > V.own_hi)
+  if (V.gsize >= (1LL << 38) || V.g1 > V.gsize || V.own_hi > V.gsize || V.own_lo > V.own_hi)
     return YRB_ERROR_BAD_ARGUMENT;
 
   const uint8_t* d_data = d_data_in;
@@ -821,6 +890,12 @@ static int scan_impl(
     CK(cudaMemsetAsync(&s->d_status->n_retry3, 0, 2 * sizeof(unsigned int), s->stream));   // n_retry3, n_chain_raw
   }
 
+  if (hs->key_overflow)
+  {
+    fprintf(stderr, "yrb200: one candidate produced more than %u match callbacks; the discovery key cannot order them\n", KEY_SEQ_MAX);
+    return YRB_ERROR_INTERNAL_FATAL;
+  }
+
   if (hs->margin_fault)
     return YRB_ERROR_MARGIN;
 
@@ -867,6 +942,16 @@ static int scan_impl(
       res->matches = s->h_finals.p;
     }
     CK(cudaMemcpyAsync(s->h_item_dirty.p, bp->d_dirty, bp->n, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaEventRecord(s->ev[3], s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  else if (params->defer_resolve && s->shard_of_multi)
+  {
+    // one device's share of a yrb_multi scan: the records stay in d_raw, the per-string error keys in
+    // str_err; yrb_multi brings both to the resolving device with peer copies
+    s->h_raw_n = (size_t) n_raw;
+    s->shard_n_chain_raw = hs->n_chain_raw;
+    s->shard_any_error = hs->any_error;
     CK(cudaEventRecord(s->ev[3], s->stream));
     CK(cudaStreamSynchronize(s->stream));
   }
@@ -989,7 +1074,7 @@ extern "C" int yrb_scan_batch(
       total += (len[k] + 15) & ~(int64_t) 15;
     }
   }
-  if (total >= (1LL << 40)) return YRB_ERROR_BAD_ARGUMENT;
+  if (total >= (1LL << 38)) return YRB_ERROR_BAD_ARGUMENT;
 
   CK(cudaMemcpyAsync(s->seg_tab.p, s->h_seg_tab.p, sizeof(int64_t) * 2 * n_items, cudaMemcpyHostToDevice, s->stream));
   CK(cudaMemsetAsync(s->item_dirty.p, 0, n_items, s->stream));
@@ -1077,6 +1162,323 @@ extern "C" int yrb_resolve_raw(
   res->stats.kernel_launches = launches;
   cudaEventElapsedTime(&res->stats.ms_resolve, s->ev[2], s->ev[3]);
   return rc;
+}
+
+// ------------------------------------------------- one block over several GPUs
+//
+// byte-range shards with read margins, no exchange step, no collective.  One
+// process drives all devices (the drop-in's yr_rules_scan_mem is one call on one thread): a
+// persistent worker thread per device runs that device's H2D + scan + verify; the Raw records
+// (tiny compared with the input) are brought to the first device with cudaMemcpyPeerAsync and
+// resolved there ONCE -- dedup across atoms, the 1M cap and chained strings are global.
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+struct MultiJob
+{
+  const uint8_t* h_data = nullptr;   // host block (whole), or
+  const uint8_t* d_shard = nullptr;  // this device's resident shard (points at block byte g0)
+  uint64_t g0 = 0, g1 = 0, own0 = 0, own1 = 0, block_size = 0;
+  yrb_scan_params params;
+  yrb_scan_result res;
+  int rc = 0;
+};
+
+struct MultiWorker
+{
+  int device = 0;
+  yrb_rules* rules = nullptr;
+  yrb_scanner* scanner = nullptr;
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  int state = 0;   // 0 idle, 1 job posted, 2 job done, 3 quit
+  MultiJob job;
+};
+
+struct yrb_multi
+{
+  std::vector<MultiWorker*> w;
+  uint64_t margin = 0;
+  std::mutex scan_mu;   // one scan at a time
+  DevBuf<unsigned long long> err_tmp;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static void multi_worker_main(MultiWorker* w)
+{
+  cudaSetDevice(w->device);
+  for (;;)
+  {
+    std::unique_lock<std::mutex> lk(w->mu);
+    w->cv.wait(lk, [w] { return w->state == 1 || w->state == 3; });
+    if (w->state == 3) return;
+    lk.unlock();
+
+    MultiJob& j = w->job;
+    yrb_scan_params p = j.params;
+    p.data_offset = j.g0;
+    p.block_size = j.block_size;
+    p.own_begin = j.own0;
+    p.own_end = j.own1;
+    p.defer_resolve = 1;
+    p.n_seeds = 0;
+    p.seeds = nullptr;
+    static const uint8_t dummy = 0;
+    const size_t len = (size_t) (j.g1 - j.g0);
+    if (j.h_data)
+      j.rc = scan_impl(w->scanner, len ? j.h_data + j.g0 : &dummy, nullptr, len, &p, &j.res);
+    else
+      j.rc = scan_impl(w->scanner, nullptr, j.d_shard ? j.d_shard : &dummy, len, &p, &j.res);
+
+    lk.lock();
+    w->state = 2;
+    w->cv.notify_all();
+  }
+}
+
+static uint64_t image_margin(const void* image)
+{
+  const yrb_image_header* h = (const yrb_image_header*) image;
+  const yrb_string* S = yrb_img_strings(image);
+  int64_t longest = 0;
+  for (uint32_t i = 0; i < h->num_strings; i++)
+    if (S[i].length > longest) longest = S[i].length;
+  uint64_t m = (uint64_t) (longest * 2 > YRB_RE_SCAN_LIMIT ? longest * 2 : YRB_RE_SCAN_LIMIT) + 64;
+  return (m + 4095) & ~(uint64_t) 4095;
+}
+
+extern "C" void yrb_multi_destroy(yrb_multi* m)
+{
+  if (!m) return;
+  for (MultiWorker* w : m->w)
+  {
+    if (w->th.joinable())
+    {
+      { std::lock_guard<std::mutex> lk(w->mu); w->state = 3; }
+      w->cv.notify_all();
+      w->th.join();
+    }
+    if (w->scanner) yrb_scanner_destroy(w->scanner);
+    if (w->rules) yrb_rules_release(w->rules);
+    delete w;
+  }
+  if (!m->w.empty()) cudaSetDevice(m->w[0]->device);
+  m->err_tmp.release();
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  delete m;
+}
+
+extern "C" int yrb_multi_create(const void* image, size_t image_size, const int* devices, int n_devices, yrb_multi** out)
+{
+  if (!image || !out || !devices || n_devices < 1 || n_devices > 64) return YRB_ERROR_BAD_ARGUMENT;
+  for (int a = 0; a < n_devices; a++)
+    for (int b = a + 1; b < n_devices; b++)
+      if (devices[a] == devices[b]) return YRB_ERROR_BAD_ARGUMENT;
+
+  yrb_multi* m = new (std::nothrow) yrb_multi();
+  if (!m) return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  for (int g = 0; g < n_devices; g++)
+  {
+    MultiWorker* w = new (std::nothrow) MultiWorker();
+    if (!w) { yrb_multi_destroy(m); return YRB_ERROR_INSUFFICIENT_MEMORY; }
+    m->w.push_back(w);
+    w->device = devices[g];
+    int rc = yrb_rules_create(image, image_size, devices[g], &w->rules);
+    if (rc == YRB_SUCCESS) rc = yrb_scanner_create(w->rules, &w->scanner);
+    if (rc != YRB_SUCCESS) { yrb_multi_destroy(m); return rc; }
+    w->scanner->shard_of_multi = true;
+  }
+  m->margin = image_margin(image);
+
+  // records travel device -> first device directly where the topology allows it (NVLink/NVSwitch)
+  cudaSetDevice(devices[0]);
+  for (int g = 1; g < n_devices; g++)
+  {
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, devices[0], devices[g]) == cudaSuccess && can)
+      cudaDeviceEnablePeerAccess(devices[g], 0);
+    cudaGetLastError();
+  }
+  if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess)
+  { cudaGetLastError(); yrb_multi_destroy(m); return YRB_ERROR_CUDA; }
+
+  for (MultiWorker* w : m->w) w->th = std::thread(multi_worker_main, w);
+  *out = m;
+  return YRB_SUCCESS;
+}
+
+extern "C" int yrb_multi_device_count(const yrb_multi* m) { return m ? (int) m->w.size() : 0; }
+extern "C" uint64_t yrb_multi_margin(const yrb_multi* m) { return m ? m->margin : 0; }
+
+// Shard g owns the events of bytes [own0, own1) and reads [g0, g1): boundaries at multiples of 4096.
+extern "C" int yrb_multi_plan(const yrb_multi* m, uint64_t block_size, uint64_t* g0, uint64_t* g1, uint64_t* own0, uint64_t* own1)
+{
+  if (!m || !g0 || !g1 || !own0 || !own1) return YRB_ERROR_BAD_ARGUMENT;
+  const uint64_t n = m->w.size();
+  const uint64_t per = ((block_size + n - 1) / n + 4095) & ~(uint64_t) 4095;
+  for (uint64_t g = 0; g < n; g++)
+  {
+    const uint64_t lo = g * per < block_size ? g * per : block_size;
+    const uint64_t hi = (g + 1) * per < block_size ? (g + 1) * per : block_size;
+    own0[g] = lo;
+    own1[g] = hi;
+    g0[g] = lo > m->margin ? lo - m->margin : 0;
+    g1[g] = hi + m->margin < block_size ? hi + m->margin : block_size;
+  }
+  return YRB_SUCCESS;
+}
+
+__global__ void err_min_merge_kernel(unsigned long long* dst, const unsigned long long* src, uint32_t n)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n && src[k] < dst[k]) dst[k] = src[k];
+}
+
+static int multi_run(yrb_multi* m, const yrb_scan_params* params, yrb_scan_result* res)
+{
+  const size_t n = m->w.size();
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+
+  for (MultiWorker* w : m->w)
+  {
+    { std::lock_guard<std::mutex> lk(w->mu); w->state = 1; }
+    w->cv.notify_all();
+  }
+  for (MultiWorker* w : m->w)
+  {
+    std::unique_lock<std::mutex> lk(w->mu);
+    w->cv.wait(lk, [w] { return w->state == 2; });
+    w->state = 0;
+  }
+  std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+
+  memset(res, 0, sizeof(*res));
+  res->error_string = YRB_NONE;
+  size_t total = 0;
+  uint32_t chain_raw = 0, any_error = 0;
+  for (MultiWorker* w : m->w)
+  {
+    if (w->job.rc != YRB_SUCCESS) return w->job.rc;
+    total += w->scanner->h_raw_n;
+    chain_raw |= w->scanner->shard_n_chain_raw;
+    any_error |= w->scanner->shard_any_error;
+    res->stats.bytes += w->job.res.stats.bytes;
+    res->stats.n_candidates += w->job.res.stats.n_candidates;
+    res->stats.kernel_launches += w->job.res.stats.kernel_launches;
+    if (w->job.res.stats.ms_scan > res->stats.ms_scan) res->stats.ms_scan = w->job.res.stats.ms_scan;
+    if (w->job.res.stats.ms_verify > res->stats.ms_verify) res->stats.ms_verify = w->job.res.stats.ms_verify;
+    if (w->job.res.stats.ms_h2d > res->stats.ms_h2d) res->stats.ms_h2d = w->job.res.stats.ms_h2d;
+  }
+  res->stats.scan_kernel = m->w[0]->job.res.stats.scan_kernel;
+  if (total >= (1ULL << 31)) return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  // ---- gather on the first device, then ONE global resolve
+  yrb_scanner* s0 = m->w[0]->scanner;
+  CK(cudaSetDevice(s0->device));
+  if (s0->d_raw.ensure(total ? total : 1, true) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+  CK(cudaEventRecord(m->ev0, s0->stream));
+  size_t at = s0->h_raw_n;
+  for (size_t g = 1; g < n; g++)
+  {
+    yrb_scanner* sg = m->w[g]->scanner;
+    if (sg->h_raw_n)
+      CK(cudaMemcpyPeerAsync(s0->d_raw.p + at, s0->device, sg->d_raw.p, sg->device, sg->h_raw_n * sizeof(Raw), s0->stream));
+    at += sg->h_raw_n;
+  }
+  if (any_error)
+  {
+    const uint32_t ns = s0->rules->R.num_strings;
+    if (m->err_tmp.ensure(ns ? ns : 1) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+    for (size_t g = 1; g < n; g++)
+    {
+      yrb_scanner* sg = m->w[g]->scanner;
+      if (!sg->shard_any_error) continue;
+      CK(cudaMemcpyPeerAsync(m->err_tmp.p, s0->device, sg->str_err.p, sg->device, sizeof(unsigned long long) * ns, s0->stream));
+      if (!s0->shard_any_error)
+      {
+        // the first device saw no error itself: its own table may never have been initialised
+        CK(cudaMemcpyAsync(s0->str_err.p, m->err_tmp.p, sizeof(unsigned long long) * ns, cudaMemcpyDeviceToDevice, s0->stream));
+        s0->shard_any_error = 1;
+      }
+      else
+        err_min_merge_kernel<<<(ns + 255) / 256, 256, 0, s0->stream>>>(s0->str_err.p, m->err_tmp.p, ns);
+    }
+    const unsigned int one = 1;
+    CK(cudaMemcpyAsync(&s0->d_status->any_error, &one, sizeof(one), cudaMemcpyHostToDevice, s0->stream));
+    s0->h_status->any_error = 1;
+  }
+
+  unsigned launches = 0;
+  yrb_scan_params p = *params;
+  p.n_seeds = 0;
+  p.seeds = nullptr;
+  int rc = run_resolve(s0, s0->d_raw.p, (uint32_t) total, &p, res, &launches, chain_raw != 0);
+  CK(cudaEventRecord(m->ev1, s0->stream));
+  CK(cudaStreamSynchronize(s0->stream));
+  std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();
+
+  res->stats.n_raw = total;
+  res->stats.kernel_launches += launches;
+  cudaEventElapsedTime(&res->stats.ms_resolve, m->ev0, m->ev1);
+  res->stats.ms_total = std::chrono::duration<float, std::milli>(t2 - t0).count();
+  (void) t1;
+  s0->last_n_final = 0;   // yrb_gather_match_data is a single-device facility
+  return rc;
+}
+
+extern "C" int yrb_multi_scan_host(
+    yrb_multi* m, const uint8_t* data, size_t size, const yrb_scan_params* params, yrb_scan_result* result)
+{
+  if (!m || !params || !result || (size > 0 && !data)) return YRB_ERROR_BAD_ARGUMENT;
+  if (params->n_seeds > 0 || params->block_size != 0 || params->defer_resolve) return YRB_ERROR_BAD_ARGUMENT;
+  std::lock_guard<std::mutex> lk(m->scan_mu);
+  const size_t n = m->w.size();
+  if (n == 1 || size < n * 4 * (size_t) m->margin)
+  {
+    // not worth sharding (and an empty block has exactly one i == 0 event): the first device alone
+    yrb_scanner* s0 = m->w[0]->scanner;
+    s0->shard_of_multi = false;
+    static const uint8_t dummy = 0;
+    const int rc = scan_impl(s0, data ? data : &dummy, nullptr, size, params, result);
+    s0->shard_of_multi = true;
+    return rc;
+  }
+  std::vector<uint64_t> g0(n), g1(n), o0(n), o1(n);
+  yrb_multi_plan(m, size, g0.data(), g1.data(), o0.data(), o1.data());
+  for (size_t g = 0; g < n; g++)
+  {
+    MultiJob& j = m->w[g]->job;
+    j = MultiJob();
+    j.h_data = data;
+    j.g0 = g0[g]; j.g1 = g1[g]; j.own0 = o0[g]; j.own1 = o1[g];
+    j.block_size = size;
+    j.params = *params;
+  }
+  return multi_run(m, params, result);
+}
+
+extern "C" int yrb_multi_scan_device(
+    yrb_multi* m, const uint8_t* const* d_shards, const uint64_t* g0, const uint64_t* g1, const uint64_t* own0,
+    const uint64_t* own1, uint64_t block_size, const yrb_scan_params* params, yrb_scan_result* result)
+{
+  if (!m || !params || !result || !d_shards || !g0 || !g1 || !own0 || !own1) return YRB_ERROR_BAD_ARGUMENT;
+  if (params->n_seeds > 0 || params->defer_resolve) return YRB_ERROR_BAD_ARGUMENT;
+  std::lock_guard<std::mutex> lk(m->scan_mu);
+  for (size_t g = 0; g < m->w.size(); g++)
+  {
+    if (g1[g] < g0[g] || g1[g] > block_size || own1[g] < own0[g]) return YRB_ERROR_BAD_ARGUMENT;
+    MultiJob& j = m->w[g]->job;
+    j = MultiJob();
+    j.d_shard = d_shards[g];
+    j.g0 = g0[g]; j.g1 = g1[g]; j.own0 = own0[g]; j.own1 = own1[g];
+    j.block_size = block_size;
+    j.params = *params;
+  }
+  return multi_run(m, params, result);
 }
 
 // ------------------------------------------------------------ match data copy

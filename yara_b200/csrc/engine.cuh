@@ -17,9 +17,14 @@
 
 // Discovery key (SURVEY.md 8(a) "Order dependence"): lexicographic in
 // (i ascending, position in the state's match chain, callback order inside one
-// exhaustive backward exec).
-#define KEY_SEQ_BITS   13
-#define KEY_CHAIN_BITS 10
+// exhaustive backward exec).  39 bits of i (blocks < 2^38 bytes), 8 bits of chain
+// position (the longest YR_AC_MATCH chain of the 100k-string set is 17;
+// yrb_rules_create refuses a ruleset with a chain longer than 255), 17 bits of callback
+// sequence: the fast hex VM's backward position lists keep duplicates (re.c:2323-2333) and
+// one candidate can fire tens of thousands of callbacks (tests/cases.py case 53); a
+// candidate that fires more than 131,070 fails the scan loudly instead of saturating.
+#define KEY_SEQ_BITS   17
+#define KEY_CHAIN_BITS 8
 #define KEY_I_SHIFT    (KEY_SEQ_BITS + KEY_CHAIN_BITS)
 #define KEY_SEQ_MAX    ((1u << KEY_SEQ_BITS) - 1)
 #define KEY_CHAIN_MAX  ((1u << KEY_CHAIN_BITS) - 1)
@@ -135,6 +140,7 @@ struct ScanStatus
   unsigned int n_chain_raw;     // Raw records of chained strings (0: the chain kernels are skipped)
   unsigned int err_string1;     // 1 + string of the candidate behind the error (scanner->last_error_string); 0 = none
   unsigned int n_chain_starts;  // chains present among the Raw records (resolve.cu: one warp each)
+  unsigned int key_overflow;    // one candidate fired more than KEY_SEQ_MAX match callbacks: its records cannot be ordered
 };
 
 struct CandOut
@@ -193,7 +199,7 @@ void launch_ac_scan_walk(const DevRules& R, const ScanView& V, const CandOut& ou
 void launch_ac_scan_filter(
     const DevRules& R, const FilterTables& F, const ScanView& V, const CandOut& out, int64_t lo, int64_t hi,
     int num_sms, cudaStream_t s);
-int build_filter_tables(const void* host_image, int device, FilterTables* out, void** d_storage);
+int build_filter_tables(const void* host_image, size_t image_size, int device, FilterTables* out, void** d_storage);
 
 struct VerifyWs
 {

@@ -95,6 +95,9 @@ static __device__ void match_callback(Ctx& c, int64_t match_pos, int32_t match_l
   if (a.group != YRB_NONE)
     atomicAdd(&c.out.st->n_chain_raw, 1u);
 
+  if (c.seq >= KEY_SEQ_MAX)
+    atomicExch(&c.out.st->key_overflow, 1u);   // fail loudly (api.cu) rather than order records by a saturated key
+
   c.seq++;
 }
 

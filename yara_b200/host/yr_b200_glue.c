@@ -128,8 +128,15 @@ static int get_rules(YR_RULES* rules, rules_entry** out)
   if (e->n_chain_strings > 0)
   {
     e->chain_strings = (uint32_t*) malloc(sizeof(uint32_t) * e->n_chain_strings);
+    if (e->chain_strings == NULL)
+    {
+      /* without this list multi-block chain matches would be resolved without their seeds: fail instead */
+      yrb_rules_release(dev);
+      free(e);
+      return ERROR_INSUFFICIENT_MEMORY;
+    }
     uint32_t k = 0;
-    for (uint32_t i = 0; i < rules->num_strings && e->chain_strings != NULL; i++)
+    for (uint32_t i = 0; i < rules->num_strings; i++)
       if (STRING_IS_CHAIN_PART(&rules->strings_table[i]))
         e->chain_strings[k++] = i;
   }
@@ -412,13 +419,28 @@ void yr_b200_coalesce_stats(uint64_t* batches, uint64_t* scans)
   *scans = __atomic_load_n(&g_co_scans, __ATOMIC_RELAXED);
 }
 
-/* the leader's part: one engine batch over reqs[0..n), all of one YR_RULES and one flag set */
-static void co_run_batch(co_req** reqs, uint32_t n)
+/* What the leader found out about one request.  Results are built here, in leader-local storage, and
+   only PUBLISHED into the waiters' co_req (which live on the waiters' stacks) by co_submit under
+   g_co_lock, state last: a waiter that sees state != 0 may return and pop its co_req at once, so
+   nothing may be written to a request after its state, and nothing outside the lock. */
+typedef struct co_out
+{
+  int state;
+  int rc;
+  yrb_match* recs;
+  size_t n_recs;
+} co_out;
+
+/* the leader's part: one engine batch over reqs[0..n), all of one YR_RULES and one flag set.
+   Reads the requests (immutable while pending), writes only outs[]. */
+static void co_run_batch(co_req* const* reqs, co_out* outs, uint32_t n)
 {
   int rc = ERROR_SUCCESS;
   rules_entry* re = NULL;
   yrb_scanner* dev = NULL;
   yrb_batch_item* items = (yrb_batch_item*) malloc(sizeof(yrb_batch_item) * n);
+
+  memset(outs, 0, sizeof(co_out) * n);
 
   if (items == NULL)
     rc = ERROR_INSUFFICIENT_MEMORY;
@@ -455,22 +477,22 @@ static void co_run_batch(co_req** reqs, uint32_t n)
     {
       for (uint32_t k = 0; k < n; k++)
       {
-        co_req* r = reqs[k];
+        co_out* o = &outs[k];
         if (res.item_state[k] != YRB_ITEM_DONE)
         {
-          r->state = 2;
+          o->state = 2;
           continue;
         }
-        r->n_recs = (size_t) (res.item_first[k + 1] - res.item_first[k]);
-        r->recs = (yrb_match*) malloc(sizeof(yrb_match) * (r->n_recs ? r->n_recs : 1));
-        if (r->recs == NULL)
+        o->n_recs = (size_t) (res.item_first[k + 1] - res.item_first[k]);
+        o->recs = (yrb_match*) malloc(sizeof(yrb_match) * (o->n_recs ? o->n_recs : 1));
+        if (o->recs == NULL)
         {
-          r->state = 3;
-          r->rc = ERROR_INSUFFICIENT_MEMORY;
+          o->rc = ERROR_INSUFFICIENT_MEMORY;
+          o->state = 3;
           continue;
         }
-        memcpy(r->recs, res.matches + res.item_first[k], sizeof(yrb_match) * r->n_recs);
-        r->state = 1;
+        memcpy(o->recs, res.matches + res.item_first[k], sizeof(yrb_match) * o->n_recs);
+        o->state = 1;
       }
     }
     pthread_mutex_lock(&g_lock);
@@ -483,8 +505,11 @@ static void co_run_batch(co_req** reqs, uint32_t n)
   {
     for (uint32_t k = 0; k < n; k++)
     {
-      reqs[k]->state = 3;
-      reqs[k]->rc = rc;
+      free(outs[k].recs);
+      outs[k].recs = NULL;
+      outs[k].n_recs = 0;
+      outs[k].rc = rc;
+      outs[k].state = 3;
     }
   }
   __atomic_fetch_add(&g_co_batches, 1, __ATOMIC_RELAXED);
@@ -495,6 +520,7 @@ static void co_run_batch(co_req** reqs, uint32_t n)
 static int co_submit(co_req* r)
 {
   co_req* mine[1024];
+  co_out* outs = NULL;
 
   pthread_mutex_lock(&g_co_lock);
   r->next = NULL;
@@ -545,14 +571,36 @@ static int co_submit(co_req* r)
     g_co_tail = last;
     pthread_mutex_unlock(&g_co_lock);
 
-    co_run_batch(mine, n);
+    outs = (co_out*) malloc(sizeof(co_out) * n);
+    if (outs != NULL)
+      co_run_batch(mine, outs, n);
 
+    /* publish under the lock, state last; after this line a waiter's co_req may be gone */
     pthread_mutex_lock(&g_co_lock);
+    for (uint32_t k = 0; k < n; k++)
+    {
+      co_req* q = mine[k];
+      if (outs != NULL)
+      {
+        q->rc = outs[k].rc;
+        q->recs = outs[k].recs;
+        q->n_recs = outs[k].n_recs;
+        q->state = outs[k].state;
+      }
+      else
+      {
+        q->rc = ERROR_INSUFFICIENT_MEMORY;
+        q->state = 3;
+      }
+    }
+    free(outs);
+    outs = NULL;
     g_co_leading = 0;
     pthread_cond_broadcast(&g_co_cond);
   }
+  const int st = r->state;
   pthread_mutex_unlock(&g_co_lock);
-  return r->state;
+  return st;
 }
 
 static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out, rules_entry** re_out)
@@ -594,6 +642,12 @@ static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out, rules_entry** re_
     else
     {
       e = (scanner_entry*) calloc(1, sizeof(*e));
+      if (e == NULL)
+      {
+        pool_put(dev, dev_rules);
+        pthread_mutex_unlock(&g_lock);
+        return ERROR_INSUFFICIENT_MEMORY;
+      }
       e->scanner = scanner;
       e->dev = dev;
       e->dev_rules = dev_rules;
