@@ -2,19 +2,35 @@
 """bench.py -- scanned GB/s of the YARA byte-scanning hot path on B200.
 
 Workload (BASELINE.json configs[2]): 20,000 declared hex strings with
-wildcards/jumps (+ nocase/wide text), 16 GiB of seeded random bytes with one
-planted instance per 64 KiB.  A "step" = one pass of the hot path (AC scan ->
-verify -> resolve -> match records back on the host) over the whole block.
+wildcards/jumps (+ nocase/wide text), ONE 16 GiB block of seeded random bytes with
+one planted instance per 64 KiB, instances straddling every shard boundary and
+chained strings whose parts lie in different shards.  A "step" = one pass of the
+hot path (AC scan -> verify -> resolve -> match records back on the host) over
+the whole block.
 
-  value   HBM-resident: the block is already in device memory (yrb_scan_device)
+  value   HBM-resident: the block (N = 1) or every rank's byte-range shard with its
+          read margins (N > 1) is already in device memory.
   e2e     the same block in PINNED HOST memory scanned through the unchanged
           libyara API of the drop-in (yr_rules_scan_mem -> H2D -> kernels -> D2H
-          -> YR_MATCH materialisation), copies inside the timed region
+          -> YR_MATCH materialisation), copies inside the timed region.  For N > 1
+          it is ONE yr_rules_scan_mem call on rank 0 that the drop-in fans out over
+          the N GPUs ($YR_B200_DEVICES -> yrb_multi_scan_host).
 
-N > 1 (torchrun, one process per GPU): byte-range sharding with read margins,
-no data-path collective; rank r owns bytes [r*S, (r+1)*S) of one N*S-byte block
-(weak scaling: S = --size-gib per GPU).  torch.distributed is used only for the
-barrier and the max-over-ranks of the timings.
+N > 1 (torchrun, one process per GPU), default = STRONG scaling of the 16 GiB block
+(BASELINE configs[2] as written): rank r owns bytes [r*S/N, (r+1)*S/N) and reads
+a margin either side; no data-path collective.  Every step each rank scans and
+verifies its shard (yrb_scan_device, defer_resolve), hands its raw records to rank
+0 through host memory (plain D2H + a POSIX shared-memory mailbox: no NCCL, no
+pickle), and rank 0 runs the ONE global resolve (yrb_resolve_raw) -- all inside the
+timed region.  The weak-scaling figure (16 GiB per GPU, same flow) is measured in
+the same run and reported under "weak".  torch.distributed (gloo) is used only for
+start/stop barriers and the max-over-ranks of the timings.
+
+What is timed is also checked (config.parity): windows of the block -- its start,
+its end and every shard boundary -- are scanned by the reference libyara on the
+CPU (oracle/_ref; the oracle restatement if that is absent) and compared bit for
+bit with the GPU scan of the same bytes, and the records the timed whole-block /
+sharded scan returned inside those windows must be exactly those.
 
 `--impl reference` times the reference libyara (oracle/_ref, built from
 /root/reference) on the host cores, all threads, on a bounded sample.
@@ -33,7 +49,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "scanned GB/s (HBM-resident & end-to-end), 20k-string ruleset"
-MARGIN = 8192  # >= YR_RE_SCAN_LIMIT (4096) and 2x the longest literal, plus the 3-byte AC look-back
+INTERIOR = 16384   # a window's records are compared this far away from its edges (longest chained instance < 4 KiB)
 
 
 def peaks():
@@ -92,6 +108,13 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def workload_name(args, S):
+    if args.config == 3 and args.strings == 20000:
+        return ("configs[2]: 20,000 hex strings with wildcards/jumps + nocase/wide text over one %.3g GiB block, "
+                "byte-range sharded with read margins" % (S / 2**30))
+    return "synthetic ruleset shape %d, %d declared strings, one %.3g GiB block" % (args.config, args.strings, S / 2**30)
+
+
 def reference_arm(args):
     """The reference's own CPU implementation of the path, all host threads."""
     rank, _, world = dist_env()
@@ -116,9 +139,9 @@ def reference_arm(args):
     gbs = sample / t / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[2]: 20k hex/wild/jump + nocase/wide strings", "strings_declared": args.strings,
+        "config": {"workload": workload_name(args, int(args.size_gib * 2**30)), "strings_declared": args.strings,
                    "strings_compiled": rules.num_strings, "sample_bytes": sample},
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": ncores, "kind": "reference",
                          "sample": "%d MiB of the same corpus, %d threads x yr_rules_scan_mem over contiguous slices" % (args.ref_sample_mib, ncores)},
@@ -127,21 +150,106 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ corpus on the device
+def make_shard(api, synth, rs, device, block, g0, g1, every, parts, with_tail):
+    """Block bytes [g0, g1) on `device`: counter-based random bytes, one planted instance per cell, the
+    boundary plants of SURVEY.md 8(d) row 3, and the edge plants (offset 0, last byte)."""
+    def clip(pl):   # the part of every plant that lies inside [g0, g1): shards see identical bytes in their overlaps
+        out = []
+        for o, b in pl:
+            a, e = max(o, g0), min(o + len(b), g1)
+            if e > a:
+                out.append((a, b[a - o : e - o]))
+        return out
+
+    dbuf = api.DeviceBuffer(device, g1 - g0)
+    dbuf.fill_random(7, g0)
+    n = dbuf.scatter(clip(synth.plants(rs, g1 - g0, every, 11, start=g0, edge=(g0 == 0))), local_start=g0)
+    n += dbuf.scatter(clip(synth.boundary_plants(rs, block, parts)), local_start=g0)
+    if with_tail and g1 == block and rs.specs:
+        import random
+        rng = random.Random(0x7A11)
+        inst = rs.specs[-1 if rs.specs[-1].kind != "regex" else 0].instance(rng)
+        n += dbuf.scatter([(block - len(inst), inst)], local_start=g0)   # ends at the last byte of the block
+    return dbuf, n
+
+
+# ------------------------------------------------------------------ shared-memory mailbox (N > 1)
+class Mailbox:
+    """Raw records of every rank -> rank 0 through host memory: one file in /dev/shm per rank,
+    header = [seq, n_records, ack] (u64), then the 32-byte records.  No collective, no pickle."""
+
+    HDR = 64
+
+    def __init__(self, tag, rank, world, cap_records):
+        self.rank, self.world, self.cap = rank, world, cap_records
+        self.paths = ["/dev/shm/yrb_bench_%s_%d" % (tag, r) for r in range(world)]
+        nbytes = self.HDR + cap_records * 32
+        with open(self.paths[rank], "wb") as f:   # always fresh: a stale file would carry old sequence numbers
+            f.truncate(nbytes)
+        self.maps = [None] * world
+        self.nbytes = nbytes
+
+    def open_all(self):
+        for r in range(self.world):
+            self.maps[r] = np.memmap(self.paths[r], dtype=np.uint8, mode="r+", shape=(self.nbytes,))
+        self.hdr = [m[: self.HDR].view(np.uint64) for m in self.maps]
+
+    def publish(self, step, raw_bytes_view, n):
+        """rank r > 0: wait until rank 0 has consumed the previous step, then write"""
+        h = self.hdr[self.rank]
+        h0 = self.hdr[0]
+        while int(h0[2]) < step:     # ack of step - 1 (acks count completed steps)
+            pass
+        if n > self.cap:
+            raise RuntimeError("mailbox too small: %d records" % n)
+        if n:
+            self.maps[self.rank][self.HDR : self.HDR + n * 32] = raw_bytes_view
+        h[1] = n
+        h[0] = step + 1
+
+    def collect(self, step):
+        """rank 0: every other rank's records of this step, as a list of uint8 views"""
+        out = []
+        for r in range(1, self.world):
+            h = self.hdr[r]
+            while int(h[0]) < step + 1:
+                pass
+            n = int(h[1])
+            out.append(self.maps[r][self.HDR : self.HDR + n * 32])
+        return out
+
+    def ack(self, step):
+        self.hdr[0][2] = step + 1
+
+    def close(self):
+        self.maps = None
+        try:
+            os.unlink(self.paths[self.rank])
+        except Exception:
+            pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--size-gib", type=float, default=16.0, help="bytes owned per GPU")
+    ap.add_argument("--size-gib", type=float, default=16.0, help="the block (strong scaling) / bytes owned per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--strings", type=int, default=20000)
     ap.add_argument("--config", type=int, default=3, help="synthetic ruleset shape (BASELINE configs): 2, 3 (headline), 4, 5")
     ap.add_argument("--every", type=int, default=65536, help="one planted instance per this many bytes")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 walk, 2 filter")
     ap.add_argument("--ref-sample-mib", type=int, default=2048)
     ap.add_argument("--cpu-sample-mib", type=int, default=2048)
+    ap.add_argument("--window-mib", type=int, default=64, help="size of each parity window")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-weak", action="store_true")
+    ap.add_argument("--corpus", default="random", choices=["random", "zero", "text"], help="background bytes (plants always)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -150,155 +258,279 @@ def main():
     rank, local_rank, world = dist_env()
     dist = None
     if world > 1:
-        import torch
+        # read once per process by the drop-in's glue: large one-block scans fan out over these GPUs (the e2e leg)
+        os.environ["YR_B200_DEVICES"] = ",".join(str(d) for d in range(world))
         import torch.distributed as dist
-
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("gloo")   # harness only: barriers and the max over ranks; nothing on the data path
 
     from yara_b200 import Engine, LibYara, DeviceBuffer, PinnedBuffer, synth
     from yara_b200 import api
 
     device = local_rank
     S = int(args.size_gib * (1 << 30)) & ~4095
-    block = S * world
-    own_lo, own_hi = rank * S, (rank + 1) * S
-    g0, g1 = max(0, own_lo - MARGIN), min(block, own_hi + MARGIN)
-
-    # ---- rules: compiled on the host by the (unchanged) libyara compiler, uploaded once
-    t0 = time.time()
-    ly = LibYara()
-    ly.set_device(device)
-    rs = synth.ruleset(args.config, args.strings)
-    rules = ly.compile(rs.source)
-    image = ly.flatten(rules)
-    hdr = np.frombuffer(image[:64], dtype=np.uint32)
-    eng = Engine(image, device)
-    if args.kernel:
-        eng.set_option(api.OPT_SCAN_KERNEL, args.kernel)
-    t_compile = time.time() - t0
-
-    # ---- corpus, generated on the device: counter-based random bytes + planted instances
-    t0 = time.time()
-    dbuf = DeviceBuffer(device, g1 - g0)
-    dbuf.fill_random(7, g0)
-    pl = synth.plants(rs, g1 - g0, args.every, 11, start=g0, edge=(rank == 0))
-    n_plants = dbuf.scatter(pl, local_start=g0)
-    t_corpus = time.time() - t0
-
-    kw = dict(data_offset=g0, block_size=block, own=(own_lo, own_hi)) if world > 1 else {}
 
     def barrier():
         if dist is not None:
             dist.barrier()
 
-    # ---- HBM-resident
+    # ---- rules: compiled on the host by the (unchanged) libyara compiler once, then loaded from the
+    # compiled-rules file like any yara deployment does (yarac -> yr_rules_load); the prefilter tables come
+    # from the engine's own cache keyed by the rules image
+    setup = {}
+    t0 = time.time()
+    ly = LibYara()
+    ly.set_device(device)
+    rs = synth.ruleset(args.config, args.strings)
+    cache_dir = os.environ.get("YR_B200_CACHE_DIR") or os.path.join(ROOT, "build", "cache")
+    os.makedirs(cache_dir, exist_ok=True)
+    os.environ.setdefault("YR_B200_CACHE_DIR", cache_dir)
+    yarc = os.path.join(cache_dir, "bench_cfg%d_n%d.yarc" % (args.config, args.strings))
+    if os.path.exists(yarc):
+        rules = ly.load(yarc)
+        setup["rules"] = "yr_rules_load(%s)" % os.path.basename(yarc)
+    else:
+        rules = ly.compile(rs.source)
+        setup["rules"] = "compiled"
+        if rank == 0:
+            try:
+                ly.save(rules, yarc + ".tmp%d" % os.getpid())
+                os.replace(yarc + ".tmp%d" % os.getpid(), yarc)
+            except Exception:
+                pass
+    setup["rules_s"] = round(time.time() - t0, 3)
+    t0 = time.time()
+    image = ly.flatten(rules)
+    hdr = np.frombuffer(image[:64], dtype=np.uint32)
+    eng = Engine(image, device)
+    if args.kernel:
+        eng.set_option(api.OPT_SCAN_KERNEL, args.kernel)
+    setup["flatten_upload_s"] = round(time.time() - t0, 3)
+    setup["filter_tables_from"] = api.filter_cache_stats()
+
+    from yara_b200 import shard as shard_mod
+    MARGIN = shard_mod.required_margin(image)
+    PARTS = 8   # boundary plants sit at the eighths of the block whatever N is
+
+    def geometry(scaling):
+        """(block, own_lo, own_hi, g0, g1) of this rank"""
+        if scaling == "weak":
+            block = S * world
+            lo, hi = rank * S, (rank + 1) * S
+        else:
+            block = S
+            per = ((block + world - 1) // world + 4095) & ~4095
+            lo, hi = min(block, rank * per), min(block, (rank + 1) * per)
+        return block, lo, hi, max(0, lo - MARGIN), min(block, hi + MARGIN)
+
+    def background(dbuf, g0):
+        if args.corpus == "random":
+            return
+        n = dbuf.size
+        if args.corpus == "zero":
+            chunk = np.zeros(min(n, 1 << 26), dtype=np.uint8)
+        else:
+            words = (b"the quick brown fox jumps over the lazy dog while kernel32.dll loads CreateFileW and "
+                     b"http://example.com/index.php?id=1234 returns <html><body>Hello, World!</body></html>\r\n")
+            chunk = np.frombuffer((words * ((1 << 26) // len(words) + 1))[: min(n, 1 << 26)], dtype=np.uint8)
+        for o in range(0, n, len(chunk)):
+            dbuf.write(o, chunk[: min(len(chunk), n - o)])
+
+    def build_corpus(scaling):
+        block, lo, hi, g0, g1 = geometry(scaling)
+        t0 = time.time()
+        if args.corpus == "random":
+            dbuf, n_pl = make_shard(api, synth, rs, device, block, g0, g1, args.every, PARTS, True)
+        else:
+            dbuf = DeviceBuffer(device, g1 - g0)
+            background(dbuf, g0)
+            pl = synth.plants(rs, g1 - g0, args.every, 11, start=g0, edge=(g0 == 0))
+            n_pl = dbuf.scatter(pl, local_start=g0)
+        return dbuf, n_pl, time.time() - t0
+
+    # ---- one sharded step (N > 1): local scan + verify, records to rank 0, ONE global resolve there
+    mbox = None
+    if world > 1:
+        tag = os.environ.get("MASTER_PORT", "0")
+        mbox = Mailbox(tag, rank, world, cap_records=max(1 << 16, int(S // 2048)))
+        barrier()
+        mbox.open_all()
+        barrier()
+
+    step_no = [0]
+
+    def step_sharded(dbuf, geo):
+        block, lo, hi, g0, g1 = geo
+        st = step_no[0]
+        step_no[0] += 1
+        r = eng.scan_device(dbuf, copy=False, data_offset=g0, block_size=block, own=(lo, hi), defer=True)
+        assert r.rc == 0 and r.error == 0, (r.rc, r.error)
+        raw = eng.shard_raw()
+        if rank != 0:
+            mbox.publish(st, raw.view(np.uint8).reshape(-1), len(raw))
+            return r, None, 0.0
+        t0 = time.perf_counter()
+        parts = [raw.view(np.uint8).reshape(-1)] + mbox.collect(st)
+        allraw = np.concatenate(parts).view(api.RAW_DTYPE)
+        res = eng.resolve_raw(allraw)
+        mbox.ack(st)
+        assert res.rc == 0 and res.error == 0, (res.rc, res.error)
+        return r, res, (time.perf_counter() - t0) * 1e3
+
+    def timed_run(dbuf, geo):
+        """W warm-up steps, K timed steps; returns dict of timings (this rank) and the last result"""
+        last = None
+        if world == 1:
+            for _ in range(args.warmup):
+                last = eng.scan_device(dbuf, copy=False)
+                assert last.rc == 0 and last.error == 0, (last.rc, last.error)
+            barrier()
+            ev_ms, ms_scan, ms_verify, ms_resolve, ms_kernel, launches = [], [], [], [], [], 0
+            w0 = time.perf_counter()
+            for it in range(args.steps):
+                last = eng.scan_device(dbuf, copy=(it == args.steps - 1))
+                assert last.rc == 0 and last.error == 0, (last.rc, last.error)
+                st = last.stats
+                ev_ms.append(st["ms_total"]); ms_scan.append(st["ms_scan"]); ms_verify.append(st["ms_verify"])
+                ms_resolve.append(st["ms_resolve"]); ms_kernel.append(st["ms_kernel"]); launches += st["kernel_launches"]
+            wall = time.perf_counter() - w0
+            barrier()
+            return dict(seconds=float(np.sum(ev_ms)) / 1e3, wall=wall, scan=ms_scan, verify=ms_verify, resolve=ms_resolve,
+                        kernel=ms_kernel, launches=launches, local=last, final=last, gather_resolve=[])
+        for _ in range(args.warmup):
+            step_sharded(dbuf, geo)
+        barrier()
+        ms_scan, ms_verify, ms_kernel, ms_gr, launches = [], [], [], [], 0
+        final = None
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            r, res, gr = step_sharded(dbuf, geo)
+            st = r.stats
+            ms_scan.append(st["ms_scan"]); ms_verify.append(st["ms_verify"]); ms_kernel.append(st["ms_kernel"])
+            launches += st["kernel_launches"] + (res.stats["kernel_launches"] if res is not None else 0)
+            ms_gr.append(gr)
+            last, final = r, (res if res is not None else final)
+        wall = time.perf_counter() - w0   # rank 0: ends when the last global resolve has returned its records
+        barrier()
+        return dict(seconds=wall, wall=wall, scan=ms_scan, verify=ms_verify, resolve=[], kernel=ms_kernel, launches=launches,
+                    local=last, final=final, gather_resolve=ms_gr)
+
     clocks = ClockSampler(device)  # nvidia-smi needs ~0.1 s to start: it runs from the warm-up to the end of the e2e loop
-    for _ in range(args.warmup):
-        r = eng.scan_device(dbuf, copy=False, **kw)
-        assert r.rc == 0 and r.error == 0, (r.rc, r.error)
-    barrier()
-    ms_total, ms_scan, ms_verify, ms_resolve, launches, wall0 = [], [], [], [], 0, time.time()
-    for _ in range(args.steps):
-        r = eng.scan_device(dbuf, copy=False, **kw)
-        assert r.rc == 0 and r.error == 0, (r.rc, r.error)
-        ms_total.append(r.stats["ms_total"])
-        ms_scan.append(r.stats["ms_scan"])
-        ms_verify.append(r.stats["ms_verify"])
-        ms_resolve.append(r.stats["ms_resolve"])
-        launches += r.stats["kernel_launches"]
-    wall = time.time() - wall0
-    barrier()
-    n_matches, n_cand, scan_kernel = r.n_matches, r.stats["n_candidates"], r.stats["scan_kernel"]
-    dev_s = float(np.sum(ms_total)) / 1e3
+
+    # ---- the headline run
+    geo = geometry(args.scaling)
+    dbuf, n_plants, t_corpus = build_corpus(args.scaling)
+    setup["corpus_s"] = round(t_corpus, 2)
+    T = timed_run(dbuf, geo)
+
+    # ---- parity of what was just timed
+    parity = None
+    if not args.no_parity and args.corpus == "random":
+        parity = check_parity(args, api, synth, rs, ly, rules, image, eng, device, geo, world, rank, T["final"], MARGIN, PARTS, barrier)
+
+    # ---- the other scaling mode, same flow (N > 1 only)
+    other = None
+    if world > 1 and not args.no_weak:
+        other_mode = "weak" if args.scaling == "strong" else "strong"
+        dbuf.free()
+        geo2 = geometry(other_mode)
+        dbuf2, _, _ = build_corpus(other_mode)
+        T2 = timed_run(dbuf2, geo2)
+        other = (other_mode, geo2, T2)
+        dbuf2.free()
+        dbuf = None
 
     # ---- end to end through the drop-in libyara API, from pinned host memory
     e2e = None
     if not args.no_e2e:
-        hbuf = PinnedBuffer(S)
-        dbuf.read_into(own_lo - g0, S, hbuf.ptr)
-        rc, nrules = ly.scan_mem(rules, hbuf.ptr, S)  # warm-up (also sizes the scanner's device buffers)
-        assert rc == 0, rc
-        barrier()
-        w0 = time.time()
-        for _ in range(args.steps):
-            rc, nrules = ly.scan_mem(rules, hbuf.ptr, S)
-            assert rc == 0, rc
-        e2e_s = time.time() - w0
-        barrier()
-        e2e = {"seconds": e2e_s, "rules_matching": nrules}
-        # what PCIe gives a bare copy of the same pinned block (the bytes are already what the device holds)
-        try:
-            dbuf.write(own_lo - g0, hbuf.array[: min(S, 1 << 30)])
-            w0 = time.time()
-            dbuf.write(own_lo - g0, hbuf.array)
-            e2e["h2d_gbs"] = float(S) / (time.time() - w0) / 1e9
-        except Exception:
-            pass
+        e2e = run_e2e(args, api, synth, rs, ly, rules, device, geo, world, rank, dbuf, barrier, PinnedBuffer, DeviceBuffer, PARTS)
 
     clk = clocks.stop()
 
     # ---- max over ranks
-    if dist is not None:
+    def maxr(x):
+        if dist is None:
+            return x
         import torch
-
-        t = torch.tensor([dev_s, wall, e2e["seconds"] if e2e else 0.0], device="cuda", dtype=torch.float64)
+        t = torch.tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, wall, e2e_max = [float(x) for x in t.tolist()]
-        if e2e:
-            e2e["seconds"] = e2e_max
+        return float(t[0])
 
+    secs = maxr(T["seconds"])
+    wall = maxr(T["wall"])
+    scan_ms = maxr(float(np.mean(T["scan"])))
+    verify_ms = maxr(float(np.mean(T["verify"])))
+    kernel_ms = maxr(float(np.mean(T["kernel"])))
+    other_secs = maxr(other[2]["seconds"]) if other else None
+    parity_ok = maxr(0.0 if (parity is None or parity.get("ok")) else 1.0) == 0.0
+
+    if mbox is not None:
+        barrier()
+        mbox.close()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
     peak, peak_src = peaks()
-    traffic = None
-    try:  # dram__bytes_read+write of the dominant kernel, from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    block, lo, hi, g0, g1 = geo
+    total_bytes = float(block) * args.steps
+    value = total_bytes / secs / 1e9
+    scan_kernel = T["local"].stats["scan_kernel"]
+    own_bytes = hi - lo
+    kernel_gbs = (float(own_bytes) / (kernel_ms / 1e3) / 1e9) if kernel_ms > 0 else float(own_bytes) / (scan_ms / 1e3) / 1e9
+
+    traffic, traffic_src = None, None
+    try:  # dram__bytes_read+write of the dominant kernel per algorithmic byte, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         if scan_kernel == 2:
-            traffic = float(tj["dram_bytes_per_algorithmic_byte"]) * S
+            traffic = float(tj["dram_bytes_per_algorithmic_byte"]) * own_bytes
+            traffic_src = "profile-derived, not measured in this run: %s" % tj.get("source", "profiles/r02_traffic.json")
     except Exception:
         pass
-    total_bytes = float(S) * world * args.steps
-    value = total_bytes / dev_s / 1e9
-    scan_gbs = float(S) / (float(np.mean(ms_scan)) / 1e3) / 1e9
 
+    final = T["final"]
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": {
-            "workload": ("configs[2]: 20,000 hex strings with wildcards/jumps + nocase/wide text over %.3g GiB per GPU, "
-                         "byte-range sharded with %d-byte read margins" % (S / 2**30, MARGIN)) if args.config == 3 and args.strings == 20000
-                        else "synthetic ruleset shape %d, %d declared strings, %.3g GiB per GPU" % (args.config, args.strings, S / 2**30),
+            "workload": workload_name(args, block),
             "strings_declared": args.strings, "strings_compiled": int(hdr[6]), "ac_slots": int(hdr[4]),
-            "bytes_per_gpu": S, "plants_per_gpu": n_plants, "matches_rank0": int(n_matches), "candidates_rank0": int(n_cand),
-            "scan_kernel": {1: "walk", 2: "filter"}.get(scan_kernel, "?"),
-            "l2_policy": "input (%.3g GiB) is larger than L2 (126 MB); no flush needed" % (S / 2**30),
-            "timing": "CUDA events on the scanner stream per step (sum over steps), max over ranks; wall-clock %.4f s" % wall,
-            "setup_s": {"compile_upload": round(t_compile, 2), "corpus": round(t_corpus, 2)},
-            "ms_breakdown": {"scan": round(float(np.mean(ms_scan)), 3), "verify": round(float(np.mean(ms_verify)), 3),
-                             "resolve_and_d2h": round(float(np.mean(ms_resolve)), 3)},
+            "block_bytes": block, "bytes_owned_rank0": own_bytes, "margin_bytes": MARGIN, "plants_rank0": n_plants,
+            "matches": int(final.n_matches) if final is not None else None,
+            "candidates_rank0": int(T["local"].stats["n_candidates"]),
+            "scan_kernel": {1: "walk", 2: "filter"}.get(scan_kernel, "?"), "corpus": args.corpus,
+            "l2_policy": "each rank's input (%.3g GiB) is larger than L2 (126 MB); no flush needed" % ((g1 - g0) / 2**30),
+            "timing": ("CUDA events on the scanner stream per step (sum over steps); wall-clock of the same loop %.4f s" % wall) if world == 1 else
+                      ("wall-clock of the K-step loop between barriers, max over ranks (rank 0's ends when the last global "
+                       "resolve has returned its records); per-phase figures are CUDA events, max over ranks"),
+            "setup": setup,
+            "ms_breakdown": {"scan": round(scan_ms, 3), "verify": round(verify_ms, 3),
+                             "resolve_and_d2h": round(float(np.mean(T["resolve"])), 3) if T["resolve"] else None,
+                             "filter_kernel": round(kernel_ms, 3),
+                             "gather_and_global_resolve": round(float(np.mean(T["gather_resolve"])), 3) if T["gather_resolve"] else None},
+            "parity_checked": bool(parity is not None and parity_ok), "parity": parity,
         },
         "clocks": clk,
-        "gpu_launches": int(launches),
+        "gpu_launches": int(T["launches"]),
         "roofline": {
-            "bound": "hbm", "achieved": scan_gbs, "peak": peak, "unit": "GB/s", "frac": scan_gbs / peak, "traffic": traffic,
-            "kernel": "AC scan kernel (%s)" % {1: "ac_walk_kernel", 2: "ac_filter_kernel"}.get(scan_kernel, "?"),
-            "algorithmic_bytes_per_launch": S, "peak_source": peak_src,
+            "bound": "hbm", "achieved": kernel_gbs, "peak": peak, "unit": "GB/s", "frac": kernel_gbs / peak, "traffic": traffic,
+            "traffic_source": traffic_src,
+            "kernel": "AC scan kernel (%s), one launch over rank 0's %.3g GiB" % (
+                {1: "ac_walk_kernel", 2: "ac_filter_tma_kernel"}.get(scan_kernel, "?"), own_bytes / 2**30),
+            "algorithmic_bytes_per_launch": own_bytes, "peak_source": peak_src,
+            "timed_with": "CUDA events around the kernel launch on the scanner's stream (yrb_scan_stats.ms_kernel), mean over the timed steps",
+            "whole_step_frac": value / world / peak,
         },
     }
+    if other:
+        mode, geo2, T2 = other
+        line[mode] = {"value": float(geo2[0]) * args.steps / other_secs / 1e9, "unit": "GB/s", "block_bytes": geo2[0],
+                      "ms_per_step": other_secs / args.steps * 1e3, "scaling": mode,
+                      "note": "same sharded flow (local scan + verify, records to rank 0, one global resolve) inside the timed region"}
     if e2e:
-        line["e2e"] = {
-            "value": float(S) * world * args.steps / e2e["seconds"] / 1e9, "unit": "GB/s",
-            "h2d_bytes_per_step": S, "d2h_bytes_per_step": int(n_matches) * 24 + 256,
-            "api": "yr_rules_scan_mem (drop-in libyara_b200.so), pinned host block", "rules_matching": e2e["rules_matching"],
-        }
-        if "h2d_gbs" in e2e and world == 1:
-            line["e2e"]["h2d_copy_gbs"] = e2e["h2d_gbs"]   # bare cudaMemcpy of the same pinned block, same run
-            line["e2e"]["frac_of_h2d_copy"] = line["e2e"]["value"] / e2e["h2d_gbs"]
+        e2e["d2h_bytes_per_step"] = (int(final.n_matches) * 24 + 256) if final is not None else None
+        line["e2e"] = e2e
 
     if not args.no_cpu and world == 1:
         try:
@@ -306,13 +538,13 @@ def main():
             import yrh
 
             ncores = os.cpu_count() or 1
-            sample = min(S, int(args.cpu_sample_mib) << 20)
-            host = hbuf.array[:sample] if e2e else dbuf.read(own_lo - g0, sample)
+            sample = min(block, int(args.cpu_sample_mib) << 20)
+            host = dbuf.read(0, sample)
             rr = yrh.ref().compile(rs.source)
-            secs, rc = rr.scan_mt(host, ncores)
+            secs_c, rc = rr.scan_mt(host, ncores)
             secs1, rc1 = rr.scan_mt(host[: sample // 8], 1)
             line["cpu_baseline"] = {
-                "value": sample / secs / 1e9, "unit": "GB/s", "cores": ncores, "kind": "reference",
+                "value": sample / secs_c / 1e9, "unit": "GB/s", "cores": ncores, "kind": "reference",
                 "sample": "first %d MiB of the same corpus; %d threads x yr_rules_scan_mem (reference libyara 4.2.1, gcc -O2) "
                           "over contiguous slices; 1 thread: %.4f GB/s" % (sample >> 20, ncores, sample / 8 / secs1 / 1e9),
             }
@@ -322,6 +554,123 @@ def main():
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------- parity of the timed scan
+def check_parity(args, api, synth, rs, ly, rules, image, eng, device, geo, world, rank, final, MARGIN, PARTS, barrier):
+    """Rank 0: windows at the start of the block, at its end and across every shard boundary.  Each is
+    regenerated on this rank's GPU, scanned there as a block of its own and compared with the reference
+    libyara's scan of the same bytes (all fields); then the records of the TIMED scan (whole block at N = 1,
+    sharded flow at N > 1) that lie inside the window's interior must be exactly the window scan's."""
+    if rank != 0:
+        return {"ok": True}
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import yrh
+
+    block = geo[0]
+    W = min(int(args.window_mib) << 20, block)
+    per = ((block + PARTS - 1) // PARTS + 4095) & ~4095
+    starts = [0, max(0, block - W)]
+    if world > 1:
+        wper = ((block + world - 1) // world + 4095) & ~4095
+        starts += [max(0, min(block - W, k * wper - W // 2)) for k in range(1, world)]
+    else:
+        starts += [max(0, min(block - W, (PARTS // 2) * per - W // 2))]
+    starts = sorted(set(s & ~4095 for s in starts))
+
+    if os.path.exists(yrh.ref_path()):
+        checker, ref_rules = "reference libyara 4.2.1 (oracle/_ref)", yrh.ref().compile(rs.source)
+    else:
+        checker, ref_rules = "oracle restatement (oracle/yr_oracle.c)", None
+    drop = yrh.b200().compile(rs.source) if ref_rules is not None else None
+
+    fm = final.matches
+    out = {"checker": checker, "windows": [], "ok": True, "whole_block_matches": int(final.n_matches)}
+    t0 = time.time()
+    for w0 in starts:
+        w1 = min(block, w0 + W)
+        wbuf, _ = make_shard(api, synth, rs, device, block, w0, w1, args.every, PARTS, True)
+        host = wbuf.read(0, w1 - w0)
+        g = eng.scan_device(wbuf, copy=True)
+        assert g.rc == 0 and g.error == 0
+        gm = g.matches
+        if ref_rules is not None:
+            a = ref_rules.scan(host, cap=1 << 20)
+            b = drop.scan(host, cap=1 << 20)      # through the drop-in: every YR_MATCH field incl. the data bytes
+            same = (a.rc == b.rc and a.matches.tobytes() == b.matches.tobytes() and a.rule_bits.tobytes() == b.rule_bits.tobytes())
+            n_ref = len(a.matches)
+            # and the engine's own records for the window are the reference's (string, offset, length, xor key)
+            ka = sorted(zip(a.matches["string_idx"].tolist(), a.matches["offset"].tolist(), a.matches["match_length"].tolist(), a.matches["xor_key"].tolist()))
+            kg = sorted(zip(gm["string_idx"].tolist(), gm["offset"].tolist(), gm["match_length"].tolist(), gm["xor_key"].tolist()))
+            same = same and ka == kg
+        else:
+            o = yrh.oracle_scan(image, host)
+            om = yrh.matches_from_flat(o.matches, host)
+            n_ref = len(om)
+            same = len(om) == len(gm) and all((om[f] == gm[f]).all() for f in ("offset", "string_idx", "match_length", "xor_key"))
+        # the timed result inside the window's interior
+        lo_i = w0 + (INTERIOR if w0 > 0 else 0)
+        hi_i = w1 - (INTERIOR if w1 < block else 0)
+        sel = (fm["offset"] >= lo_i) & (fm["offset"] + fm["match_length"] <= hi_i)
+        t = fm[sel]
+        selw = (gm["offset"] + w0 >= lo_i) & (gm["offset"] + w0 + gm["match_length"] <= hi_i)
+        wloc = gm[selw]
+        key_t = sorted(zip(t["string_idx"].tolist(), t["offset"].tolist(), t["match_length"].tolist(), t["xor_key"].tolist()))
+        key_w = sorted(zip(wloc["string_idx"].tolist(), (wloc["offset"] + w0).tolist(), wloc["match_length"].tolist(), wloc["xor_key"].tolist()))
+        inside = key_t == key_w
+        out["windows"].append({"bytes": [w0, w1], "reference_matches": int(n_ref), "window_equals_reference": bool(same),
+                               "timed_scan_records_in_interior": len(key_t), "timed_scan_equals_window": bool(inside)})
+        out["ok"] = out["ok"] and bool(same) and bool(inside)
+        wbuf.free()
+    out["seconds"] = round(time.time() - t0, 1)
+    return out
+
+
+# ------------------------------------------------------------------------- end to end
+def run_e2e(args, api, synth, rs, ly, rules, device, geo, world, rank, dbuf, barrier, PinnedBuffer, DeviceBuffer, PARTS):
+    """yr_rules_scan_mem of the drop-in on the whole block in pinned host memory.  N > 1: ONE call on rank 0
+    that the drop-in fans out over the N GPUs; the other ranks wait."""
+    block = geo[0] if args.scaling == "strong" else int(args.size_gib * (1 << 30)) & ~4095
+    out = None
+    if rank == 0:
+        hbuf = PinnedBuffer(block)
+        # the block's bytes, produced on this rank's GPU piece by piece (identical to what the shards hold)
+        piece = 1 << 30
+        if world == 1 and dbuf is not None and dbuf.size == block:
+            dbuf.read_into(0, block, hbuf.ptr)
+        else:
+            for o in range(0, block, piece):
+                e = min(block, o + piece)
+                pb, _ = make_shard(api, synth, rs, device, block, o, e, args.every, PARTS, True)
+                pb.read_into(0, e - o, hbuf.ptr + o)
+                pb.free()
+        rc, nrules = ly.scan_mem(rules, hbuf.ptr, block)  # warm-up (also sizes the scanners' device buffers)
+        assert rc == 0, rc
+        rc, nrules = ly.scan_mem(rules, hbuf.ptr, block)
+        assert rc == 0, rc
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            rc, nrules = ly.scan_mem(rules, hbuf.ptr, block)
+            assert rc == 0, rc
+        secs = time.perf_counter() - w0
+        out = {"value": float(block) * args.steps / secs / 1e9, "unit": "GB/s", "h2d_bytes_per_step": block,
+               "d2h_bytes_per_step": None, "rules_matching": nrules, "seconds": secs,
+               "api": "yr_rules_scan_mem (drop-in libyara_b200.so), pinned host block" +
+                      ("" if world == 1 else "; one call on rank 0 fanned out over %d GPUs (YR_B200_DEVICES -> yrb_multi_scan_host)" % world)}
+        if world == 1:
+            # what PCIe gives a bare copy of the same pinned block
+            try:
+                tmp = dbuf if (dbuf is not None and dbuf.size == block) else DeviceBuffer(device, block)
+                tmp.write(0, hbuf.array[: min(block, 1 << 30)])
+                w0 = time.perf_counter()
+                tmp.write(0, hbuf.array)
+                out["h2d_copy_gbs"] = float(block) / (time.perf_counter() - w0) / 1e9
+                out["frac_of_h2d_copy"] = out["value"] / out["h2d_copy_gbs"]
+            except Exception:
+                pass
+        hbuf.free()
+    barrier()
+    return out
 
 
 if __name__ == "__main__":

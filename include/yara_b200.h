@@ -134,6 +134,8 @@ typedef struct yrb_scan_stats
   float ms_verify;
   float ms_resolve;
   float ms_total;
+  float ms_kernel;         /* the last filter-kernel launch alone (0 when the walk kernel ran): the roofline figure */
+  uint32_t reserved;
 } yrb_scan_stats;
 
 typedef struct yrb_scan_result

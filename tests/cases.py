@@ -71,4 +71,12 @@ CASES = [
     (R("$a = /abcd(x|y|z)+.{0,90}q/"), b"abcd" + b"xyz" * 40 + b"q" + b"x" * 30 + b"q"),
     # backward-mode position lists keep duplicates (re.c:2323-2333): 52k live positions, far beyond the 4096-byte window
     (R("$a = { 61 [0-40] ?? [0-40] ?? [0-30] 62 63 64 65 }"), b"x" * 50 + b"a" * 200 + b"bcde" + b"y" * 20),
+    # scan.c:1021-1023 for CHAINED strings: in fast mode, once a tail has completed the first chain, matches[head] is
+    # non-empty and later candidates of the head string are not verified -- so the one that would exhaust the fiber
+    # pool (ERROR_TOO_MANY_RE_FIBERS) never runs: rc 46 normally, rc 0 with one match in fast mode.  The other way
+    # round (the exploding candidate first) both modes fail.
+    (R("$s = /wxyz(a1(.??)+?c)??mn.{0,300}?QWERTY/", "$s"),
+     b"...wxyzmn...." + b"-" * 50 + b"QWERTY" + b"." * 40 + b"wxyza1" + b"q" * 60 + b"QWERTY"),
+    (R("$s = /wxyz(a1(.??)+?c)??mn.{0,300}?QWERTY/", "$s"),
+     b"wxyza1" + b"q" * 60 + b"...wxyzmn...." + b"-" * 50 + b"QWERTY" + b"." * 40),
 ]

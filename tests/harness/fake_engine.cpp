@@ -166,6 +166,45 @@ int yrb_scan_host(yrb_scanner* s, const uint8_t* data, size_t size, const yrb_sc
 }
 
 /* the host half of yrb_scan_batch (api.cu), restated over the CPU replay of its device half */
+/* yrb_multi_*: the stand-in has one "device"; a sharded scan must equal a single-device scan by
+   definition (include/yara_b200.h), so it IS one here.  What this exercises on the CPU is the
+   glue's routing of large single-block scans ($YR_B200_DEVICES), its locking and its release path. */
+struct yrb_multi
+{
+  yrb_rules* rules;
+  yrb_scanner* scanner;
+  int n;
+};
+static unsigned g_multi_scans = 0;
+unsigned yrb_test_multi_scans(void) { return g_multi_scans; }
+
+int yrb_multi_create(const void* image, size_t image_size, const int* devices, int n_devices, yrb_multi** out)
+{
+  if (!devices || n_devices < 1) return YRB_ERROR_BAD_ARGUMENT;
+  yrb_multi* m = new yrb_multi;
+  m->n = n_devices;
+  int rc = yrb_rules_create(image, image_size, 0, &m->rules);
+  if (rc != YRB_SUCCESS) { delete m; return rc; }
+  yrb_scanner_create(m->rules, &m->scanner);
+  *out = m;
+  return YRB_SUCCESS;
+}
+
+void yrb_multi_destroy(yrb_multi* m)
+{
+  if (!m) return;
+  yrb_scanner_destroy(m->scanner);
+  yrb_rules_release(m->rules);
+  delete m;
+}
+
+int yrb_multi_scan_host(yrb_multi* m, const uint8_t* data, size_t size, const yrb_scan_params* p, yrb_scan_result* out)
+{
+  if (p->n_seeds > 0) return YRB_ERROR_BAD_ARGUMENT;
+  g_multi_scans++;
+  return yrb_scan_host(m->scanner, data, size, p, out);
+}
+
 int yrb_scan_batch(
     yrb_scanner* s, const yrb_batch_item* items, uint32_t n_items, int scan_flags, int batch_flags, yrb_batch_result* out)
 {

@@ -260,6 +260,7 @@ static int scan_common(
       L.mhead = lists.data() + 3 * (size_t) ns; L.mtail = lists.data() + 4 * (size_t) ns; L.mcnt = lists.data() + 5 * (size_t) ns;
       L.uvhead = lists.data() + 6 * (size_t) ns; L.prior = lists.data() + 7 * (size_t) ns;
       L.uvn = uvn.data();
+      L.first_conf = (scan_flags & YRB_SCAN_FAST_MODE) ? str_min_key.data() : nullptr;
       launch_per_thread(R.num_strings, 256, [&] { chain_init_kernel(L, R.num_strings); });
       st.n_chain_starts = 0;
       launch_per_thread(n, 256, [&] { chain_gather_kernel(raw.data(), ix1.data(), k1.data(), n, sraw.data(), starts.data(), &st); });

@@ -209,3 +209,42 @@ def test_concurrent_scans_through_the_glue():
         assert got == want
     secs, rc = rb.scan_mt(files[0], 8)
     assert rc == 0
+
+
+MULTI_CODE = r"""
+import ctypes as C, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import yrh
+from yara_b200 import synth
+rs = synth.ruleset(3, 1200)
+R, B = yrh.ref(), yrh.b200cpu()
+rr, rb = R.compile(rs.source), B.compile(rs.source)
+eng = C.CDLL(yrh.b200cpu_path().replace("libyrh_b200cpu.so", "libyrb200cpu.so"))
+big = synth.corpus(rs, (1 << 21) + 4321, 2048)
+small = synth.corpus(rs, 60000, 2048, seed=3)
+before = eng.yrb_test_multi_scans()
+assert rb.scan(big, cap=1 << 18).key() == rr.scan(big, cap=1 << 18).key()            # >= 1 MiB, one block: sharded path
+mid = eng.yrb_test_multi_scans()
+assert rb.scan(small).key() == rr.scan(small).key()                                  # below the threshold: one device
+assert rb.scan_blocks(big, 1 << 20, 4096, cap=1 << 18).key() == rr.scan_blocks(big, 1 << 20, 4096, cap=1 << 18).key()
+after = eng.yrb_test_multi_scans()
+from concurrent.futures import ThreadPoolExecutor
+with ThreadPoolExecutor(4) as ex:                                                    # the sharded engine is shared: one at a time
+    got = list(ex.map(lambda k: rb.scan(big, cap=1 << 18).key(), range(8)))
+assert all(g == rr.scan(big, cap=1 << 18).key() for g in got)
+print("MULTI_OK", mid - before, after - mid)
+"""
+
+
+def test_large_single_block_scans_go_to_the_sharded_engine():
+    """$YR_B200_DEVICES lists several GPUs: a block of at least $YR_B200_MULTI_MIN_MIB that is the only block of
+    its scan goes through yrb_multi_scan_host; smaller blocks stay on one device.  Blocks of a
+    multi-block scan carry chain state (seeds) from block to block; from the second block on -- as soon as
+    there is something to carry -- they are not sharded.  Results stay those of the reference."""
+    env = dict(os.environ, YR_B200_DEVICES="0,1,2,3", YR_B200_MULTI_MIN_MIB="1")
+    p = subprocess.run([sys.executable, "-c", MULTI_CODE % (ROOT, os.path.join(ROOT, "tests"))], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert p.returncode == 0 and "MULTI_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("MULTI_OK")][0].split()
+    assert int(line[1]) == 1          # the big one-block scan was sharded

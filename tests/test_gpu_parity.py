@@ -183,3 +183,165 @@ def test_repeat_any_recursion_as_deep_as_the_fiber_pool():
     for data in (b"a1dx", b"zza1dxabcyy0 tail", b"nothing here"):
         assert_same(rr.scan(data), rb.scan(data))
     assert rb.scan(b"a1dx").rc == 46
+
+
+# ---- round 2: the full-size rulesets of BASELINE configs[3] and [4], and the sharded engine
+
+def test_config4_100k_string_ruleset():
+    """BASELINE configs[3]: the 100,000-string mixed ruleset (transition table > shared memory, B3 too dense
+    for the prefilter -> whatever kernel the engine picks), a single buffer and a 40-item file batch."""
+    rs = synth.ruleset(4, 100000)
+    rr, rb = both(rs.source)
+    assert rr.num_strings >= 100000
+    data = synth.corpus(rs, 1 << 23, 2048)
+    a = rr.scan(data, cap=1 << 20)
+    b = rb.scan(data, cap=1 << 20)
+    assert len(a.matches) > 2000
+    assert_same(a, b)
+    files = [synth.corpus(rs, 65536 + 37 * 1024 * k, 4096, seed=200 + k, plant_seed=k) for k in range(40)]
+    want = [rr.scan(f) for f in files]
+    with rb.batch(files) as bt:
+        assert bt.rc == 0
+        for k, f in enumerate(files):
+            assert_same(want[k], rb.scan(f))
+    for k, f in enumerate(files[:8]):      # and one by one, without the batch
+        assert_same(want[k], rb.scan(f))
+
+
+def test_config5_5000_regexes_64mib():
+    """BASELINE configs[4] at its declared size: 5,000 strings (5/6 regex, 1/6 xor/base64 text), 64 MiB with one
+    generated instance per 16 KiB so that the fiber VM is really exercised."""
+    rs = synth.ruleset(5, 5000)
+    rr, rb = both(rs.source)
+    data = synth.corpus(rs, 1 << 26, 16384)
+    a = rr.scan(data, cap=1 << 20)
+    b = rb.scan(data, cap=1 << 20)
+    assert len(a.matches) > 3000
+    assert_same(a, b)
+    assert_same(rr.scan(data[: 1 << 22], flags=1, cap=1 << 20), rb.scan(data[: 1 << 22], flags=1, cap=1 << 20))
+
+
+def _canon(m):
+    """records string-major, ascending offset: the lists of chained strings' heads are appended by one warp
+    per chain, in whatever order the warps finish, so only the order INSIDE a string's list is defined"""
+    return np.sort(m, order=["string_idx", "offset"]).tobytes()
+
+
+def _lists_in_order(m):
+    """... and inside every string's list the offsets ascend as handed back"""
+    last = {}
+    for s_, o_ in zip(m["string_idx"].tolist(), m["offset"].tolist()):
+        if s_ in last and last[s_] >= o_:
+            return False
+        last[s_] = o_
+    return True
+
+
+def _corpus_with_boundary_plants(rs, size, every, parts):
+    buf = synth.corpus(rs, size, every)
+    for off, inst in synth.boundary_plants(rs, size, parts):
+        buf[off : off + len(inst)] = np.frombuffer(inst, dtype=np.uint8)
+    return buf
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_engine_equals_single_device(shards):
+    """yrb_multi_scan_host (one block over several GPUs) == yrb_scan_host on one device ==
+    the reference, with instances straddling every shard boundary and chained strings whose parts lie in
+    different shards.  Uses as many GPUs as are visible; with fewer than `shards` some get several shards."""
+    from yara_b200.api import Engine, MultiEngine
+    rs = synth.ruleset(3, 6000)
+    rr, rb = both(rs.source)
+    size = (48 << 20) + 12288 * shards
+    data = _corpus_with_boundary_plants(rs, size, 4096, shards)
+    image = rb.flatten()
+    ndev = Engine.device_count()
+    multi = MultiEngine(image, [g % ndev for g in range(shards)])
+    single = Engine(image, 0)
+    try:
+        per = ((size + shards - 1) // shards + 4095) & ~4095
+        assert [p[2] for p in multi.plan(size)] == [min(size, g * per) for g in range(shards)]
+        m = multi.scan_host(data)
+        s = single.scan_host(data)
+        assert m.rc == 0 and s.rc == 0 and m.error == 0
+        assert _canon(m.matches) == _canon(s.matches) and len(m.matches) > 10000
+        assert _lists_in_order(m.matches) and _lists_in_order(s.matches)
+        # matches that straddle a boundary are there, and the reference agrees with all of it
+        a = rr.scan(data, cap=1 << 20)
+        got = sorted(zip(m.matches["string_idx"].tolist(), m.matches["offset"].tolist(), m.matches["match_length"].tolist()))
+        want = sorted(zip(a.matches["string_idx"].tolist(), a.matches["offset"].tolist(), a.matches["match_length"].tolist()))
+        assert got == want
+        for k in range(1, shards):
+            assert sum(1 for (_, o, l) in want if o < k * per < o + l) >= 2, "no match straddles boundary %d" % k
+        # fast mode and a tiny block (not worth sharding: the first device alone) go the same way
+        assert _canon(multi.scan_host(data[: 1 << 20], flags=1).matches) == _canon(single.scan_host(data[: 1 << 20], flags=1).matches)
+        assert _canon(multi.scan_host(data[:100]).matches) == _canon(single.scan_host(data[:100]).matches)
+        assert len(multi.scan_host(b"").matches) == 0
+    finally:
+        multi.close()
+        single.close()
+
+
+def test_sharded_engine_verifier_error_and_cap():
+    """what stays global in a sharded scan: the earliest failing candidate (ERROR_TOO_MANY_RE_FIBERS) and the
+    1,000,000-match cap with its TOO_MANY callback"""
+    from yara_b200.api import Engine, MultiEngine
+    rb = yrh.b200().compile('rule t { strings: $a = "aa" $b = /a1dx((.?)+yy0)/ condition: any of them }')
+    image = rb.flatten()
+    ndev = Engine.device_count()
+    multi, single = MultiEngine(image, [g % ndev for g in range(4)]), Engine(image, 0)
+    try:
+        data = np.full(6 << 20, ord("a"), dtype=np.uint8)
+        m, s = multi.scan_host(data), single.scan_host(data)
+        assert m.rc == 0 and s.rc == 0 and m.too_many == s.too_many == [0]
+        assert _canon(m.matches) == _canon(s.matches) and len(m.matches) == 1_000_000
+        data2 = np.frombuffer(b"." * (5 << 20) + b"zza1dx" + b"." * (1 << 20), dtype=np.uint8)
+        m, s = multi.scan_host(data2), single.scan_host(data2)
+        assert (m.rc, m.error, m.error_string) == (s.rc, s.error, s.error_string) and s.error == 46
+    finally:
+        multi.close()
+        single.close()
+
+
+CACHE_CODE = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+from yara_b200 import synth
+from yara_b200.api import Engine, LibYara, filter_cache_stats
+import time
+rs = synth.ruleset(3, 4000)
+ly = LibYara()
+yarc = sys.argv[1]
+import os
+if os.path.exists(yarc):
+    rules = ly.load(yarc)
+else:
+    rules = ly.compile(rs.source); ly.save(rules, yarc)
+image = ly.flatten(rules)
+t0 = time.time(); eng = Engine(image, 0); t1 = time.time() - t0
+eng2 = Engine(image, 0)
+data = synth.corpus(rs, 1 << 22, 2048)
+r = eng.scan_host(data)
+assert r.rc == 0 and r.error == 0 and r.stats["scan_kernel"] == 2
+import hashlib
+print("CACHE", filter_cache_stats(), hashlib.sha1(r.matches.tobytes()).hexdigest(), len(r.matches), round(t1, 3))
+"""
+
+
+def test_filter_tables_come_from_the_disk_cache_in_a_second_process(tmp_path):
+    """rules saved with yr_rules_save and loaded with yr_rules_load (arena.c:543/627) in a new
+    process find their prefilter tables in the engine's cache keyed by the rules image -- no rebuild -- and the
+    scan results are the same."""
+    import subprocess, sys
+    env = dict(os.environ, YR_B200_CACHE_DIR=str(tmp_path / "cache"))
+    outs = []
+    for _ in range(2):
+        p = subprocess.run([sys.executable, "-c", CACHE_CODE % (yrh.ROOT, os.path.join(yrh.ROOT, "tests")), str(tmp_path / "r.yarc")],
+                           env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0 and "CACHE" in p.stdout, (p.stdout + p.stderr)[-3000:]
+        outs.append([l for l in p.stdout.splitlines() if l.startswith("CACHE")][0])
+    first, second = outs
+    assert "'built': 1" in first and "'registry': 1" in first          # built once, the second Engine took it from the registry
+    assert "'built': 0" in second and "'disk': 1" in second            # new process, rules from the .yarc: tables from disk
+    assert first.split()[-3:-1] == second.split()[-3:-1]               # same matches

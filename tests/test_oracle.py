@@ -38,8 +38,10 @@ def test_known_answer_cases(idx):
     rule, data = CASES[idx]
     r = yrh.ref().compile(rule)
     ref = r.scan(data)
-    assert ref.rc == 0
     o = yrh.oracle_scan(r.flatten(), data)
+    if ref.rc != 0:     # cases that pin an error code (a failed scan reports no matches)
+        assert o.error == ref.rc
+        return
     compare(ref, o, data, r)
 
 

@@ -49,6 +49,8 @@ class ScanStats(C.Structure):
         ("ms_verify", C.c_float),
         ("ms_resolve", C.c_float),
         ("ms_total", C.c_float),
+        ("ms_kernel", C.c_float),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -162,6 +164,16 @@ class _Lib:
             L.yrb_dev_scatter.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
             L.yrb_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
             L.yrb_host_free.argtypes = [C.c_void_p]
+            L.yrb_multi_create.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+            L.yrb_multi_destroy.argtypes = [C.c_void_p]
+            L.yrb_multi_device_count.argtypes = [C.c_void_p]
+            L.yrb_multi_margin.argtypes = [C.c_void_p]
+            L.yrb_multi_margin.restype = C.c_uint64
+            L.yrb_multi_plan.argtypes = [C.c_void_p, C.c_uint64] + [C.POINTER(C.c_uint64)] * 4
+            L.yrb_multi_scan_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(ScanParams), C.POINTER(ScanResultC)]
+            L.yrb_multi_scan_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)] + [C.POINTER(C.c_uint64)] * 4 + [
+                C.c_uint64, C.POINTER(ScanParams), C.POINTER(ScanResultC)]
+            L.yrb_filter_cache_stats.argtypes = [C.POINTER(C.c_uint)] * 3
             cls._lib = L
         return cls._lib
 
@@ -336,6 +348,74 @@ class Engine:
             pass
 
 
+class MultiEngine:
+    """ONE block over several GPUs from one process (yrb_multi_*): a rules replica and a
+    scanner per device, byte-range shards with read margins, one global resolve on the first device."""
+
+    def __init__(self, image: bytes, devices):
+        self.L = _Lib.get()
+        self.devices = list(devices)
+        self._img = np.frombuffer(image, dtype=np.uint8)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        m = C.c_void_p()
+        _check(self.L.yrb_multi_create(self._img.ctypes.data_as(C.c_void_p), len(image), arr, len(self.devices), C.byref(m)),
+               "yrb_multi_create")
+        self.m = m
+
+    @property
+    def margin(self):
+        return int(self.L.yrb_multi_margin(self.m))
+
+    def plan(self, block_size):
+        """[(g0, g1, own0, own1)] per device"""
+        n = len(self.devices)
+        a = [(C.c_uint64 * n)() for _ in range(4)]
+        _check(self.L.yrb_multi_plan(self.m, block_size, *a), "yrb_multi_plan")
+        return [tuple(int(a[j][g]) for j in range(4)) for g in range(n)]
+
+    def _params(self, base=0, flags=0, too_many_action=0):
+        p = ScanParams()
+        p.base, p.scan_flags, p.too_many_action = base, flags, too_many_action
+        return p
+
+    def scan_host(self, data, copy=True, **kw):
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        p, r = self._params(**kw), ScanResultC()
+        rc = self.L.yrb_multi_scan_host(self.m, a.ctypes.data_as(C.c_void_p), a.size, C.byref(p), C.byref(r))
+        return ScanResult(rc, r, copy)
+
+    def scan_host_ptr(self, ptr, size, copy=True, **kw):
+        p, r = self._params(**kw), ScanResultC()
+        rc = self.L.yrb_multi_scan_host(self.m, C.c_void_p(ptr), size, C.byref(p), C.byref(r))
+        return ScanResult(rc, r, copy)
+
+    def scan_device(self, dbufs, plan, block_size, copy=True, **kw):
+        """dbufs[g]: DeviceBuffer on device g holding block bytes [g0, g1) of plan[g]"""
+        n = len(self.devices)
+        ptrs = (C.c_void_p * n)(*[d.ptr for d in dbufs])
+        cols = [(C.c_uint64 * n)(*[pl[j] for pl in plan]) for j in range(4)]
+        p, r = self._params(**kw), ScanResultC()
+        rc = self.L.yrb_multi_scan_device(self.m, ptrs, cols[0], cols[1], cols[2], cols[3], block_size, C.byref(p), C.byref(r))
+        return ScanResult(rc, r, copy)
+
+    def close(self):
+        if self.m:
+            self.L.yrb_multi_destroy(self.m)
+            self.m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def filter_cache_stats():
+    a, b, c = C.c_uint(), C.c_uint(), C.c_uint()
+    _Lib.get().yrb_filter_cache_stats(C.byref(a), C.byref(b), C.byref(c))
+    return {"registry": a.value, "disk": b.value, "built": c.value}
+
+
 # -------------------------------------------------------------------- libyara
 YR_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p)
 CALLBACK_MSG_RULE_MATCHING = 1
@@ -357,6 +437,8 @@ class LibYara:
         L.yr_compiler_get_rules.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.yr_rules_destroy.argtypes = [C.c_void_p]
         L.yr_rules_scan_mem.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, YR_CALLBACK, C.c_void_p, C.c_int]
+        L.yr_rules_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.yr_rules_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.yr_b200_rules_flatten.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.yr_b200_image_free.argtypes = [C.c_void_p]
         if hasattr(L, "yr_b200_set_device"):
@@ -381,6 +463,16 @@ class LibYara:
 
     def destroy(self, rules):
         self.lib.yr_rules_destroy(rules)
+
+    def save(self, rules, path):
+        """yr_rules_save (rules.c:433): the compiled-rules file `yarac` writes"""
+        _check(self.lib.yr_rules_save(rules, path.encode()), "yr_rules_save")
+
+    def load(self, path):
+        """yr_rules_load (rules.c:372-431, arena.c:543)"""
+        rules = C.c_void_p()
+        _check(self.lib.yr_rules_load(path.encode(), C.byref(rules)), "yr_rules_load")
+        return rules
 
     def flatten(self, rules) -> bytes:
         img, size = C.c_void_p(), C.c_size_t()

@@ -1017,7 +1017,7 @@ int build_filter_tables(const void* image, size_t image_size, int device, Filter
 // a window would reach before byte 0) and the tail go to the walk kernel.
 void launch_ac_scan_filter(
     const DevRules& R, const FilterTables& F, const ScanView& V, const CandOut& out, int64_t lo, int64_t hi,
-    int num_sms, cudaStream_t s)
+    int num_sms, cudaStream_t s, cudaEvent_t before, cudaEvent_t after)
 {
   if (hi <= lo)
     return;
@@ -1048,6 +1048,7 @@ void launch_ac_scan_filter(
 
   const unsigned grid = (unsigned) (ntiles < num_sms ? ntiles : num_sms);
   const size_t smem = ft_smem_bytes(fv);
+  if (before) cudaEventRecord(before, s);
   switch (F.variant)
   {
   case 0: ac_filter_kernel<1024, 4, 18><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
@@ -1057,6 +1058,7 @@ void launch_ac_scan_filter(
   case 4: ac_filter_tma_kernel<24, 18><<<grid, 768, smem, s>>>(R, fd, V, out, flo, fhi); break;
   default: ac_filter_kernel<1024, 4, 18><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   }
+  if (after) cudaEventRecord(after, s);
 
   launch_ac_scan_walk(R, V, out, fhi, hi, s);
 }

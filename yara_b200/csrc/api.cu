@@ -105,7 +105,8 @@ struct yrb_scanner
   yrb_rules* rules;
   int device;
   cudaStream_t stream, copy_stream;
-  cudaEvent_t ev[6];
+  cudaEvent_t ev[8];   // 0-3 phases, 5 copy fork, 6-7 around the last filter-kernel launch
+  bool kernel_timed = false;
   std::vector<cudaEvent_t> slice_ev;
 
   int opt_kernel = YRB_KERNEL_AUTO;
@@ -292,7 +293,7 @@ static int scanner_init(yrb_scanner* s)
 {
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 6; i++) CK(cudaEventCreate(&s->ev[i]));
+  for (int i = 0; i < 8; i++) CK(cudaEventCreate(&s->ev[i]));
   CK(cudaMalloc((void**) &s->d_status, sizeof(ScanStatus)));
   CK(cudaHostAlloc((void**) &s->h_status, sizeof(ScanStatus), cudaHostAllocDefault));
   memset(s->h_status, 0, sizeof(ScanStatus));
@@ -343,7 +344,7 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   if (s->d_status) cudaFree(s->d_status);
   if (s->h_status) cudaFreeHost(s->h_status);
   for (auto e : s->slice_ev) cudaEventDestroy(e);
-  for (int i = 0; i < 6; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  for (int i = 0; i < 8; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   if (s->stream) cudaStreamDestroy(s->stream);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   cudaGetLastError();
@@ -415,7 +416,10 @@ static int pick_kernel(const yrb_scanner* s)
 static void launch_scan_slice(yrb_scanner* s, int kernel, const ScanView& V, const CandOut& co, int64_t lo, int64_t hi)
 {
   if (kernel == YRB_KERNEL_FILTER)
-    launch_ac_scan_filter(s->rules->R, s->rules->F, V, co, lo, hi, s->rules->num_sms, s->stream);
+  {
+    launch_ac_scan_filter(s->rules->R, s->rules->F, V, co, lo, hi, s->rules->num_sms, s->stream, s->ev[6], s->ev[7]);
+    s->kernel_timed = true;
+  }
   else
     launch_ac_scan_walk(s->rules->R, V, co, lo, hi, s->stream);
 }
@@ -605,6 +609,7 @@ static int scan_impl(
   memset(res, 0, sizeof(*res));
   res->error_string = YRB_NONE;
   unsigned launches = 0;
+  s->kernel_timed = false;
 
   ScanView V;
   memset(&V, 0, sizeof(V));
@@ -993,6 +998,8 @@ static int scan_impl(
   cudaEventElapsedTime(&res->stats.ms_resolve, s->ev[2], s->ev[3]);
   cudaEventElapsedTime(&res->stats.ms_total, s->ev[0], s->ev[3]);
   res->stats.ms_h2d = h_data ? res->stats.ms_scan : 0.f;
+  if (s->kernel_timed && cudaEventElapsedTime(&res->stats.ms_kernel, s->ev[6], s->ev[7]) != cudaSuccess)
+  { cudaGetLastError(); res->stats.ms_kernel = 0.f; }
   return rc;
 }
 
@@ -1273,10 +1280,9 @@ extern "C" void yrb_multi_destroy(yrb_multi* m)
 
 extern "C" int yrb_multi_create(const void* image, size_t image_size, const int* devices, int n_devices, yrb_multi** out)
 {
+  // (a device may be listed more than once: it then gets several shards, each with its own scanner --
+  // no use in production, but it lets one GPU exercise the whole sharded flow)
   if (!image || !out || !devices || n_devices < 1 || n_devices > 64) return YRB_ERROR_BAD_ARGUMENT;
-  for (int a = 0; a < n_devices; a++)
-    for (int b = a + 1; b < n_devices; b++)
-      if (devices[a] == devices[b]) return YRB_ERROR_BAD_ARGUMENT;
 
   yrb_multi* m = new (std::nothrow) yrb_multi();
   if (!m) return YRB_ERROR_INSUFFICIENT_MEMORY;
@@ -1299,7 +1305,7 @@ extern "C" int yrb_multi_create(const void* image, size_t image_size, const int*
   for (int g = 1; g < n_devices; g++)
   {
     int can = 0;
-    if (cudaDeviceCanAccessPeer(&can, devices[0], devices[g]) == cudaSuccess && can)
+    if (devices[g] != devices[0] && cudaDeviceCanAccessPeer(&can, devices[0], devices[g]) == cudaSuccess && can)
       cudaDeviceEnablePeerAccess(devices[g], 0);
     cudaGetLastError();
   }
@@ -1372,6 +1378,7 @@ static int multi_run(yrb_multi* m, const yrb_scan_params* params, yrb_scan_resul
     if (w->job.res.stats.ms_scan > res->stats.ms_scan) res->stats.ms_scan = w->job.res.stats.ms_scan;
     if (w->job.res.stats.ms_verify > res->stats.ms_verify) res->stats.ms_verify = w->job.res.stats.ms_verify;
     if (w->job.res.stats.ms_h2d > res->stats.ms_h2d) res->stats.ms_h2d = w->job.res.stats.ms_h2d;
+    if (w->job.res.stats.ms_kernel > res->stats.ms_kernel) res->stats.ms_kernel = w->job.res.stats.ms_kernel;
   }
   res->stats.scan_kernel = m->w[0]->job.res.stats.scan_kernel;
   if (total >= (1ULL << 31)) return YRB_ERROR_INSUFFICIENT_MEMORY;

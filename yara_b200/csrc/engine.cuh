@@ -198,7 +198,7 @@ void launch_ac_event0(const DevRules& R, const ScanView& V, const CandOut& out, 
 void launch_ac_scan_walk(const DevRules& R, const ScanView& V, const CandOut& out, int64_t lo, int64_t hi, cudaStream_t s);
 void launch_ac_scan_filter(
     const DevRules& R, const FilterTables& F, const ScanView& V, const CandOut& out, int64_t lo, int64_t hi,
-    int num_sms, cudaStream_t s);
+    int num_sms, cudaStream_t s, cudaEvent_t before = nullptr, cudaEvent_t after = nullptr);
 int build_filter_tables(const void* host_image, size_t image_size, int device, FilterTables* out, void** d_storage);
 
 struct VerifyWs

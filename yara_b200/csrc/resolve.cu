@@ -81,6 +81,7 @@ void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches)
     L.uvhead = w.s_lists + 6 * (size_t) w.R.num_strings;
     L.prior = w.s_lists + 7 * (size_t) w.R.num_strings;
     L.uvn = w.c_uvn;
+    L.first_conf = (w.scan_flags & YRB_SCAN_FAST_MODE) ? w.str_min_key : nullptr;
     chain_init_kernel<<<GRID(w.R.num_strings), 0, s>>>(L, w.R.num_strings);
     cudaMemsetAsync(&w.st->n_chain_starts, 0, sizeof(unsigned int), s);
     chain_gather_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.sraw, w.c_scratch_u32, w.st);

@@ -24,7 +24,11 @@ __global__ void fastmode_min_kernel(const Raw* raw, uint32_t n, DevRules R, unsi
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const Raw r = raw[j];
-  if (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH)
+  // plain strings: matches[string] becomes non-empty at the string's first matching candidate.  Chained
+  // strings: only a chain's HEAD ever gets entries in matches[], and it gets them when a tail completes a
+  // chain -- chain_resolve_kernel notes that moment (ChainLists::first_conf); a callback of a chain part is
+  // not a match of anything yet.
+  if ((R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) && r.group == YRB_NONE)
     atomicMin(&str_min_key[r.string_idx], (unsigned long long) (r.key >> KEY_SEQ_BITS));
 }
 
@@ -157,6 +161,10 @@ struct ChainLists
   int32_t* mhead; // per string: matches[s] (only chain heads are used)
   int32_t* mtail;
   int32_t* mcnt;
+  // FAST_MODE only (else nullptr): per string, the candidate (key >> KEY_SEQ_BITS) at which matches[string]
+  // became non-empty -- the threshold of the scan.c:1021-1023 guard, which error_select_kernel applies to
+  // failing candidates.  The chain kernel fills in the entries of chain heads.
+  unsigned long long* first_conf = nullptr;
   int32_t* uvn;    // per record: next in its string's not-yet-visited list / in the ready list
   int32_t* uvhead; // per string
   int32_t* prior;  // per string: matches[s] was already non-empty before this block
@@ -508,6 +516,12 @@ chain_resolve_kernel(
   c.steps[0] = c.steps[1] = c.steps[2] = 0;
 
   const uint32_t head_string = sraw[j0].group;
+  bool conf_noted = false;              // lane 0: first_conf[head_string] is final
+  if (lane == 0 && L.first_conf != nullptr && L.prior[head_string])
+  {
+    L.first_conf[head_string] = 0;      // matches[head] was non-empty before this block: no candidate of the head is verified
+    conf_noted = true;
+  }
   uint32_t j = j0;                      // uniform across the warp
   uint64_t prev_key = ~0ULL;            // lane 0's replay state from here on
   uint32_t disabled_string = YRB_NONE;  // strings_temp_disabled after a TOO_MANY (at most one tracked per chain)
@@ -833,6 +847,13 @@ chain_resolve_kernel(
             disabled_string = r.string_idx;
             if (n_seg > 0) item_dirty[cur_item] = 1;   // the callback protocol needs the per-item path
           }
+          if (!conf_noted && L.first_conf != nullptr && L.mcnt[head_string] > 0)
+          {
+            // this callback completed the first chain: from the next candidate on the head string is no
+            // longer verified in fast mode -- neither its matches (skip_cand above) nor its errors count
+            L.first_conf[head_string] = (unsigned long long) (r.key >> KEY_SEQ_BITS);
+            conf_noted = true;
+          }
         }
         if (flags_next) break;
       }
@@ -928,8 +949,10 @@ __global__ void error_select_kernel(
   const unsigned long long cand = e >> KEY_SEQ_BITS;
 
   // scan.c:1021-1023: later candidates of a SINGLE_MATCH string that already matched are not verified
+  // (for a chain's head string the threshold is the candidate that completed its first chain; the other
+  // parts of a chain never have matches[] entries and keep ~0)
   if (str_min_key != nullptr && (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[s].flags & YRB_SF_SINGLE_MATCH) &&
-      R.S[s].chain_head == YRB_NONE && str_min_key[s] < cand)
+      str_min_key[s] < cand)
     return;
   // scan.c:1018: neither are candidates of a string disabled by the 1M cap
   if (str_cut_key != nullptr && str_cut_key[s] != ~0ULL && (str_cut_key[s] >> KEY_SEQ_BITS) < cand)

@@ -34,6 +34,8 @@ typedef struct rules_entry
   YR_RULES* rules;
   yrb_rules* dev;
   int device;
+  yrb_multi* multi;            /* all configured GPUs ($YR_B200_DEVICES), created on the first large block */
+  pthread_mutex_t multi_lock;  /* one sharded scan (and its materialisation) at a time */
   uint32_t* chain_strings; /* idx of every STRING_FLAGS_CHAIN_PART string */
   uint32_t n_chain_strings;
   struct rules_entry* next;
@@ -78,6 +80,55 @@ static int current_device(void)
   return e ? atoi(e) : 0;
 }
 
+/* ---- several GPUs for ONE block: $YR_B200_DEVICES = "0,1,2,3" or "all".  A block of
+   at least $YR_B200_MULTI_MIN_MIB (default 256) MiB that is the only block of its scan is cut into
+   byte-range shards, one per device (yrb_multi_scan_host); everything else stays on one device. */
+static int g_multi_n = -1;
+static int g_multi_dev[64];
+
+static int multi_devices(const int** devs)
+{
+  if (g_multi_n < 0)
+  {
+    int n = 0;
+    const char* e = getenv("YR_B200_DEVICES");
+    if (e != NULL && strcmp(e, "all") == 0)
+    {
+      n = yrb_device_count();
+      if (n > 64) n = 64;
+      for (int i = 0; i < n; i++) g_multi_dev[i] = i;
+    }
+    else if (e != NULL)
+    {
+      while (*e != 0 && n < 64)
+      {
+        char* end = NULL;
+        long v = strtol(e, &end, 10);
+        if (end == e) break;
+        int dup = 0;
+        for (int i = 0; i < n; i++) dup |= g_multi_dev[i] == (int) v;
+        if (!dup && v >= 0) g_multi_dev[n++] = (int) v;
+        e = (*end == ',') ? end + 1 : end;
+      }
+    }
+    g_multi_n = n;
+  }
+  *devs = g_multi_dev;
+  return g_multi_n;
+}
+
+static size_t multi_min_bytes(void)
+{
+  static size_t v = 0;
+  if (v == 0)
+  {
+    const char* e = getenv("YR_B200_MULTI_MIN_MIB");
+    long mib = e ? atol(e) : 256;
+    v = (size_t) (mib < 1 ? 1 : mib) << 20;
+  }
+  return v;
+}
+
 static int fail_loudly(const char* what, int rc)
 {
   fprintf(stderr, "yara_b200: %s failed (code %d); the B200 scan path has no CPU fallback\n", what, rc);
@@ -120,6 +171,7 @@ static int get_rules(YR_RULES* rules, rules_entry** out)
   e->rules = rules;
   e->dev = dev;
   e->device = device;
+  pthread_mutex_init(&e->multi_lock, NULL);
 
   for (uint32_t i = 0; i < rules->num_strings; i++)
     if (STRING_IS_CHAIN_PART(&rules->strings_table[i]))
@@ -145,6 +197,31 @@ static int get_rules(YR_RULES* rules, rules_entry** out)
   g_rules = e;
   *out = e;
   return ERROR_SUCCESS;
+}
+
+/* the sharded engine of this YR_RULES over all configured devices, created on first use */
+static int get_multi(rules_entry* re, yrb_multi** out)
+{
+  int rc = ERROR_SUCCESS;
+  pthread_mutex_lock(&g_lock);
+  if (re->multi == NULL)
+  {
+    const int* devs = NULL;
+    const int n = multi_devices(&devs);
+    void* image = NULL;
+    size_t image_size = 0;
+    rc = yr_b200_rules_flatten(re->rules, &image, &image_size);
+    if (rc == ERROR_SUCCESS)
+    {
+      int r2 = yrb_multi_create(image, image_size, devs, n, &re->multi);
+      yr_b200_image_free(image);
+      if (r2 != YRB_SUCCESS)
+        rc = fail_loudly("rules upload to $YR_B200_DEVICES (yrb_multi_create)", r2);
+    }
+  }
+  *out = re->multi;
+  pthread_mutex_unlock(&g_lock);
+  return rc;
 }
 
 /* ---- pool of idle device scanners; call with g_lock held */
@@ -706,6 +783,9 @@ void yr_b200_rules_release(YR_RULES* rules)
           i++;
         }
       }
+      if (e->multi != NULL)
+        yrb_multi_destroy(e->multi);
+      pthread_mutex_destroy(&e->multi_lock);
       yrb_rules_release(e->dev);
       free(e->chain_strings);
       free(e);
@@ -1019,17 +1099,39 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
   if (timing) clock_gettime(CLOCK_MONOTONIC, &t0);
 
   yrb_scan_result res;
-  rc = yrb_scan_host(dev, block_data, block->size, &params, &res);
+  const int* multi_devs = NULL;
+  rules_entry* locked = NULL;   /* holds re->multi_lock until the records have been materialised */
+  if (n_seeds == 0 && multi_devices(&multi_devs) > 1 && block->size >= multi_min_bytes())
+  {
+    yrb_multi* multi = NULL;
+    rc = get_multi(re, &multi);
+    if (rc != ERROR_SUCCESS)
+    {
+      free(seeds);
+      free(seed_nodes);
+      return rc;
+    }
+    pthread_mutex_lock(&re->multi_lock);
+    locked = re;
+    rc = yrb_multi_scan_host(multi, block_data, block->size, &params, &res);
+  }
+  else
+  {
+    rc = yrb_scan_host(dev, block_data, block->size, &params, &res);
+  }
   if (timing) clock_gettime(CLOCK_MONOTONIC, &t1);
   free(seeds);
+#define YR_B200_UNLOCK_MULTI() do { if (locked != NULL) { pthread_mutex_unlock(&locked->multi_lock); locked = NULL; } } while (0)
   if (rc != YRB_SUCCESS)
   {
+    YR_B200_UNLOCK_MULTI();
     free(seed_nodes);
     return rc < 1000 ? rc : fail_loudly("yrb_scan_host", rc);
   }
 
   if (res.error != 0)
   {
+    YR_B200_UNLOCK_MULTI();
     free(seed_nodes);
     if (res.error_string != YRB_NONE)
       scanner->last_error_string = &scanner->rules->strings_table[res.error_string];
@@ -1073,7 +1175,10 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
 
   free(seed_nodes);
   if (rc != ERROR_SUCCESS)
+  {
+    YR_B200_UNLOCK_MULTI();
     return rc;
+  }
 
   /* strings that hit YR_MAX_STRING_MATCHES inside this block, in firing order */
   for (uint32_t i = 0; i < res.n_too_many; i++)
@@ -1083,8 +1188,12 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
       continue;
     rc = too_many_protocol(scanner, string);
     if (rc != ERROR_SUCCESS)
+    {
+      YR_B200_UNLOCK_MULTI();
       return rc;
+    }
   }
+  YR_B200_UNLOCK_MULTI();
 
   if (timing)
   {

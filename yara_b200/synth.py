@@ -148,7 +148,9 @@ def hex_wild(rng, allow_chain=True) -> Spec:
                 out += bytes(r.randrange(256) for _ in range(r.randint(t[1], t[2])))
         return bytes(out)
 
-    return Spec("{ %s }" % " ".join(parts), make, "hexwild")
+    sp = Spec("{ %s }" % " ".join(parts), make, "hexwild")
+    sp.toks = toks
+    return sp
 
 
 def regex(rng) -> Spec:
@@ -264,6 +266,56 @@ def plants(rs: Ruleset, size: int, every: int, seed: int = 11, start: int = 0, e
     if edge and start == 0 and rs.specs:
         rng = random.Random(seed ^ 0x5EED)
         out.append((0, rs.specs[0].instance(rng)))          # starts at offset 0
+    return out
+
+
+def _chained_instance(sp: Spec, rng, min_gap=0):
+    """An instance of a hex string with a big jump ([a-b], b >= 250: the compiler splits it into a chain,
+    re.c:452-512) whose first big jump is at least min_gap bytes long; returns the bytes and the offset of
+    the middle of that jump."""
+    out = bytearray()
+    cut = None
+    for t in sp.toks:
+        if t[0] == "b":
+            out.append(t[1])
+        elif t[0] == "any":
+            out.append(rng.randrange(256))
+        elif t[0] == "hi":
+            out.append((t[1] << 4) | rng.randrange(16))
+        elif t[0] == "lo":
+            out.append((rng.randrange(16) << 4) | t[1])
+        else:
+            n = rng.randint(t[1], t[2])
+            if cut is None and t[2] >= 250:
+                n = min(max(n, min_gap), t[2])
+                cut = len(out) + n // 2
+            out += bytes(rng.randrange(256) for _ in range(n))
+    return bytes(out), cut
+
+
+def boundary_plants(rs: Ruleset, block_size: int, parts: int = 8, seed: int = 23):
+    """an instance straddling EVERY shard boundary, and chained strings whose parts
+    lie in different shards.  Boundaries are those of yrb_multi_plan / shard.plan for `parts` shards (which
+    include those for every divisor of `parts`): multiples of ceil(block / parts) rounded up to 4096.  At
+    each boundary b: a chained instance placed so that b falls into the middle of its big jump (head part
+    in one shard, tail part in the next), and -- written after it, into the jump's filler bytes -- an
+    instance of an ordinary string cut by b at a random byte.  Deterministic, and independent of how many
+    shards actually scan the block.  Apply AFTER plants(): these overwrite whatever the cells put there."""
+    out = []
+    per = ((block_size + parts - 1) // parts + 4095) & ~4095
+    chained = [sp for sp in rs.specs if getattr(sp, "toks", None) and any(t[0] == "jump" and t[2] >= 250 for t in sp.toks)]
+    plain = [sp for sp in rs.specs if sp.kind != "regex" and sp not in chained] or rs.specs
+    for k in range(1, parts):
+        b = k * per
+        if b + 8192 >= block_size:
+            continue
+        rng = random.Random((seed << 32) ^ k)
+        inst = plain[rng.randrange(len(plain))].instance(rng)
+        if chained:
+            cinst, cut = _chained_instance(chained[rng.randrange(len(chained))], rng, min_gap=len(inst) + 16)
+            if cut is not None and b - cut >= 0:
+                out.append((b - cut, cinst))
+        out.append((b - rng.randint(1, len(inst) - 1), inst))
     return out
 
 
