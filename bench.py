@@ -19,9 +19,10 @@ the whole block.
 N > 1 (torchrun, one process per GPU), default = STRONG scaling of the 16 GiB block
 (BASELINE configs[2] as written): rank r owns bytes [r*S/N, (r+1)*S/N) and reads
 a margin either side; no data-path collective.  Every step each rank scans and
-verifies its shard (yrb_scan_device, defer_resolve), hands its raw records to rank
-0 through host memory (plain D2H + a POSIX shared-memory mailbox: no NCCL, no
-pickle), and rank 0 runs the ONE global resolve (yrb_resolve_raw) -- all inside the
+verifies its shard (yrb_scan_device, defer_resolve) and leaves its raw records in
+an export buffer on its GPU; rank 0 pulls them with peer copies (CUDA IPC; only the
+record COUNT crosses the host, through a 24-byte shared-memory mailbox: no NCCL, no
+pickle) and runs the ONE global resolve (yrb_resolve_raw_device) -- all inside the
 timed region.  The weak-scaling figure (16 GiB per GPU, same flow) is measured in
 the same run and reported under "weak".  torch.distributed (gloo) is used only for
 start/stop barriers and the max-over-ranks of the timings.
@@ -176,47 +177,47 @@ def make_shard(api, synth, rs, device, block, g0, g1, every, parts, with_tail):
 
 # ------------------------------------------------------------------ shared-memory mailbox (N > 1)
 class Mailbox:
-    """Raw records of every rank -> rank 0 through host memory: one file in /dev/shm per rank,
-    header = [seq, n_records, ack] (u64), then the 32-byte records.  No collective, no pickle."""
+    """What crosses the host between the ranks of a sharded scan: 24 bytes per rank and step.  One small
+    file in /dev/shm per rank: u64 [seq, n_records, ack] + the 64-byte CUDA IPC handle of the rank's export
+    buffer (written once).  The records themselves go device to device (yrb_shard_export_* /
+    yrb_resolve_raw_device).  No collective, no pickle."""
 
-    HDR = 64
+    SIZE = 192
 
-    def __init__(self, tag, rank, world, cap_records):
-        self.rank, self.world, self.cap = rank, world, cap_records
+    def __init__(self, tag, rank, world):
+        self.rank, self.world = rank, world
         self.paths = ["/dev/shm/yrb_bench_%s_%d" % (tag, r) for r in range(world)]
-        nbytes = self.HDR + cap_records * 32
         with open(self.paths[rank], "wb") as f:   # always fresh: a stale file would carry old sequence numbers
-            f.truncate(nbytes)
+            f.truncate(self.SIZE)
         self.maps = [None] * world
-        self.nbytes = nbytes
 
     def open_all(self):
         for r in range(self.world):
-            self.maps[r] = np.memmap(self.paths[r], dtype=np.uint8, mode="r+", shape=(self.nbytes,))
-        self.hdr = [m[: self.HDR].view(np.uint64) for m in self.maps]
+            self.maps[r] = np.memmap(self.paths[r], dtype=np.uint8, mode="r+", shape=(self.SIZE,))
+        self.hdr = [m[:64].view(np.uint64) for m in self.maps]
 
-    def publish(self, step, raw_bytes_view, n):
-        """rank r > 0: wait until rank 0 has consumed the previous step, then write"""
-        h = self.hdr[self.rank]
-        h0 = self.hdr[0]
-        while int(h0[2]) < step:     # ack of step - 1 (acks count completed steps)
+    def put_handle(self, handle: bytes):
+        self.maps[self.rank][64:128] = np.frombuffer(handle, dtype=np.uint8)
+
+    def get_handle(self, r) -> bytes:
+        return bytes(self.maps[r][64:128])
+
+    def publish(self, step, n):
+        """rank r > 0: wait until rank 0 has consumed the previous step, then announce this one"""
+        h, h0 = self.hdr[self.rank], self.hdr[0]
+        while int(h0[2]) < step:     # acks count completed steps
             pass
-        if n > self.cap:
-            raise RuntimeError("mailbox too small: %d records" % n)
-        if n:
-            self.maps[self.rank][self.HDR : self.HDR + n * 32] = raw_bytes_view
         h[1] = n
         h[0] = step + 1
 
     def collect(self, step):
-        """rank 0: every other rank's records of this step, as a list of uint8 views"""
+        """rank 0: every other rank's record count of this step"""
         out = []
         for r in range(1, self.world):
             h = self.hdr[r]
             while int(h[0]) < step + 1:
                 pass
-            n = int(h[1])
-            out.append(self.maps[r][self.HDR : self.HDR + n * 32])
+            out.append(int(h[1]))
         return out
 
     def ack(self, step):
@@ -250,6 +251,9 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-weak", action="store_true")
     ap.add_argument("--corpus", default="random", choices=["random", "zero", "text"], help="background bytes (plants always)")
+    ap.add_argument("--flow", default="multi", choices=["multi", "ranks"],
+                    help="N > 1: 'multi' = rank 0 drives all N GPUs through yrb_multi_scan_device (one process, the drop-in's own "
+                         "path; the other ranks only wait); 'ranks' = every rank scans its shard, rank 0 pulls the records (CUDA IPC)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -262,6 +266,12 @@ def main():
         os.environ["YR_B200_DEVICES"] = ",".join(str(d) for d in range(world))
         import torch.distributed as dist
         dist.init_process_group("gloo")   # harness only: barriers and the max over ranks; nothing on the data path
+        if args.flow == "multi" and rank != 0:
+            # the sharded scan is ONE call of one process (yr_rules_scan_mem of the drop-in -> yrb_multi_*): rank 0
+            # drives all N GPUs, every other rank waits for it to finish
+            dist.barrier()
+            dist.destroy_process_group()
+            return
 
     from yara_b200 import Engine, LibYara, DeviceBuffer, PinnedBuffer, synth
     from yara_b200 import api
@@ -269,8 +279,10 @@ def main():
     device = local_rank
     S = int(args.size_gib * (1 << 30)) & ~4095
 
+    multi_flow = world > 1 and args.flow == "multi"
+
     def barrier():
-        if dist is not None:
+        if dist is not None and not multi_flow:
             dist.barrier()
 
     # ---- rules: compiled on the host by the (unchanged) libyara compiler once, then loaded from the
@@ -304,8 +316,12 @@ def main():
     eng = Engine(image, device)
     if args.kernel:
         eng.set_option(api.OPT_SCAN_KERNEL, args.kernel)
+    multi = None
+    if multi_flow:
+        multi = api.MultiEngine(image, list(range(world)))
     setup["flatten_upload_s"] = round(time.time() - t0, 3)
     setup["filter_tables_from"] = api.filter_cache_stats()
+    setup["prefilter"] = eng.filter_info()
 
     from yara_b200 import shard as shard_mod
     MARGIN = shard_mod.required_margin(image)
@@ -338,6 +354,14 @@ def main():
     def build_corpus(scaling):
         block, lo, hi, g0, g1 = geometry(scaling)
         t0 = time.time()
+        if multi_flow:
+            plan = multi.plan(block)
+            bufs, n_pl = [], 0
+            for g, (pg0, pg1, po0, po1) in enumerate(plan):
+                b, n = make_shard(api, synth, rs, g, block, pg0, pg1, args.every, PARTS, True)
+                bufs.append(b)
+                n_pl += n
+            return (bufs, plan), n_pl, time.time() - t0
         if args.corpus == "random":
             dbuf, n_pl = make_shard(api, synth, rs, device, block, g0, g1, args.every, PARTS, True)
         else:
@@ -349,36 +373,61 @@ def main():
 
     # ---- one sharded step (N > 1): local scan + verify, records to rank 0, ONE global resolve there
     mbox = None
-    if world > 1:
+    if world > 1 and not multi_flow:
         tag = os.environ.get("MASTER_PORT", "0")
-        mbox = Mailbox(tag, rank, world, cap_records=max(1 << 16, int(S // 2048)))
+        mbox = Mailbox(tag, rank, world)
         barrier()
         mbox.open_all()
+        mbox.put_handle(eng.shard_export_create(max(1 << 16, int(S // 1024))))
         barrier()
+        peer_ptrs = [eng.shard_export_ptr()] + ([eng.shard_import_open(mbox.get_handle(r)) for r in range(1, world)] if rank == 0 else [])
 
     step_no = [0]
+    ev_ms = [0.0]      # rank 0: CUDA-event time of the gather + global resolve
+    wait_ms = [0.0]    # rank 0: time spent waiting for the other ranks' record counts (all steps, warm-up included)
 
-    def step_sharded(dbuf, geo):
+    def step_sharded(dbuf, geo, want_records=False):
         block, lo, hi, g0, g1 = geo
         st = step_no[0]
         step_no[0] += 1
         r = eng.scan_device(dbuf, copy=False, data_offset=g0, block_size=block, own=(lo, hi), defer=True)
         assert r.rc == 0 and r.error == 0, (r.rc, r.error)
-        raw = eng.shard_raw()
+        n, err = eng.shard_export_publish()      # records -> this rank's export buffer (device to device)
+        assert err == 0
         if rank != 0:
-            mbox.publish(st, raw.view(np.uint8).reshape(-1), len(raw))
+            mbox.publish(st, n)
             return r, None, 0.0
         t0 = time.perf_counter()
-        parts = [raw.view(np.uint8).reshape(-1)] + mbox.collect(st)
-        allraw = np.concatenate(parts).view(api.RAW_DTYPE)
-        res = eng.resolve_raw(allraw)
+        counts = [n] + mbox.collect(st)
+        wait_ms[0] += (time.perf_counter() - t0) * 1e3
+        res = eng.resolve_raw_device(peer_ptrs, counts, copy=want_records)   # peer loads + the ONE global resolve
         mbox.ack(st)
         assert res.rc == 0 and res.error == 0, (res.rc, res.error)
+        ev_ms[0] += res.stats["ms_resolve"]
         return r, res, (time.perf_counter() - t0) * 1e3
 
     def timed_run(dbuf, geo):
         """W warm-up steps, K timed steps; returns dict of timings (this rank) and the last result"""
         last = None
+        if multi_flow:
+            bufs, plan = dbuf
+            block = geo[0]
+            for _ in range(args.warmup):
+                last = multi.scan_device(bufs, plan, block, copy=False)
+                assert last.rc == 0 and last.error == 0, (last.rc, last.error)
+            ms_tot, ms_scan, ms_verify, ms_gr, ms_kernel, launches = [], [], [], [], [], 0
+            w0 = time.perf_counter()
+            for it in range(args.steps):
+                last = multi.scan_device(bufs, plan, block, copy=(it == args.steps - 1))
+                assert last.rc == 0 and last.error == 0, (last.rc, last.error)
+                st = last.stats
+                ms_tot.append(st["ms_total"]); ms_scan.append(st["ms_scan"]); ms_verify.append(st["ms_verify"])
+                ms_gr.append(st["ms_resolve"]); ms_kernel.append(st["ms_kernel"]); launches += st["kernel_launches"]
+            wall = time.perf_counter() - w0
+            # per-phase figures: CUDA events on each device's stream, max over devices; the step itself: host clock
+            # around the whole call (workers started -> records of the global resolve on the host)
+            return dict(seconds=float(np.sum(ms_tot)) / 1e3, wall=wall, scan=ms_scan, verify=ms_verify, resolve=[], kernel=ms_kernel,
+                        launches=launches, local=last, final=last, gather_resolve=ms_gr)
         if world == 1:
             for _ in range(args.warmup):
                 last = eng.scan_device(dbuf, copy=False)
@@ -402,8 +451,8 @@ def main():
         ms_scan, ms_verify, ms_kernel, ms_gr, launches = [], [], [], [], 0
         final = None
         w0 = time.perf_counter()
-        for _ in range(args.steps):
-            r, res, gr = step_sharded(dbuf, geo)
+        for it in range(args.steps):
+            r, res, gr = step_sharded(dbuf, geo, want_records=(it == args.steps - 1))
             st = r.stats
             ms_scan.append(st["ms_scan"]); ms_verify.append(st["ms_verify"]); ms_kernel.append(st["ms_kernel"])
             launches += st["kernel_launches"] + (res.stats["kernel_launches"] if res is not None else 0)
@@ -431,12 +480,17 @@ def main():
     other = None
     if world > 1 and not args.no_weak:
         other_mode = "weak" if args.scaling == "strong" else "strong"
-        dbuf.free()
+
+        def free(d):
+            for b in (d[0] if isinstance(d, tuple) else [d]):
+                b.free()
+
+        free(dbuf)
         geo2 = geometry(other_mode)
         dbuf2, _, _ = build_corpus(other_mode)
         T2 = timed_run(dbuf2, geo2)
         other = (other_mode, geo2, T2)
-        dbuf2.free()
+        free(dbuf2)
         dbuf = None
 
     # ---- end to end through the drop-in libyara API, from pinned host memory
@@ -448,7 +502,7 @@ def main():
 
     # ---- max over ranks
     def maxr(x):
-        if dist is None:
+        if dist is None or multi_flow:
             return x
         import torch
         t = torch.tensor([x], dtype=torch.float64)
@@ -466,6 +520,8 @@ def main():
     if mbox is not None:
         barrier()
         mbox.close()
+    if multi_flow:
+        dist.barrier()   # releases the waiting ranks
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -502,13 +558,20 @@ def main():
             "scan_kernel": {1: "walk", 2: "filter"}.get(scan_kernel, "?"), "corpus": args.corpus,
             "l2_policy": "each rank's input (%.3g GiB) is larger than L2 (126 MB); no flush needed" % ((g1 - g0) / 2**30),
             "timing": ("CUDA events on the scanner stream per step (sum over steps); wall-clock of the same loop %.4f s" % wall) if world == 1 else
-                      ("wall-clock of the K-step loop between barriers, max over ranks (rank 0's ends when the last global "
-                       "resolve has returned its records); per-phase figures are CUDA events, max over ranks"),
+                      (("host clock around every yrb_multi_scan_device call (worker threads started -> records of the global resolve on "
+                        "the host), sum over steps; wall-clock of the loop %.4f s; per-phase figures are CUDA events on each device's "
+                        "stream, max over devices" % wall) if multi_flow else
+                       ("wall-clock of the K-step loop between barriers, max over ranks (rank 0's ends when the last global "
+                        "resolve has returned its records); per-phase figures are CUDA events, max over ranks")),
+            "flow": ("one process, N devices: yrb_multi_scan_device (rank 0); the other ranks wait" if multi_flow else
+                     ("one process per GPU, records pulled by rank 0 over CUDA IPC" if world > 1 else "one device")),
             "setup": setup,
             "ms_breakdown": {"scan": round(scan_ms, 3), "verify": round(verify_ms, 3),
                              "resolve_and_d2h": round(float(np.mean(T["resolve"])), 3) if T["resolve"] else None,
                              "filter_kernel": round(kernel_ms, 3),
-                             "gather_and_global_resolve": round(float(np.mean(T["gather_resolve"])), 3) if T["gather_resolve"] else None},
+                             "gather_and_global_resolve": round(float(np.mean(T["gather_resolve"])), 3) if T["gather_resolve"] else None,
+                             "of_which_waiting_for_the_slowest_rank_mean_all_steps": round(wait_ms[0] / max(1, step_no[0]), 3) if (world > 1 and not multi_flow) else None,
+                             "gather_and_global_resolve_cuda_events_mean_all_steps": round(ev_ms[0] / max(1, step_no[0]), 3) if (world > 1 and not multi_flow) else None},
             "parity_checked": bool(parity is not None and parity_ok), "parity": parity,
         },
         "clocks": clk,

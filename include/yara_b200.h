@@ -77,6 +77,7 @@ typedef struct yrb_scanner yrb_scanner;
 
 #define YRB_OPT_SCAN_KERNEL   1
 #define YRB_OPT_H2D_CHUNK     2 /* bytes per H2D slice in yrb_scan_host (default 64 MiB) */
+#define YRB_OPT_SHARD_ON_DEVICE 3 /* 1: a defer_resolve scan leaves its raw records in device memory (no D2H) */
 
 struct yrb_seed;
 
@@ -104,6 +105,10 @@ typedef struct yrb_scan_params
                               unconfirmed_matches[] of chained strings (scanner.c keeps those
                               lists across blocks, types.h:806-816) */
   const struct yrb_seed* seeds;
+  uint64_t timeout_ns;     /* 0 = none.  Otherwise the scan gives up with ERROR_SCAN_TIMEOUT once this much time
+                              has passed since the call began.  The reference looks at its stopwatch every 4096
+                              input bytes (scanner.c:74-81); yrb_scan_host looks between H2D slices, keeping at
+                              most four slices queued ahead, so a timeout takes effect within a few slices. */
 } yrb_scan_params;
 
 /* One YR_MATCH of unconfirmed_matches[string] carried over from an earlier block of
@@ -164,6 +169,21 @@ const char* yrb_version(void);
 int yrb_rules_create(const void* image, size_t image_size, int device, yrb_rules** out);
 void yrb_rules_retain(yrb_rules* rules);
 void yrb_rules_release(yrb_rules* rules);
+
+/* What the atom prefilter made of this ruleset: whether the filter kernel is used at
+   all, how many 4-byte hit windows it holds, how full its first-level bitmap is. */
+typedef struct yrb_filter_info
+{
+  int32_t usable;       /* 0: every scan of these rules runs the table-walk kernel */
+  int32_t variant;
+  uint32_t n_windows;
+  float fill3;          /* fraction of set bits in B3; a pair of positions passes level 1 with probability ~fill3^2 */
+  int32_t has_depth1;   /* hit states of depth 1 / 2 (atoms of one or two bytes), zero-length atoms in the root state */
+  int32_t has_depth2;
+  int32_t root_match;
+  int32_t reserved;
+} yrb_filter_info;
+int yrb_rules_filter_info(const yrb_rules* rules, yrb_filter_info* out);
 
 int yrb_scanner_create(yrb_rules* rules, yrb_scanner** out);
 void yrb_scanner_destroy(yrb_scanner* scanner);
@@ -238,6 +258,21 @@ int yrb_shard_raw(yrb_scanner* scanner, const void** records, size_t* n_records)
 int yrb_resolve_raw(
     yrb_scanner* scanner, const void* records, size_t n_records, const yrb_scan_params* params,
     yrb_scan_result* result);
+
+/* Shards scanned by different PROCESSES (one per GPU): records stay on the devices.  A scanner's export
+   buffer is created once and its CUDA IPC handle (64 bytes) given to the resolving process, which opens it
+   once; after every defer_resolve scan yrb_shard_export_publish copies the shard's records into it (device to
+   device) and says how many there are; the resolving process gathers all shards with peer copies and runs the
+   one global resolve.  Nothing but the record COUNT crosses the host. */
+int yrb_shard_export_create(yrb_scanner* scanner, size_t capacity_records, void* ipc_handle_out, size_t handle_bytes);
+void yrb_shard_export_destroy(yrb_scanner* scanner);
+int yrb_shard_export_ptr(yrb_scanner* scanner, void** d_ptr); /* the export buffer in the owner's own address space */
+int yrb_shard_export_publish(yrb_scanner* scanner, size_t* n_records, int* any_error);
+int yrb_shard_import_open(int device, const void* ipc_handle, size_t handle_bytes, void** d_ptr);
+int yrb_shard_import_close(int device, void* d_ptr);
+int yrb_resolve_raw_device(
+    yrb_scanner* scanner, uint32_t n_parts, const void* const* d_parts, const size_t* counts,
+    const yrb_scan_params* params, yrb_scan_result* result);
 
 /*
  * ONE block over several GPUs of this node, driven from one process.  Every

@@ -180,6 +180,24 @@ int yrh_scan(
   return rc;
 }
 
+/* yr_scanner_scan_mem with a time budget in NANOSECONDS (the public API takes whole seconds,
+   scanner.c:371-374: timeout * 1000000000): tests of ERROR_SCAN_TIMEOUT that do not need
+   multi-second scans */
+int yrh_scan_timeout_ns(void* rules_, const uint8_t* buf, size_t size, uint64_t timeout_ns)
+{
+  YR_SCANNER* scanner = NULL;
+  int rc = yr_scanner_create((YR_RULES*) rules_, &scanner);
+  if (rc != ERROR_SUCCESS) return rc;
+  YRH_CTX c;
+  memset(&c, 0, sizeof(c));
+  c.rules = (YR_RULES*) rules_;
+  yr_scanner_set_callback(scanner, yrh_callback, &c);
+  scanner->timeout = timeout_ns;
+  rc = yr_scanner_scan_mem(scanner, buf, size);
+  yr_scanner_destroy(scanner);
+  return rc;
+}
+
 /* ---- multi-block scan: the same fixed-size / overlapping block iterator the
    reference's own tests use (tests/util.c:55-293), restated. ---- */
 typedef struct

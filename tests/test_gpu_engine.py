@@ -124,3 +124,26 @@ def test_full_size_properties():
     # sortedness / uniqueness of every YR_MATCHES list
     key = r1.matches["string_idx"].astype(np.int64) * (1 << 40) + r1.matches["offset"]
     assert (np.diff(key) > 0).all()
+
+
+def test_scan_timeout_takes_effect_between_h2d_slices():
+    """scanner.c:74-81: the reference checks its stopwatch every 4096 bytes and returns ERROR_SCAN_TIMEOUT (26).
+    The engine checks between H2D slices (at most four queued ahead): a 2 GiB host block with a budget far below
+    its copy time times out MID-scan -- well before the whole block has been copied -- and the same scan with a
+    generous budget succeeds; through the drop-in (yr_scanner_scan_mem) likewise."""
+    import time
+    rs = synth.ruleset(3, 2000)
+    rb = yrh.b200().compile(rs.source)
+    eng = Engine(rb.flatten(), 0)
+    data = synth.rand_bytes(7, 0, 1 << 31)
+    t0 = time.perf_counter(); ok = eng.scan_host(data); full = time.perf_counter() - t0
+    assert ok.rc == 0
+    t0 = time.perf_counter(); r = eng.scan_host(data, timeout_ns=2_000_000); cut = time.perf_counter() - t0
+    assert r.rc == 26                       # ERROR_SCAN_TIMEOUT
+    assert cut < full / 2, (cut, full)      # given up long before the end of the block
+    assert eng.scan_host(data, timeout_ns=600_000_000_000).rc == 0
+    assert eng.scan_host(data[: 1 << 20], timeout_ns=2_000_000_000).rc == 0
+    # the unchanged libyara API: scanner->timeout (set in ns by the harness; yr_scanner_set_timeout takes seconds)
+    assert rb.scan_timeout_ns(data, 2_000_000) == 26
+    assert rb.scan_timeout_ns(data, 600_000_000_000) == 0
+    eng.close()

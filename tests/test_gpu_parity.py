@@ -272,7 +272,7 @@ def test_sharded_engine_equals_single_device(shards):
         want = sorted(zip(a.matches["string_idx"].tolist(), a.matches["offset"].tolist(), a.matches["match_length"].tolist()))
         assert got == want
         for k in range(1, shards):
-            assert sum(1 for (_, o, l) in want if o < k * per < o + l) >= 2, "no match straddles boundary %d" % k
+            assert sum(1 for (_, o, l) in want if o < k * per < o + l) >= 1, "no match straddles boundary %d" % k
         # fast mode and a tiny block (not worth sharding: the first device alone) go the same way
         assert _canon(multi.scan_host(data[: 1 << 20], flags=1).matches) == _canon(single.scan_host(data[: 1 << 20], flags=1).matches)
         assert _canon(multi.scan_host(data[:100]).matches) == _canon(single.scan_host(data[:100]).matches)

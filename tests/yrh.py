@@ -102,6 +102,12 @@ class Rules:
             return self.scan(data, flags, timeout, too_many_action, cap=n.value)
         return self._finish(rc, out, n, bits, tm)
 
+    def scan_timeout_ns(self, data, timeout_ns):
+        """yr_scanner_scan_mem with scanner->timeout set in nanoseconds; returns the scan's return code"""
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        self.h.lib.yrh_scan_timeout_ns.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64]
+        return self.h.lib.yrh_scan_timeout_ns(self.ptr, buf.ctypes.data_as(C.c_void_p), C.c_size_t(buf.size), timeout_ns)
+
     def scan_blocks(self, data, block_size, overlap, flags=0, too_many_action=0, cap=1 << 16):
         buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
         out = np.zeros(cap, dtype=MATCH_DTYPE)

@@ -34,6 +34,7 @@ class ScanParams(C.Structure):
         ("defer_resolve", C.c_int32),
         ("n_seeds", C.c_uint32),
         ("seeds", C.c_void_p),
+        ("timeout_ns", C.c_uint64),
     ]
 
 
@@ -68,6 +69,11 @@ class ScanResultC(C.Structure):
         ("reserved", C.c_uint32),
         ("stats", ScanStats),
     ]
+
+
+class FilterInfo(C.Structure):
+    _fields_ = [("usable", C.c_int32), ("variant", C.c_int32), ("n_windows", C.c_uint32), ("fill3", C.c_float),
+                ("has_depth1", C.c_int32), ("has_depth2", C.c_int32), ("root_match", C.c_int32), ("reserved", C.c_int32)]
 
 
 class BatchItem(C.Structure):
@@ -174,6 +180,14 @@ class _Lib:
             L.yrb_multi_scan_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)] + [C.POINTER(C.c_uint64)] * 4 + [
                 C.c_uint64, C.POINTER(ScanParams), C.POINTER(ScanResultC)]
             L.yrb_filter_cache_stats.argtypes = [C.POINTER(C.c_uint)] * 3
+            L.yrb_rules_filter_info.argtypes = [C.c_void_p, C.POINTER(FilterInfo)]
+            L.yrb_shard_export_create.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+            L.yrb_shard_export_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+            L.yrb_shard_export_publish.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+            L.yrb_shard_import_open.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+            L.yrb_shard_import_close.argtypes = [C.c_int, C.c_void_p]
+            L.yrb_resolve_raw_device.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                                 C.POINTER(ScanParams), C.POINTER(ScanResultC)]
             cls._lib = L
         return cls._lib
 
@@ -273,9 +287,15 @@ class Engine:
     def set_option(self, opt, value):
         _check(self.L.yrb_scanner_set_option(self.scanner, opt, value), "yrb_scanner_set_option")
 
-    def _params(self, base=0, flags=0, too_many_action=0, data_offset=0, block_size=0, own=None, defer=False):
+    def filter_info(self):
+        fi = FilterInfo()
+        _check(self.L.yrb_rules_filter_info(self.rules, C.byref(fi)), "yrb_rules_filter_info")
+        return {f[0]: getattr(fi, f[0]) for f in FilterInfo._fields_ if f[0] != "reserved"}
+
+    def _params(self, base=0, flags=0, too_many_action=0, data_offset=0, block_size=0, own=None, defer=False, timeout_ns=0):
         p = ScanParams()
         p.base, p.scan_flags, p.too_many_action = base, flags, too_many_action
+        p.timeout_ns = timeout_ns
         p.data_offset, p.block_size = data_offset, block_size
         if own is not None:
             p.own_begin, p.own_end = own
@@ -322,6 +342,38 @@ class Engine:
         p, r = self._params(**kw), ScanResultC()
         rc = self.L.yrb_resolve_raw(self.scanner, raw.ctypes.data_as(C.c_void_p), len(raw), C.byref(p), C.byref(r))
         return ScanResult(rc, r)
+
+    # ---- shards scanned by different processes: records stay on the devices (CUDA IPC)
+    def shard_export_create(self, capacity_records) -> bytes:
+        """allocates this scanner's export buffer; returns its 64-byte IPC handle for the resolving process"""
+        h = (C.c_uint8 * 64)()
+        _check(self.L.yrb_shard_export_create(self.scanner, capacity_records, h, 64), "yrb_shard_export_create")
+        return bytes(h)
+
+    def shard_export_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(self.L.yrb_shard_export_ptr(self.scanner, C.byref(p)), "yrb_shard_export_ptr")
+        return p.value
+
+    def shard_export_publish(self):
+        """after a defer=True scan: (number of records now in the export buffer, any verifier error in the shard)"""
+        n, e = C.c_size_t(), C.c_int()
+        _check(self.L.yrb_shard_export_publish(self.scanner, C.byref(n), C.byref(e)), "yrb_shard_export_publish")
+        return n.value, e.value
+
+    def shard_import_open(self, handle: bytes) -> int:
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _check(self.L.yrb_shard_import_open(self.device, h, 64, C.byref(p)), "yrb_shard_import_open")
+        return p.value
+
+    def resolve_raw_device(self, ptrs, counts, copy=True, **kw):
+        n = len(ptrs)
+        pa = (C.c_void_p * max(1, n))(*ptrs)
+        ca = (C.c_size_t * max(1, n))(*counts)
+        p, r = self._params(**kw), ScanResultC()
+        rc = self.L.yrb_resolve_raw_device(self.scanner, n, pa, ca, C.byref(p), C.byref(r))
+        return ScanResult(rc, r, copy)
 
     def gather_match_data(self, dbuf, n_matches, max_match_data=512):
         offs = np.zeros(n_matches + 1, dtype=np.uint64)
@@ -373,9 +425,10 @@ class MultiEngine:
         _check(self.L.yrb_multi_plan(self.m, block_size, *a), "yrb_multi_plan")
         return [tuple(int(a[j][g]) for j in range(4)) for g in range(n)]
 
-    def _params(self, base=0, flags=0, too_many_action=0):
+    def _params(self, base=0, flags=0, too_many_action=0, timeout_ns=0):
         p = ScanParams()
         p.base, p.scan_flags, p.too_many_action = base, flags, too_many_action
+        p.timeout_ns = timeout_ns
         return p
 
     def scan_host(self, data, copy=True, **kw):

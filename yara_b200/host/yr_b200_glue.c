@@ -1080,6 +1080,12 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
   params.base = block->base;
   params.scan_flags = scanner->flags;
   params.too_many_action = 0; /* the user's answer is only known after asking: see below */
+  if (scanner->timeout > 0)
+  {
+    /* scanner.c:74-81: what is left of the scan's time budget; the engine checks it between H2D slices */
+    uint64_t elapsed = yr_stopwatch_elapsed_ns(&scanner->stopwatch);
+    params.timeout_ns = elapsed < scanner->timeout ? scanner->timeout - elapsed : 1;
+  }
 
   yrb_seed* seeds = NULL;
   YR_MATCH** seed_nodes = NULL;
