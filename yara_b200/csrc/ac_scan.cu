@@ -952,7 +952,11 @@ static std::shared_ptr<const FilterHost> filter_host_tables(const void* image, s
   if (it != g_ft_registry.end()) { g_ft_stats[0]++; return it->second; }
 
   std::shared_ptr<FilterHost> f(new FilterHost());
-  const std::string dir = ft_cache_dir();
+  // files only for rulesets whose tables take a while to build (tens of thousands of AC slots); a small ruleset
+  // is rebuilt in microseconds and would only litter the cache directory (the reference's test suite compiles
+  // a fresh rule for each of its ~1,500 assertions)
+  const bool worth_a_file = ((const yrb_image_header*) image)->tables_size >= (1u << 15);
+  const std::string dir = worth_a_file ? ft_cache_dir() : std::string();
   const std::string path = dir.empty() ? std::string() : ft_cache_path(dir, key, variant);
   if (!path.empty() && ft_cache_load(path, key, image_size, variant, f.get()))
   {
