@@ -79,4 +79,9 @@ CASES = [
      b"...wxyzmn...." + b"-" * 50 + b"QWERTY" + b"." * 40 + b"wxyza1" + b"q" * 60 + b"QWERTY"),
     (R("$s = /wxyz(a1(.??)+?c)??mn.{0,300}?QWERTY/", "$s"),
      b"wxyza1" + b"q" * 60 + b"...wxyzmn...." + b"-" * 50 + b"QWERTY" + b"." * 40),
+    # the same (string, offset) reported by two candidates (both "abcd" reach back to the same "x": scan.c:311-326 keeps
+    # the first) in a scan that also completes a chain: the engine copies the plain strings' records to the host while
+    # the chain replay is still running and must notice that the dedup moved the chain heads' records forward
+    (R("$a = /x.{0,10}abcd/ $b = { 31 32 33 34 35 [250-300] 36 37 38 39 30 }", "$a and $b"),
+     b"..x..abcd.abcd.." + b"12345" + b"-" * 260 + b"67890" + b"..x.abcdabcd" + b"12345" + b"+" * 290 + b"67890" + b"x" * 30),
 ]

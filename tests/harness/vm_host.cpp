@@ -412,6 +412,9 @@ static long long run_verify(
   std::vector<unsigned long long> str_err(R.num_strings ? R.num_strings : 1, ~0ULL);
   std::vector<Raw> raw((size_t) 1 << 16);
   std::vector<uint32_t> retry_fast(n_cand[CLS_FAST] + 1), retry_fast3(n_cand[CLS_FAST] + 1), retry_re(n_cand[CLS_RE] + 1);
+  std::vector<uint32_t> retry_re0(n_cand[CLS_RE] + 1);
+  /* fiber VM: tier 0 (local-memory pool) -> tier 1 -> tier 2 when the repeat stacks fit, else tier 1 -> tier 2 (api.cu) */
+  const bool re_t0 = R.stack_words <= RE_LOCAL_STACK && !getenv("YRB_RE_TIER0_OFF");
   std::vector<uint8_t> ws;
   std::vector<unsigned long long> stage_end;
   std::vector<std::unordered_set<uint64_t>> handed_on;
@@ -419,7 +422,7 @@ static long long run_verify(
   for (;;)
   {
     st.n_raw = 0;
-    st.n_retry[0] = st.n_retry[1] = st.n_retry3 = 0;
+    st.n_retry[0] = st.n_retry[1] = st.n_retry3 = st.n_retry_re0 = 0;
     st.any_error = 0;
     st.n_chain_raw = 0;
     std::fill(str_err.begin(), str_err.end(), ~0ULL);
@@ -456,15 +459,19 @@ static long long run_verify(
       verify_fast_kernel<1>(R, V, cand[CLS_FAST].data(), n_cand[CLS_FAST], ro, ws.data(), fast_ws_bytes_per_thread(1),
                             FAST_POS_CAP_SMALL, nullptr, retry_fast.data());
     }
-    if (n_cand[CLS_RE])
+    if (n_cand[CLS_RE] && re_t0)
+      verify_re_kernel<0>(R, V, cand[CLS_RE].data(), n_cand[CLS_RE], ro, nullptr, 0, RE_FIBERS_LOCAL, nullptr, retry_re0.data());
+    else if (n_cand[CLS_RE])
     {
       ws.assign(re_ws_bytes_per_thread(R.stack_words, 1), 0);
-      verify_re_kernel<false>(R, V, cand[CLS_RE].data(), n_cand[CLS_RE], ro, ws.data(), re_ws_bytes_per_thread(R.stack_words, 1),
-                              RE_FIBERS_SMALL, retry_re.data());
+      verify_re_kernel<1>(R, V, cand[CLS_RE].data(), n_cand[CLS_RE], ro, ws.data(), re_ws_bytes_per_thread(R.stack_words, 1),
+                          RE_FIBERS_SMALL, nullptr, retry_re.data());
     }
     stats->retry_fast = st.n_retry[0];
-    stats->retry_re = st.n_retry[1];
-    close_stage(&retry_fast, st.n_retry[0], CLS_FAST, &retry_re, st.n_retry[1], CLS_RE);
+    if (re_t0)
+      close_stage(&retry_fast, st.n_retry[0], CLS_FAST, &retry_re0, st.n_retry_re0, CLS_RE);
+    else
+      close_stage(&retry_fast, st.n_retry[0], CLS_FAST, &retry_re, st.n_retry[1], CLS_RE);
 
     if (st.n_retry[0])
     {
@@ -472,14 +479,29 @@ static long long run_verify(
       verify_fast_kernel<2>(R, V, cand[CLS_FAST].data(), 0, ro, ws.data(), fast_ws_bytes_per_thread(2), FAST_POS_CAP,
                             retry_fast.data(), retry_fast3.data());
     }
-    if (st.n_retry[1])
+    if (re_t0 && st.n_retry_re0)
+    {
+      ws.assign(re_ws_bytes_per_thread(R.stack_words, 1), 0);
+      verify_re_kernel<1>(R, V, cand[CLS_RE].data(), 0, ro, ws.data(), re_ws_bytes_per_thread(R.stack_words, 1),
+                          RE_FIBERS_SMALL, retry_re0.data(), retry_re.data());
+    }
+    else if (!re_t0 && st.n_retry[1])
     {
       ws.assign(re_ws_bytes_per_thread(R.stack_words, 2), 0);
-      verify_re_kernel<true>(R, V, cand[CLS_RE].data(), 0, ro, ws.data(), re_ws_bytes_per_thread(R.stack_words, 2),
-                             YRB_RE_MAX_FIBERS, retry_re.data());
+      verify_re_kernel<2>(R, V, cand[CLS_RE].data(), 0, ro, ws.data(), re_ws_bytes_per_thread(R.stack_words, 2),
+                          YRB_RE_MAX_FIBERS, retry_re.data(), nullptr);
     }
+    stats->retry_re = st.n_retry[1];
     stats->retry_fast3 = st.n_retry3;
-    close_stage(&retry_fast3, st.n_retry3, CLS_FAST, nullptr, 0, 0);
+    close_stage(&retry_fast3, st.n_retry3, CLS_FAST, re_t0 ? &retry_re : nullptr, re_t0 ? st.n_retry[1] : 0, CLS_RE);
+
+    if (re_t0 && st.n_retry[1])
+    {
+      /* stage 3 of the fiber VM (the fast VM's tier 3 below belongs to the same stage) */
+      ws.assign(re_ws_bytes_per_thread(R.stack_words, 2), 0);
+      verify_re_kernel<2>(R, V, cand[CLS_RE].data(), 0, ro, ws.data(), re_ws_bytes_per_thread(R.stack_words, 2),
+                          YRB_RE_MAX_FIBERS, retry_re.data(), nullptr);
+    }
 
     if (st.n_retry3)
     {

@@ -347,3 +347,28 @@ def test_filter_tables_come_from_the_disk_cache_in_a_second_process(tmp_path):
     assert "'built': 1" in first and "'registry': 1" in first          # built once, the second Engine took it from the registry
     assert "'built': 0" in second and "'disk': 1" in second            # new process, rules from the .yarc: tables from disk
     assert first.split()[-3:-1] == second.split()[-3:-1]               # same matches
+
+
+DEDUP_CODE = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import cases, yrh
+rule, data = cases.CASES[-1]
+a = yrh.ref().compile(rule).scan(data)
+b = yrh.b200().compile(rule).scan(data)
+assert a.rc == b.rc == 0 and a.matches.tobytes() == b.matches.tobytes() and len(a.matches) >= 4, (a.rc, b.rc, len(a.matches))
+print("DEDUP ok", len(a.matches))
+"""
+
+
+def test_dedup_moves_the_chain_heads_records_forward():
+    """The resolve copies finals[0, n - chain parts) to the host while the chain replay still runs; when plain records
+    were deduplicated (scan.c:311-326) the chain heads' lists begin inside that range and are fetched again.  The last
+    known-answer case is built to take that path: check that it really does (trace line) and that the result is the
+    reference's."""
+    import subprocess, sys
+    env = dict(os.environ, YRB_TRACE="1")
+    p = subprocess.run([sys.executable, "-c", DEDUP_CODE % (yrh.ROOT, os.path.join(yrh.ROOT, "tests"))],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "DEDUP ok" in p.stdout, (p.stdout + p.stderr)[-3000:]
+    assert "plain records deduplicated" in p.stderr, p.stderr[-3000:]

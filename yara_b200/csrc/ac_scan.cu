@@ -143,12 +143,22 @@ void launch_ac_scan_walk(
 // B4 Bloom filter size); all three fit the 227 KB of shared memory with B3.
 struct FtVariant { int threads, u, b4_bits, tma_bufs; };   // tma_bufs: 0 = LDG + staging rows (round 1), else TMA buffers per warp
 static const FtVariant kVariants[] = {{1024, 4, 18, 0}, {512, 4, 19, 0}, {1024, 2, 19, 0},
-                                      {1024, 4, 18, 1}, {768, 4, 18, 1}};   // 3-4: variant T
-#define FT_NUM_VARIANTS 5
+                                      {1024, 4, 18, 1}, {768, 4, 18, 1},    // 3-4: variant T
+                                      {1024, 4, 0, 1}};                     // 5: variant T for dense rulesets (below)
+#define FT_NUM_VARIANTS 6
 #define FT_DEFAULT_VARIANT 3
+#define FT_DENSE_VARIANT 5
+// Dense rulesets (100,000 strings: 190k hit windows): B4 at 2^18 bits would be ~95 % full and filter nothing, and
+// B3 at 2^20 bits is a third full (12 % of the pairs pass level 1, and level 2 -- ~100 instructions per survivor
+// round and an L2 lookup for what passes -- becomes the kernel).  Variant 5 gives ALL the table space to B3:
+// 40,960 words (1.25 x), indexed by the high product of the hash and the word count instead of its top 15 bits,
+// and no B4.  Chosen automatically when the standard B3 would be more than FT_DENSE_FILL full.
+#define B3_WORDS_DENSE 40960u
+#define FT_DENSE_FILL 0.20f
+static inline uint32_t ft_b3_words(const FtVariant& v) { return v.b4_bits == 0 ? B3_WORDS_DENSE : B3_WORDS; }
 static inline size_t ft_smem_bytes(const FtVariant& v)
 {
-  return (size_t) B3_WORDS * 4 + ((size_t) 1 << (v.b4_bits - 3)) +
+  return (size_t) ft_b3_words(v) * 4 + (v.b4_bits == 0 ? 0 : ((size_t) 1 << (v.b4_bits - 3))) +
          (v.tma_bufs == 0 ? (size_t) (v.threads / 32) * (v.u * FT_ROW + 32)
                           : (size_t) (v.threads / 32) * (16 + 2048 + 16 + 64));
 }
@@ -471,9 +481,12 @@ static __device__ __forceinline__ void sts_u16_v(uint32_t a, uint32_t v)
 static __device__ __forceinline__ uint32_t word_addr_fma(uint32_t idx, uint32_t four, uint32_t base)
 { uint32_t r; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(idx), "r"(four), "r"(base)); return r; }
 
+template <bool DENSE>
 static __device__ __forceinline__ bool b3_test_a(uint32_t sB3_a, uint32_t key3)
 {
-  const uint32_t w = lds_u32(sB3_a + ((((key3 << 8) * HASH3_MUL) >> 17) << 2));
+  const uint32_t h = (key3 << 8) * HASH3_MUL;
+  const uint32_t idx = DENSE ? __umulhi(h, B3_WORDS_DENSE) : (h >> 17);
+  const uint32_t w = lds_u32(sB3_a + (idx << 2));
   return ((w >> (key3 & 31)) & (w >> ((key3 >> 16) & 31)) & 1u) != 0;
 }
 
@@ -499,18 +512,20 @@ ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t l
 {
   constexpr int FT_THREADS = NWARPS * 32, FT_U = FT_T_TILE / 512;
   constexpr int FT_TILE = NWARPS * FT_T_TILE;         // bytes per CTA and round; warp w owns [w * 2048, (w + 1) * 2048) of it
-  constexpr uint32_t B4_WORDS = 1u << (B4BITS - 5);
+  constexpr bool DENSE = (B4BITS == 0);               // all table space to B3, no B4 (see FT_DENSE_VARIANT)
+  constexpr uint32_t B3W = DENSE ? B3_WORDS_DENSE : B3_WORDS;
+  constexpr uint32_t B4_WORDS = DENSE ? 0u : (1u << ((DENSE ? 5 : B4BITS) - 5));
   constexpr int WARP_BYTES = FT_T_BUF + 16 + 64;      // buffer | mbarrier (8 B) + pad | survivor queue (32 x u16)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t* sB3 = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* sB4 = sB3 + B3_WORDS;
-  uint8_t* stage = smem_raw + (B3_WORDS + B4_WORDS) * 4;
+  uint32_t* sB4 = sB3 + B3W;
+  uint8_t* stage = smem_raw + (B3W + B4_WORDS) * 4;
 
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5;
   const uint8_t* wbuf = stage + warp * WARP_BYTES;    // 16 B halo | 4 x 512 B chunks, contiguous
   const uint32_t sB3_a = smem_u32(sB3);
-  const uint32_t sB4_a = sB3_a + B3_WORDS * 4;
+  const uint32_t sB4_a = sB3_a + B3W * 4;
   const uint32_t wbuf_a = smem_u32(wbuf);
   const uint32_t wbar_a = wbuf_a + FT_T_BUF;
   const uint32_t wq_a = wbuf_a + FT_T_BUF + 16;
@@ -526,13 +541,16 @@ ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t l
     const uint4* g4 = reinterpret_cast<const uint4*>(F.b4);
     uint4* s3 = reinterpret_cast<uint4*>(sB3);
     uint4* s4 = reinterpret_cast<uint4*>(sB4);
-    for (uint32_t i = threadIdx.x; i < B3_WORDS / 4; i += FT_THREADS) s3[i] = __ldg(&g3[i]);
+    for (uint32_t i = threadIdx.x; i < B3W / 4; i += FT_THREADS) s3[i] = __ldg(&g3[i]);
     for (uint32_t i = threadIdx.x; i < B4_WORDS / 4; i += FT_THREADS) s4[i] = __ldg(&g4[i]);
   }
   __syncthreads();
 
   const uint8_t* __restrict__ d = V.d - V.g0; // d[p] = block byte p; (d + lo) is 16-byte aligned and lo >= 16
-  const int64_t ntiles = (hi - lo) / FT_TILE;
+  // [lo, hi) is a whole number of WARP-tiles; the warps of a CTA share nothing inside the loop, so the last round
+  // may be a partial CTA-tile: this warp has rounds `tile` = blockIdx.x, blockIdx.x + gridDim.x, ... < ntiles
+  const int64_t nwt = (hi - lo) / FT_T_TILE;
+  const int64_t ntiles = (nwt - (int64_t) warp + NWARPS - 1) / NWARPS;
   const uint32_t H3 = HASH3_MUL << 8;
   const int64_t tstep = (int64_t) gridDim.x * FT_TILE;
   const uint32_t four = 4u + (F.ht_bits >> 31);   // == 4 (ht_bits <= 28), opaque to the compiler: see word_addr_fma
@@ -580,7 +598,7 @@ ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t l
 #define PROBE3(x, y)                                                                \
   {                                                                                 \
     const uint32_t h_ = (x) * H3;                                                   \
-    const uint32_t w_ = lds_u32(word_addr_fma(h_ >> 17, four, sB3_a));              \
+    const uint32_t w_ = lds_u32(word_addr_fma(DENSE ? __umulhi(h_, B3W) : (h_ >> 17), four, sB3_a)); \
     const uint32_t t_ = __funnelshift_r(w_, 0u, (x)) & __funnelshift_r(w_, 0u, (y)) & 1u; \
     mask = push_bit_fma(mask, t_);                                                  \
   }
@@ -643,12 +661,12 @@ ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t l
         const uint32_t x1 = *reinterpret_cast<const uint32_t*>(src - al + 4);
         const uint32_t wa = __funnelshift_r(x0, x1, al * 8);          // W(p)
         const uint32_t wb = __funnelshift_rc(x0, x1, al * 8 + 8);     // W(p + 1)
-        if (b3_test_a(sB3_a, wa & 0xFFFFFFu) && bloom4_test_a<B4BITS>(sB4_a, wa))
+        if (b3_test_a<DENSE>(sB3_a, wa & 0xFFFFFFu) && (DENSE || bloom4_test_a<DENSE ? 18 : B4BITS>(sB4_a, wa)))
         {
           const uint32_t mv = ht_lookup(F, wa);
           if (mv != 0) emit_events(R, V, out, wpos + pb + 1, mv);
         }
-        if (b3_test_a(sB3_a, wb >> 8) && bloom4_test_a<B4BITS>(sB4_a, wb))
+        if (b3_test_a<DENSE>(sB3_a, wb >> 8) && (DENSE || bloom4_test_a<DENSE ? 18 : B4BITS>(sB4_a, wb)))
         {
           const uint32_t mv = ht_lookup(F, wb);
           if (mv != 0) emit_events(R, V, out, wpos + pb + 2, mv);
@@ -768,15 +786,12 @@ static void filter_host_build(const void* image, FilterHost* out)
   if (out->has_d1 || out->has_d2 || windows.empty() || n_d3 > 512)
     return; // not usable: the engine falls back to the walk kernel
 
-  const int b4_bits = kVariants[out->variant].b4_bits;
-  out->b3.assign(B3_WORDS, 0);
-  out->b4.assign((size_t) 1 << (b4_bits - 5), 0);
-
   uint32_t ht_bits = 4;
   while ((1ull << ht_bits) < windows.size() * 2) ht_bits++;
   out->ht.assign((size_t) 1 << ht_bits, make_uint2(0, 0));
   const uint32_t ht_mask = (1u << ht_bits) - 1;
 
+  std::vector<uint32_t> live;   // the windows that really are hits
   for (uint32_t w : windows)
   {
     // the state the reference walk is in after these 4 bytes (ROOT restart is exact: depth <= 4)
@@ -784,31 +799,54 @@ static void filter_host_build(const void* image, FilterHost* out)
     for (int j = 0; j < 4; j++) st = host_ac_step(T, st, (w >> (8 * j)) & 0xFF);
     const uint32_t mv = M[st];
     if (mv == 0) continue;
-
-    const uint32_t k_suffix = w >> 8, k_prefix = w & 0xFFFFFF;
-    // B3 entry of a 3-byte key: word = top 15 bits of the hash; TWO bits per key, numbered
-    // (bit n = 1u << n): low 5 bits of the key's first byte and low 5 bits of its third byte
-    out->b3[hash3(k_suffix) >> 5] |= (1u << (k_suffix & 31)) | (1u << ((k_suffix >> 16) & 31));
-    out->b3[hash3(k_prefix) >> 5] |= (1u << (k_prefix & 31)) | (1u << ((k_prefix >> 16) & 31));
-    {
-      const uint32_t g1 = w * HASH4_MUL, g2 = (w * HASH4_MUL2) | 1u;
-      uint32_t g = g1;
-      for (int k = 0; k < BLOOM_K; k++)
-      {
-        const uint32_t i4 = g >> (32 - b4_bits);
-        out->b4[i4 >> 5] |= 0x80000000u >> (i4 & 31);
-        g += g2;
-      }
-    }
+    live.push_back(w);
 
     uint32_t slot = (w * HT_MUL) >> (32 - ht_bits);
     while (out->ht[slot].y != 0 && out->ht[slot].x != w) slot = (slot + 1) & ht_mask;
     out->ht[slot] = make_uint2(w, mv);
   }
 
-  size_t pop3 = 0;
-  for (uint32_t i = 0; i < B3_WORDS; i++) pop3 += (size_t) __builtin_popcount(out->b3[i]);
-  out->fill3 = (float) ((double) pop3 / (double) (1u << B3_BITS));
+  // B3 / B4 for the kernel variant; the default variant hands over to the dense one when its B3 would be too full
+  for (;;)
+  {
+    const FtVariant& fv = kVariants[out->variant];
+    const int b4_bits = fv.b4_bits;
+    const uint32_t b3_words = ft_b3_words(fv);
+    out->b3.assign(b3_words, 0);
+    out->b4.assign(b4_bits ? ((size_t) 1 << (b4_bits - 5)) : 0, 0);
+    for (uint32_t w : live)
+    {
+      const uint32_t keys[2] = {w >> 8, w & 0xFFFFFF};   // suffix3, prefix3
+      for (uint32_t k3 : keys)
+      {
+        // B3 entry of a 3-byte key: word from the hash (its top 15 bits; dense variant: high product with the word
+        // count); TWO bits per key, numbered (bit n = 1u << n): low 5 bits of the key's first byte and of its third
+        const uint32_t h = (k3 << 8) * HASH3_MUL;
+        const uint32_t idx = b4_bits ? (h >> 17) : (uint32_t) (((uint64_t) h * B3_WORDS_DENSE) >> 32);
+        out->b3[idx] |= (1u << (k3 & 31)) | (1u << ((k3 >> 16) & 31));
+      }
+      if (b4_bits)
+      {
+        const uint32_t g1 = w * HASH4_MUL, g2 = (w * HASH4_MUL2) | 1u;
+        uint32_t g = g1;
+        for (int k = 0; k < BLOOM_K; k++)
+        {
+          const uint32_t i4 = g >> (32 - b4_bits);
+          out->b4[i4 >> 5] |= 0x80000000u >> (i4 & 31);
+          g += g2;
+        }
+      }
+    }
+    size_t pop3 = 0;
+    for (uint32_t i = 0; i < b3_words; i++) pop3 += (size_t) __builtin_popcount(out->b3[i]);
+    out->fill3 = (float) ((double) pop3 / ((double) b3_words * 32.0));
+    if (out->variant == FT_DEFAULT_VARIANT && out->fill3 > FT_DENSE_FILL && !getenv("YRB_FILTER_NO_DENSE"))
+    {
+      out->variant = FT_DENSE_VARIANT;
+      continue;
+    }
+    break;
+  }
   out->ht_bits = ht_bits;
   out->n_windows = (uint32_t) windows.size();
 
@@ -823,7 +861,7 @@ static void filter_host_build(const void* image, FilterHost* out)
 // ---- the cache: process-wide registry + files
 
 #define FT_CACHE_MAGIC 0x42544659u /* "YFTB" */
-#define FT_CACHE_VERSION 3u
+#define FT_CACHE_VERSION 4u
 
 struct FtCacheHeader
 {
@@ -891,7 +929,8 @@ static bool ft_cache_load(const std::string& path, uint64_t key, uint64_t image_
   if (!fp) return false;
   FtCacheHeader hd;
   bool ok = fread(&hd, sizeof(hd), 1, fp) == 1 && hd.magic == FT_CACHE_MAGIC && hd.version == FT_CACHE_VERSION &&
-            hd.image_hash == key && hd.image_size == image_size && hd.variant == variant && hd.n_b3 <= B3_WORDS &&
+            hd.image_hash == key && hd.image_size == image_size && hd.n_b3 <= B3_WORDS_DENSE &&
+            (hd.variant == variant || (variant == FT_DEFAULT_VARIANT && hd.variant == FT_DENSE_VARIANT)) &&
             hd.n_b4 <= (1u << 20) && hd.n_ht <= (1ull << 28);
   if (ok)
   {
@@ -1011,6 +1050,7 @@ int build_filter_tables(const void* image, size_t image_size, int device, Filter
     cudaFuncSetAttribute(ac_filter_kernel<1024, 2, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[2]));
     cudaFuncSetAttribute(ac_filter_tma_kernel<32, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[3]));
     cudaFuncSetAttribute(ac_filter_tma_kernel<24, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[4]));
+    cudaFuncSetAttribute(ac_filter_tma_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[5]));
     attr_set[dev] = true;
   }
   return YRB_SUCCESS;
@@ -1033,8 +1073,10 @@ void launch_ac_scan_filter(
   flo += (int64_t) ((16 - ((uintptr_t) (d + flo) & 15)) & 15);
   const FtVariant& fv = kVariants[F.variant];
   const int64_t tile_bytes = (int64_t) fv.threads * 16 * fv.u;
-  const int64_t ntiles = (hi - flo) / tile_bytes;
-  const int64_t fhi = flo + ntiles * tile_bytes;   // whole tiles only; the rest is walked
+  // whole tiles only, the rest is walked: CTA-tiles for the LDG variants, warp-tiles (2 KB) for the TMA variants
+  const int64_t unit = fv.tma_bufs ? (int64_t) FT_T_TILE : tile_bytes;
+  const int64_t fhi = flo + (hi - flo) / unit * unit;
+  const int64_t ntiles = (fhi - flo + tile_bytes - 1) / tile_bytes;
 
   if (ntiles < 1)
   {
@@ -1060,6 +1102,7 @@ void launch_ac_scan_filter(
   case 2: ac_filter_kernel<1024, 2, 19><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   case 3: ac_filter_tma_kernel<32, 18><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   case 4: ac_filter_tma_kernel<24, 18><<<grid, 768, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  case 5: ac_filter_tma_kernel<32, 0><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   default: ac_filter_kernel<1024, 4, 18><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   }
   if (after) cudaEventRecord(after, s);

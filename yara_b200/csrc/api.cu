@@ -90,7 +90,7 @@ struct PinBuf
     size_t ncap = cap ? cap : 1;
     while (ncap < n) ncap *= 2;
     T* np = nullptr;
-    if (cudaHostAlloc((void**) &np, ncap * sizeof(T), cudaHostAllocDefault) != cudaSuccess)
+    if (cudaHostAlloc((void**) &np, ncap * sizeof(T), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess)
     { cudaGetLastError(); return YRB_ERROR_INSUFFICIENT_MEMORY; }
     if (p) cudaFreeHost(p);
     p = np;
@@ -105,6 +105,8 @@ struct yrb_scanner
   yrb_rules* rules;
   int device;
   cudaStream_t stream, copy_stream;
+  SideStreams side = {};       // verifier classes / chain replay next to each other (engine.cuh)
+  bool use_side = true;        // YRB_SIDE_STREAMS=0: everything on `stream` (measurements)
   cudaEvent_t ev[8];   // 0-3 phases, 5 copy fork, 6-7 around the last filter-kernel launch
   bool kernel_timed = false;
   std::vector<cudaEvent_t> slice_ev;
@@ -119,7 +121,7 @@ struct yrb_scanner
   DevBuf<Cand> d_cand[NUM_CLS];
   DevBuf<Raw> d_raw;
   DevBuf<uint8_t> ws_fast1, ws_fast2, ws_fast3, ws_re1, ws_re2;
-  DevBuf<uint32_t> retry_fast, retry_fast3, retry_re;
+  DevBuf<uint32_t> retry_fast, retry_fast3, retry_re, retry_re0;
   VerifyWs vws = {};
   ScanStatus* d_status = nullptr;
   ScanStatus* h_status = nullptr;
@@ -308,6 +310,9 @@ static int scanner_init(yrb_scanner* s)
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&s->ev[i]));
+  for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&s->side.aux[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 6; i++) CK(cudaEventCreateWithFlags(&s->side.ev[i], cudaEventDisableTiming));
+  if (const char* e = getenv("YRB_SIDE_STREAMS")) s->use_side = atoi(e) != 0;
   CK(cudaMalloc((void**) &s->d_status, sizeof(ScanStatus)));
   CK(cudaHostAlloc((void**) &s->h_status, sizeof(ScanStatus), cudaHostAllocDefault));
   memset(s->h_status, 0, sizeof(ScanStatus));
@@ -347,10 +352,12 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+  for (int i = 0; i < 2; i++) if (s->side.aux[i]) { cudaStreamSynchronize(s->side.aux[i]); cudaStreamDestroy(s->side.aux[i]); }
+  for (int i = 0; i < 6; i++) if (s->side.ev[i]) cudaEventDestroy(s->side.ev[i]);
   s->d_data.release();
   for (int c = 0; c < NUM_CLS; c++) s->d_cand[c].release();
   s->d_raw.release(); s->ws_fast1.release(); s->ws_fast2.release(); s->ws_re1.release(); s->ws_re2.release();
-  s->retry_fast.release(); s->retry_fast3.release(); s->retry_re.release(); s->ws_fast3.release();
+  s->retry_fast.release(); s->retry_fast3.release(); s->retry_re.release(); s->retry_re0.release(); s->ws_fast3.release();
   s->k0.release(); s->k1.release(); s->kF.release(); s->ix0.release(); s->ix1.release(); s->scr32.release();
   s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release(); s->c_uvn.release(); s->sraw.release(); s->d_seeds.release(); s->seed_base.release();
   s->s_lists.release(); s->c_where.release(); s->flags8.release(); s->finals.release(); s->unconf.release();
@@ -490,13 +497,17 @@ static void fill_work(yrb_scanner* s, ResolveWork& w, const Raw* raw, uint32_t n
   w.str_min_key = s->str_min_key.p; w.str_cut_key = s->str_cut_key.p; w.str_count = s->str_count.p;
   w.s_lists = s->s_lists.p;
   w.finals = s->finals.p; w.unconf = s->unconf.p;
+  w.side = s->use_side ? &s->side : nullptr;
+  w.finals_host = nullptr;
+  w.n_plain_max = 0;
   w.too_many = s->too_many.p; w.too_many_cap = 1024;
   w.st = s->d_status;
 }
 
 // Resolve `n` raw records resident at d_raw; fills result (matches, unconfirmed, too_many, error).
+// `n_chain_records`: how many of the records are chain parts (Raw.group set), or -1 when the caller does not know.
 static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_scan_params* params, yrb_scan_result* res,
-                       unsigned* launches, bool chain_records)
+                       unsigned* launches, bool chain_records, int64_t n_chain_records = -1)
 {
   ScanStatus* hs = s->h_status;
   res->n_matches = res->n_unconfirmed = 0;
@@ -516,11 +527,34 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
 
     for (int pass = 0;; pass++)
     {
-      // one queue of kernels, the result records (at most n) and the status come back with ONE synchronisation
+      // One queue of kernels, the result records (at most n) and the status come back with ONE synchronisation.
+      // finals = [plain strings' lists: n_sel records][confirmed lists of chain heads: n_chain_out records].  At
+      // most n_plain = n - (chain parts) records are plain, so finals[0, n_plain) can leave for the host as soon
+      // as it is written, while the chain replay (the long pole of the resolve) is still running on the side
+      // stream; what the replay adds lies in [n_sel, n) and follows.  Only when records were deduplicated
+      // (n_sel < n_plain) does the chain part begin inside the range that was copied early: one more small copy.
+      uint32_t n_plain = 0;   // chain parts among the records, count unknown: everything is copied after the replay
+      if (!w.has_chains)
+        n_plain = n;
+      else if (n_chain_records >= 0 && (uint64_t) n_chain_records <= n)
+        n_plain = n - (uint32_t) n_chain_records;
+      w.finals_host = s->h_finals.p;
+      w.n_plain_max = n_plain;
       launch_resolve(w, s->stream, launches);
-      CK(cudaMemcpyAsync(s->h_finals.p, s->finals.p, (size_t) n * sizeof(yrb_match), cudaMemcpyDeviceToHost, s->stream));
+      if (n_plain < n)
+        CK(cudaMemcpyAsync(s->h_finals.p + n_plain, s->finals.p + n_plain, (size_t) (n - n_plain) * sizeof(yrb_match),
+                           cudaMemcpyDeviceToHost, s->stream));
       rc = read_status(s);
       if (rc != YRB_SUCCESS) return rc;
+      if (n_plain < n && (uint32_t) hs->n_sel < n_plain && hs->n_chain_out > 0)
+      {
+        size_t hi = (size_t) hs->n_sel + (size_t) hs->n_chain_out;
+        if (hi > n_plain) hi = n_plain;
+        TRACE("resolve: %u plain records deduplicated, chain part re-copied from %d", n_plain - (uint32_t) hs->n_sel, hs->n_sel);
+        CK(cudaMemcpyAsync(s->h_finals.p + hs->n_sel, s->finals.p + hs->n_sel, (hi - (size_t) hs->n_sel) * sizeof(yrb_match),
+                           cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+      }
       if (!hs->over_cap || pass == 1) break;
 
       // rare, exact path: find each over-cap string's cut key, then resolve again without the cut records
@@ -843,14 +877,20 @@ static int scan_impl(
   if (n_cand[CLS_RE] > 0)
   {
     const uint32_t sw = s->rules->R.stack_words;
+    // tier 0 (fiber pool in local memory) takes every candidate when the repeat stacks fit; tier 1 then only sees
+    // what outgrew it and gets by with far fewer threads (and a far smaller work area)
+    static const bool tier0_on = !(getenv("YRB_RE_TIER0") && atoi(getenv("YRB_RE_TIER0")) == 0);
+    const bool tier0 = tier0_on && sw <= RE_LOCAL_STACK;
     size_t want = (size_t) ((n_cand[CLS_RE] + 127) / 128) * 128;
-    const size_t maxt = (size_t) s->rules->num_sms * 2048;
+    const size_t maxt = (size_t) s->rules->num_sms * (tier0 ? 256 : 2048);
     if (want > maxt) want = maxt;
     if (s->ws_re1.ensure(want * re_ws_bytes_per_thread(sw, 1)) != YRB_SUCCESS ||
-        s->retry_re.ensure((size_t) n_cand[CLS_RE]) != YRB_SUCCESS)
+        s->retry_re.ensure((size_t) n_cand[CLS_RE]) != YRB_SUCCESS ||
+        (tier0 && s->retry_re0.ensure((size_t) n_cand[CLS_RE]) != YRB_SUCCESS))
       return YRB_ERROR_INSUFFICIENT_MEMORY;
-    s->vws.re1 = s->ws_re1.p; s->vws.re1_threads = s->ws_re1.cap / re_ws_bytes_per_thread(sw, 1) / 128 * 128;
+    s->vws.re1 = s->ws_re1.p; s->vws.re1_threads = want;
     s->vws.retry_re = s->retry_re.p;
+    s->vws.retry_re0 = tier0 ? s->retry_re0.p : nullptr;
   }
 
   if (s->d_raw.ensure((size_t) total_cand * 2 + 4096) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
@@ -870,7 +910,7 @@ static int scan_impl(
       CK(cudaMemsetAsync(s->str_err.p, 0xFF, sizeof(unsigned long long) * s->rules->R.num_strings, s->stream));
 
     TRACE("verify tier 1: %llu literal, %llu fast, %llu re candidates", n_cand[0], n_cand[1], n_cand[2]);
-    launch_verify(s->rules->R, V, co, n_cand, ro, s->vws, s->stream, &launches);
+    launch_verify(s->rules->R, V, co, n_cand, ro, s->vws, s->stream, &launches, s->use_side ? &s->side : nullptr);
     int rc = read_status(s);
     if (rc != YRB_SUCCESS) return rc;
     TRACE("tier 1 done: retry fast %u re %u, raw %llu, any_error %u", hs->n_retry[0], hs->n_retry[1], hs->n_raw, hs->any_error);
@@ -935,6 +975,7 @@ static int scan_impl(
     if (s->d_raw.ensure((size_t) hs->n_raw + 1024) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
     CK(cudaMemsetAsync(&s->d_status->n_raw, 0, sizeof(unsigned long long), s->stream));
     CK(cudaMemsetAsync(&s->d_status->n_retry[0], 0, 2 * sizeof(unsigned int), s->stream));
+    CK(cudaMemsetAsync(&s->d_status->n_retry_re0, 0, sizeof(unsigned int), s->stream));
     CK(cudaMemsetAsync(&s->d_status->any_error, 0, sizeof(unsigned int), s->stream));
     CK(cudaMemsetAsync(&s->d_status->n_retry3, 0, 2 * sizeof(unsigned int), s->stream));   // n_retry3, n_chain_raw
   }
@@ -1029,7 +1070,8 @@ static int scan_impl(
   else
   {
     TRACE("resolve: %u records, chain records %u", n_resolve, hs->n_chain_raw);
-    rc = run_resolve(s, s->d_raw.p, n_resolve, params, res, &launches, hs->n_chain_raw > 0 || n_resolve > (uint32_t) n_raw);
+    rc = run_resolve(s, s->d_raw.p, n_resolve, params, res, &launches, hs->n_chain_raw > 0 || n_resolve > (uint32_t) n_raw,
+                     (int64_t) hs->n_chain_raw + (int64_t) (n_resolve - (uint32_t) n_raw));
     TRACE("resolve done: rc %d error %d", rc, res->error);
     res->seeds_consumed = (n_resolve > (uint32_t) n_raw) ? 1 : 0;
     CK(cudaEventRecord(s->ev[3], s->stream));
@@ -1411,11 +1453,13 @@ static int multi_run(yrb_multi* m, const yrb_scan_params* params, yrb_scan_resul
   res->error_string = YRB_NONE;
   size_t total = 0;
   uint32_t chain_raw = 0, any_error = 0;
+  int64_t chain_raw_total = 0;
   for (MultiWorker* w : m->w)
   {
     if (w->job.rc != YRB_SUCCESS) return w->job.rc;
     total += w->scanner->h_raw_n;
     chain_raw |= w->scanner->shard_n_chain_raw;
+    chain_raw_total += w->scanner->shard_n_chain_raw;
     any_error |= w->scanner->shard_any_error;
     res->stats.bytes += w->job.res.stats.bytes;
     res->stats.n_candidates += w->job.res.stats.n_candidates;
@@ -1468,7 +1512,7 @@ static int multi_run(yrb_multi* m, const yrb_scan_params* params, yrb_scan_resul
   yrb_scan_params p = *params;
   p.n_seeds = 0;
   p.seeds = nullptr;
-  int rc = run_resolve(s0, s0->d_raw.p, (uint32_t) total, &p, res, &launches, chain_raw != 0);
+  int rc = run_resolve(s0, s0->d_raw.p, (uint32_t) total, &p, res, &launches, chain_raw != 0, chain_raw_total);
   CK(cudaEventRecord(m->ev1, s0->stream));
   CK(cudaStreamSynchronize(s0->stream));
   std::chrono::steady_clock::time_point t2 = std::chrono::steady_clock::now();

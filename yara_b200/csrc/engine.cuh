@@ -141,6 +141,7 @@ struct ScanStatus
   unsigned int err_string1;     // 1 + string of the candidate behind the error (scanner->last_error_string); 0 = none
   unsigned int n_chain_starts;  // chains present among the Raw records (resolve.cu: one warp each)
   unsigned int key_overflow;    // one candidate fired more than KEY_SEQ_MAX match callbacks: its records cannot be ordered
+  unsigned int n_retry_re0;     // fiber-VM candidates that outgrew the local-memory tier (verify.cu, tier 0 -> tier 1)
 };
 
 struct CandOut
@@ -201,6 +202,8 @@ void launch_ac_scan_filter(
     int num_sms, cudaStream_t s, cudaEvent_t before = nullptr, cudaEvent_t after = nullptr);
 int build_filter_tables(const void* host_image, size_t image_size, int device, FilterTables* out, void** d_storage);
 
+#define RE_LOCAL_STACK 8   // fiber VM, tier 0 (verify.cu): repeat-counter stack words per fiber held in local memory
+
 struct VerifyWs
 {
   void* fast1; size_t fast1_threads;   // tier 1 work areas (small, many threads)
@@ -209,13 +212,22 @@ struct VerifyWs
   void* re2;   size_t re2_threads;
   uint32_t* retry_fast;
   uint32_t* retry_re;
+  uint32_t* retry_re0;                 // fiber VM, tier 0 -> tier 1 queue (nullptr: no tier 0)
   uint32_t* retry_fast3;               // tier 2 -> tier 3 queue
   void* fast3; size_t fast3_threads;   // tier 3: allocated only when something reaches it
 };
 
+// Side streams and fork/join events of a scanner: the three verifier classes run next to each other, and so
+// do the chain replay and the writing-out of the plain strings' lists (all of them latency bound, none fills the GPU).
+struct SideStreams
+{
+  cudaStream_t aux[2];
+  cudaEvent_t ev[6];
+};
+
 void launch_verify(
     const DevRules& R, const ScanView& V, const CandOut& cands, const unsigned long long n_cand[NUM_CLS],
-    const RawOut& out, const VerifyWs& W, cudaStream_t s, unsigned* launches);
+    const RawOut& out, const VerifyWs& W, cudaStream_t s, unsigned* launches, const SideStreams* side = nullptr);
 size_t fast_ws_bytes_per_thread(int tier);
 void launch_verify_tier2(
     const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, bool fast, bool re,

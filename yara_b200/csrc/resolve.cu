@@ -63,17 +63,20 @@ void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches)
   size_t b = w.cub_tmp_bytes;
   cub::DeviceRadixSort::SortPairs(w.cub_tmp, b, w.k0, w.k1, w.ix0, w.ix1, (int) n, 0, 64, s); // -> k1, ix1
 
-  cudaMemsetAsync(w.str_count, 0, sizeof(uint32_t) * w.R.num_strings, s);
-  select_plain_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.R, w.str_count, w.flags);
-  check_cap_kernel<<<GRID(w.R.num_strings), 0, s>>>(w.str_count, w.R.num_strings, w.st);
-  b = w.cub_tmp_bytes;
-  cub::DeviceSelect::Flagged(w.cub_tmp, b, cub::CountingInputIterator<uint32_t>(0), w.flags, w.ix0, &w.st->n_sel, (int) n, s);
-  write_plain_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.ix0, w.st, n, w.finals);
-  (*launches) += 4 + 10 + 3;
+  // From here on two independent strands work on the sorted records: the plain strings' selection and
+  // write-out, and the chain replay.  With a side stream they run next to each other -- the replay (one warp
+  // per chain, latency bound) only has to wait for n_sel, the slot its confirmed lists start at.
+  const bool fork = w.has_chains && w.side != nullptr;
+  cudaStream_t cs = fork ? w.side->aux[0] : s;
+  if (fork)
+  {
+    cudaEventRecord(w.side->ev[3], s);
+    cudaStreamWaitEvent(cs, w.side->ev[3], 0);
+  }
 
+  ChainLists L;
   if (w.has_chains)   // the ruleset has chained strings AND this block produced records for them (or carries seeds)
   {
-    ChainLists L;
     L.nxt = w.c_nxt; L.prv = w.c_prv; L.clen = w.c_clen; L.mlen = w.c_mlen; L.where = w.c_where;
     L.uhead = w.s_lists; L.utail = w.s_lists + w.R.num_strings; L.ucnt = w.s_lists + 2 * (size_t) w.R.num_strings;
     L.mhead = w.s_lists + 3 * (size_t) w.R.num_strings; L.mtail = w.s_lists + 4 * (size_t) w.R.num_strings;
@@ -82,15 +85,39 @@ void launch_resolve(ResolveWork& w, cudaStream_t s, unsigned* launches)
     L.prior = w.s_lists + 7 * (size_t) w.R.num_strings;
     L.uvn = w.c_uvn;
     L.first_conf = (w.scan_flags & YRB_SCAN_FAST_MODE) ? w.str_min_key : nullptr;
-    chain_init_kernel<<<GRID(w.R.num_strings), 0, s>>>(L, w.R.num_strings);
-    cudaMemsetAsync(&w.st->n_chain_starts, 0, sizeof(unsigned int), s);
-    chain_gather_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.sraw, w.c_scratch_u32, w.st);
+    chain_init_kernel<<<GRID(w.R.num_strings), 0, cs>>>(L, w.R.num_strings);
+    cudaMemsetAsync(&w.st->n_chain_starts, 0, sizeof(unsigned int), cs);
+    chain_gather_kernel<<<GRID(n), 0, cs>>>(w.raw, w.ix1, w.k1, n, w.sraw, w.c_scratch_u32, w.st);
+  }
+
+  cudaMemsetAsync(w.str_count, 0, sizeof(uint32_t) * w.R.num_strings, s);
+  select_plain_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.k1, n, w.R, w.str_count, w.flags);
+  check_cap_kernel<<<GRID(w.R.num_strings), 0, s>>>(w.str_count, w.R.num_strings, w.st);
+  b = w.cub_tmp_bytes;
+  cub::DeviceSelect::Flagged(w.cub_tmp, b, cub::CountingInputIterator<uint32_t>(0), w.flags, w.ix0, &w.st->n_sel, (int) n, s);
+  if (fork)
+  {
+    cudaEventRecord(w.side->ev[4], s);
+    cudaStreamWaitEvent(cs, w.side->ev[4], 0);
+  }
+  write_plain_kernel<<<GRID(n), 0, s>>>(w.raw, w.ix1, w.ix0, w.st, n, w.finals);
+  if (w.finals_host != nullptr && w.n_plain_max > 0)
+    cudaMemcpyAsync(w.finals_host, w.finals, (size_t) w.n_plain_max * sizeof(yrb_match), cudaMemcpyDeviceToHost, s);
+  (*launches) += 4 + 10 + 3;
+
+  if (w.has_chains)
+  {
     // one warp per chain present in the records (at most one chain per string)
     const uint32_t max_chains = w.R.num_strings < n ? w.R.num_strings : n;
-    chain_resolve_kernel<<<(max_chains * 32 + 127) / 128, 128, 0, s>>>(
+    chain_resolve_kernel<<<(max_chains * 32 + 127) / 128, 128, 0, cs>>>(
         w.sraw, w.k1, n, w.R, L, w.finals, w.unconf, w.st, w.too_many, w.too_many_cap, w.scan_flags, w.seed_base, w.cur_base,
         w.n_seg, w.seg_start, w.seg_len, w.item_dirty, w.c_scratch_u32);
     (*launches) += 3;
+    if (fork)
+    {
+      cudaEventRecord(w.side->ev[5], cs);
+      cudaStreamWaitEvent(s, w.side->ev[5], 0);
+    }
   }
 }
 

@@ -43,6 +43,14 @@ struct ResolveWork
   uint32_t* str_count;             // num_strings
   int32_t* s_lists;                // 8 * num_strings
 
+  // optional: side stream + events (the chain replay runs next to the plain strings' selection and write-out)
+  // and where the plain strings' records go on the host: with `finals_host` set and `n_plain_max` = an upper
+  // bound of the number of plain records (records that are not chain parts), launch_resolve queues the copy of
+  // finals[0, n_plain_max) right behind write_plain_kernel, while the chain replay is still running
+  const SideStreams* side;
+  yrb_match* finals_host;
+  uint32_t n_plain_max;
+
   // outputs
   yrb_match* finals;
   yrb_match* unconf;

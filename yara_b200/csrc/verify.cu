@@ -166,16 +166,57 @@ static __device__ int re_fast_exec(
     max_bytes_matched = (int) (input_forwards_size < YRB_RE_SCAN_LIMIT ? input_forwards_size : YRB_RE_SCAN_LIMIT);
 
   uint32_t ip = code_off;
-
-  int first = n_used++;
-  P[first].input = (flags & RE_FLAGS_BACKWARDS) ? -1 : 0;
-  P[first].round = 0;
-  P[first].prev = P[first].next = -1;
-
-  int last = first;
   int round = 0;
 
   if (matches) *matches = -1;
+
+  // Until the first jump the position list holds ONE entry (re.c:2184-2196 seeds it with the exec's input
+  // position and only OP_REPEAT_ANY_UNGREEDY adds to it), and nearly every candidate -- a 4-byte atom that
+  // happened to occur in unrelated bytes -- dies on the first opcode behind its atom.  That prefix is run on
+  // registers: same opcodes, same bounds, same effects as the list loop below with a one-element list; the
+  // entry is written to the work area only when a jump or a match is reached.
+  int cin0 = (flags & RE_FLAGS_BACKWARDS) ? -1 : 0;
+  for (;;)
+  {
+    const uint32_t op = code_u8(c, ip);
+    const int bm = (flags & RE_FLAGS_BACKWARDS) ? (-cin0 - 1) : cin0;
+    bool match;
+    uint32_t len;
+    if (op == OP_ANY)
+    {
+      match = bm < max_bytes_matched;
+      len = 1;
+    }
+    else if (op == OP_LITERAL || op == OP_NOT_LITERAL)
+    {
+      match = bm < max_bytes_matched && ((byte_at(c, pos + cin0) == code_u8(c, ip + 1)) == (op == OP_LITERAL));
+      len = 2;
+    }
+    else if (op == OP_MASKED_LITERAL || op == OP_MASKED_NOT_LITERAL)
+    {
+      match = false;
+      if (bm < max_bytes_matched)
+      {
+        const uint32_t args = code_u16(c, ip + 1);
+        match = ((byte_at(c, pos + cin0) & (args >> 8)) == (args & 0xFF)) == (op == OP_MASKED_LITERAL);
+      }
+      len = 3;
+    }
+    else
+      break;   // OP_REPEAT_ANY_UNGREEDY, OP_MATCH, anything unknown: the list loop takes over
+    if (!match)
+      return YRB_SUCCESS;   // the only entry is dropped: the list is empty, the exec ends (re.c:2445-2465)
+    cin0 += input_incr;
+    ip += len;
+    round++;
+  }
+
+  int first = n_used++;
+  P[first].input = cin0;
+  P[first].round = round;
+  P[first].prev = P[first].next = -1;
+
+  int last = first;
 
   while (first >= 0)
   {
@@ -1203,25 +1244,48 @@ verify_fast_kernel(
   }
 }
 
-template <bool TIER2>
+// Fiber VM tiers.  TIER 0: every candidate, with a pool of RE_FIBERS_LOCAL fibers in a per-thread LOCAL array:
+// local memory is interleaved across the lanes of a warp by the hardware (the same field of the same fiber of 32
+// candidates is one 128-byte line) and cached write-back in L1, where the per-thread slices of a global work
+// area (1.5 KB apart) cost a line per lane and access.  Nearly every regex lives with a handful of fibers, so this
+// is where the class is verified; what outgrows it is queued (retry_out, n_retry_re0) for TIER 1: RE_FIBERS_SMALL
+// fibers in the global work area (also the entry tier when the ruleset's repeat stacks are deeper than
+// RE_LOCAL_STACK: then retry_in == nullptr and it takes every candidate), which queues for TIER 2 (n_retry[1]):
+// the reference's limits, RE_MAX_FIBERS and a frame per fiber.
+#define RE_FIBERS_LOCAL 16
+
+template <int TIER>
 __global__ void __launch_bounds__(128)
 verify_re_kernel(
     DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out, uint8_t* ws, size_t ws_per_thread,
-    int cap, uint32_t* retry)
+    int cap, const uint32_t* retry_in, uint32_t* retry_out)
 {
   const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
 
-  if (TIER2) n = out.st->n_retry[1];
+  if (TIER == 1 && retry_in != nullptr) n = out.st->n_retry_re0;
+  if (TIER == 2) n = out.st->n_retry[1];
   if (tid >= n) return;
 
+  Fiber local_f[TIER == 0 ? RE_FIBERS_LOCAL : 1];
+  uint16_t local_s[TIER == 0 ? RE_FIBERS_LOCAL * RE_LOCAL_STACK : 1];
+
   FiberPool p;
-  p.f = reinterpret_cast<Fiber*>(ws + tid * ws_per_thread);
-  p.stacks = reinterpret_cast<uint16_t*>(p.f + cap);
+  if (TIER == 0)
+  {
+    p.f = local_f;
+    p.stacks = local_s;
+    cap = RE_FIBERS_LOCAL;
+  }
+  else
+  {
+    p.f = reinterpret_cast<Fiber*>(ws + tid * ws_per_thread);
+    p.stacks = reinterpret_cast<uint16_t*>(p.f + cap);
+  }
   p.cap = cap;
   p.stack_words = (int) R.stack_words;
   p.frames = nullptr;
-  if (TIER2)
+  if (TIER == 2)
   {
     size_t fb = (size_t) cap * (sizeof(Fiber) + sizeof(uint16_t) * R.stack_words);
     fb = (fb + 15) & ~(size_t) 15;
@@ -1236,7 +1300,7 @@ verify_re_kernel(
 
   for (unsigned long long t = tid; t < n; t += stride)
   {
-    const unsigned long long ci = TIER2 ? retry[t] : t;
+    const unsigned long long ci = (TIER == 2 || (TIER == 1 && retry_in != nullptr)) ? retry_in[t] : t;
     const Cand cd = cands[ci];
     const yrb_acm m = R.acm[cd.acm_idx];
     const yrb_string s = R.S[m.string_idx];
@@ -1245,9 +1309,14 @@ verify_re_kernel(
     int rc = verify_re<false>(c, nullptr, &p, m, s, at);
     if (rc == WS_RETRY)
     {
-      if (!TIER2)
+      if (TIER == 0)
       {
-        retry[atomicAdd(&out.st->n_retry[1], 1u)] = (uint32_t) ci;
+        retry_out[atomicAdd(&out.st->n_retry_re0, 1u)] = (uint32_t) ci;
+        continue;
+      }
+      if (TIER == 1)
+      {
+        retry_out[atomicAdd(&out.st->n_retry[1], 1u)] = (uint32_t) ci;
         continue;
       }
       rc = YRB_ERROR_INTERNAL_FATAL;
@@ -1260,15 +1329,36 @@ verify_re_kernel(
 #ifndef YRB_HOST_EMULATION   // tests/harness/vm_host.cpp compiles the device code above for the CPU and drives it itself
 void launch_verify(
     const DevRules& R, const ScanView& V, const CandOut& cands, const unsigned long long n_cand[NUM_CLS],
-    const RawOut& out, const VerifyWs& W, cudaStream_t s, unsigned* launches)
+    const RawOut& out, const VerifyWs& W, cudaStream_t s, unsigned* launches, const SideStreams* side)
 {
   const int T = 128;
+
+  // The classes only share atomically appended outputs, so they run side by side: the largest class (by
+  // count) stays on the scanner's stream, the others go to the side streams and are joined at the end.
+  const int n_classes = (n_cand[CLS_LITERAL] > 0) + (n_cand[CLS_FAST] > 0) + (n_cand[CLS_RE] > 0);
+  cudaStream_t cs[NUM_CLS] = {s, s, s};
+  bool joined[2] = {false, false};
+  if (side != nullptr && n_classes > 1)
+  {
+    int main_cls = CLS_LITERAL;
+    for (int c = 0; c < NUM_CLS; c++) if (n_cand[c] > n_cand[main_cls]) main_cls = c;
+    cudaEventRecord(side->ev[0], s);
+    int k = 0;
+    for (int c = 0; c < NUM_CLS; c++)
+    {
+      if (c == main_cls || n_cand[c] == 0) continue;
+      cs[c] = side->aux[k];
+      cudaStreamWaitEvent(side->aux[k], side->ev[0], 0);
+      joined[k] = true;
+      k++;
+    }
+  }
 
   if (n_cand[CLS_LITERAL] > 0)
   {
     unsigned long long blocks = (n_cand[CLS_LITERAL] + T - 1) / T;
     if (blocks > 148 * 64) blocks = 148 * 64;
-    verify_literal_kernel<<<(unsigned) blocks, T, 0, s>>>(R, V, cands.cand[CLS_LITERAL], n_cand[CLS_LITERAL], out);
+    verify_literal_kernel<<<(unsigned) blocks, T, 0, cs[CLS_LITERAL]>>>(R, V, cands.cand[CLS_LITERAL], n_cand[CLS_LITERAL], out);
     (*launches)++;
   }
 
@@ -1278,7 +1368,7 @@ void launch_verify(
     unsigned blocks = (unsigned) ((threads + T - 1) / T);
     if ((unsigned long long) blocks * T > W.fast1_threads) blocks = (unsigned) (W.fast1_threads / T);
     if (blocks == 0) blocks = 1;
-    verify_fast_kernel<1><<<blocks, T, 0, s>>>(
+    verify_fast_kernel<1><<<blocks, T, 0, cs[CLS_FAST]>>>(
         R, V, cands.cand[CLS_FAST], n_cand[CLS_FAST], out, (uint8_t*) W.fast1, fast_ws_bytes_per_thread(1),
         FAST_POS_CAP_SMALL, nullptr, W.retry_fast);
     (*launches)++;
@@ -1290,10 +1380,32 @@ void launch_verify(
     unsigned blocks = (unsigned) ((threads + T - 1) / T);
     if ((unsigned long long) blocks * T > W.re1_threads) blocks = (unsigned) (W.re1_threads / T);
     if (blocks == 0) blocks = 1;
-    verify_re_kernel<false><<<blocks, T, 0, s>>>(
-        R, V, cands.cand[CLS_RE], n_cand[CLS_RE], out, (uint8_t*) W.re1, re_ws_bytes_per_thread(R.stack_words, 1),
-        RE_FIBERS_SMALL, W.retry_re);
-    (*launches)++;
+    if (W.retry_re0 != nullptr && R.stack_words <= RE_LOCAL_STACK)
+    {
+      // tier 0 needs no work area: a thread per candidate; tier 1 follows for what it queued (count read on the device)
+      unsigned long long b0 = (n_cand[CLS_RE] + T - 1) / T;
+      if (b0 > 148ull * 256) b0 = 148ull * 256;
+      verify_re_kernel<0><<<(unsigned) b0, T, 0, cs[CLS_RE]>>>(
+          R, V, cands.cand[CLS_RE], n_cand[CLS_RE], out, nullptr, 0, RE_FIBERS_LOCAL, nullptr, W.retry_re0);
+      verify_re_kernel<1><<<blocks, T, 0, cs[CLS_RE]>>>(
+          R, V, cands.cand[CLS_RE], 0, out, (uint8_t*) W.re1, re_ws_bytes_per_thread(R.stack_words, 1),
+          RE_FIBERS_SMALL, W.retry_re0, W.retry_re);
+      (*launches) += 2;
+    }
+    else
+    {
+      verify_re_kernel<1><<<blocks, T, 0, cs[CLS_RE]>>>(
+          R, V, cands.cand[CLS_RE], n_cand[CLS_RE], out, (uint8_t*) W.re1, re_ws_bytes_per_thread(R.stack_words, 1),
+          RE_FIBERS_SMALL, nullptr, W.retry_re);
+      (*launches)++;
+    }
+  }
+
+  for (int k = 0; k < 2; k++)
+  {
+    if (!joined[k]) continue;
+    cudaEventRecord(side->ev[1 + k], side->aux[k]);
+    cudaStreamWaitEvent(s, side->ev[1 + k], 0);
   }
 }
 
@@ -1313,9 +1425,9 @@ void launch_verify_tier2(
   }
   if (re)
   {
-    verify_re_kernel<true><<<(unsigned) ((W.re2_threads + T - 1) / T), T, 0, s>>>(
+    verify_re_kernel<2><<<(unsigned) ((W.re2_threads + T - 1) / T), T, 0, s>>>(
         R, V, cands.cand[CLS_RE], 0, out, (uint8_t*) W.re2, re_ws_bytes_per_thread(R.stack_words, 2),
-        YRB_RE_MAX_FIBERS, W.retry_re);
+        YRB_RE_MAX_FIBERS, W.retry_re, nullptr);
     (*launches)++;
   }
 }
