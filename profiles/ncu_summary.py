@@ -42,7 +42,7 @@ def main():
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_")]
     data = []
     for r in rows[2:]:
-        if len(r) <= ws or r[0] == "Address":
+        if len(r) < len(hdr) or r[0] == "Address":
             if data:
                 break
             continue

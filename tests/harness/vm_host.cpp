@@ -460,7 +460,7 @@ static long long run_verify(
                             FAST_POS_CAP_SMALL, nullptr, retry_fast.data());
     }
     if (n_cand[CLS_RE] && re_t0)
-      verify_re_kernel<0>(R, V, cand[CLS_RE].data(), n_cand[CLS_RE], ro, nullptr, 0, RE_FIBERS_LOCAL, nullptr, retry_re0.data());
+      verify_re_kernel<0>(R, V, cand[CLS_RE].data(), n_cand[CLS_RE], ro, nullptr, 32, RE_FIBERS_LOCAL, nullptr, retry_re0.data());
     else if (n_cand[CLS_RE])
     {
       ws.assign(re_ws_bytes_per_thread(R.stack_words, 1), 0);

@@ -122,6 +122,8 @@ struct yrb_scanner
   DevBuf<Raw> d_raw;
   DevBuf<uint8_t> ws_fast1, ws_fast2, ws_fast3, ws_re1, ws_re2;
   DevBuf<uint32_t> retry_fast, retry_fast3, retry_re, retry_re0;
+  DevBuf<uint32_t> cs_k0, cs_k1, cs_v0, cs_v1;   // candidates in AC-match order (VerifyWs::sort_*)
+  DevBuf<uint8_t> cs_tmp;
   VerifyWs vws = {};
   ScanStatus* d_status = nullptr;
   ScanStatus* h_status = nullptr;
@@ -358,6 +360,7 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   for (int c = 0; c < NUM_CLS; c++) s->d_cand[c].release();
   s->d_raw.release(); s->ws_fast1.release(); s->ws_fast2.release(); s->ws_re1.release(); s->ws_re2.release();
   s->retry_fast.release(); s->retry_fast3.release(); s->retry_re.release(); s->retry_re0.release(); s->ws_fast3.release();
+  s->cs_k0.release(); s->cs_k1.release(); s->cs_v0.release(); s->cs_v1.release(); s->cs_tmp.release();
   s->k0.release(); s->k1.release(); s->kF.release(); s->ix0.release(); s->ix1.release(); s->scr32.release();
   s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release(); s->c_uvn.release(); s->sraw.release(); s->d_seeds.release(); s->seed_base.release();
   s->s_lists.release(); s->c_where.release(); s->flags8.release(); s->finals.release(); s->unconf.release();
@@ -894,6 +897,31 @@ static int scan_impl(
   }
 
   if (s->d_raw.ensure((size_t) total_cand * 2 + 4096) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+
+  {
+    // the VM classes are verified in AC-match order when there are enough candidates for warps to share strings
+    static const int sort_mask = getenv("YRB_SORT_CANDS") ? atoi(getenv("YRB_SORT_CANDS")) : ((1 << CLS_FAST) | (1 << CLS_RE));
+    size_t need = 0, nmax = 0;
+    for (int c = 0; c < NUM_CLS; c++)
+    {
+      s->vws.sort_cls[c] = ((sort_mask >> c) & 1) && c != CLS_LITERAL && n_cand[c] >= 2048 && n_cand[c] < (1ull << 31);
+      if (s->vws.sort_cls[c]) { need += (size_t) n_cand[c]; if (n_cand[c] > nmax) nmax = (size_t) n_cand[c]; }
+    }
+    if (need > 0)
+    {
+      const size_t tb = (cand_sort_temp_bytes((uint32_t) nmax) + 255) & ~(size_t) 255;
+      if (s->cs_k0.ensure(need) != YRB_SUCCESS || s->cs_k1.ensure(need) != YRB_SUCCESS || s->cs_v0.ensure(need) != YRB_SUCCESS ||
+          s->cs_v1.ensure(need) != YRB_SUCCESS || s->cs_tmp.ensure(2 * tb) != YRB_SUCCESS)
+        return YRB_ERROR_INSUFFICIENT_MEMORY;
+      s->vws.sort_k[0] = s->cs_k0.p; s->vws.sort_k[1] = s->cs_k1.p;
+      s->vws.sort_v[0] = s->cs_v0.p; s->vws.sort_v[1] = s->cs_v1.p;
+      s->vws.sort_cap = need;
+      s->vws.sort_tmp = s->cs_tmp.p;
+      s->vws.sort_tmp_bytes = 2 * tb;
+    }
+    else
+      s->vws.sort_cap = 0;
+  }
 
   for (int attempt = 0;; attempt++)
   {

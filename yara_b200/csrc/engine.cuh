@@ -213,6 +213,17 @@ struct VerifyWs
   uint32_t* retry_fast;
   uint32_t* retry_re;
   uint32_t* retry_re0;                 // fiber VM, tier 0 -> tier 1 queue (nullptr: no tier 0)
+  // Candidates are appended by whichever warp of the scan kernel finds them; verified in that order, the 32
+  // lanes of a warp run 32 different strings' code (3.4 lanes active per instruction, a third of the stall
+  // samples waiting for instructions: profiles/r02_ncu_verify_re_tier0_cfg5_summary.txt).  Order only matters
+  // through the discovery key each candidate carries, so the VM classes are verified in AC-match order: a
+  // radix sort by acm index gives sort_perm[c] (nullptr: class not sorted), and a warp's lanes then share the
+  // string, its code and most of their control flow.
+  uint32_t* sort_k[2];                 // scratch for the sort: keys and values, double buffered, sort_cap entries each
+  uint32_t* sort_v[2];
+  size_t sort_cap;
+  void* sort_tmp; size_t sort_tmp_bytes;
+  int sort_cls[NUM_CLS];               // 1: verify this class in sorted order
   uint32_t* retry_fast3;               // tier 2 -> tier 3 queue
   void* fast3; size_t fast3_threads;   // tier 3: allocated only when something reaches it
 };
@@ -229,6 +240,11 @@ void launch_verify(
     const DevRules& R, const ScanView& V, const CandOut& cands, const unsigned long long n_cand[NUM_CLS],
     const RawOut& out, const VerifyWs& W, cudaStream_t s, unsigned* launches, const SideStreams* side = nullptr);
 size_t fast_ws_bytes_per_thread(int tier);
+size_t cand_sort_temp_bytes(uint32_t n);
+// perm_out (= v_b or v_a, returned) lists the candidate indices in ascending acm order
+const uint32_t* launch_cand_sort(
+    const Cand* cands, uint32_t n, uint32_t num_acm, uint32_t* k_a, uint32_t* k_b, uint32_t* v_a, uint32_t* v_b, void* tmp,
+    size_t tmp_bytes, cudaStream_t s);
 void launch_verify_tier2(
     const DevRules& R, const ScanView& V, const CandOut& cands, const RawOut& out, const VerifyWs& W, bool fast, bool re,
     cudaStream_t s, unsigned* launches);

@@ -44,6 +44,33 @@ size_t resolve_cub_temp_bytes(uint32_t n)
 
 #define GRID(n) (unsigned) (((n) + 255) / 256), 256
 
+// ---- candidates in AC-match order for the verifiers (engine.cuh, VerifyWs)
+__global__ void cand_keys_kernel(const Cand* cands, uint32_t n, uint32_t* keys, uint32_t* vals)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  keys[j] = cands[j].acm_idx;
+  vals[j] = j;
+}
+
+size_t cand_sort_temp_bytes(uint32_t n)
+{
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t*) nullptr, (uint32_t*) nullptr, (uint32_t*) nullptr, (uint32_t*) nullptr, (int) n);
+  return b + 256;
+}
+
+const uint32_t* launch_cand_sort(
+    const Cand* cands, uint32_t n, uint32_t num_acm, uint32_t* k_a, uint32_t* k_b, uint32_t* v_a, uint32_t* v_b, void* tmp,
+    size_t tmp_bytes, cudaStream_t s)
+{
+  int bits = 1;
+  while (bits < 32 && (1ull << bits) < (unsigned long long) num_acm) bits++;
+  cand_keys_kernel<<<GRID(n), 0, s>>>(cands, n, k_a, v_a);
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_a, k_b, v_a, v_b, (int) n, 0, bits, s);
+  return v_b;
+}
+
 // Everything from Raw records to final records, queued on the stream without any
 // host synchronisation; the caller reads ScanStatus (n_sel, n_chain_out, n_unconf,
 // over_cap) afterwards.  With w.use_cut the records at or after each string's cut

@@ -16,6 +16,16 @@
 // per-thread work area in global memory, indexed with 16-bit links.
 #include "engine.cuh"
 
+// The fiber VM inlined into its three call sites is 150 KB of SASS and its warps spend a third of their stall
+// samples waiting for instructions -- but as real functions (__noinline__: 74 KB) re_exec and fiber_sync get the
+// candidate's context and the fiber pool by reference, i.e. in local memory instead of registers, and the class
+// took 40 % longer (cfg 5, 1 GiB: 0.55 -> 0.76 ms; profiles/r02_kernel_notes.txt).  Kept inline.
+#if defined(__CUDACC__) && defined(YRB_VM_NOINLINE)
+#define YRB_NOINLINE __noinline__
+#else
+#define YRB_NOINLINE
+#endif
+
 // ----------------------------------------------------------------- data access
 
 struct Ctx
@@ -406,6 +416,9 @@ struct SyncFrame
   uint32_t mask[4];
 };
 
+#ifndef YRB_RE_NO_FASTPATH
+#define YRB_RE_NO_FASTPATH 0
+#endif
 #define RE_STEPS_PER_POSITION_MAX (1u << 20)
 #define RE_FIBERS_SMALL 64      // tier 1 pool; tier 2 has the reference's RE_MAX_FIBERS = 1024
 
@@ -548,7 +561,7 @@ static __device__ __forceinline__ void fiber_kill_all(FiberPool& p)
 // (re.c:1626); here the recursion is an explicit frame stack.  The set of
 // already-executed split ids (ids < RE_MAX_SPLIT_ID = 128) is a 128-bit mask.
 
-static __device__ int fiber_sync(Ctx& c, FiberPool& p, int fiber_to_sync)
+static __device__ YRB_NOINLINE int fiber_sync(Ctx& c, FiberPool& p, int fiber_to_sync)
 {
   SyncFrame local_frames[SYNC_MAX_DEPTH];
   SyncFrame* frames = p.frames ? p.frames : local_frames;
@@ -725,8 +738,87 @@ static __device__ __forceinline__ bool is_word_char(Ctx& c, int64_t p, int chara
   return result;
 }
 
+// One input-consuming opcode against the byte(s) at `input` (the cases of yr_re_exec's switch that read a
+// character and move on, re.c:1770-1917, without their prologue); *len = size of the instruction.  Returns
+// -1 for any other opcode.
+static __device__ __forceinline__ int re_consume_op(
+    Ctx& c, uint32_t op, uint32_t ip, int64_t input, int flags, int character_size, uint32_t* len)
+{
+  bool match;
+  switch (op)
+  {
+  case OP_ANY:
+    match = (flags & RE_FLAGS_DOT_ALL) || (byte_at(c, input) != 0x0A);
+    *len = 1;
+    break;
+  case OP_LITERAL:
+    if (flags & RE_FLAGS_NO_CASE)
+      match = __ldg(c.R->lower + byte_at(c, input)) == __ldg(c.R->lower + code_u8(c, ip + 1));
+    else
+      match = (byte_at(c, input) == code_u8(c, ip + 1));
+    *len = 2;
+    break;
+  case OP_NOT_LITERAL:
+    match = (byte_at(c, input) != code_u8(c, ip + 1));
+    *len = 2;
+    break;
+  case OP_MASKED_LITERAL:
+  case OP_MASKED_NOT_LITERAL:
+  {
+    const uint32_t args = code_u16(c, ip + 1);
+    match = ((byte_at(c, input) & (args >> 8)) == (args & 0xFF)) == (op == OP_MASKED_LITERAL);
+    *len = 3;
+    break;
+  }
+  case OP_CLASS:
+  {
+    const uint32_t chr = byte_at(c, input);
+    uint32_t r = code_u8(c, ip + 2 + chr / 8) & (1u << (chr % 8));
+    if (flags & RE_FLAGS_NO_CASE)
+    {
+      const uint32_t alt = __ldg(c.R->alter + chr);
+      r |= code_u8(c, ip + 2 + alt / 8) & (1u << (alt % 8));
+    }
+    match = (r != 0);
+    if (code_u8(c, ip + 1)) match = !match;
+    *len = 34;
+    break;
+  }
+  case OP_WORD_CHAR:
+  case OP_NON_WORD_CHAR:
+    match = is_word_char(c, input, character_size) == (op == OP_WORD_CHAR);
+    *len = 1;
+    break;
+  case OP_SPACE:
+  case OP_NON_SPACE:
+  {
+    const uint8_t b = byte_at(c, input);
+    match = (b == ' ' || b == '\t' || b == '\r' || b == '\n' || b == '\v' || b == '\f') == (op == OP_SPACE);
+    *len = 1;
+    break;
+  }
+  case OP_DIGIT:
+  case OP_NON_DIGIT:
+  {
+    const uint8_t b = byte_at(c, input);
+    match = (b >= '0' && b <= '9') == (op == OP_DIGIT);
+    *len = 1;
+    break;
+  }
+  default:
+    return -1;
+  }
+  return match ? 1 : 0;
+}
+
+// opcodes _yr_re_fiber_sync acts on (re.c:1465-1650); at any other opcode it just moves to the next fiber
+static __device__ __forceinline__ bool re_is_sync_op(uint32_t op)
+{
+  return (op >= OP_SPLIT_A && op <= OP_REPEAT_END_UNGREEDY) || op == OP_REPEAT_ANY_GREEDY || op == OP_REPEAT_ANY_UNGREEDY;
+}
+
 // re.c:1693-2068 yr_re_exec
-static __device__ int re_exec(
+static __device__ YRB_NOINLINE int re_exec(
     Ctx& c, FiberPool& p, uint32_t code_off, int64_t pos, int64_t input_forwards_size, int64_t input_backwards_size,
     int flags, const CbArgs* cb, int* matches)
 {
@@ -764,6 +856,53 @@ static __device__ int re_exec(
 
   while (p.head >= 0)
   {
+    // ONE live fiber (most regexes most of the time: literal runs between the alternations and loops): there is
+    // nothing to deduplicate and nothing to order, and while its opcodes just consume characters
+    // _yr_re_fiber_sync has nothing to do either -- that stretch runs on registers, same tests, same bounds, same
+    // effects as the general loop below with a one-element list.  The fiber record is written back when an
+    // opcode needs the machinery (splits, repeats, jumps, anchors, boundaries, OP_MATCH).
+    if (p.head == p.tail && !YRB_RE_NO_FASTPATH)
+    {
+      fiber = p.head;
+      uint32_t fip = p.f[fiber].ip;
+      bool synced = false;
+      for (;;)
+      {
+        uint32_t len;
+        const uint32_t op = code_u8(c, fip);
+        if (op < OP_ANY || op > OP_MASKED_NOT_LITERAL || op == OP_MATCH)   // quick reject before the switch
+          break;
+        // the prologue of every consuming opcode (re.c:1733-1742)
+        if ((bytes_matched >= max_bytes_matched) || (character_size == 2 && byte_at(c, input + 1) != 0))
+        {
+          fiber_kill(p, fiber);
+          return YRB_SUCCESS;
+        }
+        const int m = re_consume_op(c, op, fip, input, flags, character_size, &len);
+        if (m < 0)
+          break;
+        if (m == 0)
+        {
+          fiber_kill(p, fiber);
+          return YRB_SUCCESS;
+        }
+        fip += len;
+        input += input_incr;
+        bytes_matched += character_size;
+        if (re_is_sync_op(code_u8(c, fip)))
+        {
+          p.f[fiber].ip = fip;
+          rc = fiber_sync(c, p, fiber);
+          if (rc != YRB_SUCCESS) { fiber_kill_all(p); return rc; }
+          synced = true;
+          break;
+        }
+      }
+      if (synced)
+        continue;   // the position is done (the fiber's offspring, if any, runs from the next character on)
+      p.f[fiber].ip = fip;
+    }
+
     fiber = p.head;
 
     while (fiber >= 0)
@@ -1199,7 +1338,7 @@ template <int TIER>
 __global__ void __launch_bounds__(128)
 verify_fast_kernel(
     DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out, uint8_t* ws, size_t ws_per_thread,
-    int cap, const uint32_t* retry, uint32_t* retry_next)
+    int cap, const uint32_t* retry, uint32_t* retry_next, const uint32_t* perm = nullptr)   // perm: tier 1, sorted order
 {
   const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
@@ -1212,7 +1351,7 @@ verify_fast_kernel(
 
   for (unsigned long long t = tid; t < n; t += stride)
   {
-    const unsigned long long ci = TIER > 1 ? retry[t] : t;
+    const unsigned long long ci = TIER > 1 ? retry[t] : (perm != nullptr ? perm[t] : t);
     const Cand cd = cands[ci];
     const yrb_acm m = R.acm[cd.acm_idx];
     const yrb_string s = R.S[m.string_idx];
@@ -1258,10 +1397,22 @@ template <int TIER>
 __global__ void __launch_bounds__(128)
 verify_re_kernel(
     DevRules R, ScanView V, const Cand* cands, unsigned long long n, RawOut out, uint8_t* ws, size_t ws_per_thread,
-    int cap, const uint32_t* retry_in, uint32_t* retry_out)
+    int cap, const uint32_t* retry_in, uint32_t* retry_out, const uint32_t* perm = nullptr)   // perm: entry tier, sorted order
 {
-  const unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+  unsigned long long tid = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+
+  if (TIER == 0 && ws_per_thread < 32)
+  {
+    // The candidates of a warp run different regexes over different bytes: the warp executes their paths one
+    // after the other (3.4 of 32 lanes active per instruction, profiles/r02_ncu_verify_re*), so a warp's time
+    // grows with its candidates while a scan with a few thousand candidates per SM leaves most warp slots
+    // empty.  With `ws_per_thread` (< 32) active lanes per warp the same candidates spread over more warps.
+    const unsigned lanes = (unsigned) ws_per_thread, lane = threadIdx.x & 31u;
+    if (lane >= lanes) return;
+    tid = (tid >> 5) * lanes + lane;
+    stride = (stride >> 5) * lanes;
+  }
 
   if (TIER == 1 && retry_in != nullptr) n = out.st->n_retry_re0;
   if (TIER == 2) n = out.st->n_retry[1];
@@ -1300,7 +1451,8 @@ verify_re_kernel(
 
   for (unsigned long long t = tid; t < n; t += stride)
   {
-    const unsigned long long ci = (TIER == 2 || (TIER == 1 && retry_in != nullptr)) ? retry_in[t] : t;
+    const unsigned long long ci =
+        (TIER == 2 || (TIER == 1 && retry_in != nullptr)) ? retry_in[t] : (perm != nullptr ? perm[t] : t);
     const Cand cd = cands[ci];
     const yrb_acm m = R.acm[cd.acm_idx];
     const yrb_string s = R.S[m.string_idx];
@@ -1362,6 +1514,20 @@ void launch_verify(
     (*launches)++;
   }
 
+  const uint32_t* perm[NUM_CLS] = {nullptr, nullptr, nullptr};
+  {
+    size_t at = 0;   // the classes share the scratch: each takes its slice
+    for (int c = CLS_FAST; c <= CLS_RE; c++)
+    {
+      if (!W.sort_cls[c] || n_cand[c] == 0 || at + n_cand[c] > W.sort_cap) continue;
+      perm[c] = launch_cand_sort(cands.cand[c], (uint32_t) n_cand[c], R.num_acm, W.sort_k[0] + at, W.sort_k[1] + at,
+                                 W.sort_v[0] + at, W.sort_v[1] + at, (uint8_t*) W.sort_tmp + (c == CLS_RE ? W.sort_tmp_bytes / 2 : 0),
+                                 W.sort_tmp_bytes / 2, cs[c]);
+      at += n_cand[c];
+      (*launches) += 4;
+    }
+  }
+
   if (n_cand[CLS_FAST] > 0)
   {
     unsigned long long threads = n_cand[CLS_FAST] < W.fast1_threads ? n_cand[CLS_FAST] : W.fast1_threads;
@@ -1370,7 +1536,7 @@ void launch_verify(
     if (blocks == 0) blocks = 1;
     verify_fast_kernel<1><<<blocks, T, 0, cs[CLS_FAST]>>>(
         R, V, cands.cand[CLS_FAST], n_cand[CLS_FAST], out, (uint8_t*) W.fast1, fast_ws_bytes_per_thread(1),
-        FAST_POS_CAP_SMALL, nullptr, W.retry_fast);
+        FAST_POS_CAP_SMALL, nullptr, W.retry_fast, perm[CLS_FAST]);
     (*launches)++;
   }
 
@@ -1383,10 +1549,13 @@ void launch_verify(
     if (W.retry_re0 != nullptr && R.stack_words <= RE_LOCAL_STACK)
     {
       // tier 0 needs no work area: a thread per candidate; tier 1 follows for what it queued (count read on the device)
-      unsigned long long b0 = (n_cand[CLS_RE] + T - 1) / T;
-      if (b0 > 148ull * 256) b0 = 148ull * 256;
+      // (fewer active lanes per warp spread the candidates over more warps, but the kernel is bound by
+      // instruction fetch, not by warp slots: measured 2x slower with 8 lanes, profiles/r02_kernel_notes.txt)
+      const unsigned lanes = 32;
+      unsigned long long b0 = (n_cand[CLS_RE] * (32 / lanes) + T - 1) / T;
+      if (b0 > 148ull * 1024) b0 = 148ull * 1024;
       verify_re_kernel<0><<<(unsigned) b0, T, 0, cs[CLS_RE]>>>(
-          R, V, cands.cand[CLS_RE], n_cand[CLS_RE], out, nullptr, 0, RE_FIBERS_LOCAL, nullptr, W.retry_re0);
+          R, V, cands.cand[CLS_RE], n_cand[CLS_RE], out, nullptr, lanes, RE_FIBERS_LOCAL, nullptr, W.retry_re0, perm[CLS_RE]);
       verify_re_kernel<1><<<blocks, T, 0, cs[CLS_RE]>>>(
           R, V, cands.cand[CLS_RE], 0, out, (uint8_t*) W.re1, re_ws_bytes_per_thread(R.stack_words, 1),
           RE_FIBERS_SMALL, W.retry_re0, W.retry_re);
@@ -1396,7 +1565,7 @@ void launch_verify(
     {
       verify_re_kernel<1><<<blocks, T, 0, cs[CLS_RE]>>>(
           R, V, cands.cand[CLS_RE], n_cand[CLS_RE], out, (uint8_t*) W.re1, re_ws_bytes_per_thread(R.stack_words, 1),
-          RE_FIBERS_SMALL, nullptr, W.retry_re);
+          RE_FIBERS_SMALL, nullptr, W.retry_re, perm[CLS_RE]);
       (*launches)++;
     }
   }
