@@ -1,0 +1,60 @@
+#!/usr/bin/env python3
+"""`yara -p N` over a directory of blobs (BASELINE configs[3] shape: log-uniform 64 KiB - 8 MiB) through the
+UNMODIFIED reference CLI (cli/yara.c: file queue + N scanner threads, :365-457, :1246-1293), linked once against
+the reference libyara (oracle/_ref/yara_ref) and once against the GPU drop-in (oracle/_ref/yara_b200cli), the
+latter with and without request coalescing ($YR_B200_COALESCE) and the condition-VM pre-filter
+($YR_B200_RULE_PREFILTER).  Compiled rules are loaded from a .yarc (yarac is not built: the drop-in library saves
+them).  Prints one JSON line per arm; the output lines of all arms must be identical (sorted).
+
+  python scripts/cli_feeder.py [nstrings=20000] [nfiles=600] [threads=16] [dir=/dev/shm/yrb_cli]"""
+import json, math, os, random, subprocess, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from yara_b200 import synth
+from yara_b200.api import LibYara
+
+nstrings = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+nfiles = int(sys.argv[2]) if len(sys.argv) > 2 else 600
+threads = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+d = sys.argv[4] if len(sys.argv) > 4 else "/dev/shm/yrb_cli"
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+os.makedirs(os.path.join(d, "files"), exist_ok=True)
+rs = synth.ruleset(4, nstrings)
+rng = random.Random(3)
+sizes = [int(math.exp(rng.uniform(math.log(65536), math.log(8 << 20)))) for _ in range(nfiles)]
+total = 0
+for k, s in enumerate(sizes):
+    p = os.path.join(d, "files", "blob%05d.bin" % k)
+    if not (os.path.exists(p) and os.path.getsize(p) == s):
+        synth.corpus(rs, s, 65536, seed=1000 + k, plant_seed=k, tail_plant=False).tofile(p)
+    total += s
+yarc = os.path.join(d, "rules.yarc")
+ly = LibYara()
+t0 = time.time()
+ly.save(ly.compile(rs.source), yarc)
+print("# %d declared strings compiled and saved in %.1f s; %d files, %.2f GiB" % (nstrings, time.time() - t0, nfiles, total / 2**30), file=sys.stderr)
+
+def arm(name, exe, env_extra):
+    env = dict(os.environ, **env_extra)
+    best, out = None, None
+    for rep in range(2):   # second run: page cache warm, device scanners' first-use costs are per process either way
+        t = time.time()
+        p = subprocess.run([os.path.join(REFDIR, exe), "-C", "-p", str(threads), yarc, os.path.join(d, "files")],
+                           capture_output=True, text=True, env=env, timeout=3600)
+        dt = time.time() - t
+        assert p.returncode == 0, (name, p.returncode, p.stderr[-2000:])
+        best = dt if best is None else min(best, dt)
+        out = sorted(p.stdout.splitlines())
+    print(json.dumps({"arm": name, "exe": exe, "threads": threads, "env": env_extra, "seconds": round(best, 3),
+                      "files_per_s": round(nfiles / best, 1), "GB_per_s": round(total / best / 1e9, 3), "output_lines": len(out),
+                      "files": nfiles, "bytes": total, "strings_declared": nstrings,
+                      "what": "whole process: rules load, device upload, directory walk, scans, condition VM, printing"}), flush=True)
+    return out
+
+ref = arm("reference libyara", "yara_ref", {})
+a = arm("drop-in", "yara_b200cli", {"YR_B200_COALESCE": "0"})
+b = arm("drop-in + coalescing", "yara_b200cli", {"YR_B200_COALESCE": str(threads)})
+c = arm("drop-in + coalescing, pre-filter off", "yara_b200cli", {"YR_B200_COALESCE": str(threads), "YR_B200_RULE_PREFILTER": "0"})
+print(json.dumps({"outputs_identical": ref == a == b == c, "matching_lines": len(ref)}))
+sys.exit(0 if ref == a == b == c else 1)

@@ -372,7 +372,7 @@ ac_filter_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, i
       {                                                                                             \
         const uint32_t mv_ = ht_lookup(F, w_);                                                      \
         if (mv_ != 0)                                                                               \
-          emit_events(R, V, out, wpos + (int64_t) u_ * (FT_THREADS * 16) + (OL_) * 16 + k_ + e_ + 1, mv_); \
+          emit_events<false>(R, V, out, wpos + (int64_t) u_ * (FT_THREADS * 16) + (OL_) * 16 + k_ + e_ + 1, mv_); \
       }                                                                                             \
     }                                                                                               \
   }
@@ -664,12 +664,12 @@ ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t l
         if (b3_test_a<DENSE>(sB3_a, wa & 0xFFFFFFu) && (DENSE || bloom4_test_a<DENSE ? 18 : B4BITS>(sB4_a, wa)))
         {
           const uint32_t mv = ht_lookup(F, wa);
-          if (mv != 0) emit_events(R, V, out, wpos + pb + 1, mv);
+          if (mv != 0) emit_events<false>(R, V, out, wpos + pb + 1, mv);
         }
         if (b3_test_a<DENSE>(sB3_a, wb >> 8) && (DENSE || bloom4_test_a<DENSE ? 18 : B4BITS>(sB4_a, wb)))
         {
           const uint32_t mv = ht_lookup(F, wb);
-          if (mv != 0) emit_events(R, V, out, wpos + pb + 2, mv);
+          if (mv != 0) emit_events<false>(R, V, out, wpos + pb + 2, mv);
         }
       }
       __syncwarp();
@@ -840,7 +840,8 @@ static void filter_host_build(const void* image, FilterHost* out)
     size_t pop3 = 0;
     for (uint32_t i = 0; i < b3_words; i++) pop3 += (size_t) __builtin_popcount(out->b3[i]);
     out->fill3 = (float) ((double) pop3 / ((double) b3_words * 32.0));
-    if (out->variant == FT_DEFAULT_VARIANT && out->fill3 > FT_DENSE_FILL && !getenv("YRB_FILTER_NO_DENSE"))
+    const float dense_fill = getenv("YRB_FILTER_DENSE_FILL") ? (float) atof(getenv("YRB_FILTER_DENSE_FILL")) : FT_DENSE_FILL;
+    if (out->variant == FT_DEFAULT_VARIANT && out->fill3 > dense_fill && !getenv("YRB_FILTER_NO_DENSE"))
     {
       out->variant = FT_DENSE_VARIANT;
       continue;

@@ -36,6 +36,7 @@ static bool trace_on() { static int t = -1; if (t < 0) t = getenv("YRB_TRACE") !
 
 struct yrb_rules
 {
+  size_t l2_window_bytes = 0;   // leading bytes of d_image under the persisting L2 window of every scanner stream
   int device;
   std::atomic<int> refs;
   void* d_image;
@@ -239,6 +240,23 @@ static int rules_init(yrb_rules* r, const void* image, size_t image_size, int de
   CK(cudaGetDeviceProperties(&prop, device));
   r->num_sms = prop.multiProcessorCount;
 
+  // The rules image (transition/match tables, YR_AC_MATCH entries, strings, RE code: a few MB that every
+  // candidate touches) is kept in L2 under a persisting access-policy window on each scanner's streams, so that
+  // the block bytes streaming through -- tens of GB per scan -- do not evict it (north star: "the transition
+  // table ... in an L2-persisting window").  The carve-out is set once per device; YRB_L2_PERSIST=0 turns it off.
+  static const bool persist_on = !(getenv("YRB_L2_PERSIST") && atoi(getenv("YRB_L2_PERSIST")) == 0);
+  r->l2_window_bytes = 0;
+  if (persist_on && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0)
+  {
+    size_t want = image_size;
+    if (want > (size_t) prop.accessPolicyMaxWindowSize) want = (size_t) prop.accessPolicyMaxWindowSize;
+    if (want > (size_t) prop.persistingL2CacheMaxSize) want = (size_t) prop.persistingL2CacheMaxSize;
+    size_t cur = 0;
+    cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+    if (cur < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) { cudaGetLastError(); want = cur; }
+    r->l2_window_bytes = want;
+  }
+
   memset(&r->F, 0, sizeof(r->F));
   int rc = build_filter_tables(image, image_size, device, &r->F, &r->d_filter);
   if (rc != YRB_SUCCESS) return rc;
@@ -315,6 +333,19 @@ static int scanner_init(yrb_scanner* s)
   for (int i = 0; i < 2; i++) CK(cudaStreamCreateWithFlags(&s->side.aux[i], cudaStreamNonBlocking));
   for (int i = 0; i < 6; i++) CK(cudaEventCreateWithFlags(&s->side.ev[i], cudaEventDisableTiming));
   if (const char* e = getenv("YRB_SIDE_STREAMS")) s->use_side = atoi(e) != 0;
+  if (s->rules->l2_window_bytes > 0)
+  {
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof(av));
+    av.accessPolicyWindow.base_ptr = s->rules->d_image;
+    av.accessPolicyWindow.num_bytes = s->rules->l2_window_bytes;
+    av.accessPolicyWindow.hitRatio = 1.0f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStream_t all[3] = {s->stream, s->side.aux[0], s->side.aux[1]};
+    for (cudaStream_t st : all)
+      if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+  }
   CK(cudaMalloc((void**) &s->d_status, sizeof(ScanStatus)));
   CK(cudaHostAlloc((void**) &s->h_status, sizeof(ScanStatus), cudaHostAllocDefault));
   memset(s->h_status, 0, sizeof(ScanStatus));
@@ -900,7 +931,7 @@ static int scan_impl(
 
   {
     // the VM classes are verified in AC-match order when there are enough candidates for warps to share strings
-    static const int sort_mask = getenv("YRB_SORT_CANDS") ? atoi(getenv("YRB_SORT_CANDS")) : ((1 << CLS_FAST) | (1 << CLS_RE));
+    static const int sort_mask = getenv("YRB_SORT_CANDS") ? atoi(getenv("YRB_SORT_CANDS")) : (1 << CLS_RE);   // the fast-hex class does not repay its sort (profiles/r02_kernel_notes.txt)
     size_t need = 0, nmax = 0;
     for (int c = 0; c < NUM_CLS; c++)
     {

@@ -8,6 +8,12 @@
 // One candidate per YR_AC_MATCH of the state's chain with backtrack <= i.
 // chain_pos numbers the chain entries so that (i, chain_pos) reproduces the
 // order in which the reference would have called yr_scan_verify_match.
+// AGGREGATE: the lanes of a warp that append to the same class at the same time share one atomicAdd
+// (engine.cuh, warp_append_slot) -- what the walk kernel wants, where every lane walks its own chunk and dense
+// data makes many of them emit at once.  The filter kernel reaches this point with one lane in a thousand
+// (0.15 events per 2 KB warp-tile) and pays for the collectives' registers in its hot loop (53 instead of 48,
+// -2.3 % scanned bytes/s): it appends with a plain atomicAdd.
+template <bool AGGREGATE = true>
 static __device__ __forceinline__ void emit_events(
     const DevRules& R, const ScanView& V, const CandOut& out, int64_t i, uint32_t first /* M[state], 1-based */)
 {
@@ -49,7 +55,7 @@ static __device__ __forceinline__ void emit_events(
         if (ok)
         {
           int cls = (sflags & YRB_SF_LITERAL) ? CLS_LITERAL : ((sflags & YRB_SF_FAST_REGEXP) ? CLS_FAST : CLS_RE);
-          unsigned long long slot = atomicAdd(&out.st->n_cand[cls], 1ULL);
+          unsigned long long slot = AGGREGATE ? warp_append_slot(&out.st->n_cand[cls]) : atomicAdd(&out.st->n_cand[cls], 1ULL);
 
           if (slot < out.cap[cls])
           {

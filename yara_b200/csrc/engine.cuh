@@ -144,6 +144,27 @@ struct ScanStatus
   unsigned int n_retry_re0;     // fiber-VM candidates that outgrew the local-memory tier (verify.cu, tier 0 -> tier 1)
 };
 
+// Appends from a warp: the lanes that arrive here together and add to the SAME counter elect one of them to do
+// ONE atomicAdd for all (match.any groups them by counter address, popc gives each its rank): on dense data --
+// a ruleset whose atoms occur in every other line of a text corpus -- thousands of candidates per tile would
+// otherwise queue up on one address.  Returns this lane's slot.
+static __device__ __forceinline__ unsigned long long warp_append_slot(unsigned long long* counter)
+{
+#ifdef YRB_HOST_EMULATION
+  return atomicAdd(counter, 1ULL);
+#else
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, (unsigned long long) (uintptr_t) counter);
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs(peers) - 1;
+  unsigned long long base = 0;
+  if ((int) lane == leader)
+    base = atomicAdd(counter, (unsigned long long) __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + (unsigned long long) __popc(peers & ((1u << lane) - 1u));
+#endif
+}
+
 struct CandOut
 {
   Cand* cand[NUM_CLS];

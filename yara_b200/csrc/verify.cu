@@ -88,7 +88,7 @@ static __device__ void match_callback(Ctx& c, int64_t match_pos, int32_t match_l
     }
   }
 
-  const unsigned long long slot = atomicAdd(&c.out.st->n_raw, 1ULL);
+  const unsigned long long slot = warp_append_slot(&c.out.st->n_raw);
 
   if (slot < c.out.cap)
   {
