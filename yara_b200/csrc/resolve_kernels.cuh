@@ -14,6 +14,7 @@
 
 #define OFFSET_BITS 40
 #define FLOOD_RUN 16   // chain replay: consecutive no-op callbacks after which the warp looks ahead
+#define CHAIN_ROUND 96 // chain replay: records lane 0 replays before the warp meets again (the other lanes fetch that far ahead)
 #define A_CHAIN_BIT (1ULL << 63)
 #define A_DROPPED   (~0ULL)
 
@@ -711,7 +712,28 @@ chain_resolve_kernel(
     // ---- lane 0 replays records from j on, group by group, until the chain ends or it has seen
     // FLOOD_RUN no-op callbacks in a row (then the warp looks ahead instead)
     uint32_t j_next = j, sorted_next = sorted_until;
-    int flags_next = 0;   // 1: flood, 2: chain finished
+    int flags_next = 0;   // 1: flood, 2: chain finished, 0: lane 0 used up its round
+#if YRB_WARP > 1
+    // The replay is one dependent chain of loads per record (sort key, record, its string, the predecessor's list
+    // count, the list nodes) at L2 latency each.  While lane 0 replays a round of CHAIN_ROUND records the other
+    // lanes run ahead of it over the same records and pull what does not depend on list state into L1.
+    if (lane != 0)
+    {
+      for (uint32_t x = j + lane - 1; x < n && x < j + CHAIN_ROUND + 64; x += YRB_WARP - 1)
+      {
+        if ((kA[x] >> OFFSET_BITS) != chain) break;
+        const uint32_t sx = sraw[x].string_idx;
+        const uint32_t pred = R.S[sx].chained_to;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(&sraw[x].string_idx));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(&R.S[sx].chain_gap_max));
+        if (pred != YRB_NONE)
+        {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(&L.ucnt[pred]));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(&L.utail[pred]));
+        }
+      }
+    }
+#endif
     if (lane == 0)
     {
       uint32_t jq = j;
@@ -723,6 +745,8 @@ chain_resolve_kernel(
 
         if (jq >= su)
         {
+          if (YRB_WARP > 1 && jq - j >= CHAIN_ROUND) break;   // group boundary: meet the warp, which fetches the next round
+
           // records of this chain that share the input position: put them in discovery-key order.
           // The seeds -- position 0 -- keep the order the caller gave them in, ascending base + offset
           // per string: each then goes to the tail of its list in O(1); their `key` is a chain length.
