@@ -50,6 +50,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "scanned GB/s (HBM-resident & end-to-end), 20k-string ruleset"
+SHORT_ATOMS_RULE = 'rule short_atoms { strings: $mz = "MZ" $pk = { 50 4B 03 } $w = "Zz" wide condition: any of them }\n'
 INTERIOR = 16384   # a window's records are compared this far away from its edges (longest chained instance < 4 KiB)
 
 
@@ -110,6 +111,8 @@ def dist_env():
 
 
 def workload_name(args, S):
+    if getattr(args, "short_atoms", False):
+        return "synthetic ruleset shape %d, %d declared strings + a rule with 2- and 3-byte atoms, one %.3g GiB block" % (args.config, args.strings, S / 2**30)
     if args.config == 3 and args.strings == 20000:
         return ("configs[2]: 20,000 hex strings with wildcards/jumps + nocase/wide text over one %.3g GiB block, "
                 "byte-range sharded with read margins" % (S / 2**30))
@@ -248,6 +251,8 @@ def main():
     ap.add_argument("--window-mib", type=int, default=64, help="size of each parity window")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--short-atoms", action="store_true",
+                    help="append a rule with 2- and 3-byte atoms (\"MZ\", { 50 4B 03 }, \"Zz\" wide): the filter kernel's short-atom variant")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--parity-full", action="store_true",
                     help="parity windows tile the WHOLE block (reference scans on all host cores; minutes for 16 GiB)")
@@ -295,10 +300,12 @@ def main():
     ly = LibYara()
     ly.set_device(device)
     rs = synth.ruleset(args.config, args.strings)
+    if args.short_atoms:
+        rs.extra = SHORT_ATOMS_RULE
     cache_dir = os.environ.get("YR_B200_CACHE_DIR") or os.path.join(ROOT, "build", "cache")
     os.makedirs(cache_dir, exist_ok=True)
     os.environ.setdefault("YR_B200_CACHE_DIR", cache_dir)
-    yarc = os.path.join(cache_dir, "bench_cfg%d_n%d.yarc" % (args.config, args.strings))
+    yarc = os.path.join(cache_dir, "bench_cfg%d_n%d%s.yarc" % (args.config, args.strings, "_short" if args.short_atoms else ""))
     if os.path.exists(yarc):
         rules = ly.load(yarc)
         setup["rules"] = "yr_rules_load(%s)" % os.path.basename(yarc)

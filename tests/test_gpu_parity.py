@@ -372,3 +372,55 @@ def test_dedup_moves_the_chain_heads_records_forward():
                        env=env, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "DEDUP ok" in p.stdout, (p.stdout + p.stderr)[-3000:]
     assert "plain records deduplicated" in p.stderr, p.stderr[-3000:]
+
+
+SHORT_ATOM_RULES = r"""
+rule short_atoms {
+ strings:
+  $mz = "MZ"
+  $pk = { 50 4B 03 }
+  $q = "q" fullword
+  $w = "Zz" wide
+  $re1 = /k[0-9]{2,4}!/
+  $re2 = /ab\d+c/
+  $hx = { 7F ?? 45 [2-6] 46 }
+ condition:
+  any of them
+}
+"""
+
+
+@pytest.mark.parametrize("extra", [0, 1500])
+def test_short_atoms_go_through_the_filter_kernel(extra):
+    """Rulesets with 1-, 2- and 3-byte atoms (round 1: walk kernel only) run on the filter kernel's short-atom variant:
+    an exact 2-byte bitmap probed per position, flagged positions walked from the root (ac_scan.cu, variant 6).  Alone
+    and mixed into a 1,500-string synthetic ruleset; data with low-entropy stretches so that the short atoms fire a lot;
+    compared with the reference library, all fields, and with the walk kernel."""
+    rs = synth.ruleset(3, extra) if extra else None
+    src = SHORT_ATOM_RULES + (rs.source if rs else "")
+    from yara_b200 import Engine
+    rr, rb = both(src)
+    image = rb.flatten()
+    eng = Engine(image, 0)
+    fi = eng.filter_info()
+    assert fi["usable"] == 1 and fi["variant"] == 6 and (fi["has_depth1"] or fi["has_depth2"]), fi
+    n = (1 << 23) + 4099
+    data = synth.corpus(rs, n, 4096) if rs else synth.rand_bytes(99, 0, n)
+    data = np.array(data, dtype=np.uint8)
+    rng = np.random.RandomState(5)
+    for k in range(64):   # stretches of text-like bytes and of one repeated 2-byte atom
+        o = int(rng.randint(0, n - 70000))
+        data[o:o + 4096] = np.frombuffer((b"MZqk12! ab123c PK\x03 q Z\x00z\x00 \x7f1E..F " * 128)[:4096], dtype=np.uint8)
+    data[n // 2: n // 2 + 3000] = np.frombuffer(b"MZ" * 1500, dtype=np.uint8)
+    a = rr.scan(data, cap=1 << 21)
+    b = rb.scan(data, cap=1 << 21)
+    assert a.rc == 0 and len(a.matches) > 20000
+    assert_same(a, b)
+    from yara_b200 import api as _api
+    for kernel in (_api.KERNEL_FILTER, _api.KERNEL_WALK):
+        eng.set_option(_api.OPT_SCAN_KERNEL, kernel)
+        r = eng.scan_host(data)
+        assert r.rc == 0 and r.error == 0 and r.stats["scan_kernel"] == kernel
+        got = sorted(zip(r.matches["string_idx"].tolist(), r.matches["offset"].tolist(), r.matches["match_length"].tolist()))
+        want = sorted(zip(a.matches["string_idx"].tolist(), a.matches["offset"].tolist(), a.matches["match_length"].tolist()))
+        assert got == want

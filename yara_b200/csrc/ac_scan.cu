@@ -155,21 +155,36 @@ void launch_ac_scan_walk(
 struct FtVariant { int threads, u, b4_bits, tma_bufs; };   // tma_bufs: 0 = LDG + staging rows (round 1), else TMA buffers per warp
 static const FtVariant kVariants[] = {{1024, 4, 18, 0}, {512, 4, 19, 0}, {1024, 2, 19, 0},
                                       {1024, 4, 18, 1}, {768, 4, 18, 1},    // 3-4: variant T
-                                      {1024, 4, 0, 1}};                     // 5: variant T for dense rulesets (below)
-#define FT_NUM_VARIANTS 6
+                                      {1024, 4, 0, 1},                      // 5: variant T for dense rulesets (below)
+                                      {1024, 4, 0, 2}};                     // 6: variant T for rulesets with short atoms (below)
+#define FT_NUM_VARIANTS 7
 #define FT_DEFAULT_VARIANT 3
 #define FT_DENSE_VARIANT 5
+#define FT_SHORT_VARIANT 6
 // Dense rulesets (100,000 strings: 190k hit windows): B4 at 2^18 bits would be ~95 % full and filter nothing, and
 // B3 at 2^20 bits is a third full (12 % of the pairs pass level 1, and level 2 -- ~100 instructions per survivor
 // round and an L2 lookup for what passes -- becomes the kernel).  Variant 5 gives ALL the table space to B3:
 // 40,960 words (1.25 x), indexed by the high product of the hash and the word count instead of its top 15 bits,
 // and no B4.  Chosen automatically when the standard B3 would be more than FT_DENSE_FILL full.
 #define B3_WORDS_DENSE 40960u
+// Rulesets with SHORT atoms (round 1: walk kernel, 0.025 of the HBM peak).  A hit state of depth 2 (a 2-byte atom
+// "xy") makes every window that ends in xy a hit, a depth-1 state every window that ends in y, and more than 512
+// depth-3 states are too many to enumerate their 256 windows each: none of that fits a filter over 3-byte keys
+// shared by two positions.  Variant 6 adds B2, an EXACT 2^16-bit bitmap (8 KB of the table space, taken from B3)
+// over the last two bytes of a window, probed once per position: it is set for the last two bytes of every such
+// state's path (depth 1: for all 256 first bytes).  A position B2 flags gets the exact treatment -- its state is
+// walked from the root over its four bytes (exact: depth <= 4), match_table looked up, events emitted -- and B2 is
+// authoritative for it: the B3/B4/hash-table path skips flagged positions, so nothing is emitted twice.
+#define B2_WORDS 2048u
+#define B3_WORDS_SHORT (B3_WORDS_DENSE - B2_WORDS - 64u)
 #define FT_DENSE_FILL 0.10f   // the 20k-string set (0.108) gains 1 % as well (16 GiB: 0.505 -> 0.510); below that nothing changes
-static inline uint32_t ft_b3_words(const FtVariant& v) { return v.b4_bits == 0 ? B3_WORDS_DENSE : B3_WORDS; }
+static inline uint32_t ft_b3_words(const FtVariant& v)
+{ return v.b4_bits != 0 ? B3_WORDS : (v.tma_bufs == 2 ? B3_WORDS_SHORT : B3_WORDS_DENSE); }
+static inline uint32_t ft_table_words(const FtVariant& v)   // B3 (+ B2 + pad) as laid out in shared memory
+{ return v.b4_bits != 0 ? B3_WORDS : B3_WORDS_DENSE; }
 static inline size_t ft_smem_bytes(const FtVariant& v)
 {
-  return (size_t) ft_b3_words(v) * 4 + (v.b4_bits == 0 ? 0 : ((size_t) 1 << (v.b4_bits - 3))) +
+  return (size_t) ft_table_words(v) * 4 + (v.b4_bits == 0 ? 0 : ((size_t) 1 << (v.b4_bits - 3))) +
          (v.tma_bufs == 0 ? (size_t) (v.threads / 32) * (v.u * FT_ROW + 32)
                           : (size_t) (v.threads / 32) * (16 + 2048 + 16 + 64));
 }
@@ -178,6 +193,7 @@ struct FilterDev
 {
   const uint32_t* b3;
   const uint32_t* b4;
+  const uint32_t* b2;  // variant 6 only
   const uint2* ht;     // {window, match_table value}; .y == 0 means empty
   uint32_t ht_bits;
 };
@@ -492,11 +508,11 @@ static __device__ __forceinline__ void sts_u16_v(uint32_t a, uint32_t v)
 static __device__ __forceinline__ uint32_t word_addr_fma(uint32_t idx, uint32_t four, uint32_t base)
 { uint32_t r; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(idx), "r"(four), "r"(base)); return r; }
 
-template <bool DENSE>
+template <uint32_t NW>   // B3_WORDS: top 15 bits of the hash; anything else: high product with the word count
 static __device__ __forceinline__ bool b3_test_a(uint32_t sB3_a, uint32_t key3)
 {
   const uint32_t h = (key3 << 8) * HASH3_MUL;
-  const uint32_t idx = DENSE ? __umulhi(h, B3_WORDS_DENSE) : (h >> 17);
+  const uint32_t idx = NW != B3_WORDS ? __umulhi(h, NW) : (h >> 17);
   const uint32_t w = lds_u32(sB3_a + (idx << 2));
   return ((w >> (key3 & 31)) & (w >> ((key3 >> 16) & 31)) & 1u) != 0;
 }
@@ -517,26 +533,29 @@ static __device__ __forceinline__ bool bloom4_test_a(uint32_t sB4_a, uint32_t w)
   return true;
 }
 
-template <int NWARPS, int B4BITS>
+template <int NWARPS, int B4BITS, bool SHORT = false>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t lo, int64_t hi)
 {
   constexpr int FT_THREADS = NWARPS * 32, FT_U = FT_T_TILE / 512;
   constexpr int FT_TILE = NWARPS * FT_T_TILE;         // bytes per CTA and round; warp w owns [w * 2048, (w + 1) * 2048) of it
   constexpr bool DENSE = (B4BITS == 0);               // all table space to B3, no B4 (see FT_DENSE_VARIANT)
-  constexpr uint32_t B3W = DENSE ? B3_WORDS_DENSE : B3_WORDS;
+  constexpr uint32_t B3W = SHORT ? B3_WORDS_SHORT : (DENSE ? B3_WORDS_DENSE : B3_WORDS);
+  constexpr uint32_t TABW = DENSE ? B3_WORDS_DENSE : B3_WORDS;   // B3 (+ B2 + pad, variant 6) in shared memory
   constexpr uint32_t B4_WORDS = DENSE ? 0u : (1u << ((DENSE ? 5 : B4BITS) - 5));
+  static_assert(!SHORT || DENSE, "the short-atom variant takes B2 out of the dense layout");
   constexpr int WARP_BYTES = FT_T_BUF + 16 + 64;      // buffer | mbarrier (8 B) + pad | survivor queue (32 x u16)
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t* sB3 = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* sB4 = sB3 + B3W;
-  uint8_t* stage = smem_raw + (B3W + B4_WORDS) * 4;
+  uint32_t* sB4 = sB3 + TABW;
+  uint8_t* stage = smem_raw + (TABW + B4_WORDS) * 4;
 
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5;
   const uint8_t* wbuf = stage + warp * WARP_BYTES;    // 16 B halo | 4 x 512 B chunks, contiguous
   const uint32_t sB3_a = smem_u32(sB3);
-  const uint32_t sB4_a = sB3_a + B3W * 4;
+  const uint32_t sB4_a = sB3_a + TABW * 4;
+  const uint32_t sB2_a = sB3_a + B3W * 4;   // variant 6: B2 sits behind B3
   const uint32_t wbuf_a = smem_u32(wbuf);
   const uint32_t wbar_a = wbuf_a + FT_T_BUF;
   const uint32_t wq_a = wbuf_a + FT_T_BUF + 16;
@@ -554,6 +573,12 @@ ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t l
     uint4* s4 = reinterpret_cast<uint4*>(sB4);
     for (uint32_t i = threadIdx.x; i < B3W / 4; i += FT_THREADS) s3[i] = __ldg(&g3[i]);
     for (uint32_t i = threadIdx.x; i < B4_WORDS / 4; i += FT_THREADS) s4[i] = __ldg(&g4[i]);
+    if (SHORT)
+    {
+      const uint4* g2 = reinterpret_cast<const uint4*>(F.b2);
+      uint4* s2 = reinterpret_cast<uint4*>(sB3 + B3W);
+      for (uint32_t i = threadIdx.x; i < B2_WORDS / 4; i += FT_THREADS) s2[i] = __ldg(&g2[i]);
+    }
   }
   __syncthreads();
 
@@ -605,6 +630,7 @@ ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t l
     // ---- level 1: one B3 probe per pair of positions, branch-free.  Per probe: IMAD (hash), SHF,
     // IMAD (word address), LDS, 2 SHF + LOP3 (the two bits), IMAD (append): 4 ALU-pipe instructions.
     uint32_t mask = 0;
+    uint32_t m2[FT_U];   // variant 6: B2 survivors, 16 positions per chunk
 
 #define PROBE3(x, y)                                                                \
   {                                                                                 \
@@ -629,6 +655,25 @@ ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t l
       PROBE3(w2, f3);
       PROBE3(f3, w3);
       PROBE3(w3, w3 >> 16);
+
+      if (SHORT)
+      {
+        // B2: one exact probe per POSITION with its last two bytes; bit (15 - j) of m2[u] <- byte j of the chunk
+        uint32_t t2 = 0;
+        const uint32_t ww[5] = {m, w0, w1, w2, w3};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+        {
+          const uint32_t cur = ww[q + 1];
+          const uint32_t k0 = __funnelshift_r(ww[q], cur, 24) & 0xFFFFu;   // (prev.b3, cur.b0)
+          const uint32_t k1 = cur & 0xFFFFu, k2 = (cur >> 8) & 0xFFFFu, k3 = cur >> 16;
+          t2 = t2 * 2 + ((lds_u32(sB2_a + ((k0 >> 5) << 2)) >> (k0 & 31)) & 1u);
+          t2 = t2 * 2 + ((lds_u32(sB2_a + ((k1 >> 5) << 2)) >> (k1 & 31)) & 1u);
+          t2 = t2 * 2 + ((lds_u32(sB2_a + ((k2 >> 5) << 2)) >> (k2 & 31)) & 1u);
+          t2 = t2 * 2 + ((lds_u32(sB2_a + ((k3 >> 5) << 2)) >> (k3 & 31)) & 1u);
+        }
+        m2[u] = t2;
+      }
     }
 #undef PROBE3
     // mask bit (31 - sl) belongs to slot sl = u * 8 + pair: clz(mask) is the first slot that passed
@@ -672,18 +717,44 @@ ac_filter_tma_kernel(DevRules R, FilterDev F, ScanView V, CandOut out, int64_t l
         const uint32_t x1 = *reinterpret_cast<const uint32_t*>(src - al + 4);
         const uint32_t wa = __funnelshift_r(x0, x1, al * 8);          // W(p)
         const uint32_t wb = __funnelshift_rc(x0, x1, al * 8 + 8);     // W(p + 1)
-        if (b3_test_a<DENSE>(sB3_a, wa & 0xFFFFFFu) && (DENSE || bloom4_test_a<DENSE ? 18 : B4BITS>(sB4_a, wa)))
+        // variant 6: a position B2 flags is handled by the exact walk below, never here
+        if (b3_test_a<B3W>(sB3_a, wa & 0xFFFFFFu) && (DENSE || bloom4_test_a<DENSE ? 18 : B4BITS>(sB4_a, wa)) &&
+            !(SHORT && ((lds_u32(sB2_a + (((wa >> 16) >> 5) << 2)) >> ((wa >> 16) & 31)) & 1u)))
         {
           const uint32_t mv = ht_lookup(F, wa);
           if (mv != 0) emit_events<false>(R, V, out, wpos + pb + 1, mv);
         }
-        if (b3_test_a<DENSE>(sB3_a, wb >> 8) && (DENSE || bloom4_test_a<DENSE ? 18 : B4BITS>(sB4_a, wb)))
+        if (b3_test_a<B3W>(sB3_a, wb >> 8) && (DENSE || bloom4_test_a<DENSE ? 18 : B4BITS>(sB4_a, wb)) &&
+            !(SHORT && ((lds_u32(sB2_a + (((wb >> 16) >> 5) << 2)) >> ((wb >> 16) & 31)) & 1u)))
         {
           const uint32_t mv = ht_lookup(F, wb);
           if (mv != 0) emit_events<false>(R, V, out, wpos + pb + 2, mv);
         }
       }
       __syncwarp();
+    }
+
+    if (SHORT)
+    {
+      // ---- the positions B2 flagged: the reference walk's state after byte p is a function of bytes p-3..p (trie
+      // depth <= 4), so it is walked from the root over those four bytes -- exact for any atom length
+#pragma unroll
+      for (int u = 0; u < FT_U; u++)
+      {
+        uint32_t rem2 = m2[u];
+        while (rem2 != 0)
+        {
+          const uint32_t j = (uint32_t) __clz(rem2) - 16u;   // byte j of this lane's chunk u
+          rem2 &= ~(0x80000000u >> (j + 16u));
+          const uint32_t pb = (uint32_t) u * 512u + lane * 16u + j;   // position p = tile byte pb
+          const uint8_t* src = tp + pb - 3;
+          uint32_t st = 0;
+#pragma unroll
+          for (int q = 0; q < 4; q++) st = ac_step(R.T, st, (uint32_t) __ldg(src + q));
+          const uint32_t mv = __ldg(&R.M[st]);
+          if (mv != 0) emit_events<false>(R, V, out, wpos + pb + 1, mv);
+        }
+      }
     }
   }
 }
@@ -714,7 +785,7 @@ struct FilterHost
   int usable = 0, has_d1 = 0, has_d2 = 0, root_match = 0, variant = 0;
   uint32_t ht_bits = 0, n_windows = 0;
   float fill3 = 0.f;
-  std::vector<uint32_t> b3, b4;
+  std::vector<uint32_t> b3, b4, b2;
   std::vector<uint2> ht;
 };
 
@@ -757,6 +828,8 @@ static void filter_host_build(const void* image, FilterHost* out)
   struct Node { uint32_t state; uint32_t path; int depth; };
   std::vector<Node> level, next;
   std::vector<uint32_t> windows; // hit windows, little-endian: data[p-3] in bits 0-7
+  std::vector<uint32_t> d3_paths;
+  std::vector<uint32_t> short_keys;   // B2 entries: (second-to-last, last) byte of a short hit state's path, last in bits 8-15
   level.push_back({0, 0, 0});
   size_t n_d3 = 0;
 
@@ -767,14 +840,20 @@ static void filter_host_build(const void* image, FilterHost* out)
     {
       if (n.depth > 0 && M[n.state] != 0)
       {
-        if (n.depth <= 2)
+        if (n.depth == 1)
         {
-          if (n.depth == 1) out->has_d1 = 1; else out->has_d2 = 1;
+          out->has_d1 = 1;
+          for (uint32_t x = 0; x < 256; x++) short_keys.push_back(x | (n.path << 8));
+        }
+        else if (n.depth == 2)
+        {
+          out->has_d2 = 1;
+          short_keys.push_back(n.path & 0xFFFF);
         }
         else if (n.depth == 3)
         {
           n_d3++;
-          for (uint32_t x = 0; x < 256; x++) windows.push_back(x | (n.path << 8));
+          d3_paths.push_back(n.path);
         }
         else
         {
@@ -794,8 +873,30 @@ static void filter_host_build(const void* image, FilterHost* out)
     level.swap(next);
   }
 
-  if (out->has_d1 || out->has_d2 || windows.empty() || n_d3 > 512)
-    return; // not usable: the engine falls back to the walk kernel
+  const bool short_ok = !getenv("YRB_FILTER_NO_SHORT") && kVariants[out->variant].tma_bufs != 0;
+  if (n_d3 > 512 && short_ok)
+    for (uint32_t pth : d3_paths) short_keys.push_back((pth >> 8) & 0xFFFF);   // too many to enumerate: their last two bytes go to B2
+  else
+    for (uint32_t pth : d3_paths)
+      for (uint32_t x = 0; x < 256; x++) windows.push_back(x | (pth << 8));
+
+  if (!short_keys.empty() || n_d3 > 512)
+  {
+    if (!short_ok)
+      return; // not usable: the engine falls back to the walk kernel
+    out->variant = FT_SHORT_VARIANT;
+    out->b2.assign(B2_WORDS, 0);
+    for (uint32_t k2 : short_keys) out->b2[k2 >> 5] |= 1u << (k2 & 31);
+    size_t pop2 = 0;
+    for (uint32_t w : out->b2) pop2 += (size_t) __builtin_popcount(w);
+    if (pop2 > 65536 / 8)
+    {
+      out->b2.clear();
+      return; // more than one position in eight would be walked exactly: the walk kernel does that better
+    }
+  }
+  else if (windows.empty())
+    return;
 
   uint32_t ht_bits = 4;
   while ((1ull << ht_bits) < windows.size() * 2) ht_bits++;
@@ -833,7 +934,7 @@ static void filter_host_build(const void* image, FilterHost* out)
         // B3 entry of a 3-byte key: word from the hash (its top 15 bits; dense variant: high product with the word
         // count); TWO bits per key, numbered (bit n = 1u << n): low 5 bits of the key's first byte and of its third
         const uint32_t h = (k3 << 8) * HASH3_MUL;
-        const uint32_t idx = b4_bits ? (h >> 17) : (uint32_t) (((uint64_t) h * B3_WORDS_DENSE) >> 32);
+        const uint32_t idx = b4_bits ? (h >> 17) : (uint32_t) (((uint64_t) h * b3_words) >> 32);
         out->b3[idx] |= (1u << (k3 & 31)) | (1u << ((k3 >> 16) & 31));
       }
       if (b4_bits)
@@ -873,7 +974,7 @@ static void filter_host_build(const void* image, FilterHost* out)
 // ---- the cache: process-wide registry + files
 
 #define FT_CACHE_MAGIC 0x42544659u /* "YFTB" */
-#define FT_CACHE_VERSION 4u
+#define FT_CACHE_VERSION 5u
 
 struct FtCacheHeader
 {
@@ -882,7 +983,7 @@ struct FtCacheHeader
   int32_t usable, has_d1, has_d2, root_match, variant;
   uint32_t ht_bits, n_windows;
   float fill3;
-  uint64_t n_b3, n_b4, n_ht;
+  uint64_t n_b3, n_b4, n_ht, n_b2;
   uint64_t payload_hash;
 };
 
@@ -932,6 +1033,7 @@ static uint64_t ft_payload_hash(const FilterHost& f)
 {
   uint64_t h = hash64(f.b3.data(), f.b3.size() * 4, 1);
   h = hash64(f.b4.data(), f.b4.size() * 4, h);
+  h = hash64(f.b2.data(), f.b2.size() * 4, h);
   return hash64(f.ht.data(), f.ht.size() * sizeof(uint2), h);
 }
 
@@ -942,15 +1044,18 @@ static bool ft_cache_load(const std::string& path, uint64_t key, uint64_t image_
   FtCacheHeader hd;
   bool ok = fread(&hd, sizeof(hd), 1, fp) == 1 && hd.magic == FT_CACHE_MAGIC && hd.version == FT_CACHE_VERSION &&
             hd.image_hash == key && hd.image_size == image_size && hd.n_b3 <= B3_WORDS_DENSE &&
-            (hd.variant == variant || (variant == FT_DEFAULT_VARIANT && hd.variant == FT_DENSE_VARIANT)) &&
+            hd.n_b2 <= B2_WORDS &&
+            (hd.variant == variant || (variant == FT_DEFAULT_VARIANT && (hd.variant == FT_DENSE_VARIANT || hd.variant == FT_SHORT_VARIANT))) &&
             hd.n_b4 <= (1u << 20) && hd.n_ht <= (1ull << 28);
   if (ok)
   {
     out->usable = hd.usable; out->has_d1 = hd.has_d1; out->has_d2 = hd.has_d2; out->root_match = hd.root_match;
     out->variant = hd.variant; out->ht_bits = hd.ht_bits; out->n_windows = hd.n_windows; out->fill3 = hd.fill3;
     out->b3.resize((size_t) hd.n_b3); out->b4.resize((size_t) hd.n_b4); out->ht.resize((size_t) hd.n_ht);
+    out->b2.resize((size_t) hd.n_b2);
     ok = (hd.n_b3 == 0 || fread(out->b3.data(), 4, out->b3.size(), fp) == out->b3.size()) &&
          (hd.n_b4 == 0 || fread(out->b4.data(), 4, out->b4.size(), fp) == out->b4.size()) &&
+         (hd.n_b2 == 0 || fread(out->b2.data(), 4, out->b2.size(), fp) == out->b2.size()) &&
          (hd.n_ht == 0 || fread(out->ht.data(), sizeof(uint2), out->ht.size(), fp) == out->ht.size()) &&
          ft_payload_hash(*out) == hd.payload_hash;
   }
@@ -972,11 +1077,12 @@ static void ft_cache_store(const std::string& path, uint64_t key, uint64_t image
   hd.magic = FT_CACHE_MAGIC; hd.version = FT_CACHE_VERSION; hd.image_hash = key; hd.image_size = image_size;
   hd.usable = f.usable; hd.has_d1 = f.has_d1; hd.has_d2 = f.has_d2; hd.root_match = f.root_match; hd.variant = f.variant;
   hd.ht_bits = f.ht_bits; hd.n_windows = f.n_windows; hd.fill3 = f.fill3;
-  hd.n_b3 = f.b3.size(); hd.n_b4 = f.b4.size(); hd.n_ht = f.ht.size();
+  hd.n_b3 = f.b3.size(); hd.n_b4 = f.b4.size(); hd.n_ht = f.ht.size(); hd.n_b2 = f.b2.size();
   hd.payload_hash = ft_payload_hash(f);
   bool ok = fwrite(&hd, sizeof(hd), 1, fp) == 1 &&
             (f.b3.empty() || fwrite(f.b3.data(), 4, f.b3.size(), fp) == f.b3.size()) &&
             (f.b4.empty() || fwrite(f.b4.data(), 4, f.b4.size(), fp) == f.b4.size()) &&
+            (f.b2.empty() || fwrite(f.b2.data(), 4, f.b2.size(), fp) == f.b2.size()) &&
             (f.ht.empty() || fwrite(f.ht.data(), sizeof(uint2), f.ht.size(), fp) == f.ht.size());
   ok = (fclose(fp) == 0) && ok;
   if (!ok || rename(tpath.c_str(), path.c_str()) != 0) unlink(tpath.c_str());
@@ -1036,15 +1142,18 @@ int build_filter_tables(const void* image, size_t image_size, int device, Filter
     return YRB_SUCCESS;
 
   uint8_t* dptr = nullptr;
-  const size_t b3_bytes = f->b3.size() * 4, b4_bytes = f->b4.size() * 4, ht_bytes = f->ht.size() * sizeof(uint2);
+  const size_t b3_bytes = f->b3.size() * 4, b4_bytes = f->b4.size() * 4 + f->b2.size() * 4 /* B2 rides behind B4 */,
+               ht_bytes = f->ht.size() * sizeof(uint2);
   const size_t total = b3_bytes + b4_bytes + ht_bytes;
   if (cudaMalloc((void**) &dptr, total) != cudaSuccess) { cudaGetLastError(); return YRB_ERROR_INSUFFICIENT_MEMORY; }
   cudaMemcpy(dptr, f->b3.data(), b3_bytes, cudaMemcpyHostToDevice);
-  cudaMemcpy(dptr + b3_bytes, f->b4.data(), b4_bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(dptr + b3_bytes, f->b4.data(), f->b4.size() * 4, cudaMemcpyHostToDevice);
+  if (!f->b2.empty()) cudaMemcpy(dptr + b3_bytes + f->b4.size() * 4, f->b2.data(), f->b2.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(dptr + b3_bytes + b4_bytes, f->ht.data(), ht_bytes, cudaMemcpyHostToDevice);
 
   out->b3 = reinterpret_cast<const uint32_t*>(dptr);
   out->b4 = reinterpret_cast<const uint32_t*>(dptr + b3_bytes);
+  out->b2 = f->b2.empty() ? nullptr : reinterpret_cast<const uint32_t*>(dptr + b3_bytes + f->b4.size() * 4);
   out->ht = reinterpret_cast<const void*>(dptr + b3_bytes + b4_bytes);
   out->ht_bits = f->ht_bits;
   out->n_windows = f->n_windows;
@@ -1063,6 +1172,7 @@ int build_filter_tables(const void* image, size_t image_size, int device, Filter
     cudaFuncSetAttribute(ac_filter_tma_kernel<32, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[3]));
     cudaFuncSetAttribute(ac_filter_tma_kernel<24, 18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[4]));
     cudaFuncSetAttribute(ac_filter_tma_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[5]));
+    cudaFuncSetAttribute(ac_filter_tma_kernel<32, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ft_smem_bytes(kVariants[6]));
     attr_set[dev] = true;
   }
   return YRB_SUCCESS;
@@ -1108,6 +1218,7 @@ void launch_ac_scan_filter(
   FilterDev fd;
   fd.b3 = F.b3;
   fd.b4 = F.b4;
+  fd.b2 = F.b2;
   fd.ht = reinterpret_cast<const uint2*>(F.ht);
   fd.ht_bits = F.ht_bits;
 
@@ -1122,6 +1233,7 @@ void launch_ac_scan_filter(
   case 3: ac_filter_tma_kernel<32, 18><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   case 4: ac_filter_tma_kernel<24, 18><<<grid, 768, smem, s>>>(R, fd, V, out, flo, fhi); break;
   case 5: ac_filter_tma_kernel<32, 0><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
+  case 6: ac_filter_tma_kernel<32, 0, true><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   default: ac_filter_kernel<1024, 4, 18><<<grid, 1024, smem, s>>>(R, fd, V, out, flo, fhi); break;
   }
   if (after) cudaEventRecord(after, s);

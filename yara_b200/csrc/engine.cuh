@@ -186,6 +186,7 @@ struct FilterTables
 {
   const uint32_t* b3;     // 2^20-bit blocked Bloom filter over 3-byte keys (pair probe, 2 bits per key)
   const uint32_t* b4;     // 2^19-bit Bloom filter (BLOOM_K probes) over 4-byte windows
+  const uint32_t* b2;     // variant 6: exact 2^16-bit bitmap over the last two bytes of short hit states' windows
   const void* ht;         // open-addressed {window, match_table value} table
   uint32_t ht_bits;
   uint32_t n_windows;

@@ -213,6 +213,7 @@ class Ruleset:
         self.name = name
         self.specs = specs
         self.per_rule = per_rule
+        self.extra = ""   # rule text appended verbatim (bench.py --short-atoms)
 
     @property
     def source(self) -> str:
@@ -223,7 +224,7 @@ class Ruleset:
             for j, sp in enumerate(chunk):
                 out.append("  $s%d = %s\n" % (j, sp.text))
             out.append(" condition:\n  any of them\n}\n")
-        return "".join(out)
+        return "".join(out) + self.extra
 
 
 def ruleset(config: int, n: int = None, seed: int = None) -> Ruleset:
