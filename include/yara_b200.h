@@ -246,6 +246,10 @@ typedef struct yrb_batch_result
 
 #define YRB_BATCH_ONE_ALLOCATION 1 /* all items lie inside ONE host allocation: the bytes between
                                      them are readable and may be copied along */
+#define YRB_BATCH_BLOCKS_OF_ONE_SCAN 2 /* the items are consecutive blocks of ONE multi-block scan (scanner.c:467-500):
+                                          chained strings connect across them, so an item in which a chain part
+                                          matched is flagged YRB_ITEM_RESCAN as well (its result needs the chain
+                                          state the blocks before it left; the caller scans it with seeds) */
 
 int yrb_scan_batch(
     yrb_scanner* scanner, const yrb_batch_item* items, uint32_t n_items, int scan_flags, int batch_flags,

@@ -55,6 +55,7 @@ int vmh_scan_seeds(
 int vmh_scan_batch(
     const void* image, const uint8_t* data, size_t size, int n_seg, const int64_t* seg_start, const int64_t* seg_len,
     yrb_match* matches, size_t cap_m, uint8_t* item_dirty, vmh_result* res, vmh_stats* stats);
+void vmh_set_chain_marks_dirty(int on);
 
 struct yrb_rules
 {
@@ -112,10 +113,15 @@ int yrb_scanner_set_option(yrb_scanner*, int, uint64_t) { return YRB_SUCCESS; }
 size_t yrb_scanner_footprint(yrb_scanner*) { return 0; }
 void yrb_scanner_trim(yrb_scanner*) {}
 
+static unsigned g_host_scans = 0, g_batch_calls = 0;
+unsigned yrb_test_host_scans(void) { return g_host_scans; }
+unsigned yrb_test_batch_calls(void) { return g_batch_calls; }
+
 int yrb_scan_host(yrb_scanner* s, const uint8_t* data, size_t size, const yrb_scan_params* p, yrb_scan_result* out)
 {
   if (!s || !p || !out || p->block_size != 0 || p->defer_resolve)
     return YRB_ERROR_BAD_ARGUMENT;
+  __atomic_fetch_add(&g_host_scans, 1, __ATOMIC_RELAXED);
   memset(out, 0, sizeof(*out));
   out->error_string = YRB_NONE;
   static const uint8_t dummy = 0;
@@ -208,9 +214,9 @@ int yrb_multi_scan_host(yrb_multi* m, const uint8_t* data, size_t size, const yr
 int yrb_scan_batch(
     yrb_scanner* s, const yrb_batch_item* items, uint32_t n_items, int scan_flags, int batch_flags, yrb_batch_result* out)
 {
-  (void) batch_flags;
   if (!s || !out || (n_items > 0 && !items))
     return YRB_ERROR_BAD_ARGUMENT;
+  __atomic_fetch_add(&g_batch_calls, 1, __ATOMIC_RELAXED);
   memset(out, 0, sizeof(*out));
   out->n_items = n_items;
   s->state.assign(n_items ? n_items : 1, YRB_ITEM_DONE);
@@ -250,6 +256,7 @@ int yrb_scan_batch(
   {
     s->m.resize(cap);
     std::fill(dirty.begin(), dirty.end(), 0);
+    vmh_set_chain_marks_dirty((batch_flags & YRB_BATCH_BLOCKS_OF_ONE_SCAN) != 0);
     if (vmh_scan_batch(s->rules->image.data(), concat.data(), (size_t) total, (int) n_items, start.data(), len.data(), s->m.data(),
                        cap, dirty.data(), &res, &st) != 0)
       return YRB_ERROR_BAD_ARGUMENT;

@@ -154,6 +154,9 @@ int vmh_scan(
 /* Batch mode (yrb_scan_batch): `data` is the concatenation, item k = [seg_start[k], seg_start[k] + seg_len[k]).
    matches come back string-major with CONCATENATION offsets (the host side of yrb_scan_batch splits them by item);
    item_dirty[k] != 0: the item needs the per-item path. */
+static thread_local int g_chain_marks_dirty = 0;   /* YRB_BATCH_BLOCKS_OF_ONE_SCAN for the next vmh_scan_batch of this thread */
+void vmh_set_chain_marks_dirty(int on) { g_chain_marks_dirty = on; }
+
 int vmh_scan_batch(
     const void* image, const uint8_t* data, size_t size, int n_seg, const int64_t* seg_start, const int64_t* seg_len,
     yrb_match* matches, size_t cap_m, uint8_t* item_dirty, vmh_result* res, vmh_stats* stats)
@@ -434,6 +437,7 @@ static long long run_verify(
     ro.st = &st;
     ro.str_err = str_err.data();
     ro.item_dirty = item_dirty;
+    ro.chain_marks_dirty = (item_dirty != nullptr && g_chain_marks_dirty) ? 1u : 0u;
 
     /* A candidate that outgrows a tier is verified again from scratch by the next one, which emits
        its records again (resolve.cu treats equal keys as one record); here the records a tier emitted

@@ -248,3 +248,44 @@ def test_large_single_block_scans_go_to_the_sharded_engine():
     assert p.returncode == 0 and "MULTI_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("MULTI_OK")][0].split()
     assert int(line[1]) == 1          # the big one-block scan was sharded
+
+
+BLOCKS_CODE = r"""
+import ctypes as C, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import yrh
+from yara_b200 import synth
+rs = synth.ruleset(2, 300)                      # literals only: no chained strings
+rc = synth.ruleset(3, 600)                      # with chained hex strings
+R, B = yrh.ref(), yrh.b200cpu()
+eng = C.CDLL(yrh.b200cpu_path().replace("libyrh_b200cpu.so", "libyrb200cpu.so"))
+out = []
+for r_ in (rs, rc):
+    rr, rb = R.compile(r_.source), B.compile(r_.source)
+    data = synth.corpus(r_, 48 * 1024 + 100, 1024)
+    h0, b0 = eng.yrb_test_host_scans(), eng.yrb_test_batch_calls()
+    got = rb.scan_blocks(data, 1024, 256, cap=1 << 18)
+    h1, b1 = eng.yrb_test_host_scans(), eng.yrb_test_batch_calls()
+    want = rr.scan_blocks(data, 1024, 256, cap=1 << 18)
+    assert got.key() == want.key() and len(want.matches) > 20
+    out += [h1 - h0, b1 - b0]
+print("BLOCKS_OK", *out)
+"""
+
+
+def test_small_blocks_of_a_multi_block_scan_are_batched():
+    """the 1 KiB blocks of a multi-block scan (63 of them here) are deferred by
+    yr_b200_scan_mem_block and scanned as ONE engine batch behind the block loop (yr_b200_blocks_flush);
+    blocks in which a chain part matched are rescanned one by one with the chain state as seeds.  Results are the
+    reference's; with $YR_B200_BLOCK_BATCH=0 every block is an engine call of its own."""
+    code = BLOCKS_CODE % (ROOT, os.path.join(ROOT, "tests"))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "BLOCKS_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+    h_plain, b_plain, h_chain, b_chain = [int(x) for x in [l for l in p.stdout.splitlines() if l.startswith("BLOCKS_OK")][0].split()[1:]]
+    assert h_plain == 0 and b_plain == 1          # no chains: every block answered by the one batch
+    assert b_chain == 1 and 0 < h_chain < 63      # only the blocks with chain-part matches were scanned on their own
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ, YR_B200_BLOCK_BATCH="0"))
+    assert p.returncode == 0 and "BLOCKS_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+    h_plain, b_plain, h_chain, b_chain = [int(x) for x in [l for l in p.stdout.splitlines() if l.startswith("BLOCKS_OK")][0].split()[1:]]
+    assert b_plain == 0 and b_chain == 0 and h_plain >= 63 and h_chain >= 63

@@ -686,6 +686,7 @@ struct BatchPlan
   const int64_t* d_start;
   const int64_t* d_len;
   uint8_t* d_dirty;
+  bool blocks_of_one_scan;  // YRB_BATCH_BLOCKS_OF_ONE_SCAN: items with chain-part matches are flagged for the per-item path
 };
 
 static int scan_impl(
@@ -965,6 +966,7 @@ static int scan_impl(
     ro.st = s->d_status;
     ro.str_err = s->str_err.p;
     ro.item_dirty = bp ? bp->d_dirty : nullptr;
+    ro.chain_marks_dirty = (bp && bp->blocks_of_one_scan) ? 1u : 0u;
     if (s->rules->h.code_size > 0) // only RE / hex strings can raise verifier errors
       CK(cudaMemsetAsync(s->str_err.p, 0xFF, sizeof(unsigned long long) * s->rules->R.num_strings, s->stream));
 
@@ -1240,6 +1242,7 @@ extern "C" int yrb_scan_batch(
   bp.d_start = s->seg_tab.p;
   bp.d_len = s->seg_tab.p + n_items;
   bp.d_dirty = s->item_dirty.p;
+  bp.blocks_of_one_scan = (batch_flags & YRB_BATCH_BLOCKS_OF_ONE_SCAN) != 0;
 
   yrb_scan_params params;
   memset(&params, 0, sizeof(params));

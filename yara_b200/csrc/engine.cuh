@@ -179,6 +179,7 @@ struct RawOut
   ScanStatus* st;
   unsigned long long* str_err;  // per string: min over its failing candidates of (candidate key | error code)
   uint8_t* item_dirty;          // batch mode: items whose result needs the general per-item path (else nullptr)
+  uint32_t chain_marks_dirty;   // batch mode, YRB_BATCH_BLOCKS_OF_ONE_SCAN: a match callback of a chain part marks its item
 };
 
 // Atom prefilter tables of one ruleset (ac_scan.cu, filter kernel).

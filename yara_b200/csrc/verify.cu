@@ -103,7 +103,11 @@ static __device__ void match_callback(Ctx& c, int64_t match_pos, int32_t match_l
   }
 
   if (a.group != YRB_NONE)
+  {
     atomicAdd(&c.out.st->n_chain_raw, 1u);
+    // the items are the blocks of ONE scan: a chain part's match needs the chain state of the blocks before it
+    if (c.out.chain_marks_dirty && c.out.item_dirty) c.out.item_dirty[c.seg] = 1;
+  }
 
   if (c.seq >= KEY_SEQ_MAX)
     atomicExch(&c.out.st->key_overflow, 1u);   // fail loudly (api.cu) rather than order records by a saturated key

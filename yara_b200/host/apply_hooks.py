@@ -11,6 +11,8 @@ anything else means the reference drifted and the build stops.
              scanner.c:287   yr_scanner_destroy: yr_b200_scanner_release(scanner)
              scanner.c:660   yr_scanner_scan_mem: yr_b200_single_block_scan(scanner, 1/0) around the scan
                              (parked file-batch results are complete one-block results)
+             scanner.c:502   behind the block loop: yr_b200_blocks_flush(scanner) (small blocks of a multi-block
+                             scan are deferred and scanned as one batch)
   rules.c    #include "yr_b200.h"
              rules.c:515     yr_rules_destroy: yr_b200_rules_release(rules)
   condition-VM pre-filter (yr_b200_prefilter.c, on unless YR_B200_RULE_PREFILTER=0):
@@ -74,6 +76,12 @@ EDITS = {
             "  yr_b200_scanner_release(scanner);\n\n  RE_FIBER* fiber = scanner->re_fiber_pool.fibers.head;\n",
         ),
         EXEC_CALL,
+        (
+            "  result = iterator->last_error;\n\n  if (result != ERROR_SUCCESS)\n    goto _exit;\n",
+            "  result = yr_b200_blocks_flush(scanner); /* blocks whose scan yr_b200_scan_mem_block deferred */\n\n"
+            "  if (result != ERROR_SUCCESS)\n    goto _exit;\n\n"
+            "  result = iterator->last_error;\n\n  if (result != ERROR_SUCCESS)\n    goto _exit;\n",
+        ),
         (
             "  int result = yr_scanner_scan_mem_blocks(scanner, &iterator);\n",
             "  yr_b200_single_block_scan(scanner, 1); /* yr_scanner_scan_mem: this block is the whole scan */\n"

@@ -31,6 +31,12 @@ int yr_b200_scan_mem_block(
     const uint8_t* block_data,
     YR_MEMORY_BLOCK* block);
 
+/* yr_b200_scan_mem_block may defer the small blocks of a multi-block scan (process memory, custom iterators) and
+   scan them as one engine batch; yr_scanner_scan_mem_blocks calls this behind its block loop (scanner.c:502) so that
+   nothing is left deferred.  Same return codes as a block scan.  $YR_B200_BLOCK_BATCH=<bytes> sets the largest block
+   that is deferred (default 262144; 0 turns the batching off). */
+int yr_b200_blocks_flush(YR_SCANNER* scanner);
+
 void yr_b200_scanner_release(YR_SCANNER* scanner);
 
 /* yr_scanner_scan_mem brackets its scan with (scanner, 1) / (scanner, 0): only then is a block known to

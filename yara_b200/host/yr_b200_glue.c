@@ -38,8 +38,17 @@ typedef struct rules_entry
   pthread_mutex_t multi_lock;  /* one sharded scan (and its materialisation) at a time */
   uint32_t* chain_strings; /* idx of every STRING_FLAGS_CHAIN_PART string */
   uint32_t n_chain_strings;
+  int has_fixed_offset;    /* some string is only verified at one absolute offset (scan.c:1025-1027: base + offset) */
   struct rules_entry* next;
 } rules_entry;
+
+/* a small block of a multi-block scan whose scan is deferred (see blocks_flush below) */
+typedef struct pend_block
+{
+  uint64_t base;
+  size_t size;
+  size_t off; /* of its bytes in scanner_entry.pend_data */
+} pend_block;
 
 typedef struct scanner_entry
 {
@@ -48,6 +57,12 @@ typedef struct scanner_entry
   yrb_rules* dev_rules;
   rules_entry* re;
   struct scanner_entry* next;
+  /* deferred blocks: copies of their bytes, packed at 16-byte boundaries, in scan order */
+  uint8_t* pend_data;
+  size_t pend_cap, pend_used;
+  pend_block* pend;
+  uint32_t n_pend, cap_pend;
+  const void* pend_scan; /* scanner->matches_notebook of the scan they belong to (a new scan gets a new notebook) */
 } scanner_entry;
 
 /* Device scanners (stream, block buffer, work areas, pinned result buffers) are
@@ -174,8 +189,12 @@ static int get_rules(YR_RULES* rules, rules_entry** out)
   pthread_mutex_init(&e->multi_lock, NULL);
 
   for (uint32_t i = 0; i < rules->num_strings; i++)
+  {
     if (STRING_IS_CHAIN_PART(&rules->strings_table[i]))
       e->n_chain_strings++;
+    if (STRING_IS_FIXED_OFFSET(&rules->strings_table[i]))
+      e->has_fixed_offset = 1;
+  }
 
   if (e->n_chain_strings > 0)
   {
@@ -680,6 +699,8 @@ static int co_submit(co_req* r)
   return st;
 }
 
+static __thread scanner_entry* t_last_entry = NULL; /* the entry get_scanner found or made for this thread's last call */
+
 static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out, rules_entry** re_out)
 {
   scanner_entry* e;
@@ -693,6 +714,7 @@ static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out, rules_entry** re_
     {
       *out = e->dev;
       *re_out = e->re;
+      t_last_entry = e;
       pthread_mutex_unlock(&g_lock);
       return ERROR_SUCCESS;
     }
@@ -731,6 +753,7 @@ static int get_scanner(YR_SCANNER* scanner, yrb_scanner** out, rules_entry** re_
       e->re = re;
       e->next = g_scanners;
       g_scanners = e;
+      t_last_entry = e;
       *out = dev;
       *re_out = re;
     }
@@ -752,6 +775,8 @@ void yr_b200_scanner_release(YR_SCANNER* scanner)
       scanner_entry* e = *pp;
       *pp = e->next;
       pool_put(e->dev, e->dev_rules);
+      free(e->pend_data);
+      free(e->pend);
       free(e);
       break;
     }
@@ -1021,6 +1046,154 @@ static int collect_seeds(YR_SCANNER* scanner, rules_entry* re, yrb_seed** seeds_
   return ERROR_SUCCESS;
 }
 
+static int scan_block_now(
+    YR_SCANNER* scanner, const uint8_t* block_data, YR_MEMORY_BLOCK* block, yrb_scanner* dev, rules_entry* re,
+    uint32_t max_match_data);
+
+/* blocks of at most this many bytes are deferred and batched ($YR_B200_BLOCK_BATCH, bytes; 0 = off) */
+static size_t block_batch_max(void)
+{
+  static long v = -1;
+  if (v < 0)
+  {
+    const char* e = getenv("YR_B200_BLOCK_BATCH");
+    v = e ? atol(e) : (256 << 10);
+    if (v < 0) v = 0;
+  }
+  return (size_t) v;
+}
+
+static int pend_append(scanner_entry* e, YR_SCANNER* scanner, const uint8_t* data, YR_MEMORY_BLOCK* block)
+{
+  const size_t off = (e->pend_used + 15) & ~(size_t) 15;
+  if (off + block->size + 16 > e->pend_cap)
+  {
+    size_t ncap = e->pend_cap ? e->pend_cap : ((size_t) 64 << 10);
+    while (ncap < off + block->size + 16) ncap *= 2;
+    uint8_t* nd = (uint8_t*) realloc(e->pend_data, ncap);
+    if (nd == NULL) return ERROR_INSUFFICIENT_MEMORY;
+    e->pend_data = nd;
+    e->pend_cap = ncap;
+  }
+  if (e->n_pend == e->cap_pend)
+  {
+    const uint32_t nc = e->cap_pend ? e->cap_pend * 2 : 64;
+    pend_block* np = (pend_block*) realloc(e->pend, sizeof(pend_block) * nc);
+    if (np == NULL) return ERROR_INSUFFICIENT_MEMORY;
+    e->pend = np;
+    e->cap_pend = nc;
+  }
+  if (off > e->pend_used) memset(e->pend_data + e->pend_used, 0, off - e->pend_used);
+  if (block->size) memcpy(e->pend_data + off, data, block->size);
+  e->pend[e->n_pend].base = block->base;
+  e->pend[e->n_pend].size = block->size;
+  e->pend[e->n_pend].off = off;
+  e->n_pend++;
+  e->pend_used = off + block->size;
+  e->pend_scan = (const void*) scanner->matches_notebook;
+  return ERROR_SUCCESS;
+}
+
+/* The deferred blocks, in order: ONE yrb_scan_batch over their copies.  A block the batch answers for (no chained
+   string matched in it, no verifier error, nothing near the match cap: include/yara_b200.h) gets its YR_MATCH nodes
+   from the batch records -- dedup against earlier blocks by base + offset, the cap across blocks and temporarily
+   disabled strings are handled where the nodes are linked (materialise), as for any block.  A block the batch
+   flags is scanned on its own, now, with the chain state of everything before it as seeds: exactly what would have
+   happened without the batch.  Blocks without chain-part matches neither read nor change that state, so the order
+   of the results is the order of the blocks. */
+static int blocks_flush(YR_SCANNER* scanner, scanner_entry* e, uint32_t max_match_data)
+{
+  const uint32_t n = e->n_pend;
+  int rc = ERROR_SUCCESS;
+  if (n == 0)
+    return ERROR_SUCCESS;
+  if (e->pend_scan != (const void*) scanner->matches_notebook)
+  {
+    e->n_pend = 0;
+    e->pend_used = 0;
+    return ERROR_SUCCESS;
+  }
+
+  yrb_batch_item* items = (yrb_batch_item*) malloc(sizeof(yrb_batch_item) * n);
+  uint8_t* state = (uint8_t*) malloc(n);
+  uint64_t* first = (uint64_t*) malloc(sizeof(uint64_t) * ((size_t) n + 1));
+  yrb_match* recs = NULL;
+  if (items == NULL || state == NULL || first == NULL)
+    rc = ERROR_INSUFFICIENT_MEMORY;
+
+  if (rc == ERROR_SUCCESS)
+  {
+    for (uint32_t k = 0; k < n; k++)
+    {
+      items[k].data = e->pend_data + e->pend[k].off;
+      items[k].size = e->pend[k].size;
+    }
+    yrb_batch_result br;
+    /* a handful of blocks is cheaper one by one: a device scanner's first batch allocates its pinned segment tables
+       (milliseconds), and the reference's test suite makes a new ruleset -- hence a new scanner -- per assertion */
+    int r2 = n >= 8 ? yrb_scan_batch(e->dev, items, n, scanner->flags, YRB_BATCH_ONE_ALLOCATION | YRB_BATCH_BLOCKS_OF_ONE_SCAN, &br)
+                    : -1;
+    if (r2 == YRB_SUCCESS)
+    {
+      /* the records live in the device scanner's buffers, which the per-block scans below reuse: take a copy */
+      const uint64_t total = br.item_first[n];
+      recs = (yrb_match*) malloc(sizeof(yrb_match) * (total ? total : 1));
+      if (recs == NULL)
+        rc = ERROR_INSUFFICIENT_MEMORY;
+      else
+      {
+        memcpy(state, br.item_state, n);
+        memcpy(first, br.item_first, sizeof(uint64_t) * ((size_t) n + 1));
+        memcpy(recs, br.matches, sizeof(yrb_match) * total);
+      }
+    }
+    else if (r2 == -1 || r2 < 1000)
+      memset(state, YRB_ITEM_RESCAN, n); /* a single block, or the batch refused (its own error codes): one by one */
+    else
+      rc = fail_loudly("yrb_scan_batch", r2);
+  }
+
+  for (uint32_t k = 0; k < n && rc == ERROR_SUCCESS; k++)
+  {
+    YR_MEMORY_BLOCK blk;
+    memset(&blk, 0, sizeof(blk));
+    blk.base = e->pend[k].base;
+    blk.size = e->pend[k].size;
+    const uint8_t* data = e->pend_data + e->pend[k].off;
+    if (scanner->timeout > 0 && yr_stopwatch_elapsed_ns(&scanner->stopwatch) > scanner->timeout)
+      rc = ERROR_SCAN_TIMEOUT;
+    else if (state[k] == YRB_ITEM_DONE && recs != NULL)
+      rc = materialise(scanner, data, &blk, recs + first[k], (size_t) (first[k + 1] - first[k]), scanner->matches, 1,
+                       max_match_data, NULL);
+    else
+      rc = scan_block_now(scanner, data, &blk, e->dev, e->re, max_match_data);
+  }
+
+  free(items);
+  free(state);
+  free(first);
+  free(recs);
+  e->n_pend = 0;
+  e->pend_used = 0;
+  return rc;
+}
+
+/* scanner.c, behind the block loop of yr_scanner_scan_mem_blocks: whatever is still deferred */
+int yr_b200_blocks_flush(YR_SCANNER* scanner)
+{
+  uint32_t max_match_data;
+  scanner_entry* e;
+  pthread_mutex_lock(&g_lock);
+  for (e = g_scanners; e != NULL; e = e->next)
+    if (e->scanner == scanner)
+      break;
+  pthread_mutex_unlock(&g_lock);
+  if (e == NULL || e->n_pend == 0)
+    return ERROR_SUCCESS;
+  FAIL_ON_ERROR(yr_get_configuration_uint32(YR_CONFIG_MAX_MATCH_DATA, &max_match_data));
+  return blocks_flush(scanner, e, max_match_data);
+}
+
 int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_MEMORY_BLOCK* block)
 {
   yrb_scanner* dev = NULL;
@@ -1074,7 +1247,42 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
   rc = get_scanner(scanner, &dev, &re);
   if (rc != ERROR_SUCCESS)
     return rc;
+  scanner_entry* entry = t_last_entry;
 
+  /* ---- the small blocks of a multi-block scan (process memory, custom iterators: scanner.c:467-500,
+     proc/linux.c:309) are not scanned one launch sequence each but collected and scanned as ONE engine batch
+     (blocks_flush) -- when the next large block arrives, when enough have piled up, or behind the loop. */
+  if (block_batch_max() > 0 && entry != NULL && t_single_block_scanner != scanner && block->size <= block_batch_max() &&
+      !(scanner->flags & SCAN_FLAGS_FAST_MODE) && !re->has_fixed_offset /* a batch item has no base */)
+  {
+    if (entry->n_pend > 0 && entry->pend_scan != (const void*) scanner->matches_notebook)
+      entry->n_pend = 0, entry->pend_used = 0; /* left behind by a scan that ended in an exception */
+    if (entry->n_pend >= 1024 || entry->pend_used + block->size + 16 > ((size_t) 8 << 20))
+    {
+      rc = blocks_flush(scanner, entry, max_match_data);
+      if (rc != ERROR_SUCCESS)
+        return rc;
+    }
+    if (pend_append(entry, scanner, block_data, block) == ERROR_SUCCESS)
+      return ERROR_SUCCESS;
+    /* out of memory for the copy: scan it now */
+  }
+  if (entry != NULL && entry->n_pend > 0)
+  {
+    rc = blocks_flush(scanner, entry, max_match_data); /* keep the order of the blocks */
+    if (rc != ERROR_SUCCESS)
+      return rc;
+  }
+  return scan_block_now(scanner, block_data, block, dev, re, max_match_data);
+}
+
+/* One block through the engine, now: H2D + scan + verify + resolve with the chain state of the earlier blocks as
+   seeds, YR_MATCH lists built from the records. */
+static int scan_block_now(
+    YR_SCANNER* scanner, const uint8_t* block_data, YR_MEMORY_BLOCK* block, yrb_scanner* dev, rules_entry* re,
+    uint32_t max_match_data)
+{
+  int rc;
   yrb_scan_params params;
   memset(&params, 0, sizeof(params));
   params.base = block->base;
