@@ -601,7 +601,15 @@ def main():
                       "ms_per_step": other_secs / args.steps * 1e3, "scaling": mode,
                       "note": "same sharded flow (local scan + verify, records to rank 0, one global resolve) inside the timed region"}
     if e2e:
-        e2e["d2h_bytes_per_step"] = (int(final.n_matches) * 24 + 256) if final is not None else None
+        if final is not None:
+            d2h = int(final.n_matches) * 24 + 256        # yrb_match records + status
+            if world == 1 and int(final.n_matches) >= 8192 and os.environ.get("YR_B200_GATHER_MATCH_DATA", "1") != "0":
+                # large single-device results: the match data comes packed from the device as well (yrb_last_match_data)
+                ml = np.clip(final.matches["match_length"].astype(np.int64), 0, 512)
+                d2h += int(ml.sum()) + (int(final.n_matches) + 1) * 8
+            e2e["d2h_bytes_per_step"] = d2h
+        else:
+            e2e["d2h_bytes_per_step"] = None
         line["e2e"] = e2e
 
     if not args.no_cpu and world == 1:

@@ -311,6 +311,13 @@ int yrb_gather_match_data(
     yrb_scanner* scanner, const uint8_t* d_data, uint32_t max_match_data, uint8_t* out, size_t out_cap,
     uint64_t* offsets);
 
+/* The same for the last yrb_scan_host result, from the scanner's own resident copy of the block: data[offsets[k] ..
+   offsets[k + 1]) are the first min(match_length, max_match_data) bytes of match k (the order of result.matches).
+   Both arrays are pinned host memory owned by the scanner, valid until its next call.  YRB_ERROR_BAD_ARGUMENT when
+   the last call was not a yrb_scan_host with matches.  The libyara glue uses it for large results: one sequential
+   read instead of a cache and TLB miss per match in a multi-GiB host block. */
+int yrb_last_match_data(yrb_scanner* scanner, uint32_t max_match_data, const uint8_t** data, const uint64_t** offsets);
+
 /* The atom-prefilter tables are a pure function of the rules image; they are built once per image
    and kept in a process-wide registry and in a disk cache keyed by a hash of the image
    ($YR_B200_CACHE_DIR, default ~/.cache/yara_b200; YR_B200_CACHE=0: no files) -- the device-side

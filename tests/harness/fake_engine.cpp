@@ -71,6 +71,11 @@ struct yrb_scanner
   std::vector<uint32_t> tm;
   std::vector<uint8_t> state;
   std::vector<uint64_t> first;
+  /* yrb_last_match_data: the "resident copy" of the last yrb_scan_host block and its packed match data */
+  std::vector<uint8_t> last_block, g_data;
+  std::vector<uint64_t> g_off;
+  size_t last_n = 0;
+  bool last_host = false;
 };
 
 int yrb_device_count(void) { return 1; }
@@ -113,7 +118,32 @@ int yrb_scanner_set_option(yrb_scanner*, int, uint64_t) { return YRB_SUCCESS; }
 size_t yrb_scanner_footprint(yrb_scanner*) { return 0; }
 void yrb_scanner_trim(yrb_scanner*) {}
 
-static unsigned g_host_scans = 0, g_batch_calls = 0;
+static unsigned g_host_scans = 0, g_batch_calls = 0, g_match_data_calls = 0;
+unsigned yrb_test_match_data_calls(void) { return g_match_data_calls; }
+
+int yrb_last_match_data(yrb_scanner* s, uint32_t max_match_data, const uint8_t** data, const uint64_t** offsets)
+{
+  if (!s || !data || !offsets || !s->last_host || s->last_n == 0) return YRB_ERROR_BAD_ARGUMENT;
+  __atomic_fetch_add(&g_match_data_calls, 1, __ATOMIC_RELAXED);
+  s->g_off.assign(s->last_n + 1, 0);
+  s->g_data.clear();
+  for (size_t k = 0; k < s->last_n; k++)
+  {
+    const int32_t l = s->m[k].match_length;
+    const uint64_t len = (uint64_t) (l < 0 ? 0 : (l > (int32_t) max_match_data ? (int32_t) max_match_data : l));
+    for (uint64_t j = 0; j < len; j++)
+    {
+      const int64_t p = s->m[k].offset + (int64_t) j;
+      s->g_data.push_back((p >= 0 && (size_t) p < s->last_block.size()) ? s->last_block[(size_t) p] : 0);
+    }
+    s->g_off[k + 1] = s->g_data.size();
+  }
+  s->g_data.push_back(0);
+  *data = s->g_data.data();
+  *offsets = s->g_off.data();
+  return YRB_SUCCESS;
+}
+
 unsigned yrb_test_host_scans(void) { return g_host_scans; }
 unsigned yrb_test_batch_calls(void) { return g_batch_calls; }
 
@@ -158,6 +188,9 @@ int yrb_scan_host(yrb_scanner* s, const uint8_t* data, size_t size, const yrb_sc
     out->error = res.error;
     out->error_string = res.error_string;
   }
+  s->last_block.assign(data, data + size);
+  s->last_n = (size_t) res.n_matches;
+  s->last_host = true;
   out->n_matches = (size_t) res.n_matches;
   out->matches = s->m.data();
   out->n_unconfirmed = (size_t) res.n_unconfirmed;
@@ -217,6 +250,7 @@ int yrb_scan_batch(
   if (!s || !out || (n_items > 0 && !items))
     return YRB_ERROR_BAD_ARGUMENT;
   __atomic_fetch_add(&g_batch_calls, 1, __ATOMIC_RELAXED);
+  s->last_host = false;
   memset(out, 0, sizeof(*out));
   out->n_items = n_items;
   s->state.assign(n_items ? n_items : 1, YRB_ITEM_DONE);

@@ -289,3 +289,37 @@ def test_small_blocks_of_a_multi_block_scan_are_batched():
     assert p.returncode == 0 and "BLOCKS_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
     h_plain, b_plain, h_chain, b_chain = [int(x) for x in [l for l in p.stdout.splitlines() if l.startswith("BLOCKS_OK")][0].split()[1:]]
     assert b_plain == 0 and b_chain == 0 and h_plain >= 63 and h_chain >= 63
+
+
+PACKED_CODE = r"""
+import ctypes as C, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import yrh
+R, B = yrh.ref(), yrh.b200cpu()
+eng = C.CDLL(yrh.b200cpu_path().replace("libyrh_b200cpu.so", "libyrb200cpu.so"))
+rule = 'rule t { strings: $a = "abcd" $b = /ef[0-9]{1,600}gh/ $c = "zz" private condition: any of them }'
+data = np.frombuffer(b"abcd ef123gh " * 9000 + b"ef" + b"7" * 550 + b"gh" + b"abcd" * 300, dtype=np.uint8)
+rr, rb = R.compile(rule), B.compile(rule)
+c0 = eng.yrb_test_match_data_calls()
+a, b = rr.scan(data, cap=1 << 18), rb.scan(data, cap=1 << 18)
+c1 = eng.yrb_test_match_data_calls()
+assert a.rc == b.rc == 0 and len(a.matches) > 18000 and a.matches.tobytes() == b.matches.tobytes()
+small = data[:4000]
+assert rr.scan(small).matches.tobytes() == rb.scan(small).matches.tobytes()
+c2 = eng.yrb_test_match_data_calls()
+print("PACKED_OK", c1 - c0, c2 - c1)
+"""
+
+
+def test_large_results_take_their_match_data_packed_from_the_engine():
+    """materialise() copies min(match_length, max_match_data) bytes per match (scan.c:723-737).  For results of at
+    least 8192 matches the glue asks the engine for them packed (yrb_last_match_data: gathered from the resident copy
+    of the block) instead of reading the host block at random; every YR_MATCH field incl. the data hash must stay the
+    reference's, also for matches longer than max_match_data (512)."""
+    for env_extra, want in (({}, 1), ({"YR_B200_GATHER_MATCH_DATA": "0"}, 0)):
+        p = subprocess.run([sys.executable, "-c", PACKED_CODE % (ROOT, os.path.join(ROOT, "tests"))], capture_output=True, text=True,
+                           timeout=900, env=dict(os.environ, **env_extra))
+        assert p.returncode == 0 and "PACKED_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+        big, small = [int(x) for x in [l for l in p.stdout.splitlines() if l.startswith("PACKED_OK")][0].split()[1:]]
+        assert big == want and small == 0

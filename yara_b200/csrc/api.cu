@@ -161,6 +161,9 @@ struct yrb_scanner
   ScanView last_view;
   DevBuf<uint64_t> g_offsets;
   DevBuf<uint8_t> g_data;
+  PinBuf<uint64_t> h_g_offsets;   // yrb_last_match_data: the same, in pinned host memory owned by the scanner
+  PinBuf<uint8_t> h_g_data;
+  bool last_scan_resident = false;   // the last scan copied its block into d_data (yrb_scan_host) and it is still there
 };
 
 // ------------------------------------------------------------------- helpers
@@ -396,7 +399,7 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s)
   s->cub_tmp.release(); s->c_nxt.release(); s->c_prv.release(); s->c_clen.release(); s->c_mlen.release(); s->c_uvn.release(); s->sraw.release(); s->d_seeds.release(); s->seed_base.release();
   s->s_lists.release(); s->c_where.release(); s->flags8.release(); s->finals.release(); s->unconf.release();
   s->str_min_key.release(); s->str_cut_key.release(); s->str_err.release(); s->str_count.release(); s->too_many.release();
-  s->g_offsets.release(); s->g_data.release();
+  s->g_offsets.release(); s->g_data.release(); s->h_g_offsets.release(); s->h_g_data.release();
   s->seg_tab.release(); s->item_dirty.release(); s->h_seg_tab.release(); s->h_item_dirty.release();
   s->h_finals.release(); s->h_unconf.release(); s->h_too_many.release(); s->h_str_count.release(); s->h_raw.release();
   if (s->d_status) cudaFree(s->d_status);
@@ -700,6 +703,7 @@ static int scan_impl(
   res->error_string = YRB_NONE;
   unsigned launches = 0;
   s->kernel_timed = false;
+  s->last_scan_resident = (h_data != nullptr && bp == nullptr);
 
   ScanView V;
   memset(&V, 0, sizeof(V));
@@ -1840,6 +1844,44 @@ extern "C" int yrb_gather_match_data(
   match_copy_kernel<<<(unsigned) (((uint64_t) n * 32 + 255) / 256), 256, 0, s->stream>>>(s->finals.p, n, s->g_offsets.p, V, s->g_data.p);
   CK(cudaMemcpyAsync(out, s->g_data.p, (size_t) total, cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
+  return YRB_SUCCESS;
+}
+
+// The match data of the last yrb_scan_host result, gathered on the device from the scanner's resident copy of the
+// block and handed over packed, in pinned memory owned by the scanner: for a caller that has to copy
+// min(match_length, max_match_data) bytes per match out of a multi-GiB host block (scan.c:723-737 does, so the glue
+// must) that turns a cache and TLB miss per match into a sequential read.
+extern "C" int yrb_last_match_data(yrb_scanner* s, uint32_t max_match_data, const uint8_t** data, const uint64_t** offsets)
+{
+  if (!s || !data || !offsets) return YRB_ERROR_BAD_ARGUMENT;
+  if (!s->last_scan_resident || s->last_n_final == 0 || s->last_view.n_seg > 0) return YRB_ERROR_BAD_ARGUMENT;
+  const size_t n = s->last_n_final;
+  if (s->h_g_offsets.ensure(n + 1) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+  // sizes first (the packed total decides the size of the pinned buffer), then the bytes
+  CK(cudaSetDevice(s->device));
+  if (s->g_offsets.ensure(n + 1) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint64_t*) nullptr, (uint64_t*) nullptr, (int) n + 1);
+  if (s->cub_tmp.ensure(tb + 256) != YRB_SUCCESS || s->kF.ensure(n + 1) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
+  CK(cudaMemsetAsync(s->kF.p, 0, (n + 1) * sizeof(uint64_t), s->stream));
+  match_len_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, s->stream>>>(s->finals.p, (uint32_t) n, max_match_data, s->kF.p);
+  size_t tb2 = s->cub_tmp.cap;
+  cub::DeviceScan::ExclusiveSum(s->cub_tmp.p, tb2, s->kF.p, s->g_offsets.p, (int) n + 1, s->stream);
+  CK(cudaMemcpyAsync(s->h_g_offsets.p, s->g_offsets.p, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  const uint64_t total = s->h_g_offsets.p[n];
+  if (s->g_data.ensure((size_t) total + 1) != YRB_SUCCESS || s->h_g_data.ensure((size_t) total + 1) != YRB_SUCCESS)
+    return YRB_ERROR_INSUFFICIENT_MEMORY;
+  if (total > 0)
+  {
+    ScanView V = s->last_view;
+    V.d = s->d_data.p;
+    match_copy_kernel<<<(unsigned) (((uint64_t) n * 32 + 255) / 256), 256, 0, s->stream>>>(s->finals.p, (uint32_t) n, s->g_offsets.p, V, s->g_data.p);
+    CK(cudaMemcpyAsync(s->h_g_data.p, s->g_data.p, (size_t) total, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+  }
+  *data = s->h_g_data.p;
+  *offsets = s->h_g_offsets.p;
   return YRB_SUCCESS;
 }
 

@@ -884,10 +884,20 @@ static int too_many_protocol(YR_SCANNER* scanner, YR_STRING* string)
   return ERROR_TOO_MANY_MATCHES;
 }
 
+/* match data of records[k] packed by the engine (yrb_last_match_data), for the next materialise() of this thread:
+   data[offs[k] .. offs[k + 1]).  NULL: copy from the block. */
+static __thread const uint8_t* t_packed_data = NULL;
+static __thread const uint64_t* t_packed_offs = NULL;
+
 static int materialise(
     YR_SCANNER* scanner, const uint8_t* block_data, YR_MEMORY_BLOCK* block, const yrb_match* recs, size_t n,
     YR_MATCHES* lists, int confirmed, uint32_t max_match_data, YR_MATCH** seed_nodes)
 {
+  const uint8_t* packed = t_packed_data;
+  const uint64_t* packed_offs = t_packed_offs;
+  t_packed_data = NULL;
+  t_packed_offs = NULL;
+
   YR_RULES* rules = scanner->rules;
 
   for (size_t i = 0; i < n; i++)
@@ -899,7 +909,7 @@ static int materialise(
 
     /* the data copies below touch the block at random offsets (a cache and TLB miss each
        in a multi-GiB block): get the next ones moving */
-    if (i + 12 < n && recs[i + 12].offset >= 0 && (size_t) recs[i + 12].offset < block->size)
+    if (packed == NULL && i + 12 < n && recs[i + 12].offset >= 0 && (size_t) recs[i + 12].offset < block->size)
       __builtin_prefetch(block_data + recs[i + 12].offset);
 
     if (yr_bitmask_is_set(scanner->strings_temp_disabled, string->idx))
@@ -961,7 +971,10 @@ static int materialise(
       uint8_t* d = (uint8_t*) yr_notebook_alloc(scanner->matches_notebook, m->data_length);
       if (d == NULL)
         return ERROR_INSUFFICIENT_MEMORY;
-      memcpy(d, block_data + r->offset, m->data_length);
+      if (packed != NULL && packed_offs[i + 1] - packed_offs[i] == (uint64_t) m->data_length)
+        memcpy(d, packed + packed_offs[i], m->data_length);
+      else
+        memcpy(d, block_data + r->offset, m->data_length);
       m->data = d;
     }
     else if (m->data_length < 0)
@@ -1049,6 +1062,17 @@ static int collect_seeds(YR_SCANNER* scanner, rules_entry* re, yrb_seed** seeds_
 static int scan_block_now(
     YR_SCANNER* scanner, const uint8_t* block_data, YR_MEMORY_BLOCK* block, yrb_scanner* dev, rules_entry* re,
     uint32_t max_match_data);
+
+static int match_data_gather_on(void)
+{
+  static int v = -1;
+  if (v < 0)
+  {
+    const char* e = getenv("YR_B200_GATHER_MATCH_DATA");
+    v = e ? atoi(e) != 0 : 1;
+  }
+  return v;
+}
 
 /* blocks of at most this many bytes are deferred and batched ($YR_B200_BLOCK_BATCH, bytes; 0 = off) */
 static size_t block_batch_max(void)
@@ -1377,6 +1401,21 @@ static int scan_block_now(
       recs[k++] = recs[i];
     }
     res.n_matches = k;
+  }
+
+  /* Large results of a single-device scan: the engine gathers the match data from its resident copy of the block and
+     hands it over packed -- materialise then reads sequentially instead of taking a cache and TLB miss per match
+     in a multi-GiB host block (28 of the 340 ms of a 16 GiB scan with 262k matches). */
+  if (locked == NULL && n_seeds == 0 && res.n_matches >= 8192 && max_match_data > 0 && !(scanner->flags & SCAN_FLAGS_FAST_MODE) &&
+      match_data_gather_on())
+  {
+    const uint8_t* pd = NULL;
+    const uint64_t* po = NULL;
+    if (yrb_last_match_data(dev, max_match_data, &pd, &po) == YRB_SUCCESS)
+    {
+      t_packed_data = pd;
+      t_packed_offs = po;
+    }
   }
 
   rc = materialise(
