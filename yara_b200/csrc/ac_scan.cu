@@ -175,7 +175,7 @@ static const FtVariant kVariants[] = {{1024, 4, 18, 0}, {512, 4, 19, 0}, {1024, 
 // state's path (depth 1: for all 256 first bytes).  A position B2 flags gets the exact treatment -- its state is
 // walked from the root over its four bytes (exact: depth <= 4), match_table looked up, events emitted -- and B2 is
 // authoritative for it: the B3/B4/hash-table path skips flagged positions, so nothing is emitted twice.
-#define B2_WORDS 2048u
+// B2_WORDS (2048 words = 2^16 bits) is defined in engine.cuh
 #define B3_WORDS_SHORT (B3_WORDS_DENSE - B2_WORDS - 64u)
 #define FT_DENSE_FILL 0.10f   // the 20k-string set (0.108) gains 1 % as well (16 GiB: 0.505 -> 0.510); below that nothing changes
 static inline uint32_t ft_b3_words(const FtVariant& v)
