@@ -1353,9 +1353,30 @@ struct MultiWorker
   std::thread th;
   std::mutex mu;
   std::condition_variable cv;
-  int state = 0;   // 0 idle, 1 job posted, 2 job done, 3 quit
+  std::atomic<int> state{0};   // 0 idle, 1 job posted, 2 job done, 3 quit
+  std::atomic<int> asleep{0};  // the worker went to sleep on cv (a poster has to notify)
   MultiJob job;
 };
+
+// A sharded scan of a few milliseconds is handed to the workers and back through `state`; the wake-up of a sleeping
+// thread (tens of microseconds, twice per scan) would be a visible share of it.  Both sides therefore spin on the
+// atomic for a short while -- long enough for back-to-back scans -- before they fall back to the condition variable.
+#define MULTI_SPIN_NS 300000
+
+template <typename Pred>
+static bool spin_until(Pred pred)
+{
+  const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  for (int i = 0;; i++)
+  {
+    if (pred()) return true;
+    if ((i & 63) == 63 && std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count() > MULTI_SPIN_NS)
+      return false;
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
 
 struct yrb_multi
 {
@@ -1371,10 +1392,14 @@ static void multi_worker_main(MultiWorker* w)
   cudaSetDevice(w->device);
   for (;;)
   {
-    std::unique_lock<std::mutex> lk(w->mu);
-    w->cv.wait(lk, [w] { return w->state == 1 || w->state == 3; });
-    if (w->state == 3) return;
-    lk.unlock();
+    if (!spin_until([w] { const int st = w->state.load(std::memory_order_acquire); return st == 1 || st == 3; }))
+    {
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->asleep.store(1);
+      w->cv.wait(lk, [w] { const int st = w->state.load(); return st == 1 || st == 3; });
+      w->asleep.store(0);
+    }
+    if (w->state.load() == 3) return;
 
     MultiJob& j = w->job;
     yrb_scan_params p = j.params;
@@ -1392,8 +1417,10 @@ static void multi_worker_main(MultiWorker* w)
     else
       j.rc = scan_impl(w->scanner, nullptr, j.d_shard ? j.d_shard : &dummy, len, &p, &j.res);
 
-    lk.lock();
-    w->state = 2;
+    {
+      std::lock_guard<std::mutex> lk(w->mu);   // the waiter checks `state` under this mutex before it sleeps
+      w->state.store(2, std::memory_order_release);
+    }
     w->cv.notify_all();
   }
 }
@@ -1416,7 +1443,7 @@ extern "C" void yrb_multi_destroy(yrb_multi* m)
   {
     if (w->th.joinable())
     {
-      { std::lock_guard<std::mutex> lk(w->mu); w->state = 3; }
+      { std::lock_guard<std::mutex> lk(w->mu); w->state.store(3); }
       w->cv.notify_all();
       w->th.join();
     }
@@ -1504,14 +1531,17 @@ static int multi_run(yrb_multi* m, const yrb_scan_params* params, yrb_scan_resul
 
   for (MultiWorker* w : m->w)
   {
-    { std::lock_guard<std::mutex> lk(w->mu); w->state = 1; }
-    w->cv.notify_all();
+    { std::lock_guard<std::mutex> lk(w->mu); w->state.store(1, std::memory_order_release); }
+    if (w->asleep.load()) w->cv.notify_all();
   }
   for (MultiWorker* w : m->w)
   {
-    std::unique_lock<std::mutex> lk(w->mu);
-    w->cv.wait(lk, [w] { return w->state == 2; });
-    w->state = 0;
+    if (!spin_until([w] { return w->state.load(std::memory_order_acquire) == 2; }))
+    {
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->cv.wait(lk, [w] { return w->state.load() == 2; });
+    }
+    w->state.store(0);
   }
   std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
 
@@ -1544,12 +1574,29 @@ static int multi_run(yrb_multi* m, const yrb_scan_params* params, yrb_scan_resul
   if (s0->d_raw.ensure(total ? total : 1, true) != YRB_SUCCESS) return YRB_ERROR_INSUFFICIENT_MEMORY;
   CK(cudaEventRecord(m->ev0, s0->stream));
   size_t at = s0->h_raw_n;
-  for (size_t g = 1; g < n; g++)
   {
-    yrb_scanner* sg = m->w[g]->scanner;
-    if (sg->h_raw_n)
-      CK(cudaMemcpyPeerAsync(s0->d_raw.p + at, s0->device, sg->d_raw.p, sg->device, sg->h_raw_n * sizeof(Raw), s0->stream));
-    at += sg->h_raw_n;
+    // the shards' records arrive over several streams at once: seven small peer copies queued on one stream are
+    // seven copy latencies one after the other
+    cudaStream_t lanes[4] = {s0->stream, s0->copy_stream, s0->side.aux[0], s0->side.aux[1]};
+    bool used[4] = {false, false, false, false};
+    for (int k = 1; k < 4; k++) CK(cudaStreamWaitEvent(lanes[k], m->ev0, 0));
+    for (size_t g = 1; g < n; g++)
+    {
+      yrb_scanner* sg = m->w[g]->scanner;
+      const int k = (int) (g & 3);
+      if (sg->h_raw_n)
+      {
+        CK(cudaMemcpyPeerAsync(s0->d_raw.p + at, s0->device, sg->d_raw.p, sg->device, sg->h_raw_n * sizeof(Raw), lanes[k]));
+        used[k] = true;
+      }
+      at += sg->h_raw_n;
+    }
+    for (int k = 1; k < 4; k++)
+    {
+      if (!used[k]) continue;
+      CK(cudaEventRecord(s0->side.ev[k - 1], lanes[k]));
+      CK(cudaStreamWaitEvent(s0->stream, s0->side.ev[k - 1], 0));
+    }
   }
   if (any_error)
   {
