@@ -46,6 +46,9 @@ def arm(name, exe, env_extra):
         assert p.returncode == 0, (name, p.returncode, p.stderr[-2000:])
         best = dt if best is None else min(best, dt)
         out = sorted(p.stdout.splitlines())
+        errs = [l for l in p.stderr.splitlines() if l.strip()]
+        if errs:
+            print("# %s run %d: %d stderr lines, e.g. %s" % (name, rep, len(errs), " | ".join(errs[:3])[:600]), file=sys.stderr, flush=True)
     print(json.dumps({"arm": name, "exe": exe, "threads": threads, "env": env_extra, "seconds": round(best, 3),
                       "files_per_s": round(nfiles / best, 1), "GB_per_s": round(total / best / 1e9, 3), "output_lines": len(out),
                       "files": nfiles, "bytes": total, "strings_declared": nstrings,
@@ -54,6 +57,10 @@ def arm(name, exe, env_extra):
 
 ref = arm("reference libyara", "yara_ref", {})
 a = arm("drop-in", "yara_b200cli", {"YR_B200_COALESCE": "0"})
+if os.environ.get("CLI_FEEDER_ONLY_PLAIN"):
+    missing = sorted(set(ref) - set(a))
+    print(json.dumps({"identical": ref == a, "missing": len(missing), "extra": len(set(a) - set(ref)), "examples": missing[:5]}))
+    sys.exit(0 if ref == a else 1)
 b = arm("drop-in + coalescing", "yara_b200cli", {"YR_B200_COALESCE": str(threads)})
 c = arm("drop-in + coalescing, pre-filter off", "yara_b200cli", {"YR_B200_COALESCE": str(threads), "YR_B200_RULE_PREFILTER": "0"})
 print(json.dumps({"outputs_identical": ref == a == b == c, "matching_lines": len(ref)}))

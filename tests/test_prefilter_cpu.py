@@ -145,3 +145,20 @@ def test_threads_sharing_one_rules_object():
         with ThreadPoolExecutor(8) as ex:
             got = list(ex.map(lambda f: rp.scan(f).key(), files))
         assert got == want
+
+
+def test_many_threads_learning_at_once():
+    """OP_INIT_RULE asks the pre-filter twice per rule (the jump, and the operand stepped over when the jump is not
+    taken); the learnt table is shared by every thread scanning with the same rules, so another thread can turn a rule
+    "skippable" between the two questions.  The answers must agree (found with `yara -p 16` over the 100,000-string
+    set through the drop-in: the first scans of some threads ended in ERROR_COULD_NOT_MAP_FILE, the exception
+    handler's code).  3,000 pure rules, 16 threads that all start learning at the same time, fresh rules each round."""
+    from yara_b200 import synth
+    P = yrh.refpf()
+    for k in range(4):
+        rs = synth.ruleset(2, 6000, seed=100 + k)
+        rs.per_rule = 2
+        r = P.compile(rs.source)
+        data = synth.corpus(rs, 1 << 20, 4096, seed=k)
+        secs, rc = r.scan_mt(data, 16)
+        assert rc == 0, (k, rc)

@@ -276,6 +276,11 @@ void yr_b200_prefilter_note(YR_SCAN_CONTEXT* ctx, YR_STRING* string)
     e->hit[string->rule_idx] = 1;
 }
 
+/* the last answer of yr_b200_prefilter_skip (see there) */
+static __thread uint32_t t_asked_rule = 0xFFFFFFFFu;
+static __thread int t_asked_answer = 0;
+static __thread int t_asked_once = 0;
+
 void yr_b200_prefilter_begin(YR_SCAN_CONTEXT* ctx)
 {
   t_exec_ctx = NULL;
@@ -292,19 +297,32 @@ void yr_b200_prefilter_begin(YR_SCAN_CONTEXT* ctx)
   t_exec_state = re->state;
   t_exec_hit = se->hit;
   t_evaluated = t_skipped = 0;
+  t_asked_once = 0;
   t_exec_ctx = ctx;
 }
+
+/* OP_INIT_RULE asks TWICE (exec.c:1168 for the jump, exec.c:1172 for the operand it steps over when the jump is not
+   taken) and both answers must be the same one: the state table is shared by every thread that scans with these
+   rules, and another thread may learn "skippable" between the two questions -- the jump not taken and the operand
+   not stepped over leaves ip inside the instruction (seen as ERROR_COULD_NOT_MAP_FILE from the exception handler,
+   or worse).  The first answer is remembered per thread and repeated for the second question. */
 
 int yr_b200_prefilter_skip(YR_SCAN_CONTEXT* ctx, uint32_t rule_idx)
 {
   if (t_exec_ctx != ctx)
     return 0;
-  if (t_exec_state[rule_idx] == PF_SKIPPABLE && !t_exec_hit[rule_idx])
+  if (t_asked_once && t_asked_rule == rule_idx)
   {
-    t_skipped++;
-    return 1;
+    t_asked_once = 0;
+    return t_asked_answer;
   }
-  return 0;
+  const int answer = (*(volatile uint8_t*) &t_exec_state[rule_idx] == PF_SKIPPABLE && !t_exec_hit[rule_idx]) ? 1 : 0;
+  t_asked_rule = rule_idx;
+  t_asked_answer = answer;
+  t_asked_once = 1;
+  if (answer)
+    t_skipped++;
+  return answer;
 }
 
 void yr_b200_prefilter_learn(YR_SCAN_CONTEXT* ctx, uint32_t rule_idx, int result)
@@ -321,8 +339,7 @@ void yr_b200_prefilter_end(YR_SCAN_CONTEXT* ctx)
 {
   if (t_exec_ctx != ctx)
     return;
-  /* OP_INIT_RULE evaluates the skip test twice (the jump and the operand skip) */
-  t_skipped /= 2;
+  t_asked_once = 0;
   __atomic_fetch_add(&g_pf_evaluated, t_evaluated, __ATOMIC_RELAXED);
   __atomic_fetch_add(&g_pf_skipped, t_skipped, __ATOMIC_RELAXED);
   memset(t_exec_hit, 0, ctx->rules->num_rules);
