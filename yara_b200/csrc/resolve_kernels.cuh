@@ -492,11 +492,8 @@ __global__ void chain_gather_kernel(
 // group is skipped only as a whole); everything else goes through lane 0 one group at a
 // time.  The state only changes in lane 0's steps, so the classification is exact.
 // (capping the registers at 40 for 48 resident warps per SM -- the chains of the bench step need two waves at 80 --
-// was measured: spills cost more than the second wave, resolve 0.50 -> 0.55 ms)
-#ifndef CHAIN_BLOCKS_PER_SM
-#define CHAIN_BLOCKS_PER_SM 8   // <= 64 registers: 32 chain warps per SM instead of 24
-#endif
-__global__ void __launch_bounds__(128, CHAIN_BLOCKS_PER_SM)
+// was measured: 64 registers changes nothing (0.50 ms), at 40 the spills cost more than the second wave (0.55 ms))
+__global__ void __launch_bounds__(128)
 chain_resolve_kernel(
     Raw* sraw, const uint64_t* kA, uint32_t n, DevRules R, ChainLists L, yrb_match* finals,
     yrb_match* unconf, ScanStatus* st, uint32_t* too_many, uint32_t too_many_cap, int scan_flags,
