@@ -48,6 +48,47 @@ struct yrb_rules
   int num_sms;
 };
 
+// Device scratch comes from the device's stream-ordered memory pool (cudaMallocAsync, release threshold = never):
+// cudaMalloc / cudaFree synchronise the whole device and serialise on the driver, which a single scanner never
+// notices but sixteen scanner threads growing their buffers at the same time do -- `yara -p 16` through the drop-in
+// spent 100-300 ms per file in allocations during its first scans (profiles/r02_kernel_notes.txt).  The pool
+// hands freed blocks back without either.  YRB_POOLED_ALLOC=0 goes back to cudaMalloc.
+static bool pooled_alloc()
+{
+  static const bool on = !(getenv("YRB_POOLED_ALLOC") && atoi(getenv("YRB_POOLED_ALLOC")) == 0);
+  return on;
+}
+
+static cudaError_t dev_malloc(void** p, size_t bytes)
+{
+  if (!pooled_alloc()) return cudaMalloc(p, bytes);
+  cudaError_t e = cudaMallocAsync(p, bytes, cudaStreamPerThread);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);   // usable on any stream from here on
+  return e;
+}
+
+static void dev_free(void* p)
+{
+  // every user of the block has finished: scans synchronise their streams before they return, and buffers only
+  // grow or go between scans
+  if (pooled_alloc()) { if (cudaFreeAsync(p, cudaStreamPerThread) != cudaSuccess) { cudaGetLastError(); cudaFree(p); } }
+  else cudaFree(p);
+}
+
+static void dev_pool_setup(int device)
+{
+  static std::atomic<unsigned long long> done{0};
+  if (!pooled_alloc() || device < 0 || device >= 64 || (done.load() >> device) & 1ull) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+  {
+    unsigned long long never = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
+  }
+  cudaGetLastError();
+  done.fetch_or(1ull << device);
+}
+
 template <typename T>
 struct DevBuf
 {
@@ -68,15 +109,15 @@ struct DevBuf
       ncap = (n + gran - 1) / gran * gran;
     }
     T* np = nullptr;
-    cudaError_t e = cudaMalloc((void**) &np, ncap * sizeof(T));
+    cudaError_t e = dev_malloc((void**) &np, ncap * sizeof(T));
     if (e != cudaSuccess) { cudaGetLastError(); return YRB_ERROR_INSUFFICIENT_MEMORY; }
     if (keep && p && cap) cudaMemcpy(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = np;
     cap = ncap;
     return YRB_SUCCESS;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) dev_free(p); p = nullptr; cap = 0; }
 };
 
 template <typename T>
@@ -222,6 +263,7 @@ static int rules_init(yrb_rules* r, const void* image, size_t image_size, int de
     return YRB_ERROR_BAD_IMAGE;
   }
 
+  dev_pool_setup(device);
   CK(cudaMalloc(&r->d_image, image_size));
   CK(cudaMemcpy(r->d_image, image, image_size, cudaMemcpyHostToDevice));
 
@@ -426,6 +468,14 @@ extern "C" void yrb_scanner_trim(yrb_scanner* s)
   cudaStreamSynchronize(s->stream);
   cudaStreamSynchronize(s->copy_stream);
   s->d_data.release();
+  if (pooled_alloc())
+  {
+    // give the block buffer back to the device, not just to the pool (this is what trimming is for)
+    cudaMemPool_t pool;
+    cudaStreamSynchronize(cudaStreamPerThread);
+    if (cudaDeviceGetDefaultMemPool(&pool, s->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
+  }
 }
 
 extern "C" int yrb_scanner_set_option(yrb_scanner* s, int option, uint64_t value)

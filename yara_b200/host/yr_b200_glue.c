@@ -167,13 +167,21 @@ static int get_rules(YR_RULES* rules, rules_entry** out)
 
   void* image = NULL;
   size_t image_size = 0;
+  struct timespec ta, tb, tc;
+  clock_gettime(CLOCK_MONOTONIC, &ta);
   int rc = yr_b200_rules_flatten(rules, &image, &image_size);
   if (rc != ERROR_SUCCESS)
     return rc;
+  clock_gettime(CLOCK_MONOTONIC, &tb);
 
   yrb_rules* dev = NULL;
   rc = yrb_rules_create(image, image_size, device, &dev);
   yr_b200_image_free(image);
+  clock_gettime(CLOCK_MONOTONIC, &tc);
+  if (getenv("YRB_TIMING"))
+    fprintf(stderr, "yara_b200: rules of %u strings: flatten %.1f ms, upload (CUDA context on first use, image copy, filter tables) %.1f ms\n",
+            rules->num_strings, (tb.tv_sec - ta.tv_sec) * 1e3 + (tb.tv_nsec - ta.tv_nsec) * 1e-6,
+            (tc.tv_sec - tb.tv_sec) * 1e3 + (tc.tv_nsec - tb.tv_nsec) * 1e-6);
   if (rc != YRB_SUCCESS)
     return fail_loudly("rules upload (yrb_rules_create)", rc);
 
@@ -1451,10 +1459,13 @@ static int scan_block_now(
   if (timing)
   {
     clock_gettime(CLOCK_MONOTONIC, &t2);
+    static __thread struct timespec t_prev_end = {0, 0};
+    const double gap_ms = t_prev_end.tv_sec ? (t0.tv_sec - t_prev_end.tv_sec) * 1e3 + (t0.tv_nsec - t_prev_end.tv_nsec) * 1e-6 : 0.0;
+    t_prev_end = t2;
     fprintf(stderr,
-            "yara_b200: block %zu B: engine %.3f ms (scan+h2d %.3f verify %.3f resolve %.3f), materialise %.3f ms, "
+            "yara_b200: block %zu B: since the previous block of this thread %.3f ms (libyara, caller), engine %.3f ms (scan+h2d %.3f verify %.3f resolve %.3f), materialise %.3f ms, "
             "%zu matches, %llu candidates, %u launches\n",
-            block->size, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6, res.stats.ms_scan,
+            block->size, gap_ms, (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6, res.stats.ms_scan,
             res.stats.ms_verify, res.stats.ms_resolve, (t2.tv_sec - t1.tv_sec) * 1e3 + (t2.tv_nsec - t1.tv_nsec) * 1e-6,
             res.n_matches, (unsigned long long) res.stats.n_candidates, res.stats.kernel_launches);
   }
