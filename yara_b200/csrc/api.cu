@@ -94,6 +94,10 @@ struct DevBuf
 {
   T* p = nullptr;
   size_t cap = 0; // elements
+  // Pool memory is private to its device: a cudaMemcpyPeerAsync out of it is staged through the host (measured at 2
+  // GPUs: gather + global resolve of a sharded scan 0.52 -> 0.70 ms).  Buffers that other devices copy from -- the
+  // Raw records and the per-string error keys of a shard -- are therefore plain cudaMalloc memory.
+  bool plain = false;
 
   // Small, frequently regrown scratch doubles; anything beyond 64 MiB (the resident block above
   // all: a 16 GiB block must not take 32 GiB of HBM, nor a 130 GB one fail) is sized exactly,
@@ -109,15 +113,15 @@ struct DevBuf
       ncap = (n + gran - 1) / gran * gran;
     }
     T* np = nullptr;
-    cudaError_t e = dev_malloc((void**) &np, ncap * sizeof(T));
+    cudaError_t e = plain ? cudaMalloc((void**) &np, ncap * sizeof(T)) : dev_malloc((void**) &np, ncap * sizeof(T));
     if (e != cudaSuccess) { cudaGetLastError(); return YRB_ERROR_INSUFFICIENT_MEMORY; }
     if (keep && p && cap) cudaMemcpy(np, p, cap * sizeof(T), cudaMemcpyDeviceToDevice);
-    if (p) dev_free(p);
+    if (p) { if (plain) cudaFree(p); else dev_free(p); }
     p = np;
     cap = ncap;
     return YRB_SUCCESS;
   }
-  void release() { if (p) dev_free(p); p = nullptr; cap = 0; }
+  void release() { if (p) { if (plain) cudaFree(p); else dev_free(p); } p = nullptr; cap = 0; }
 };
 
 template <typename T>
@@ -372,6 +376,8 @@ extern "C" void yrb_scanner_destroy(yrb_scanner* s);
 
 static int scanner_init(yrb_scanner* s)
 {
+  s->d_raw.plain = true;     // what the first device of a sharded scan copies from its peers (DevBuf::plain)
+  s->str_err.plain = true;
   CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&s->ev[i]));
@@ -1515,6 +1521,7 @@ extern "C" int yrb_multi_create(const void* image, size_t image_size, const int*
   if (!image || !out || !devices || n_devices < 1 || n_devices > 64) return YRB_ERROR_BAD_ARGUMENT;
 
   yrb_multi* m = new (std::nothrow) yrb_multi();
+  if (m) m->err_tmp.plain = true;   // destination of peer copies (DevBuf::plain)
   if (!m) return YRB_ERROR_INSUFFICIENT_MEMORY;
 
   for (int g = 0; g < n_devices; g++)
