@@ -34,7 +34,7 @@ def main():
     R = yrh.ref()
     # the quirk-bearing known-answer cases
     only = [int(x) for x in sys.argv[1:]]   # `make_golden.py 59`: (re)generate just these cases
-    for k in (only or (8, 19, 22, 27, 28, 32, 33, 42, len(CASES) - 3, len(CASES) - 1)):
+    for k in (only or (8, 19, 22, 27, 28, 32, 33, 42, len(CASES) - 1)):
         rule, data = CASES[k]
         open(os.path.join(HERE, "case%02d.bin" % k), "wb").write(data)
         dump("case%02d" % k, R.compile(rule), data, {"data": "case%02d.bin" % k, "rule": rule})
