@@ -8,10 +8,11 @@
  *                            at its single call site (scanner.c:493-496)
  *   materialise()            builds the YR_MATCH nodes scan.c:714-756 would have
  *                            built, from the notebook, and links them into
- *                            scanner->matches[] with _yr_scan_add_match_to_list's
- *                            ordering (scan.c:290-368) so that multi-block scans
- *                            dedup by base+offset exactly like the reference
- *   CALLBACK_MSG_TOO_MANY_MATCHES protocol of scan.c:1054-1073, on the caller's thread
+ *                            scanner->matches[] (list_insert: the ordering and
+ *                            dedup-by-address of scan.c:290-368, so that multi-block
+ *                            scans merge exactly like the reference)
+ *   list_full()              CALLBACK_MSG_TOO_MANY_MATCHES as scan.c:1054-1073
+ *                            issues it, on the caller's thread
  *
  * There is no CPU fallback: if the CUDA engine cannot be used the block scan
  * fails with ERROR_INTERNAL_FATAL_ERROR and says why on stderr.
@@ -829,67 +830,62 @@ void yr_b200_rules_release(YR_RULES* rules)
   pthread_mutex_unlock(&g_lock);
 }
 
-/* scan.c:290-368 over real YR_MATCH nodes */
-static int add_match_to_list(YR_MATCH* match, YR_MATCHES* list, int replace_if_exists)
+/* One node into a string's address-ordered match list; the outcome the reference's list insert gives
+   (scan.c:290-368): a full list refuses the node (ERROR_TOO_MANY_MATCHES, nothing touched); a node at an
+   address the list already holds is dropped -- or, for greedy regexps (overwrite_equal), lends its lengths
+   and data to the one that is there; anything else is linked behind the last node with a smaller address.
+   The engine hands records over in ascending order, so the walk from the tail ends at once for the
+   records of one block; it only goes further when blocks come out of address order. */
+static int list_insert(YR_MATCH* m, YR_MATCHES* list, int overwrite_equal)
 {
-  YR_MATCH* ip = list->tail;
-
   if (list->count == YR_MAX_STRING_MATCHES)
     return ERROR_TOO_MANY_MATCHES;
 
-  while (ip != NULL)
+  const int64_t at = m->base + m->offset;
+  YR_MATCH* after = list->tail; /* m goes behind this one; NULL: m becomes the head */
+
+  for (; after != NULL; after = after->prev)
   {
-    if ((match->base + match->offset) == (ip->base + ip->offset))
+    const int64_t there = after->base + after->offset;
+
+    if (there < at)
+      break;
+
+    if (there == at)
     {
-      if (replace_if_exists)
+      if (overwrite_equal)
       {
-        ip->match_length = match->match_length;
-        ip->data_length = match->data_length;
-        ip->data = match->data;
+        after->match_length = m->match_length;
+        after->data_length = m->data_length;
+        after->data = m->data;
       }
       return ERROR_SUCCESS;
     }
-    if ((match->base + match->offset) > (ip->base + ip->offset))
-      break;
-    ip = ip->prev;
   }
 
-  match->prev = ip;
+  YR_MATCH* before = after != NULL ? after->next : list->head;
 
-  if (ip != NULL)
-  {
-    match->next = ip->next;
-    ip->next = match;
-  }
-  else
-  {
-    match->next = list->head;
-    list->head = match;
-  }
-
+  m->prev = after;
+  m->next = before;
+  *(after != NULL ? &after->next : &list->head) = m;
+  *(before != NULL ? &before->prev : &list->tail) = m;
   list->count++;
-
-  if (match->next != NULL)
-    match->next->prev = match;
-  else
-    list->tail = match;
 
   return ERROR_SUCCESS;
 }
 
-/* scan.c:1054-1073 */
-static int too_many_protocol(YR_SCANNER* scanner, YR_STRING* string)
+/* A string whose list is full: the callback decides (scan.c:1054-1073). CALLBACK_CONTINUE silences the
+   string for the rest of the scan; anything else ends the scan with the string recorded. */
+static int list_full(YR_SCANNER* scanner, YR_STRING* string)
 {
-  int r = scanner->callback(scanner, CALLBACK_MSG_TOO_MANY_MATCHES, (void*) string, scanner->user_data);
-
-  if (r == CALLBACK_CONTINUE)
+  if (scanner->callback(scanner, CALLBACK_MSG_TOO_MANY_MATCHES, (void*) string, scanner->user_data) != CALLBACK_CONTINUE)
   {
-    yr_bitmask_set(scanner->strings_temp_disabled, string->idx);
-    return ERROR_SUCCESS;
+    scanner->last_error_string = string;
+    return ERROR_TOO_MANY_MATCHES;
   }
 
-  scanner->last_error_string = string;
-  return ERROR_TOO_MANY_MATCHES;
+  yr_bitmask_set(scanner->strings_temp_disabled, string->idx);
+  return ERROR_SUCCESS;
 }
 
 /* match data of records[k] packed by the engine (yrb_last_match_data), for the next materialise() of this thread:
@@ -949,10 +945,10 @@ static int materialise(
         node->data = d;
       }
 
-      int rcs = add_match_to_list(node, &lists[string->idx], 0);
+      int rcs = list_insert(node, &lists[string->idx], 0);
       if (rcs == ERROR_TOO_MANY_MATCHES)
       {
-        rcs = too_many_protocol(scanner, string);
+        rcs = list_full(scanner, string);
         if (rcs != ERROR_SUCCESS)
           return rcs;
       }
@@ -990,12 +986,12 @@ static int materialise(
       m->data_length = 0;
     }
 
-    int rc = add_match_to_list(m, &lists[string->idx], confirmed && STRING_IS_GREEDY_REGEXP(string));
+    int rc = list_insert(m, &lists[string->idx], confirmed && STRING_IS_GREEDY_REGEXP(string));
 
     if (rc == ERROR_TOO_MANY_MATCHES)
     {
       /* only reachable when earlier blocks already filled the list */
-      rc = too_many_protocol(scanner, string);
+      rc = list_full(scanner, string);
       if (rc != ERROR_SUCCESS)
         return rc;
     }
@@ -1447,7 +1443,7 @@ static int scan_block_now(
     YR_STRING* string = &scanner->rules->strings_table[res.too_many[i]];
     if (yr_bitmask_is_set(scanner->strings_temp_disabled, string->idx))
       continue;
-    rc = too_many_protocol(scanner, string);
+    rc = list_full(scanner, string);
     if (rc != ERROR_SUCCESS)
     {
       YR_B200_UNLOCK_MULTI();
