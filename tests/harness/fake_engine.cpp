@@ -56,12 +56,14 @@ int vmh_scan_batch(
     const void* image, const uint8_t* data, size_t size, int n_seg, const int64_t* seg_start, const int64_t* seg_len,
     yrb_match* matches, size_t cap_m, uint8_t* item_dirty, vmh_result* res, vmh_stats* stats);
 void vmh_set_chain_marks_dirty(int on);
+uint32_t vmh_key_seq_bits(const void* image);
 
 struct yrb_rules
 {
   std::vector<uint8_t> image;
   int refs;
   bool root_match;
+  uint32_t key_seq_bits;
 };
 
 struct yrb_scanner
@@ -91,6 +93,8 @@ int yrb_rules_create(const void* image, size_t image_size, int device, yrb_rules
   r->image.assign((const uint8_t*) image, (const uint8_t*) image + image_size);
   r->refs = 1;
   r->root_match = h->tables_size > 0 && yrb_img_match(r->image.data())[0] != 0;
+  r->key_seq_bits = vmh_key_seq_bits(r->image.data());
+  if (r->key_seq_bits == 0) { delete r; return YRB_ERROR_BAD_IMAGE; }   /* as api.cu rules_init */
   *out = r;
   return YRB_SUCCESS;
 }
@@ -174,7 +178,7 @@ int yrb_scan_host(yrb_scanner* s, const uint8_t* data, size_t size, const yrb_sc
   }
   /* error precedence as in api.cu run_resolve: the earliest failing candidate in discovery order
      (scanner.c:111) vs. the earliest TOO_MANY abort */
-  const unsigned long long SEQ = (1ULL << 17) - 1;   /* KEY_SEQ_MAX (engine.cuh) */
+  const unsigned long long SEQ = (1ULL << s->rules->key_seq_bits) - 1;   /* KEY_SEQ_MASK (engine.cuh) */
   unsigned long long first_abort = ~0ULL;
   const uint32_t ntm = res.n_too_many > 1024 ? 1024 : res.n_too_many;
   if (p->too_many_action != 0 && ntm > 0)

@@ -133,6 +133,11 @@ static int scan_common(
     const int64_t* seg_len, uint8_t* item_dirty, const yrb_seed* seeds = nullptr, uint32_t n_seeds = 0,
     uint32_t* too_many_out = nullptr);
 
+uint32_t vmh_longest_match_chain(const void* image) { return yrb_longest_match_chain(image); }
+
+/* DevRules::key_seq_bits of an image (engine.cuh), for the stand-in engine's error precedence; 0 = refused */
+uint32_t vmh_key_seq_bits(const void* image) { return yrb_key_seq_bits(yrb_longest_match_chain(image)); }
+
 /* one block of a multi-block scan: `seeds` = what earlier blocks left behind (yrb_scan_params.seeds);
    too_many_out: room for 1024 string indices */
 int vmh_scan_seeds(
@@ -190,7 +195,9 @@ static int scan_common(
   R.tables_size = h->tables_size;
   R.num_acm = h->num_acm;
   R.num_strings = h->num_strings;
-  R.stack_words = h->max_re_stack + 1;
+  R.stack_words = (uint16_t) (h->max_re_stack + 1);
+  R.key_seq_bits = (uint16_t) yrb_key_seq_bits(yrb_longest_match_chain(image));
+  if (R.key_seq_bits == 0) return -1;   /* api.cu rules_init refuses such a ruleset */
 
   /* api.cu seeds_to_raw_kernel: the nodes earlier blocks left behind re-enter as records that sort first */
   std::vector<int64_t> seed_base(n_seeds ? n_seeds : 1);
@@ -324,7 +331,7 @@ static int scan_common(
     launch_per_thread(R.num_strings, 256, [&] { error_string_kernel(str_err.data(), R.num_strings, &st); });
     if (st.err_key_inv != 0ULL)
     {
-      res->error = (int32_t) (~st.err_key_inv & KEY_SEQ_MAX);
+      res->error = (int32_t) (~st.err_key_inv & KEY_SEQ_MASK(R.key_seq_bits));
       res->error_string = st.err_string1 ? st.err_string1 - 1 : YRB_NONE;
       res->error_key = ~st.err_key_inv;
     }
@@ -363,7 +370,11 @@ static long long run_verify(
   R.tables_size = h->tables_size;
   R.num_acm = h->num_acm;
   R.num_strings = h->num_strings;
-  R.stack_words = h->max_re_stack + 1;
+  R.stack_words = (uint16_t) (h->max_re_stack + 1);
+  R.key_seq_bits = (uint16_t) yrb_key_seq_bits(yrb_longest_match_chain(image));
+  if (R.key_seq_bits == 0) return -1;   /* api.cu rules_init refuses such a ruleset */
+  if (getenv("VMH_FORCE_KEY_SEQ_BITS"))   /* test_vm_host_cpu.py: the key check below has teeth */
+    R.key_seq_bits = (uint16_t) atoi(getenv("VMH_FORCE_KEY_SEQ_BITS"));
 
   ScanView V;
   memset(&V, 0, sizeof(V));
@@ -411,6 +422,25 @@ static long long run_verify(
   unsigned long long n_cand[NUM_CLS];
   for (int c = 0; c < NUM_CLS; c++) n_cand[c] = st.n_cand[c];
 
+  /* The discovery key has to tell any two candidates apart, and in emission order (here: the order they were
+     appended in, class by class; on the device nothing else orders them): position first, then the place in the
+     state's YR_AC_MATCH chain -- also beyond the 255 entries an 8-bit chain field would hold. */
+  {
+    std::vector<std::pair<uint64_t, uint64_t>> keys;   /* (key, emission order within its class) */
+    for (int c = 0; c < NUM_CLS; c++)
+    {
+      for (unsigned long long k = 0; k < n_cand[c]; k++)
+      {
+        if (cand[c][k].chain_pos > KEY_CHAIN_MAX(R.key_seq_bits)) return -3;
+        if (k > 0 && cand_key(cand[c][k], R.key_seq_bits) <= cand_key(cand[c][k - 1], R.key_seq_bits)) return -3;
+        keys.push_back(std::make_pair(cand_key(cand[c][k], R.key_seq_bits), k));
+      }
+    }
+    std::sort(keys.begin(), keys.end());
+    for (size_t k = 1; k < keys.size(); k++)
+      if (keys[k].first == keys[k - 1].first) return -3;
+  }
+
   /* ---- verification, tier by tier (api.cu scan_impl) */
   std::vector<unsigned long long> str_err(R.num_strings ? R.num_strings : 1, ~0ULL);
   std::vector<Raw> raw((size_t) 1 << 16);
@@ -448,8 +478,8 @@ static long long run_verify(
     auto close_stage = [&](const std::vector<uint32_t>* q1, unsigned n1, int cls1, const std::vector<uint32_t>* q2, unsigned n2,
                            int cls2) {
       std::unordered_set<uint64_t> set;
-      for (unsigned k = 0; q1 && k < n1; k++) set.insert(cand[cls1][(*q1)[k]].key >> KEY_SEQ_BITS);
-      for (unsigned k = 0; q2 && k < n2; k++) set.insert(cand[cls2][(*q2)[k]].key >> KEY_SEQ_BITS);
+      for (unsigned k = 0; q1 && k < n1; k++) set.insert(cand_key(cand[cls1][(*q1)[k]], R.key_seq_bits) >> R.key_seq_bits);
+      for (unsigned k = 0; q2 && k < n2; k++) set.insert(cand_key(cand[cls2][(*q2)[k]], R.key_seq_bits) >> R.key_seq_bits);
       stage_end.push_back(st.n_raw);
       handed_on.push_back(set);
     };
@@ -543,8 +573,8 @@ static long long run_verify(
   }
   if (first_err != ~0ULL)
   {
-    stats->error = (int32_t) (first_err & KEY_SEQ_MAX);
-    stats->error_key = first_err & ~(unsigned long long) KEY_SEQ_MAX;
+    stats->error = (int32_t) (first_err & KEY_SEQ_MASK(R.key_seq_bits));
+    stats->error_key = first_err & ~(unsigned long long) KEY_SEQ_MASK(R.key_seq_bits);
     stats->error_string = err_string;
   }
 
@@ -556,7 +586,7 @@ static long long run_verify(
   for (size_t k = 0; k < raw.size(); k++)
   {
     while (stage < stage_end.size() && k >= stage_end[stage]) stage++;
-    if (stage < handed_on.size() && handed_on[stage].count(raw[k].key >> KEY_SEQ_BITS))
+    if (stage < handed_on.size() && handed_on[stage].count(raw[k].key >> R.key_seq_bits))
       continue;
     kept_out.push_back(raw[k]);
   }

@@ -323,3 +323,31 @@ def test_large_results_take_their_match_data_packed_from_the_engine():
         assert p.returncode == 0 and "PACKED_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
         big, small = [int(x) for x in [l for l in p.stdout.splitlines() if l.startswith("PACKED_OK")][0].split()[1:]]
         assert big == want and small == 0
+
+
+def run_long_chains(B, n=600):
+    """tests/long_chains.py: hundreds of rules sharing one string -> one AC state with hundreds of YR_AC_MATCH
+    entries.  Whole block in both modes, 1024-byte blocks (the shared chain holds heads and tails of chained
+    strings: seeds across blocks), and the same bytes as a parked file batch, against the reference library."""
+    import long_chains
+    R = yrh.ref()
+    text = long_chains.ruleset(n)
+    rr, rb = R.compile(text), B.compile(text)
+    data = long_chains.corpus()
+    total = 0
+    for flags in (0, 1):
+        a = rr.scan(data, flags=flags, cap=1 << 20)
+        same(a, rb.scan(data, flags=flags, cap=1 << 20), "long chains flags %d" % flags)
+        total += len(a.matches)
+    same(rr.scan_blocks(data, 1024, 256, cap=1 << 20), rb.scan_blocks(data, 1024, 256, cap=1 << 20), "long chains blocks")
+    items = [np.ascontiguousarray(data[a_:b_]) for a_, b_ in ((0, 5000), (5000, 5003), (5003, 20000), (20000, len(data)))] + [data]
+    want = [rr.scan(it, cap=1 << 20) for it in items]
+    with rb.batch(items) as bt:
+        assert bt.rc == 0
+        for k, it in enumerate(items):
+            same(want[k], rb.scan(it, cap=1 << 20), "long chains batch item %d" % k)
+    return total
+
+
+def test_long_match_chains_through_the_glue():
+    assert run_long_chains(yrh.b200cpu()) > 6000

@@ -332,3 +332,43 @@ def test_scan_one_million_match_cap():
     assert res.n_too_many == 1 and res.n_cuts == 1 and not res.over_cap
     f = ("string_idx", "offset", "match_length", "xor_key")
     assert len(m) == len(o.matches) and canon(m, f) == canon(o.matches, f)
+
+
+# ------------------------------------------------------------------ long YR_AC_MATCH chains (DevRules::key_seq_bits)
+@pytest.mark.parametrize("n,seq_bits", [(300, 17), (600, 16), (1200, 15)])
+def test_long_match_chains(n, seq_bits):
+    """Hundreds of rules sharing one string put hundreds of entries on one state's chain.  The chain position's
+    share of the discovery key grows with the ruleset's longest chain (engine.cuh yrb_key_seq_bits); every candidate
+    keeps a key of its own, in emission order (checked inside the replay: vmh_run fails otherwise), the callback
+    trace in key order is the oracle's, and so are the final lists in both scan modes."""
+    import long_chains
+    image = yrh.ref().compile(long_chains.ruleset(n)).flatten()
+    img = np.frombuffer(image, dtype=np.uint8)
+    lib = vmlib()
+    lib.vmh_longest_match_chain.restype = C.c_uint32
+    lib.vmh_key_seq_bits.restype = C.c_uint32
+    longest = lib.vmh_longest_match_chain(img.ctypes.data_as(C.c_void_p))
+    assert longest >= n // 2                              # half of the kinds pick the same atom: one state's chain holds them all
+    assert lib.vmh_key_seq_bits(img.ctypes.data_as(C.c_void_p)) == seq_bits
+    assert (1 << (25 - seq_bits)) - 1 >= longest
+    data = long_chains.corpus()
+    cnt, st = check(image, data)
+    assert cnt > 20 * n
+    assert check_scan(image, data, 0) > 10 * n
+    check_scan(image, data, 1)
+
+
+def test_a_chain_field_too_narrow_for_the_ruleset_is_caught(monkeypatch):
+    """The same replay with the chain position squeezed into the 8 bits that suffice for chains of up to 255
+    entries: candidates further down the chain collide with (or overtake) their neighbours' keys, and the replay's
+    own key check refuses to go on."""
+    import long_chains
+    image = yrh.ref().compile(long_chains.ruleset(1200)).flatten()
+    img = np.frombuffer(image, dtype=np.uint8)
+    data = long_chains.corpus()
+    out = np.zeros(1 << 16, dtype=RAW)
+    st = Stats()
+    args = (img.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p), data.size, 0, 0, out.ctypes.data_as(C.c_void_p), 1 << 16, C.byref(st))
+    assert vmlib().vmh_run(*args) > 0
+    monkeypatch.setenv("VMH_FORCE_KEY_SEQ_BITS", "17")
+    assert vmlib().vmh_run(*args) == -3

@@ -1,0 +1,38 @@
+"""GPU parity (-m gpu) for rulesets with LONG YR_AC_MATCH chains (tests/long_chains.py: hundreds of rules that
+share one string hang hundreds of entries on one Aho-Corasick state).  The discovery key gives the chain position
+as many bits as the ruleset's longest chain needs (engine.cuh: DevRules::key_seq_bits); chains of more than 255
+entries used to be refused at upload.  Through the drop-in against the reference library (whole block in both
+modes, 1024-byte blocks, a parked file batch) and through the engine with both AC kernels against the oracle.
+(The file sorts last on purpose: these are the newest GPU tests of the suite.)"""
+import numpy as np
+import pytest
+
+import long_chains
+import yrh
+from test_glue_cpu import run_long_chains
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n", [600, 1200])
+def test_long_match_chains_through_the_dropin(n):
+    assert run_long_chains(yrh.b200(), n) > 10 * n
+
+
+def test_long_match_chains_both_ac_kernels():
+    from yara_b200 import api
+    from yara_b200.api import Engine
+    from test_vm_host_cpu import canon
+    fields = ("string_idx", "offset", "match_length", "xor_key")
+    image = yrh.ref().compile(long_chains.ruleset(1200)).flatten()
+    data = long_chains.corpus(1 << 18, seed=9)
+    o = yrh.oracle_scan(image, data)
+    assert o.error == 0 and len(o.matches) > 100000
+    want = canon(o.matches, fields)
+    eng = Engine(image, 0)
+    for kernel in (api.KERNEL_WALK, api.KERNEL_FILTER):       # FILTER: the filter kernel if the ruleset admits it
+        eng.set_option(api.OPT_SCAN_KERNEL, kernel)
+        r = eng.scan_host(data)
+        assert r.rc == 0 and r.error == 0
+        assert canon(r.matches, fields) == want
+    eng.close()

@@ -224,30 +224,11 @@ extern "C" const char* yrb_version(void) { return "yara_b200 0.1 (sm_100a; libya
 
 // ---------------------------------------------------------------------- rules
 
-// The discovery key gives the position inside a state's YR_AC_MATCH chain KEY_CHAIN_BITS bits
-// (emit.cuh).  A longer chain would make later entries share one key and the "first wins / last
-// wins" rules of the resolve ambiguous: refuse such a ruleset loudly instead of saturating.
+// The discovery key orders the entries of a state's YR_AC_MATCH chain by their position (emit.cuh); how many of
+// the key's bits that takes is a property of the ruleset (engine.cuh: yrb_key_seq_bits).  A chain too long for
+// any split would make later entries share one key and the "first wins / last wins" rules of the resolve
+// ambiguous: such a ruleset is refused loudly instead of saturating.
 extern "C" void yrb_rules_release(yrb_rules* r);
-
-static uint32_t longest_match_chain(const void* image)
-{
-  const yrb_image_header* h = (const yrb_image_header*) image;
-  const yrb_acm* acm = yrb_img_acm(image);
-  std::vector<uint32_t> len((size_t) h->num_acm + 1, 0);   // len[k]: entries from acm[k-1] to the end of its chain
-  std::vector<uint32_t> path;
-  uint32_t best = 0;
-  for (uint32_t k0 = 1; k0 <= h->num_acm; k0++)
-  {
-    if (len[k0]) continue;
-    path.clear();
-    uint32_t k = k0;
-    while (k != 0 && k <= h->num_acm && len[k] == 0 && path.size() <= h->num_acm) { path.push_back(k); k = acm[k - 1].next; }
-    uint32_t l = (k != 0 && k <= h->num_acm) ? len[k] : 0;
-    for (size_t j = path.size(); j-- > 0;) len[path[j]] = ++l;
-    if (len[k0] > best) best = len[k0];
-  }
-  return best;
-}
 
 static int rules_init(yrb_rules* r, const void* image, size_t image_size, int device)
 {
@@ -261,9 +242,13 @@ static int rules_init(yrb_rules* r, const void* image, size_t image_size, int de
   r->d_image = nullptr;
   r->d_filter = nullptr;
 
-  if (longest_match_chain(image) > KEY_CHAIN_MAX)
+  if (h->max_re_stack >= 0xFFFFu) return YRB_ERROR_BAD_IMAGE;   // DevRules::stack_words is 16 bits (real rulesets: a handful)
+  const uint32_t longest_chain = yrb_longest_match_chain(image);
+  r->R.key_seq_bits = (uint16_t) yrb_key_seq_bits(longest_chain);
+  if (r->R.key_seq_bits == 0)
   {
-    fprintf(stderr, "yrb200: a state's YR_AC_MATCH chain has more than %u entries; the discovery key cannot order them\n", KEY_CHAIN_MAX);
+    fprintf(stderr, "yrb200: a state's YR_AC_MATCH chain has %u entries (more than %u); the discovery key cannot order them\n",
+            longest_chain, KEY_CHAIN_MAX(KEY_SEQ_BITS_MIN));
     return YRB_ERROR_BAD_IMAGE;
   }
 
@@ -283,7 +268,7 @@ static int rules_init(yrb_rules* r, const void* image, size_t image_size, int de
   r->R.tables_size = h->tables_size;
   r->R.num_acm = h->num_acm;
   r->R.num_strings = h->num_strings;
-  r->R.stack_words = h->max_re_stack + 1;
+  r->R.stack_words = (uint16_t) (h->max_re_stack + 1);
 
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
@@ -727,9 +712,10 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
     res->error_string = res->too_many[0];
   }
   const unsigned long long err_key = ~hs->err_key_inv;
-  if (hs->err_key_inv != 0ULL && (err_key | KEY_SEQ_MAX) < (first_abort | KEY_SEQ_MAX))
+  const unsigned long long seq_mask = KEY_SEQ_MASK(s->rules->R.key_seq_bits);
+  if (hs->err_key_inv != 0ULL && (err_key | seq_mask) < (first_abort | seq_mask))
   {
-    res->error = (int32_t) (err_key & KEY_SEQ_MAX);
+    res->error = (int32_t) (err_key & seq_mask);
     res->error_string = hs->err_string1 ? hs->err_string1 - 1 : YRB_NONE;
   }
   return YRB_SUCCESS;
@@ -1103,7 +1089,8 @@ static int scan_impl(
 
   if (hs->key_overflow)
   {
-    fprintf(stderr, "yrb200: one candidate produced more than %u match callbacks; the discovery key cannot order them\n", KEY_SEQ_MAX);
+    fprintf(stderr, "yrb200: one candidate produced more than %u match callbacks; the discovery key cannot order them\n",
+            KEY_SEQ_MASK(s->rules->R.key_seq_bits) - 1);
     return YRB_ERROR_INTERNAL_FATAL;
   }
 
@@ -1181,7 +1168,7 @@ static int scan_impl(
       if (rc2 != YRB_SUCCESS) return rc2;
       if (hs->err_key_inv != 0ULL)
       {
-        res->error = (int32_t) (~hs->err_key_inv & KEY_SEQ_MAX);
+        res->error = (int32_t) (~hs->err_key_inv & KEY_SEQ_MASK(s->rules->R.key_seq_bits));
         res->error_string = hs->err_string1 ? hs->err_string1 - 1 : YRB_NONE;
       }
     }

@@ -60,10 +60,9 @@ static __device__ __forceinline__ void emit_events(
           if (slot < out.cap[cls])
           {
             Cand c;
-            c.key = ((uint64_t) i << KEY_I_SHIFT) |
-                    ((uint64_t) (chain_pos < KEY_CHAIN_MAX ? chain_pos : KEY_CHAIN_MAX) << KEY_SEQ_BITS);
+            c.key = (uint64_t) i << KEY_I_SHIFT;
             c.acm_idx = k - 1;
-            c.pad = 0;
+            c.chain_pos = chain_pos;   // shifted into the key by the verifier (cand_key), where the ruleset's split is at hand
             out.cand[cls][slot] = c;
           }
         }

@@ -13,21 +13,28 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "yara_b200.h"
 
 // Discovery key (SURVEY.md 8(a) "Order dependence"): lexicographic in
 // (i ascending, position in the state's match chain, callback order inside one
-// exhaustive backward exec).  39 bits of i (blocks < 2^38 bytes), 8 bits of chain
-// position (the longest YR_AC_MATCH chain of the 100k-string set is 17;
-// yrb_rules_create refuses a ruleset with a chain longer than 255), 17 bits of callback
-// sequence: the fast hex VM's backward position lists keep duplicates (re.c:2323-2333) and
-// one candidate can fire tens of thousands of callbacks (tests/cases.py case 53); a
-// candidate that fires more than 131,070 fails the scan loudly instead of saturating.
-#define KEY_SEQ_BITS   17
-#define KEY_CHAIN_BITS 8
-#define KEY_I_SHIFT    (KEY_SEQ_BITS + KEY_CHAIN_BITS)
-#define KEY_SEQ_MAX    ((1u << KEY_SEQ_BITS) - 1)
-#define KEY_CHAIN_MAX  ((1u << KEY_CHAIN_BITS) - 1)
+// exhaustive backward exec).  39 bits of i (blocks < 2^38 bytes); the low 25 bits hold the chain
+// position and the callback sequence, split PER RULESET (DevRules::key_seq_bits, set by
+// yrb_key_seq_bits() when the rules are uploaded): the chain position gets as many bits as the
+// longest YR_AC_MATCH chain of the ruleset needs, at least 8 -- 300 rules that share one string
+// share its atom and put 300 entries on one state's chain; the 100k-string synthetic set has 17 --
+// and the sequence gets the rest.  With chains of up to 255 entries that is 17 bits of sequence: the
+// fast hex VM's backward position lists keep duplicates (re.c:2323-2333) and one candidate can fire
+// tens of thousands of callbacks (tests/cases.py case 53); a candidate that fires more than
+// 2^key_seq_bits - 2 fails the scan loudly instead of saturating, and a ruleset whose longest
+// chain leaves fewer than 8 bits of sequence (more than 131,071 entries) is refused at upload.
+#define KEY_LOW_BITS       25
+#define KEY_I_SHIFT        KEY_LOW_BITS
+#define KEY_CHAIN_BITS_MIN 8
+#define KEY_SEQ_BITS_MIN   8
+#define KEY_SEQ_MASK(seq_bits)  ((1u << (seq_bits)) - 1)                      // also the largest sequence number
+#define KEY_CHAIN_MAX(seq_bits) ((1u << (KEY_LOW_BITS - (seq_bits))) - 1)     // largest chain position
 
 #define CLS_LITERAL 0
 #define CLS_FAST    1
@@ -55,8 +62,41 @@ struct DevRules
   uint32_t tables_size;
   uint32_t num_acm;
   uint32_t num_strings;
-  uint32_t stack_words;   // max_re_stack + 1
+  // (the two share the word that used to hold stack_words alone: the struct -- a parameter of every kernel -- keeps its layout)
+  uint16_t stack_words;   // max_re_stack + 1
+  uint16_t key_seq_bits;  // discovery key: bits of callback sequence (the chain position has KEY_LOW_BITS - key_seq_bits)
 };
+
+// Host side, at upload: the longest YR_AC_MATCH chain of a rules image (chains share their tails --
+// ahocorasick.c hangs the failure state's list behind a state's own -- so lengths are memoised per entry) ...
+static inline uint32_t yrb_longest_match_chain(const void* image)
+{
+  const yrb_image_header* h = (const yrb_image_header*) image;
+  const yrb_acm* acm = yrb_img_acm(image);
+  std::vector<uint32_t> len((size_t) h->num_acm + 1, 0);   // len[k]: entries from acm[k-1] to the end of its chain
+  std::vector<uint32_t> path;
+  uint32_t best = 0;
+  for (uint32_t k0 = 1; k0 <= h->num_acm; k0++)
+  {
+    if (len[k0]) continue;
+    path.clear();
+    uint32_t k = k0;
+    while (k != 0 && k <= h->num_acm && len[k] == 0 && path.size() <= h->num_acm) { path.push_back(k); k = acm[k - 1].next; }
+    uint32_t l = (k != 0 && k <= h->num_acm) ? len[k] : 0;
+    for (size_t j = path.size(); j-- > 0;) len[path[j]] = ++l;
+    if (len[k0] > best) best = len[k0];
+  }
+  return best;
+}
+
+// ... and the split of the key's low bits it asks for: DevRules::key_seq_bits, or 0 when no split leaves
+// KEY_SEQ_BITS_MIN bits of sequence (the ruleset is refused).
+static inline uint32_t yrb_key_seq_bits(uint32_t longest_chain)
+{
+  uint32_t chain_bits = KEY_CHAIN_BITS_MIN;
+  while (chain_bits < KEY_LOW_BITS && ((1u << chain_bits) - 1) < longest_chain) chain_bits++;
+  return KEY_LOW_BITS - chain_bits >= KEY_SEQ_BITS_MIN ? KEY_LOW_BITS - chain_bits : 0;
+}
 
 // The bytes a scan can see, in BLOCK coordinates: d[0] is block byte g0, the
 // local buffer covers [g0, g1), the whole block is [0, gsize).
@@ -97,10 +137,17 @@ static __device__ __forceinline__ int seg_find(const ScanView& V, int64_t p)
 
 struct Cand
 {
-  uint64_t key;      // i << KEY_I_SHIFT | chain_pos << KEY_SEQ_BITS
+  uint64_t key;      // i << KEY_I_SHIFT
   uint32_t acm_idx;
-  uint32_t pad;
+  uint32_t chain_pos; // position of acm_idx in the chain of the state reached at i: < the ruleset's longest chain
 };
+
+// The candidate's discovery key, sequence bits zero (the scan kernels leave the chain position beside the key: they
+// need not know the ruleset's split).  chain_pos <= KEY_CHAIN_MAX(seq_bits): yrb_key_seq_bits sized the split for it.
+static __host__ __device__ __forceinline__ uint64_t cand_key(const Cand& c, uint32_t seq_bits)
+{
+  return c.key | ((uint64_t) c.chain_pos << seq_bits);
+}
 
 struct Raw
 {
@@ -140,7 +187,7 @@ struct ScanStatus
   unsigned int n_chain_raw;     // Raw records of chained strings (0: the chain kernels are skipped)
   unsigned int err_string1;     // 1 + string of the candidate behind the error (scanner->last_error_string); 0 = none
   unsigned int n_chain_starts;  // chains present among the Raw records (resolve.cu: one warp each)
-  unsigned int key_overflow;    // one candidate fired more than KEY_SEQ_MAX match callbacks: its records cannot be ordered
+  unsigned int key_overflow;    // one candidate fired more than 2^key_seq_bits - 2 match callbacks: its records cannot be ordered
   unsigned int n_retry_re0;     // fiber-VM candidates that outgrew the local-memory tier (verify.cu, tier 0 -> tier 1)
 };
 
@@ -211,9 +258,9 @@ __host__ __device__ static inline uint32_t hash3(uint32_t key3) { return ((key3 
 // fast mode once a SINGLE_MATCH string has matched).  Both conditions are "candidate
 // key below a per-string threshold", so the earliest failing candidate per string is
 // all that needs to be kept; resolve.cu decides which of them counts.
-static __device__ __forceinline__ void report_error(const RawOut& out, uint32_t sidx, uint64_t cand_key, int code)
+static __device__ __forceinline__ void report_error(const RawOut& out, uint32_t sidx, uint64_t cand_key, int code, uint32_t seq_bits)
 {
-  atomicMin(&out.str_err[sidx], (unsigned long long) ((cand_key & ~(uint64_t) KEY_SEQ_MAX) | (uint64_t) code));
+  atomicMin(&out.str_err[sidx], (unsigned long long) ((cand_key & ~(uint64_t) KEY_SEQ_MASK(seq_bits)) | (uint64_t) code));
   atomicExch(&out.st->any_error, 1u);
 }
 

@@ -30,7 +30,7 @@ __global__ void fastmode_min_kernel(const Raw* raw, uint32_t n, DevRules R, unsi
   // chain -- chain_resolve_kernel notes that moment (ChainLists::first_conf); a callback of a chain part is
   // not a match of anything yet.
   if ((R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) && r.group == YRB_NONE)
-    atomicMin(&str_min_key[r.string_idx], (unsigned long long) (r.key >> KEY_SEQ_BITS));
+    atomicMin(&str_min_key[r.string_idx], (unsigned long long) (r.key >> R.key_seq_bits));
 }
 
 // The sort key: (string, offset) for plain strings; (chain, input position of the
@@ -57,7 +57,7 @@ __global__ void build_key_a_kernel(
   // scan.c:1021-1023: in fast mode, once a SINGLE_MATCH string has a match, later
   // candidates are not verified; all callbacks of the first matching candidate stay.
   if ((scan_flags & YRB_SCAN_FAST_MODE) && (sflags & YRB_SF_SINGLE_MATCH) && r.group == YRB_NONE &&
-      (r.key >> KEY_SEQ_BITS) != str_min_key[r.string_idx])
+      (r.key >> R.key_seq_bits) != str_min_key[r.string_idx])
     a = A_DROPPED;
 
   // 1M cap: records discovered at or after the string's cut key never reached a list
@@ -162,7 +162,7 @@ struct ChainLists
   int32_t* mhead; // per string: matches[s] (only chain heads are used)
   int32_t* mtail;
   int32_t* mcnt;
-  // FAST_MODE only (else nullptr): per string, the candidate (key >> KEY_SEQ_BITS) at which matches[string]
+  // FAST_MODE only (else nullptr): per string, the candidate (key >> key_seq_bits) at which matches[string]
   // became non-empty -- the threshold of the scan.c:1021-1023 guard, which error_select_kernel applies to
   // failing candidates.  The chain kernel fills in the entries of chain heads.
   unsigned long long* first_conf = nullptr;
@@ -858,9 +858,9 @@ chain_resolve_kernel(
           // scan.c:1021-1023: the FAST_MODE / SINGLE_MATCH guard is evaluated once per
           // candidate, before verification, against matches[string->idx] (only ever
           // non-empty for the chain's head string)
-          if ((r.key >> KEY_SEQ_BITS) != cur_cand)
+          if ((r.key >> R.key_seq_bits) != cur_cand)
           {
-            cur_cand = r.key >> KEY_SEQ_BITS;
+            cur_cand = r.key >> R.key_seq_bits;
             skip_cand = (scan_flags & YRB_SCAN_FAST_MODE) && (R.S[r.string_idx].flags & YRB_SF_SINGLE_MATCH) &&
                         (L.mcnt[r.string_idx] > 0 || L.prior[r.string_idx]);
           }
@@ -877,7 +877,7 @@ chain_resolve_kernel(
           {
             // this callback completed the first chain: from the next candidate on the head string is no
             // longer verified in fast mode -- neither its matches (skip_cand above) nor its errors count
-            L.first_conf[head_string] = (unsigned long long) (r.key >> KEY_SEQ_BITS);
+            L.first_conf[head_string] = (unsigned long long) (r.key >> R.key_seq_bits);
             conf_noted = true;
           }
         }
@@ -972,7 +972,7 @@ __global__ void error_select_kernel(
   if (s >= R.num_strings) return;
   const unsigned long long e = str_err[s];
   if (e == ~0ULL) return;
-  const unsigned long long cand = e >> KEY_SEQ_BITS;
+  const unsigned long long cand = e >> R.key_seq_bits;
 
   // scan.c:1021-1023: later candidates of a SINGLE_MATCH string that already matched are not verified
   // (for a chain's head string the threshold is the candidate that completed its first chain; the other
@@ -981,7 +981,7 @@ __global__ void error_select_kernel(
       str_min_key[s] < cand)
     return;
   // scan.c:1018: neither are candidates of a string disabled by the 1M cap
-  if (str_cut_key != nullptr && str_cut_key[s] != ~0ULL && (str_cut_key[s] >> KEY_SEQ_BITS) < cand)
+  if (str_cut_key != nullptr && str_cut_key[s] != ~0ULL && (str_cut_key[s] >> R.key_seq_bits) < cand)
     return;
 
   atomicMax(&st->err_key_inv, ~e);

@@ -88,12 +88,13 @@ static __device__ void match_callback(Ctx& c, int64_t match_pos, int32_t match_l
     }
   }
 
+  const uint32_t seq_max = KEY_SEQ_MASK(c.R->key_seq_bits);   // the largest sequence number the ruleset's key layout holds
   const unsigned long long slot = warp_append_slot(&c.out.st->n_raw);
 
   if (slot < c.out.cap)
   {
     Raw r;
-    r.key = c.cand_key | (uint64_t) (c.seq < KEY_SEQ_MAX ? c.seq : KEY_SEQ_MAX);
+    r.key = c.cand_key | (uint64_t) (c.seq < seq_max ? c.seq : seq_max);
     r.offset = match_pos + c.bias;
     r.string_idx = a.sidx;
     r.length = match_length;
@@ -109,7 +110,7 @@ static __device__ void match_callback(Ctx& c, int64_t match_pos, int32_t match_l
     if (c.out.chain_marks_dirty && c.out.item_dirty) c.out.item_dirty[c.seg] = 1;
   }
 
-  if (c.seq >= KEY_SEQ_MAX)
+  if (c.seq >= seq_max)
     atomicExch(&c.out.st->key_overflow, 1u);   // fail loudly (api.cu) rather than order records by a saturated key
 
   c.seq++;
@@ -1284,7 +1285,7 @@ static __device__ __forceinline__ int64_t ctx_init(
   const int64_t i = (int64_t) (cd.key >> KEY_I_SHIFT);
   c.R = &R;
   c.out = out;
-  c.cand_key = cd.key;
+  c.cand_key = cand_key(cd, R.key_seq_bits);
   c.seq = 0;
 
   if (V.n_seg > 0)
@@ -1308,7 +1309,7 @@ static __device__ __forceinline__ int64_t ctx_init(
 
 static __device__ __forceinline__ void report_error_ctx(const Ctx& c, uint32_t sidx, int code)
 {
-  report_error(c.out, sidx, c.cand_key, code);
+  report_error(c.out, sidx, c.cand_key, code, c.R->key_seq_bits);
   if (c.out.item_dirty) c.out.item_dirty[c.seg] = 1;
 }
 
