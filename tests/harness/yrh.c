@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include <time.h>
 #include <yara.h>
 
@@ -205,11 +206,15 @@ typedef struct
   const uint8_t* buf;
   size_t size, block_size, overlap, pos;
   YR_MEMORY_BLOCK block;
+  size_t slow_from;      /* fetching a block at or behind this offset takes slow_us (0: never) */
+  unsigned slow_us;
 } YRH_ITER;
 
 static const uint8_t* yrh_fetch(YR_MEMORY_BLOCK* b)
 {
   YRH_ITER* it = (YRH_ITER*) b->context;
+  if (it->slow_us != 0 && b->base >= it->slow_from)
+    usleep(it->slow_us);
   return it->buf + b->base;
 }
 
@@ -291,6 +296,57 @@ int yrh_scan_blocks(
 
   *n_out = c.n;
   if (too_many_calls) *too_many_calls = c.too_many_calls;
+  return rc;
+}
+
+/* ---- ONE scanner, two multi-block scans: the first runs out of its time budget part-way (the iterator turns slow
+   at `slow_from`, scanner.c:74-81), the second scans other bytes to the end.  Nothing of the first scan -- blocks the
+   drop-in had deferred, match lists -- may show up in the second (scanner.c:540-552 cleans up behind every scan). */
+int yrh_scan_blocks_after_timed_out_scan(
+    void* rules_, const uint8_t* buf1, size_t size1, size_t slow_from, uint64_t timeout_ns, const uint8_t* buf2, size_t size2,
+    size_t block_size, YRH_MATCH* out, size_t cap, size_t* n_out, uint8_t* rule_bits, int* rc_first)
+{
+  YRH_CTX c;
+  YRH_ITER it;
+  YR_MEMORY_BLOCK_ITERATOR iter;
+  YR_SCANNER* scanner;
+
+  memset(&c, 0, sizeof(c));
+  memset(&it, 0, sizeof(it));
+  memset(&iter, 0, sizeof(iter));
+  c.rules = (YR_RULES*) rules_;
+  iter.context = &it;
+  iter.first = yrh_first;
+  iter.next = yrh_next;
+  iter.file_size = yrh_file_size;
+
+  int rc = yr_scanner_create(c.rules, &scanner);
+  if (rc != ERROR_SUCCESS) return rc;
+  yr_scanner_set_callback(scanner, yrh_callback, &c);
+
+  it.buf = buf1;
+  it.size = size1;
+  it.block_size = block_size;
+  it.slow_from = slow_from;
+  it.slow_us = (unsigned) (timeout_ns / 1000) * 4 + 2000;
+  scanner->timeout = timeout_ns;
+  *rc_first = yr_scanner_scan_mem_blocks(scanner, &iter);
+
+  memset(&c, 0, sizeof(c));
+  c.rules = (YR_RULES*) rules_;
+  c.out = out;
+  c.cap = cap;
+  c.rule_bits = rule_bits;
+  if (rule_bits)
+    memset(rule_bits, 0, c.rules->num_rules);
+  yr_scanner_set_callback(scanner, yrh_callback, &c);
+  it.buf = buf2;
+  it.size = size2;
+  it.slow_us = 0;
+  scanner->timeout = 0;
+  rc = yr_scanner_scan_mem_blocks(scanner, &iter);
+  yr_scanner_destroy(scanner);
+  *n_out = c.n;
   return rc;
 }
 

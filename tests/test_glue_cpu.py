@@ -351,3 +351,24 @@ def run_long_chains(B, n=600):
 
 def test_long_match_chains_through_the_glue():
     assert run_long_chains(yrh.b200cpu()) > 6000
+
+
+def run_scanner_reuse_after_timed_out_scan(B):
+    """A scanner object is reused after a multi-block scan that ended early (scanner.c:540-552 cleans up behind every
+    scan, whatever its result): blocks the drop-in had deferred when the first scan ran out of time must not be
+    scanned as part of the next one.  The iterator of the first scan turns slow after a few 4 KiB blocks."""
+    rs = synth.ruleset(3, 300)
+    R = yrh.ref()
+    rr, rb = R.compile(rs.source), B.compile(rs.source)
+    data1 = synth.corpus(rs, 1 << 18, 512, seed=3, plant_seed=4)
+    data2 = synth.corpus(rs, 1 << 17, 2048, seed=5, plant_seed=6)
+    want = rr.scan_blocks(data2, 4096, 0)
+    assert want.rc == 0 and len(want.matches) > 30
+    for r in (rr, rb):
+        rc1, got = r.scan_blocks_after_timed_out_scan(data1, 5 * 4096, 20_000_000, data2, 4096)
+        assert rc1 == 26                   # ERROR_SCAN_TIMEOUT
+        same(want, got, "second scan of a reused scanner")
+
+
+def test_scanner_reuse_after_a_scan_that_ended_early():
+    run_scanner_reuse_after_timed_out_scan(yrh.b200cpu())

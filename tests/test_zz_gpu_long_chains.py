@@ -1,4 +1,4 @@
-"""GPU parity (-m gpu) for rulesets with LONG YR_AC_MATCH chains (tests/long_chains.py: hundreds of rules that
+"""GPU parity (-m gpu), the newest tests of round 2.  Rulesets with LONG YR_AC_MATCH chains (tests/long_chains.py: hundreds of rules that
 share one string hang hundreds of entries on one Aho-Corasick state).  The discovery key gives the chain position
 as many bits as the ruleset's longest chain needs (engine.cuh: DevRules::key_seq_bits); chains of more than 255
 entries used to be refused at upload.  Through the drop-in against the reference library (whole block in both
@@ -36,3 +36,10 @@ def test_long_match_chains_both_ac_kernels():
         assert r.rc == 0 and r.error == 0
         assert canon(r.matches, fields) == want
     eng.close()
+
+
+def test_scanner_reuse_after_a_scan_that_ended_early():
+    """tests/test_glue_cpu.py: blocks deferred by a multi-block scan that ran out of time are dropped with the scan
+    (yr_b200_blocks_discard at scanner.c:545), not scanned as part of the scanner's next scan."""
+    from test_glue_cpu import run_scanner_reuse_after_timed_out_scan
+    run_scanner_reuse_after_timed_out_scan(yrh.b200())

@@ -121,6 +121,22 @@ class Rules:
             return self.scan_blocks(data, block_size, overlap, flags, too_many_action, cap=n.value)
         return self._finish(rc, out, n, bits, tm)
 
+    def scan_blocks_after_timed_out_scan(self, data1, slow_from, timeout_ns, data2, block_size, cap=1 << 16):
+        """ONE scanner: a multi-block scan of data1 whose iterator turns slow at `slow_from` (the scan runs out of its
+        time budget part-way), then a multi-block scan of data2 to the end.  Returns (rc of the first scan, result of
+        the second)."""
+        b1 = np.frombuffer(data1, dtype=np.uint8) if not isinstance(data1, np.ndarray) else data1
+        b2 = np.frombuffer(data2, dtype=np.uint8) if not isinstance(data2, np.ndarray) else data2
+        out = np.zeros(cap, dtype=MATCH_DTYPE)
+        bits = np.zeros(max(self.num_rules, 1), dtype=np.uint8)
+        n, tm, rc1 = C.c_size_t(), C.c_int(), C.c_int()
+        rc = self.h.lib.yrh_scan_blocks_after_timed_out_scan(
+            self.ptr, b1.ctypes.data_as(C.c_void_p), C.c_size_t(b1.size), C.c_size_t(slow_from), C.c_uint64(timeout_ns),
+            b2.ctypes.data_as(C.c_void_p), C.c_size_t(b2.size), C.c_size_t(block_size), out.ctypes.data_as(C.c_void_p),
+            C.c_size_t(cap), C.byref(n), bits.ctypes.data_as(C.c_void_p), C.byref(rc1))
+        assert n.value <= cap
+        return rc1.value, self._finish(rc, out, n, bits, tm)
+
     def batch(self, arrays, flags=0, one_allocation=False):
         """GPU drop-in only: scan `arrays` as one batch; scans of the same arrays while the returned
         object is open take their matches from it (yara_b200/host/yr_b200.h)."""

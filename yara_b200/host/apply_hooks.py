@@ -13,6 +13,8 @@ anything else means the reference drifted and the build stops.
                              (parked file-batch results are complete one-block results)
              scanner.c:502   behind the block loop: yr_b200_blocks_flush(scanner) (small blocks of a multi-block
                              scan are deferred and scanned as one batch)
+             scanner.c:545   at _exit, where the scan's matches and notebook go: yr_b200_blocks_discard(scanner)
+                             (a scan that ended early -- timeout, callback abort, exception -- leaves nothing deferred)
   rules.c    #include "yr_b200.h"
              rules.c:515     yr_rules_destroy: yr_b200_rules_release(rules)
   condition-VM pre-filter (yr_b200_prefilter.c, on unless YR_B200_RULE_PREFILTER=0):
@@ -81,6 +83,11 @@ EDITS = {
             "  result = yr_b200_blocks_flush(scanner); /* blocks whose scan yr_b200_scan_mem_block deferred */\n\n"
             "  if (result != ERROR_SUCCESS)\n    goto _exit;\n\n"
             "  result = iterator->last_error;\n\n  if (result != ERROR_SUCCESS)\n    goto _exit;\n",
+        ),
+        (
+            "  if (result != ERROR_BLOCK_NOT_READY)\n  {\n    _yr_scanner_clean_matches(scanner);\n",
+            "  if (result != ERROR_BLOCK_NOT_READY)\n  {\n    yr_b200_blocks_discard(scanner); /* a scan that ended early leaves nothing deferred */\n"
+            "    _yr_scanner_clean_matches(scanner);\n",
         ),
         (
             "  int result = yr_scanner_scan_mem_blocks(scanner, &iterator);\n",

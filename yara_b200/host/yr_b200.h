@@ -37,6 +37,11 @@ int yr_b200_scan_mem_block(
    that is deferred (default 262144; 0 turns the batching off). */
 int yr_b200_blocks_flush(YR_SCANNER* scanner);
 
+/* scanner.c:545, at _exit next to _yr_scanner_clean_matches: a scan that did not reach the flush above (timeout,
+   callback abort, exception in a block) drops what it had deferred, so that a reused YR_SCANNER starts its next scan
+   with nothing pending. */
+void yr_b200_blocks_discard(YR_SCANNER* scanner);
+
 void yr_b200_scanner_release(YR_SCANNER* scanner);
 
 /* yr_scanner_scan_mem brackets its scan with (scanner, 1) / (scanner, 0): only then is a block known to

@@ -1222,6 +1222,23 @@ int yr_b200_blocks_flush(YR_SCANNER* scanner)
   return blocks_flush(scanner, e, max_match_data);
 }
 
+/* scanner.c:545 (_exit): the scan is over, whatever its result; blocks still deferred belong to it and go with it */
+void yr_b200_blocks_discard(YR_SCANNER* scanner)
+{
+  scanner_entry* e;
+  pthread_mutex_lock(&g_lock);
+  for (e = g_scanners; e != NULL; e = e->next)
+    if (e->scanner == scanner)
+      break;
+  pthread_mutex_unlock(&g_lock);
+  if (e != NULL)
+  {
+    e->n_pend = 0;
+    e->pend_used = 0;
+    e->pend_scan = NULL;
+  }
+}
+
 int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_MEMORY_BLOCK* block)
 {
   yrb_scanner* dev = NULL;
