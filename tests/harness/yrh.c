@@ -350,6 +350,59 @@ int yrh_scan_blocks_after_timed_out_scan(
   return rc;
 }
 
+/* ---- ONE YR_SCANNER (yr_scanner_create ... yr_scanner_destroy) over a sequence of scans, the way a long-lived
+   consumer of the scanner API uses it: scan k is yr_scanner_scan_mem (modes[k] == 0) or yr_scanner_scan_mem_blocks
+   with blocks of modes[k] bytes and a quarter of that as overlap, with flags[k] set just before.  All matches go to
+   `out` one scan after the other (n_per_scan[k] of them), rule verdicts to rule_bits[k * num_rules ...]. */
+int yrh_scanner_sequence(
+    void* rules_, int n, const uint8_t** bufs, const size_t* sizes, const int* modes, const int* flags, YRH_MATCH* out,
+    size_t cap, size_t* n_per_scan, uint8_t* rule_bits, int* rcs)
+{
+  YRH_CTX c;
+  YRH_ITER it;
+  YR_MEMORY_BLOCK_ITERATOR iter;
+  YR_SCANNER* scanner;
+  size_t used = 0;
+
+  memset(&iter, 0, sizeof(iter));
+  iter.context = &it;
+  iter.first = yrh_first;
+  iter.next = yrh_next;
+  iter.file_size = yrh_file_size;
+
+  int rc = yr_scanner_create((YR_RULES*) rules_, &scanner);
+  if (rc != ERROR_SUCCESS) return rc;
+
+  for (int k = 0; k < n; k++)
+  {
+    memset(&c, 0, sizeof(c));
+    c.rules = (YR_RULES*) rules_;
+    c.out = out + used;
+    c.cap = cap - used;
+    c.rule_bits = rule_bits + (size_t) k * c.rules->num_rules;
+    memset(c.rule_bits, 0, c.rules->num_rules);
+    yr_scanner_set_callback(scanner, yrh_callback, &c);
+    yr_scanner_set_flags(scanner, flags[k]);
+    if (modes[k] == 0)
+    {
+      rcs[k] = yr_scanner_scan_mem(scanner, bufs[k], sizes[k]);
+    }
+    else
+    {
+      memset(&it, 0, sizeof(it));
+      it.buf = bufs[k];
+      it.size = sizes[k];
+      it.block_size = (size_t) modes[k];
+      it.overlap = (size_t) modes[k] / 4;
+      rcs[k] = yr_scanner_scan_mem_blocks(scanner, &iter);
+    }
+    n_per_scan[k] = c.n;
+    used += c.n < c.cap ? c.n : c.cap;
+  }
+  yr_scanner_destroy(scanner);
+  return ERROR_SUCCESS;
+}
+
 /* ---- CPU baseline: N scanner threads over one shared YR_RULES, one contiguous
    slice each -- the structure `yara -p N` uses (cli/yara.c:1561-1610). ---- */
 typedef struct

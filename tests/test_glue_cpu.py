@@ -44,10 +44,11 @@ def run_cases():
                 continue
             same(a, rb.scan(data, flags=flags, cap=1 << 20), "case %d flags %d" % (idx, flags))
             n += 1
-        a = rr.scan_blocks(data, 1024, 256, cap=1 << 20)
-        if not capped(a):
-            same(a, rb.scan_blocks(data, 1024, 256, cap=1 << 20), "case %d blocks" % idx)
-            n += 1
+        for flags in (0, 1):     # fast mode over several blocks: chains completed by a later block's tail still count
+            a = rr.scan_blocks(data, 1024, 256, flags=flags, cap=1 << 20)
+            if not capped(a):
+                same(a, rb.scan_blocks(data, 1024, 256, flags=flags, cap=1 << 20), "case %d blocks flags %d" % (idx, flags))
+                n += 1
     return n
 
 
@@ -61,9 +62,10 @@ def run_fuzz(seeds):
             a = rr.scan(data, flags=flags, cap=1 << 20)
             if not capped(a):
                 same(a, rb.scan(data, flags=flags, cap=1 << 20), "seed %d flags %d" % (seed, flags))
-        a = rr.scan_blocks(data, 1024, 256, cap=1 << 20)          # chains whose parts lie in different blocks: seeds
-        if not capped(a):
-            same(a, rb.scan_blocks(data, 1024, 256, cap=1 << 20), "seed %d blocks" % seed)
+        for flags in (0, 1):
+            a = rr.scan_blocks(data, 1024, 256, flags=flags, cap=1 << 20)          # chains whose parts lie in different blocks: seeds
+            if not capped(a):
+                same(a, rb.scan_blocks(data, 1024, 256, flags=flags, cap=1 << 20), "seed %d blocks flags %d" % (seed, flags))
         # the same data as a parked file batch
         cuts = sorted(set([0, len(data)] + [(seed * 7919 + k * 10007) % len(data) for k in range(6)]))
         items = [np.ascontiguousarray(data[a_:b_]) for a_, b_ in zip(cuts, cuts[1:])] + [data]
@@ -372,3 +374,28 @@ def run_scanner_reuse_after_timed_out_scan(B):
 
 def test_scanner_reuse_after_a_scan_that_ended_early():
     run_scanner_reuse_after_timed_out_scan(yrh.b200cpu())
+
+
+def run_scanner_sequence(B, seeds=range(6)):
+    """One long-lived YR_SCANNER, many scans of different kinds one after the other -- whole buffers, 1 KiB and 4 KiB
+    blocks, fast mode switched on and off in between, an empty buffer -- as a consumer of the yr_scanner_* API does.
+    Every scan's matches and rule verdicts against the reference library driven the same way."""
+    R = yrh.ref()
+    for seed in seeds:
+        text, insts, n = fuzzgen.compile_filtered(R, seed, 40)
+        rr, rb = R.compile(text), B.compile(text)
+        datas = [np.frombuffer(bytes(fuzzgen.gen_data(seed + 100 * k, insts, (1 << 13) + 97 * k)), dtype=np.uint8) for k in range(4)]
+        scans = [(datas[0], 0, 0), (datas[1], 1024, 0), (datas[0], 0, 1), (datas[2], 4096, 0), (datas[1], 0, 0),
+                 (np.zeros(0, dtype=np.uint8), 0, 0), (datas[3], 1024, 1), (datas[3], 1024, 0), (datas[2], 0, 0), (datas[0], 0, 0)]
+        want = rr.scanner_sequence(scans)
+        got = rb.scanner_sequence(scans)
+        for k, (a, b) in enumerate(zip(want, got)):
+            assert a[0] == b[0], ("seed %d scan %d rc" % (seed, k), a[0], b[0])
+            if a[0] == 0:
+                assert a[1].tobytes() == b[1].tobytes(), "seed %d scan %d matches" % (seed, k)
+                assert a[2].tobytes() == b[2].tobytes(), "seed %d scan %d rules" % (seed, k)
+        assert want[0][1].tobytes() == want[9][1].tobytes()      # the same scan again at the end: same result
+
+
+def test_one_scanner_many_scans():
+    run_scanner_sequence(yrh.b200cpu())

@@ -137,6 +137,28 @@ class Rules:
         assert n.value <= cap
         return rc1.value, self._finish(rc, out, n, bits, tm)
 
+    def scanner_sequence(self, scans, cap=1 << 18):
+        """ONE YR_SCANNER over `scans` = [(data, mode, flags)]: mode 0 = yr_scanner_scan_mem, else yr_scanner_scan_mem_blocks
+        with blocks of `mode` bytes.  Returns [(rc, matches, rule_bits)] per scan."""
+        n = len(scans)
+        bufs = [np.ascontiguousarray(np.frombuffer(d, dtype=np.uint8) if not isinstance(d, np.ndarray) else d) for d, _, _ in scans]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_size_t * n)(*[b.size for b in bufs])
+        modes = (C.c_int * n)(*[m for _, m, _ in scans])
+        flags = (C.c_int * n)(*[f for _, _, f in scans])
+        out = np.zeros(cap, dtype=MATCH_DTYPE)
+        per = (C.c_size_t * n)()
+        rcs = (C.c_int * n)()
+        bits = np.zeros(n * max(self.num_rules, 1), dtype=np.uint8)
+        rc = self.h.lib.yrh_scanner_sequence(self.ptr, n, ptrs, sizes, modes, flags, out.ctypes.data_as(C.c_void_p), C.c_size_t(cap),
+                                             per, bits.ctypes.data_as(C.c_void_p), rcs)
+        assert rc == 0 and sum(per) <= cap
+        res, at = [], 0
+        for k in range(n):
+            res.append((rcs[k], out[at:at + per[k]].copy(), bits[k * self.num_rules:(k + 1) * self.num_rules].copy()))
+            at += per[k]
+        return res
+
     def batch(self, arrays, flags=0, one_allocation=False):
         """GPU drop-in only: scan `arrays` as one batch; scans of the same arrays while the returned
         object is open take their matches from it (yara_b200/host/yr_b200.h)."""

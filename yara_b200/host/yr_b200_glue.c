@@ -1409,7 +1409,11 @@ static int scan_block_now(
   }
 
   /* In fast mode a SINGLE_MATCH string that already matched in an earlier block is
-     not verified again (scan.c:1021-1023): drop this block's records for it. */
+     not verified again (scan.c:1021-1023): drop this block's records for it.  Not so the
+     heads of chained strings: their confirmed records are chains that a TAIL completed -- tails
+     never have matches[] entries and are always verified -- possibly with a head match an earlier
+     block left unconfirmed; that the head's own candidates are no longer verified is known to the
+     engine through the seeds (RAW_SEED_MARK). */
   if (scanner->flags & SCAN_FLAGS_FAST_MODE)
   {
     yrb_match* recs = (yrb_match*) res.matches;
@@ -1417,7 +1421,7 @@ static int scan_block_now(
     for (size_t i = 0; i < res.n_matches; i++)
     {
       YR_STRING* string = &scanner->rules->strings_table[recs[i].string_idx];
-      if (STRING_IS_SINGLE_MATCH(string) && scanner->matches[string->idx].head != NULL)
+      if (STRING_IS_SINGLE_MATCH(string) && !STRING_IS_CHAIN_PART(string) && scanner->matches[string->idx].head != NULL)
         continue;
       recs[k++] = recs[i];
     }
