@@ -6,7 +6,7 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 ( python -u -c "import __graft_entry__ as g; g.smoke()"; echo "smoke rc=$?" ) > gpurun_out/r02_last_check.log 2>&1
 python -u -m pytest -p no:cacheprovider -m gpu -v \
-  tests/test_zz_gpu_long_chains.py \
+  tests/test_zz_gpu_late_round2.py \
   "tests/test_gpu_parity.py::test_known_answer_cases" \
   "tests/test_gpu_parity.py::test_known_answer_cases_fast_mode" \
   "tests/test_gpu_parity.py::test_known_answer_cases_blocks" \
