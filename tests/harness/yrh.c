@@ -299,6 +299,88 @@ int yrh_scan_blocks(
   return rc;
 }
 
+/* ---- multi-block scan over an arbitrary list of regions: block k is `sizes[k]` bytes at buf + offs[k], reported with
+   base bases[k] -- any order, gaps, overlaps, repeats, empty blocks -- the shapes process-memory and custom iterators
+   produce (proc/linux.c:145,309). ---- */
+typedef struct
+{
+  const uint8_t* buf;
+  const size_t* offs;
+  const size_t* sizes;
+  const uint64_t* bases;
+  size_t n, k;
+  YR_MEMORY_BLOCK block;
+} YRH_REGIONS;
+
+static const uint8_t* yrh_regions_fetch(YR_MEMORY_BLOCK* b)
+{
+  YRH_REGIONS* it = (YRH_REGIONS*) b->context;
+  return it->buf + it->offs[it->k];
+}
+
+static YR_MEMORY_BLOCK* yrh_regions_at(YRH_REGIONS* it)
+{
+  if (it->k >= it->n) return NULL;
+  it->block.base = it->bases[it->k];
+  it->block.size = it->sizes[it->k];
+  it->block.context = it;
+  it->block.fetch_data = yrh_regions_fetch;
+  return &it->block;
+}
+
+static YR_MEMORY_BLOCK* yrh_regions_first(YR_MEMORY_BLOCK_ITERATOR* iter)
+{
+  YRH_REGIONS* it = (YRH_REGIONS*) iter->context;
+  it->k = 0;
+  iter->last_error = ERROR_SUCCESS;
+  return yrh_regions_at(it);
+}
+
+static YR_MEMORY_BLOCK* yrh_regions_next(YR_MEMORY_BLOCK_ITERATOR* iter)
+{
+  YRH_REGIONS* it = (YRH_REGIONS*) iter->context;
+  iter->last_error = ERROR_SUCCESS;
+  it->k++;
+  return yrh_regions_at(it);
+}
+
+int yrh_scan_regions(
+    void* rules_, const uint8_t* buf, size_t n, const size_t* offs, const size_t* sizes, const uint64_t* bases, int flags,
+    YRH_MATCH* out, size_t cap, size_t* n_out, uint8_t* rule_bits)
+{
+  YRH_CTX c;
+  YRH_REGIONS it;
+  YR_MEMORY_BLOCK_ITERATOR iter;
+  YR_SCANNER* scanner;
+
+  memset(&c, 0, sizeof(c));
+  memset(&it, 0, sizeof(it));
+  memset(&iter, 0, sizeof(iter));
+  c.rules = (YR_RULES*) rules_;
+  c.out = out;
+  c.cap = cap;
+  c.rule_bits = rule_bits;
+  if (rule_bits)
+    memset(rule_bits, 0, c.rules->num_rules);
+  it.buf = buf;
+  it.offs = offs;
+  it.sizes = sizes;
+  it.bases = bases;
+  it.n = n;
+  iter.context = &it;
+  iter.first = yrh_regions_first;
+  iter.next = yrh_regions_next;
+
+  int rc = yr_scanner_create(c.rules, &scanner);
+  if (rc != ERROR_SUCCESS) return rc;
+  yr_scanner_set_callback(scanner, yrh_callback, &c);
+  yr_scanner_set_flags(scanner, flags);
+  rc = yr_scanner_scan_mem_blocks(scanner, &iter);
+  yr_scanner_destroy(scanner);
+  *n_out = c.n;
+  return rc;
+}
+
 /* ---- ONE scanner, two multi-block scans: the first runs out of its time budget part-way (the iterator turns slow
    at `slow_from`, scanner.c:74-81), the second scans other bytes to the end.  Nothing of the first scan -- blocks the
    drop-in had deferred, match lists -- may show up in the second (scanner.c:540-552 cleans up behind every scan). */

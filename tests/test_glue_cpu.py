@@ -399,3 +399,37 @@ def run_scanner_sequence(B, seeds=range(6)):
 
 def test_one_scanner_many_scans():
     run_scanner_sequence(yrh.b200cpu())
+
+
+def region_lists(size, rng):
+    """block lists a process-memory or custom iterator may produce: ascending with gaps, descending, overlapping,
+    repeated, empty blocks, bases unrelated to the position in the buffer"""
+    step = 1500
+    asc = [(o, min(step, size - o), o) for o in range(0, size, step + 700)]
+    yield "ascending with gaps", asc
+    yield "descending", asc[::-1]
+    over = [(o, min(2048, size - o), o) for o in range(0, size - 1, 1024)]
+    yield "overlapping", over
+    yield "every block twice", [r for r in over for _ in (0, 1)]
+    yield "with empty blocks", [x for r in asc for x in (r, (r[0], 0, r[2]))]
+    sh = list(over)
+    rng.shuffle(sh)
+    yield "shuffled", sh
+    yield "foreign bases", [(o, n, 0x7F0000000000 + 3 * o) for o, n, _ in asc]
+    yield "all at base 0", [(o, n, 0) for o, n, _ in asc]
+
+
+def run_regions(B, seeds=range(5)):
+    import random
+    R = yrh.ref()
+    for seed in seeds:
+        text, insts, n = fuzzgen.compile_filtered(R, seed, 40)
+        rr, rb = R.compile(text), B.compile(text)
+        data = np.frombuffer(bytes(fuzzgen.gen_data(seed + 7, insts, (1 << 14) + 11 * seed)), dtype=np.uint8)
+        for what, regions in region_lists(len(data), random.Random(seed)):
+            for flags in (0, 1):
+                same(rr.scan_regions(data, regions, flags), rb.scan_regions(data, regions, flags), "seed %d %s flags %d" % (seed, what, flags))
+
+
+def test_block_lists_of_any_shape():
+    run_regions(yrh.b200cpu())

@@ -159,6 +159,21 @@ class Rules:
             at += per[k]
         return res
 
+    def scan_regions(self, data, regions, flags=0, cap=1 << 18):
+        """multi-block scan over regions = [(offset in data, size, base)], in that order"""
+        buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        n = len(regions)
+        offs = (C.c_size_t * n)(*[r[0] for r in regions])
+        sizes = (C.c_size_t * n)(*[r[1] for r in regions])
+        bases = (C.c_uint64 * n)(*[r[2] for r in regions])
+        out = np.zeros(cap, dtype=MATCH_DTYPE)
+        bits = np.zeros(max(self.num_rules, 1), dtype=np.uint8)
+        cnt, tm = C.c_size_t(), C.c_int()
+        rc = self.h.lib.yrh_scan_regions(self.ptr, buf.ctypes.data_as(C.c_void_p), C.c_size_t(n), offs, sizes, bases, flags,
+                                         out.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(cnt), bits.ctypes.data_as(C.c_void_p))
+        assert cnt.value <= cap
+        return self._finish(rc, out, cnt, bits, tm)
+
     def batch(self, arrays, flags=0, one_allocation=False):
         """GPU drop-in only: scan `arrays` as one batch; scans of the same arrays while the returned
         object is open take their matches from it (yara_b200/host/yr_b200.h)."""
