@@ -109,6 +109,14 @@ typedef struct yrb_scan_params
                               has passed since the call began.  The reference looks at its stopwatch every 4096
                               input bytes (scanner.c:74-81); yrb_scan_host looks between H2D slices, keeping at
                               most four slices queued ahead, so a timeout takes effect within a few slices. */
+  uint32_t n_skip_strings; /* multi-block scans: strings whose candidates the reference does not verify in this block
+                              at all (scan.c:1018-1023) because of what EARLIER blocks of the scan did -- disabled by
+                              the 1,000,000-match cap there, or SINGLE_MATCH strings that already matched, in fast
+                              mode (heads of chained strings excepted: those travel as seeds of kind 1).  A verifier
+                              error of such a string does not end the scan.  Their match records are the caller's to
+                              drop.  0 / NULL: none. */
+  uint32_t reserved2;
+  const uint32_t* skip_strings;
 } yrb_scan_params;
 
 /* One YR_MATCH of unconfirmed_matches[string] carried over from an earlier block of

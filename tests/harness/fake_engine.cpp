@@ -56,6 +56,7 @@ int vmh_scan_batch(
     const void* image, const uint8_t* data, size_t size, int n_seg, const int64_t* seg_start, const int64_t* seg_len,
     yrb_match* matches, size_t cap_m, uint8_t* item_dirty, vmh_result* res, vmh_stats* stats);
 void vmh_set_chain_marks_dirty(int on);
+void vmh_set_skip_strings(const uint32_t* strings, uint32_t n);
 uint32_t vmh_key_seq_bits(const void* image);
 
 struct yrb_rules
@@ -169,6 +170,7 @@ int yrb_scan_host(yrb_scanner* s, const uint8_t* data, size_t size, const yrb_sc
   {
     s->m.resize(cap);
     s->u.resize(cap);
+    vmh_set_skip_strings(p->skip_strings, p->skip_strings ? p->n_skip_strings : 0);
     if (vmh_scan_seeds(s->rules->image.data(), data, size, p->base, p->scan_flags, p->seeds, p->n_seeds, s->m.data(), cap,
                        s->u.data(), cap, s->tm.data(), &res, &st) != 0)
       return YRB_ERROR_BAD_ARGUMENT;

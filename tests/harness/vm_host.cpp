@@ -161,6 +161,9 @@ int vmh_scan(
    item_dirty[k] != 0: the item needs the per-item path. */
 static thread_local int g_chain_marks_dirty = 0;   /* YRB_BATCH_BLOCKS_OF_ONE_SCAN for the next vmh_scan_batch of this thread */
 void vmh_set_chain_marks_dirty(int on) { g_chain_marks_dirty = on; }
+static thread_local const uint32_t* g_skip_strings = nullptr;   /* yrb_scan_params.skip_strings for the next scan of this thread */
+static thread_local uint32_t g_n_skip_strings = 0;
+void vmh_set_skip_strings(const uint32_t* strings, uint32_t n) { g_skip_strings = strings; g_n_skip_strings = n; }
 
 int vmh_scan_batch(
     const void* image, const uint8_t* data, size_t size, int n_seg, const int64_t* seg_start, const int64_t* seg_len,
@@ -174,6 +177,10 @@ static int scan_common(
     yrb_match* unconfirmed, size_t cap_u, vmh_result* res, vmh_stats* stats, int n_seg, const int64_t* seg_start,
     const int64_t* seg_len, uint8_t* item_dirty, const yrb_seed* seeds, uint32_t n_seeds, uint32_t* too_many_out)
 {
+  const uint32_t* skip = g_skip_strings;   /* one scan's worth */
+  const uint32_t n_skip = g_n_skip_strings;
+  g_skip_strings = nullptr;
+  g_n_skip_strings = 0;
   std::vector<Raw> raw;
   std::vector<unsigned long long> str_err;
   memset(res, 0, sizeof(*res));
@@ -322,6 +329,9 @@ static int scan_common(
   bool any_err = false;
   if (n_seg > 0) std::fill(str_err.begin(), str_err.end(), ~0ULL);
   for (uint32_t s = 0; s < R.num_strings; s++) any_err = any_err || str_err[s] != ~0ULL;
+  /* api.cu run_resolve: strings the reference does not verify in this block because of earlier blocks have no say */
+  for (uint32_t k = 0; any_err && k < n_skip; k++)
+    if (skip[k] < R.num_strings) str_err[skip[k]] = ~0ULL;
   if (any_err)
   {
     launch_per_thread(R.num_strings, 256, [&] {

@@ -433,3 +433,11 @@ def run_regions(B, seeds=range(5)):
 
 def test_block_lists_of_any_shape():
     run_regions(yrh.b200cpu())
+
+
+def test_errors_of_strings_settled_by_earlier_blocks_do_not_count():
+    """Fast mode over several blocks, fuzz seeds 1325 and 1563 (found by scripts/glue_sweep.py): a SINGLE_MATCH string
+    matches in an early block; in a later block one of its candidates would overflow the fiber pool
+    (ERROR_TOO_MANY_RE_FIBERS) -- but the reference no longer verifies that string (scan.c:1021-1023) and finishes
+    the scan.  The glue asks the engine again with the string named in yrb_scan_params.skip_strings."""
+    run_fuzz([1325, 1563])

@@ -35,6 +35,9 @@ class ScanParams(C.Structure):
         ("n_seeds", C.c_uint32),
         ("seeds", C.c_void_p),
         ("timeout_ns", C.c_uint64),
+        ("n_skip_strings", C.c_uint32),
+        ("reserved2", C.c_uint32),
+        ("skip_strings", C.c_void_p),
     ]
 
 

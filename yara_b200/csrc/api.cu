@@ -693,7 +693,11 @@ static int run_resolve(yrb_scanner* s, const Raw* d_raw, uint32_t n, const yrb_s
 
   if (hs->any_error)
   {
-    // rare: pick the earliest failing candidate the reference would really have verified
+    // rare: pick the earliest failing candidate the reference would really have verified.  Strings it does not
+    // verify in this block because of what earlier blocks of the scan did (params->skip_strings) have no say.
+    for (uint32_t k = 0; k < params->n_skip_strings && params->skip_strings != nullptr; k++)
+      if (params->skip_strings[k] < s->rules->R.num_strings)
+        CK(cudaMemsetAsync(s->str_err.p + params->skip_strings[k], 0xFF, sizeof(unsigned long long), s->stream));
     ResolveWork w;
     fill_work(s, w, d_raw, n, params->scan_flags);
     w.use_cut = !cuts.empty();

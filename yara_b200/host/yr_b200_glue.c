@@ -1321,6 +1321,17 @@ int yr_b200_scan_mem_block(YR_SCANNER* scanner, const uint8_t* block_data, YR_ME
   return scan_block_now(scanner, block_data, block, dev, re, max_match_data);
 }
 
+/* scan.c:1018-1023, the part of it that depends on EARLIER blocks of the scan: a string the 1,000,000-match cap
+   disabled there, or -- in fast mode -- a SINGLE_MATCH string that matched there.  (Heads of chained strings are
+   the engine's business: their state travels as seeds.) */
+static int not_verified_because_of_earlier_blocks(YR_SCANNER* scanner, YR_STRING* string)
+{
+  if (yr_bitmask_is_set(scanner->strings_temp_disabled, string->idx))
+    return 1;
+  return (scanner->flags & SCAN_FLAGS_FAST_MODE) && STRING_IS_SINGLE_MATCH(string) && !STRING_IS_CHAIN_PART(string) &&
+         scanner->matches[string->idx].head != NULL;
+}
+
 /* One block through the engine, now: H2D + scan + verify + resolve with the chain state of the earlier blocks as
    seeds, YR_MATCH lists built from the records. */
 static int scan_block_now(
@@ -1386,6 +1397,54 @@ static int scan_block_now(
     YR_B200_UNLOCK_MULTI();
     free(seed_nodes);
     return rc < 1000 ? rc : fail_loudly("yrb_scan_host", rc);
+  }
+
+  /* A verifier error of a string whose candidates the reference would not have verified in this block, because of
+     what EARLIER blocks of the scan did to it (scan.c:1018-1023), is not the scan's error.  The engine knows a block
+     at a time; it reports the earliest failing candidate, so only when that one belongs to such a string is there
+     anything to do: the block is scanned once more with those strings named (yrb_scan_params.skip_strings), and
+     whatever comes back then stands. */
+  uint32_t* skip_strings = NULL;
+  if (res.error != 0 && res.error != ERROR_TOO_MANY_MATCHES && res.error_string != YRB_NONE &&
+      res.error_string < scanner->rules->num_strings && params.skip_strings == NULL &&
+      not_verified_because_of_earlier_blocks(scanner, &scanner->rules->strings_table[res.error_string]))
+  {
+    YR_B200_UNLOCK_MULTI();
+    uint32_t n_skip = 0;
+    skip_strings = (uint32_t*) malloc(sizeof(uint32_t) * scanner->rules->num_strings);
+    if (skip_strings == NULL)
+    {
+      free(seed_nodes);
+      return ERROR_INSUFFICIENT_MEMORY;
+    }
+    for (uint32_t i = 0; i < scanner->rules->num_strings; i++)
+      if (not_verified_because_of_earlier_blocks(scanner, &scanner->rules->strings_table[i]))
+        skip_strings[n_skip++] = i;
+    params.skip_strings = skip_strings;
+    params.n_skip_strings = n_skip;
+    if (re->n_chain_strings > 0 && re->chain_strings != NULL)
+    {
+      /* the seeds again: the first call's copy is gone (the YR_MATCH nodes they stand for are untouched) */
+      free(seed_nodes);
+      seed_nodes = NULL;
+      rc = collect_seeds(scanner, re, &seeds, &seed_nodes, &n_seeds);
+      if (rc != ERROR_SUCCESS)
+      {
+        free(skip_strings);
+        return rc;
+      }
+      params.seeds = seeds;
+      params.n_seeds = n_seeds;
+    }
+    rc = yrb_scan_host(dev, block_data, block->size, &params, &res);
+    if (re->n_chain_strings > 0 && re->chain_strings != NULL)
+      free(seeds);
+    free(skip_strings);
+    if (rc != YRB_SUCCESS)
+    {
+      free(seed_nodes);
+      return rc < 1000 ? rc : fail_loudly("yrb_scan_host", rc);
+    }
   }
 
   if (res.error != 0)
