@@ -417,6 +417,12 @@ def region_lists(size, rng):
     yield "shuffled", sh
     yield "foreign bases", [(o, n, 0x7F0000000000 + 3 * o) for o, n, _ in asc]
     yield "all at base 0", [(o, n, 0) for o, n, _ in asc]
+    mixed, o = [], 0
+    while o < size:
+        n = min(rng.choice([300, 900, 1500, 1700, 2500, 4000]), size - o)     # around $YR_B200_BLOCK_BATCH of the test below
+        mixed.append((o, n, o))
+        o += n - min(n // 2, 128)
+    yield "mixed sizes", mixed
 
 
 def run_regions(B, seeds=range(5)):
@@ -441,3 +447,12 @@ def test_errors_of_strings_settled_by_earlier_blocks_do_not_count():
     (ERROR_TOO_MANY_RE_FIBERS) -- but the reference no longer verifies that string (scan.c:1021-1023) and finishes
     the scan.  The glue asks the engine again with the string named in yrb_scan_params.skip_strings."""
     run_fuzz([1325, 1563])
+
+
+def test_block_lists_with_a_small_deferral_limit():
+    """the same shapes with $YR_B200_BLOCK_BATCH=1600 (read once per process): blocks above it are scanned at once and
+    flush the deferred ones before them, so deferred and immediate blocks alternate"""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import yrh, test_glue_cpu as t; "
+            "t.run_regions(yrh.b200cpu(), range(3)); print('REGIONS_OK')" % (ROOT, os.path.join(ROOT, "tests")))
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ, YR_B200_BLOCK_BATCH="1600"))
+    assert p.returncode == 0 and "REGIONS_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
