@@ -456,3 +456,29 @@ def test_block_lists_with_a_small_deferral_limit():
             "t.run_regions(yrh.b200cpu(), range(3)); print('REGIONS_OK')" % (ROOT, os.path.join(ROOT, "tests")))
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ, YR_B200_BLOCK_BATCH="1600"))
     assert p.returncode == 0 and "REGIONS_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+MMD_CODE = r"""
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import fuzzgen, yrh, test_glue_cpu as t
+R, B = yrh.ref(), yrh.b200cpu()
+for mmd in (0, 7, 4096):
+    assert R.lib.yrh_set_max_match_data(mmd) == 0 and B.lib.yrh_set_max_match_data(mmd) == 0
+    t.run_fuzz(range(3))
+    # a result large enough for the packed match data path (8192+ matches)
+    rule = 'rule r { strings: $a = /ab+c?/ $b = "abbbbbbbbbbbbbbbbbbbb" condition: any of them }'
+    data = np.frombuffer((b"abbbbbbbbbbbbbbbbbbbbbbbbc--" * 6000), dtype=np.uint8)
+    a, b = R.compile(rule).scan(data, cap=1 << 20), B.compile(rule).scan(data, cap=1 << 20)
+    assert len(a.matches) >= 12000
+    t.same(a, b, "max_match_data %%d" %% mmd)
+print("MMD_OK")
+"""
+
+
+def test_other_settings_of_max_match_data():
+    """YR_CONFIG_MAX_MATCH_DATA (libyara.c:306; default 512) is process-wide: 0 (no data kept), a few bytes, 4096 --
+    data_length and the copied bytes (hashed by the harness) follow it, in materialise() and in the packed path."""
+    p = subprocess.run([sys.executable, "-c", MMD_CODE % (ROOT, os.path.join(ROOT, "tests"))], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "MMD_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
