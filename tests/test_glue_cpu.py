@@ -482,3 +482,25 @@ def test_other_settings_of_max_match_data():
     data_length and the copied bytes (hashed by the harness) follow it, in materialise() and in the packed path."""
     p = subprocess.run([sys.executable, "-c", MMD_CODE % (ROOT, os.path.join(ROOT, "tests"))], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "MMD_OK" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+def run_cap_across_blocks(B):
+    """YR_MAX_STRING_MATCHES (1,000,000) reached across the blocks of one scan: inside the first block, in the middle of
+    a later block (the list already holds what earlier blocks found), with the callback answering CONTINUE (the string
+    is disabled for the rest of the scan, later blocks add nothing) and ABORT (ERROR_TOO_MANY_MATCHES).  A second string
+    keeps matching throughout."""
+    R = yrh.ref()
+    rule = 'rule r { strings: $a = "aa" $b = "aab" condition: any of them }'
+    rr, rb = R.compile(rule), B.compile(rule)
+    data = np.full(2_300_000, ord("a"), dtype=np.uint8)
+    data[::50_000] = ord("b")
+    for block_size in (1_200_000, 700_000, 300_000, 200_000):     # the last: small enough to be deferred and batched
+        for action in (0, 1):
+            a = rr.scan_blocks(data, block_size, 0, too_many_action=action, cap=1 << 21)
+            b = rb.scan_blocks(data, block_size, 0, too_many_action=action, cap=1 << 21)
+            same(a, b, "cap across blocks of %d, action %d" % (block_size, action))
+            assert a.too_many_calls == 1 and (a.rc == 0) == (action == 0)
+
+
+def test_match_cap_across_blocks():
+    run_cap_across_blocks(yrh.b200cpu())
