@@ -162,3 +162,14 @@ def test_many_threads_learning_at_once():
         data = synth.corpus(rs, 1 << 20, 4096, seed=k)
         secs, rc = r.scan_mt(data, 16)
         assert rc == 0, (k, rc)
+
+
+def test_one_long_lived_scanner_and_odd_block_lists():
+    """the usage patterns of tests/test_glue_cpu.py -- ONE YR_SCANNER over many scans of different kinds, block lists
+    of any shape, a scanner reused after a scan that timed out -- with the filter on: what it has learnt in one
+    scan is used in the next ones of the same scanner, and nothing observable changes"""
+    import test_glue_cpu as t
+    P = yrh.refpf()
+    t.run_scanner_sequence(P, range(5))
+    t.run_regions(P, range(2))
+    t.run_scanner_reuse_after_timed_out_scan(P)
