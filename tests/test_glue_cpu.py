@@ -504,3 +504,17 @@ def run_cap_across_blocks(B):
 
 def test_match_cap_across_blocks():
     run_cap_across_blocks(yrh.b200cpu())
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_block_geometries(seed):
+    """other block sizes and overlaps than the reference's own test pass uses -- tiny blocks, overlaps of all but one
+    byte (every match is found many times over: dedup by base + offset), no overlap -- in both modes"""
+    R, B = yrh.ref(), yrh.b200cpu()
+    text, insts, n = fuzzgen.compile_filtered(R, seed, 40)
+    rr, rb = R.compile(text), B.compile(text)
+    data = np.frombuffer(bytes(fuzzgen.gen_data(seed + 900, insts, 3000 + 17 * seed)), dtype=np.uint8)
+    for bs, ov in ((64, 16), (100, 99), (257, 0), (4096, 0), (1000, 500), (33, 32)):
+        for flags in (0, 1):
+            same(rr.scan_blocks(data, bs, ov, flags=flags, cap=1 << 20), rb.scan_blocks(data, bs, ov, flags=flags, cap=1 << 20),
+                 "seed %d blocks %d/%d flags %d" % (seed, bs, ov, flags))
