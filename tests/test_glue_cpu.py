@@ -518,3 +518,21 @@ def test_block_geometries(seed):
         for flags in (0, 1):
             same(rr.scan_blocks(data, bs, ov, flags=flags, cap=1 << 20), rb.scan_blocks(data, bs, ov, flags=flags, cap=1 << 20),
                  "seed %d blocks %d/%d flags %d" % (seed, bs, ov, flags))
+
+
+def test_a_fuzz_ruleset_repeated_66_times():
+    """every rule of fuzz ruleset 1 under 66 names: match chains of 264 entries (more than an 8-bit chain position
+    holds) over all string types at once -- literals, hex with jumps and chains, regexps -- through the glue in all
+    the modes of run_fuzz"""
+    import re
+    orig = fuzzgen.compile_filtered
+
+    def repeated(R, seed, n):
+        text, insts, cnt = orig(R, seed, n)
+        return "".join(re.sub(r"\brule (\w+)", lambda m: "rule %s_%d" % (m.group(1), k), text) for k in range(66)), insts, cnt * 66
+
+    fuzzgen.compile_filtered = repeated
+    try:
+        run_fuzz([1])
+    finally:
+        fuzzgen.compile_filtered = orig
