@@ -536,3 +536,23 @@ def test_a_fuzz_ruleset_repeated_66_times():
         run_fuzz([1])
     finally:
         fuzzgen.compile_filtered = orig
+
+
+def test_concurrent_multi_block_scans():
+    """eight threads, each with its own scanner, scanning different buffers in 1 KiB and 4 KiB blocks in both modes at
+    the same time over ONE YR_RULES (the deferred-block state is per scanner; device scanners come from the shared pool)"""
+    from concurrent.futures import ThreadPoolExecutor
+    R, B = yrh.ref(), yrh.b200cpu()
+    text, insts, n = fuzzgen.compile_filtered(R, 2, 40)
+    rr, rb = R.compile(text), B.compile(text)
+    datas = [np.frombuffer(bytes(fuzzgen.gen_data(2 + 50 * k, insts, (1 << 14) + 31 * k)), dtype=np.uint8) for k in range(12)]
+    jobs = [(k, bs, fl) for k in range(12) for bs in (1024, 4096) for fl in (0, 1)]
+    want = {j: rr.scan_blocks(datas[j[0]], j[1], j[1] // 4, flags=j[2], cap=1 << 20) for j in jobs}
+
+    def run(j):
+        return j, rb.scan_blocks(datas[j[0]], j[1], j[1] // 4, flags=j[2], cap=1 << 20)
+
+    for rounds in range(2):
+        with ThreadPoolExecutor(8) as ex:
+            for j, got in ex.map(run, jobs):
+                same(want[j], got, "job %s" % (j,))
