@@ -33,12 +33,19 @@ def dump(name, rules, data, meta, flags=0):
 def main():
     R = yrh.ref()
     # the quirk-bearing known-answer cases
-    only = [int(x) for x in sys.argv[1:]]   # `make_golden.py 59`: (re)generate just these cases
+    only = [int(x) for x in sys.argv[1:] if x.isdigit()]   # `make_golden.py 59`: (re)generate just these cases
     for k in (only or (8, 19, 22, 27, 28, 32, 33, 42, len(CASES) - 1)):
         rule, data = CASES[k]
         open(os.path.join(HERE, "case%02d.bin" % k), "wb").write(data)
         dump("case%02d" % k, R.compile(rule), data, {"data": "case%02d.bin" % k, "rule": rule})
     if only:
+        return
+    # match chains of 300 entries (tests/long_chains.py): more than an 8-bit chain position holds
+    import long_chains
+    data = long_chains.corpus(4096, seed=3)
+    open(os.path.join(HERE, "long_chains.bin"), "wb").write(data.tobytes())
+    dump("long_chains", R.compile(long_chains.ruleset(600)), data, {"data": "long_chains.bin", "rules": "long_chains.ruleset(600)"})
+    if "long_chains" in sys.argv:
         return
     for cfg, n, size, every in ((2, 200, 1 << 16, 1024), (3, 300, 1 << 16, 512), (5, 120, 1 << 16, 512)):
         rs = synth.ruleset(cfg, n)
